@@ -1,0 +1,196 @@
+/*
+ * recnet_b200 -- C ABI of the B200-native (sm_100a) RecNet hot path.
+ *
+ * The reference (hobincar/reconstruction-network-for-video-captioning) has no FFI / plugin layer: its
+ * boundary for this path is the Python nn.Module surface.  This header is the
+ * C-ABI a binding for that surface calls; the Python mirror lives in
+ * reconstruction-network-for-video-captioning_b200/ and loads librecnet_b200.so with ctypes.
+ * Every entry point says which reference code it replaces (file:line in /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers owned by the caller
+ *     (PyTorch's caching allocator); nothing is allocated or freed here; kernels run on `stream`
+ *     (a cudaStream_t passed as void*) and the call returns without synchronising.
+ *   - return value: 0 = ok, > 0 = cudaError_t of a failed CUDA call, < 0 = recnet_status below.
+ *   - re-entrant: no global mutable state besides lazily-resolved driver entry points and
+ *     per-kernel shared-memory attributes; safe to call from the autograd engine's thread.
+ *   - precision: RECNET_PREC_FP32 = fp32 storage + fp32 FFMA GEMMs (parity build, 1e-3 vs oracle);
+ *     RECNET_PREC_BF16 = bf16 GEMM operands on tcgen05 tensor cores with fp32 TMEM accumulation,
+ *     fp32 cell state / reductions (2e-2 vs oracle).  There is no CPU path.
+ */
+#ifndef RECNET_B200_H_
+#define RECNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RECNET_OK = 0,
+  RECNET_ERR_BAD_SHAPE = -1,
+  RECNET_ERR_ALIGNMENT = -2,
+  RECNET_ERR_UNSUPPORTED_ARCH = -3,
+  RECNET_ERR_UNSUPPORTED = -4,
+  RECNET_ERR_WORKSPACE = -5,
+  RECNET_ERR_DRIVER = -6
+} recnet_status;
+
+typedef enum { RECNET_PREC_FP32 = 0, RECNET_PREC_BF16 = 1 } recnet_precision;
+
+/* Library / device checks.  recnet_query_device fails with RECNET_ERR_UNSUPPORTED_ARCH unless the
+ * device is compute capability 10.x (sm_100a cubins only; no PTX fallback, no other arch). */
+int recnet_abi_version(void);
+int recnet_query_device(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator level (one kernel family each).  Used by the per-step nn.Module.forward mirrors and by
+ * the per-kernel parity tests.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* C[m,n] (+)= sum_k A(m,k) B(n,k) (+ bias[n]).   Replaces every nn.Linear / cuBLAS call on the path
+ * (models/decoder.py:51,54,68; models/local_reconstructor.py:39,42,54; models/global_reconstructor.py:45)
+ * and the two GEMMs inside each nn.LSTM step (decoder.py:66 etc).
+ *   transA = 0: A is [M,K] row-major, lda; 1: A is [K,M] row-major.   transB = 0: B is [N,K] row-major
+ *   (nn.Linear weight layout); 1: B is [K,N] row-major.  Element type of A/B: float (FP32) or bf16 (BF16).
+ *   C fp32 [M,N] ldc (nullable if c_op given); c_op: optional second output in the operand type (bf16 only).
+ *   splits > 1: slice s of K writes its partial to C + s*split_stride (consumers sum the partials).
+ *   bn_hint: 0 = auto, or 64/128/256 = tcgen05 tile width (BF16 only). */
+int recnet_gemm(int precision, const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB,
+                float* C, int64_t ldc, void* c_op, int64_t ldc_op, const float* bias, int M, int N, int K,
+                int splits, int64_t split_stride, int accumulate, int bn_hint, void* stream);
+
+/* out[m*ldo + n] (+)= sum_s partial[s*split_stride + m*ldp + n] */
+int recnet_splitk_reduce(const float* partial, int splits, int64_t split_stride, int64_t ldp, float* out, int64_t ldo,
+                         int M, int N, int accumulate, void* stream);
+
+/* Fused additive attention, forward (models/decoder.py:50-62, models/local_reconstructor.py:38-50 minus the
+ * U-projection, which is hoisted):  e = w.tanh(Wh + Uv + b);  ctx = mean_tau(e * V)   [no softmax: SURVEY 0.1].
+ *   wh_partials [n_wh][B,A] fp32 (split-K partials of h W^T, summed here); uv[b*uv_bs + tau*uv_ts + a] fp32;
+ *   v[b*v_bs + tau*v_ts + d] in `precision` storage; ctx_out[b*ctx_ld + d] in `precision` storage.
+ *   wh_out [B,A], e_out [B,Tn] fp32: saved for backward (nullable).  normalize=1 -> softmax over frames
+ *   (paper variant, forward only).  p_drop/rng/site/drop_base: train-mode dropout on ctx (local reconstructor). */
+int recnet_attn_fwd(int precision, const float* wh_partials, int n_wh, int64_t wh_stride, const float* uv,
+                    int64_t uv_bs, int64_t uv_ts, const float* attn_b, const float* attn_w, const void* v,
+                    int64_t v_bs, int64_t v_ts, int B, int Tn, int A, int D, int normalize, float* wh_out,
+                    float* e_out, void* ctx_out, int64_t ctx_ld, float p_drop, const uint64_t* rng, uint32_t site,
+                    int64_t drop_base, void* stream);
+
+/* Fused additive attention, backward (autograd of the same lines).  dctx arrives as n_p split-K partials
+ * [n_p][B,p_ld] (columns [0,D)).  Outputs: dwh_out [B,A]; duv_acc (same strides as uv) and dw_acc [B,A]
+ * are accumulated across timesteps (first=1 overwrites); dctx_out [B,D] optional (summed, dropout-masked). */
+int recnet_attn_bwd(int precision, const float* dctx_partials, int n_p, int64_t p_stride, int64_t p_ld, const void* v,
+                    int64_t v_bs, int64_t v_ts, const float* wh, const float* uv, int64_t uv_bs, int64_t uv_ts,
+                    const float* attn_b, const float* attn_w, int B, int Tn, int A, int D, float* dwh_out,
+                    float* duv_acc, float* dw_acc, int first, float* dctx_out, float p_drop, const uint64_t* rng,
+                    uint32_t site, int64_t drop_base, void* stream);
+
+/* Fused LSTM gate activation + cell update (the pointwise half of nn.LSTM, decoder.py:66; gate order i,f,g,o).
+ *   pre = sum_s partials[s] + gx + b1 + b2.  gates_out [B,4H] (stash, `precision` storage), c_out/h_out fp32,
+ *   h_op / h_op2: h' in operand storage written into next step's [x;h] rows (nullable). */
+int recnet_lstm_cell_fwd(int precision, const float* partials, int n_p, int64_t p_stride, int64_t p_ld, const float* gx,
+                         int64_t gx_ld, const float* b1, const float* b2, const float* c_prev, int B, int H,
+                         void* gates_out, float* c_out, float* h_out, int64_t h_ld, void* h_op, int64_t hop_ld,
+                         void* h_op2, int64_t hop2_ld, void* stream);
+
+/* Backward of the same step.  dh = dh_scale*dh_ext + dh_ext2 + sum_s dxp[s][:, col0:col0+H] + dq @ wq
+ * (dq [B,A] = d(attention query projection), wq [A,H] = attn_W).  dc is in/out ([B,H]; first=1 -> treated as 0).
+ * dg_out [B,4H] in operand storage. */
+int recnet_lstm_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const float* dh_scale, const float* dh_ext2,
+                         int64_t dh2_ld, const float* dxp, int n_p, int64_t p_stride, int64_t p_ld, int col0,
+                         const float* dq, const float* wq, int A, float* dc, int first, const void* gates,
+                         const float* c_prev, const float* c_new, int B, int H, void* dg_out, int64_t dg_ld,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sequence level: whole teacher-forced loops, forward and BPTT, one host call each.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Decoder (reference Decoder module + train.forward_decoder loop, models/decoder.py:45-70, train.py:17-75). */
+typedef struct {
+  int32_t B, T, E, H, A, EMB, V, L;     /* L = decoded steps (<= caption_max_len + 1, train.py:41,66) */
+  int32_t precision;                    /* recnet_precision */
+  int32_t train;                        /* 1 = apply dropout (embedding, logits) */
+  float embedding_scale, p_emb_drop, p_out_drop;
+} recnet_decoder_desc;
+
+typedef struct {                        /* fp32 master weights, reference state_dict layout */
+  float *embedding, *attn_W, *attn_U, *attn_b, *attn_w, *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;
+} recnet_decoder_tensors;
+
+/* bytes of caller-provided workspace that must stay alive from fwd to bwd */
+int64_t recnet_decoder_workspace_bytes(const recnet_decoder_desc* d);
+
+/* tokens_in [L,B] int64 (SOS then targets[t-1], train.py:25,44-45); targets [L,B] int64; ce_weight [L,B] fp32 =
+ * mask/(n_t * sum n_t) (train.py:54-60,68).  Outputs: hiddens [L,B,H] fp32 (train.py:61-64,73), ce_out[1] =
+ * sum_t CE_t / sum_t n_t, logits_out [L*B, ld = round_up(V,4)] lives inside the workspace
+ * (recnet_decoder_logits returns it). */
+int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats,
+                       const int64_t* tokens_in, const int64_t* targets, const float* ce_weight, const uint64_t* rng,
+                       void* workspace, int64_t workspace_bytes, float* hiddens, float* ce_out, void* stream);
+/* g_ce: device scalar dLoss/dCE (nullable = 1); g_hiddens [L,B,H] fp32 (nullable). grads: every field written
+ * (overwritten, not accumulated). */
+int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats,
+                       const int64_t* tokens_in, const int64_t* targets, const float* ce_weight, const uint64_t* rng,
+                       void* workspace, int64_t workspace_bytes, const float* g_ce, const float* g_hiddens,
+                       const recnet_decoder_tensors* grads, void* stream);
+float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld);
+
+/* Greedy decoding (eval.greedy_search, eval.py:19-33): argmax feedback on device, zero host syncs.
+ * ids_out [max_steps,B] int64; n_steps_out[1] int32 (device) = steps until every fed-back token is <PAD>. */
+int64_t recnet_greedy_workspace_bytes(const recnet_decoder_desc* d);
+int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats,
+                          int max_steps, void* workspace, int64_t workspace_bytes, int64_t* ids_out,
+                          int32_t* n_steps_out, void* stream);
+
+/* Local reconstructor (models/local_reconstructor.py:37-55 + train.forward_local_reconstructor, train.py:108-131). */
+typedef struct {
+  int32_t B, S, R, H, A, L;             /* S = encoder_output_len steps, R = hidden (= feature dim), H = decoder hidden */
+  int32_t precision, train;
+  float p_drop;
+} recnet_local_desc;
+typedef struct {
+  float *attn_W, *attn_U, *attn_b, *attn_w, *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;
+} recnet_local_tensors;
+int64_t recnet_local_workspace_bytes(const recnet_local_desc* d);
+/* hiddens [L,B,H] fp32 (decoder states), feats [B,S,R] fp32; mse_out[1] = MSELoss(outputs^T, feats). */
+int recnet_local_fwd(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
+                     const uint64_t* rng, void* workspace, int64_t workspace_bytes, float* mse_out, void* stream);
+int recnet_local_bwd(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
+                     const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
+                     const recnet_local_tensors* grads, float* g_hiddens, void* stream);
+float* recnet_local_outputs(const recnet_local_desc* d, void* workspace);   /* [S,B,R] fp32 */
+
+/* Global reconstructor (models/global_reconstructor.py:30-46 + train.forward_global_reconstructor, train.py:78-105). */
+typedef struct {
+  int32_t B, L, R, H, T;                /* T = frames of feats (mean target), L = decoder steps */
+  int32_t precision, train;
+  float p_drop, caption_max_len;
+} recnet_global_desc;
+typedef struct {
+  float *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;
+} recnet_global_tensors;
+int64_t recnet_global_workspace_bytes(const recnet_global_desc* d);
+/* loss_out[1] = MSELoss(mean_t outputs, mean_tau feats) / L  (train.py:96-100) */
+int recnet_global_fwd(const recnet_global_desc* d, const recnet_global_tensors* w, const float* hiddens, const float* feats,
+                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, float* loss_out, void* stream);
+int recnet_global_bwd(const recnet_global_desc* d, const recnet_global_tensors* w, const float* hiddens, const float* feats,
+                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_loss,
+                      const recnet_global_tensors* grads, float* g_hiddens, void* stream);
+float* recnet_global_outputs(const recnet_global_desc* d, void* workspace);  /* [L,B,R] fp32 */
+
+/* L2-norm regulariser over a parameter list (train.py:69,101,127): reg = sum_p ||p||_2.
+ * ptrs/sizes: device int64 tables of n tensors; blk_tensor/blk_chunk: device int32 tables mapping block ->
+ * (tensor, 16384-element chunk); sumsq [n] fp32 scratch kept for the backward. */
+int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
+                           const int32_t* blk_chunk, int n_blocks, float* sumsq, float* reg_out, void* stream);
+/* grad_p (+)= lambda * g * p / ||p|| */
+int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n,
+                           const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, const float* sumsq,
+                           const float* g, float lambda, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECNET_B200_H_ */

@@ -1,0 +1,127 @@
+// Shared device/host helpers for the recnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/recnet_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define RN_CUDA_OK(expr)                                  \
+  do {                                                    \
+    cudaError_t _e = (expr);                              \
+    if (_e != cudaSuccess) return (int)_e;                \
+  } while (0)
+
+#define RN_LAUNCH_OK()                                    \
+  do {                                                    \
+    cudaError_t _e = cudaGetLastError();                  \
+    if (_e != cudaSuccess) return (int)_e;                \
+  } while (0)
+
+#define RN_TRY(expr)                                      \
+  do {                                                    \
+    int _r = (expr);                                      \
+    if (_r != 0) return _r;                               \
+  } while (0)
+
+static inline int rn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- type conversion -------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of T: 4 floats or 8 bf16
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = raw; }
+  __device__ __forceinline__ void get(float* f) const { f[0] = raw.x; f[1] = raw.y; f[2] = raw.z; f[3] = raw.w; }
+  __device__ __forceinline__ void set(const float* f) { raw = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void get(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  __device__ __forceinline__ void set(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+
+// ---- reductions ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; every thread gets the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- Philox4x32-10 counter RNG (Salmon et al. 2011), used for in-kernel dropout masks --------
+struct Philox {
+  uint32_t key[2];
+  __device__ __forceinline__ Philox(uint64_t seed) { key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32); }
+  __device__ __forceinline__ uint4 operator()(uint64_t ctr, uint64_t stream) const {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+    uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// keep-mask scale for element `idx` of dropout site `site`: 0 or 1/(1-p).  rng = {seed, offset}.
+__device__ __forceinline__ float dropout_scale(const unsigned long long* rng, uint32_t site, uint64_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  Philox ph(rng[0]);
+  const uint4 r = ph(idx >> 2, (rng[1] << 8) | site);
+  const uint32_t w = ((idx & 3) == 0) ? r.x : ((idx & 3) == 1) ? r.y : ((idx & 3) == 2) ? r.z : r.w;
+  const float u = (float)(w >> 8) * (1.0f / 16777216.0f);
+  return (u >= p) ? 1.f / (1.f - p) : 0.f;
+}

@@ -1,0 +1,224 @@
+// extern "C" entry points of librecnet_b200.so (declared in include/recnet_b200.h).
+#include "runtime.cuh"
+#include "seq_decoder.cuh"
+#include "seq_recon.cuh"
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int recnet_abi_version(void) { return 1; }
+
+int recnet_query_device(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  cudaDeviceProp prop;
+  RN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (prop.major != 10) return RECNET_ERR_UNSUPPORTED_ARCH;
+  return 0;
+}
+
+int recnet_gemm(int precision, const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, float* C,
+                int64_t ldc, void* c_op, int64_t ldc_op, const float* bias, int M, int N, int K, int splits,
+                int64_t split_stride, int accumulate, int bn_hint, void* stream) {
+  if (precision == RECNET_PREC_FP32) {
+    if (c_op) return RECNET_ERR_UNSUPPORTED;
+    return sg::launch(reinterpret_cast<const float*>(A), lda, transA, reinterpret_cast<const float*>(B), ldb, transB, C, ldc,
+                      bias, M, N, K, splits, split_stride, accumulate, ST(stream));
+  }
+  if (precision == RECNET_PREC_BF16)
+    return tc::launch(reinterpret_cast<const bf16*>(A), lda, transA, reinterpret_cast<const bf16*>(B), ldb, transB, C, ldc,
+                      reinterpret_cast<bf16*>(c_op), ldc_op, bias, M, N, K, splits, split_stride, accumulate, bn_hint,
+                      ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+int recnet_splitk_reduce(const float* partial, int splits, int64_t split_stride, int64_t ldp, float* out, int64_t ldo, int M,
+                         int N, int accumulate, void* stream) {
+  return rt::splitk_reduce(partial, splits, split_stride, ldp, out, ldo, M, N, nullptr, accumulate, ST(stream));
+}
+
+int recnet_attn_fwd(int precision, const float* wh_partials, int n_wh, int64_t wh_stride, const float* uv, int64_t uv_bs,
+                    int64_t uv_ts, const float* attn_b, const float* attn_w, const void* v, int64_t v_bs, int64_t v_ts, int B,
+                    int Tn, int A, int D, int normalize, float* wh_out, float* e_out, void* ctx_out, int64_t ctx_ld,
+                    float p_drop, const uint64_t* rng, uint32_t site, int64_t drop_base, void* stream) {
+  attn::FwdArgs a{};
+  a.WhP = wh_partials; a.n_whp = n_wh; a.whp_stride = wh_stride; a.Uv = uv; a.uv_bs = uv_bs; a.uv_ts = uv_ts;
+  a.attn_b = attn_b; a.attn_w = attn_w; a.V = v; a.v_bs = v_bs; a.v_ts = v_ts; a.B = B; a.Tn = Tn; a.A = A; a.D = D;
+  a.inv_T = 1.f / Tn; a.normalize = normalize; a.Wh_out = wh_out; a.e_out = e_out; a.ctx_out = ctx_out; a.ctx_ld = ctx_ld;
+  a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng); a.site = site; a.drop_base = drop_base;
+  if (precision == RECNET_PREC_FP32) return attn::launch_fwd<float, float>(a, ST(stream));
+  if (precision == RECNET_PREC_BF16) return attn::launch_fwd<bf16, bf16>(a, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+int recnet_attn_bwd(int precision, const float* dctx_partials, int n_p, int64_t p_stride, int64_t p_ld, const void* v,
+                    int64_t v_bs, int64_t v_ts, const float* wh, const float* uv, int64_t uv_bs, int64_t uv_ts,
+                    const float* attn_b, const float* attn_w, int B, int Tn, int A, int D, float* dwh_out, float* duv_acc,
+                    float* dw_acc, int first, float* dctx_out, float p_drop, const uint64_t* rng, uint32_t site,
+                    int64_t drop_base, void* stream) {
+  attn::BwdArgs a{};
+  a.dXp = dctx_partials; a.n_p = n_p; a.p_stride = p_stride; a.p_ld = p_ld; a.V = v; a.v_bs = v_bs; a.v_ts = v_ts;
+  a.Wh = wh; a.Uv = uv; a.uv_bs = uv_bs; a.uv_ts = uv_ts; a.attn_b = attn_b; a.attn_w = attn_w; a.B = B; a.Tn = Tn; a.A = A;
+  a.D = D; a.inv_T = 1.f / Tn; a.dWh_out = dwh_out; a.dUv_acc = duv_acc; a.uv_first = first; a.dw_acc = dw_acc;
+  a.dctx_out = dctx_out; a.de_out = nullptr; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng);
+  a.site = site; a.drop_base = drop_base;
+  if (precision == RECNET_PREC_FP32) return attn::launch_bwd<float>(a, ST(stream));
+  if (precision == RECNET_PREC_BF16) return attn::launch_bwd<bf16>(a, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+int recnet_lstm_cell_fwd(int precision, const float* partials, int n_p, int64_t p_stride, int64_t p_ld, const float* gx,
+                         int64_t gx_ld, const float* b1, const float* b2, const float* c_prev, int B, int H, void* gates_out,
+                         float* c_out, float* h_out, int64_t h_ld, void* h_op, int64_t hop_ld, void* h_op2, int64_t hop2_ld,
+                         void* stream) {
+  cell::FwdArgs a{};
+  a.P = partials; a.n_p = n_p; a.p_stride = p_stride; a.p_ld = p_ld; a.Gx = gx; a.gx_ld = gx_ld; a.b1 = b1; a.b2 = b2;
+  a.c_prev = c_prev; a.B = B; a.H = H; a.gates_out = gates_out; a.c_out = c_out; a.h_out = h_out; a.h_ld = h_ld;
+  a.h_op = h_op; a.hop_ld = hop_ld; a.h_op2 = h_op2; a.hop2_ld = hop2_ld;
+  if (precision == RECNET_PREC_FP32) return cell::launch_fwd<float, float>(a, ST(stream));
+  if (precision == RECNET_PREC_BF16) return cell::launch_fwd<bf16, bf16>(a, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+int recnet_lstm_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const float* dh_scale, const float* dh_ext2,
+                         int64_t dh2_ld, const float* dxp, int n_p, int64_t p_stride, int64_t p_ld, int col0, const float* dq,
+                         const float* wq, int A, float* dc, int first, const void* gates, const float* c_prev,
+                         const float* c_new, int B, int H, void* dg_out, int64_t dg_ld, void* stream) {
+  cell::BwdArgs a{};
+  a.dh_ext = dh_ext; a.dh_ld = dh_ld; a.dh_scale = dh_scale; a.dh_ext2 = dh_ext2; a.dh2_ld = dh2_ld; a.dXp = dxp; a.n_p = n_p;
+  a.p_stride = p_stride; a.p_ld = p_ld; a.col0 = col0; a.dQ = dq; a.Wq = wq; a.A = A; a.dc = dc; a.first = first; a.gates = gates;
+  a.c_prev = c_prev; a.c_new = c_new; a.B = B; a.H = H; a.dG = dg_out; a.dg_ld = dg_ld;
+  if (precision == RECNET_PREC_FP32) return cell::launch_bwd<float, float>(a, ST(stream));
+  if (precision == RECNET_PREC_BF16) return cell::launch_bwd<bf16, bf16>(a, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+// ---- decoder ---------------------------------------------------------------------------------------------------
+int64_t recnet_decoder_workspace_bytes(const recnet_decoder_desc* d) {
+  if (!d) return RECNET_ERR_BAD_SHAPE;
+  if (d->precision == RECNET_PREC_FP32) return (int64_t)dec::plan<float>(*d, nullptr).bytes;
+  if (d->precision == RECNET_PREC_BF16) return (int64_t)dec::plan<bf16>(*d, nullptr).bytes;
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
+                       const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
+                       int64_t workspace_bytes, float* hiddens, float* ce_out, void* stream) {
+  const long long* ti = reinterpret_cast<const long long*>(tokens_in);
+  const long long* tg = reinterpret_cast<const long long*>(targets);
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32)
+    return dec::forward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
+  if (d->precision == RECNET_PREC_BF16)
+    return dec::forward<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
+                       const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
+                       int64_t workspace_bytes, const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors* grads,
+                       void* stream) {
+  const long long* ti = reinterpret_cast<const long long*>(tokens_in);
+  const long long* tg = reinterpret_cast<const long long*>(targets);
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32)
+    return dec::backward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+  if (d->precision == RECNET_PREC_BF16)
+    return dec::backward<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld) {
+  if (d->precision == RECNET_PREC_FP32) { auto w = dec::plan<float>(*d, workspace); if (ld) *ld = w.Vld; return w.logits; }
+  auto w = dec::plan<bf16>(*d, workspace); if (ld) *ld = w.Vld; return w.logits;
+}
+int64_t recnet_greedy_workspace_bytes(const recnet_decoder_desc* d) {
+  if (d->precision == RECNET_PREC_FP32) return (int64_t)dec::plan_greedy<float>(*d, nullptr, 64).bytes;
+  if (d->precision == RECNET_PREC_BF16) return (int64_t)dec::plan_greedy<bf16>(*d, nullptr, 64).bytes;
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, int max_steps,
+                          void* workspace, int64_t workspace_bytes, int64_t* ids_out, int32_t* n_steps_out, void* stream) {
+  if (max_steps < 1 || max_steps > 64) return RECNET_ERR_BAD_SHAPE;
+  if (d->precision == RECNET_PREC_FP32)
+    return dec::greedy<float>(*d, *w, feats, max_steps, workspace, workspace_bytes, reinterpret_cast<long long*>(ids_out), n_steps_out, ST(stream));
+  if (d->precision == RECNET_PREC_BF16)
+    return dec::greedy<bf16>(*d, *w, feats, max_steps, workspace, workspace_bytes, reinterpret_cast<long long*>(ids_out), n_steps_out, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+// ---- local reconstructor ---------------------------------------------------------------------------------------
+int64_t recnet_local_workspace_bytes(const recnet_local_desc* d) {
+  if (d->precision == RECNET_PREC_FP32) return (int64_t)rec::plan_local<float>(*d, nullptr).bytes;
+  if (d->precision == RECNET_PREC_BF16) return (int64_t)rec::plan_local<bf16>(*d, nullptr).bytes;
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_local_fwd(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
+                     const uint64_t* rng, void* workspace, int64_t workspace_bytes, float* mse_out, void* stream) {
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32) return rec::local_forward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, mse_out, ST(stream));
+  if (d->precision == RECNET_PREC_BF16) return rec::local_forward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, mse_out, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_local_bwd(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
+                     const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
+                     const recnet_local_tensors* grads, float* g_hiddens, void* stream) {
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32) return rec::local_backward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
+  if (d->precision == RECNET_PREC_BF16) return rec::local_backward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+float* recnet_local_outputs(const recnet_local_desc* d, void* workspace) {
+  if (d->precision == RECNET_PREC_FP32) return rec::plan_local<float>(*d, workspace).out;
+  return rec::plan_local<bf16>(*d, workspace).out;
+}
+
+// ---- global reconstructor --------------------------------------------------------------------------------------
+int64_t recnet_global_workspace_bytes(const recnet_global_desc* d) {
+  if (d->precision == RECNET_PREC_FP32) return (int64_t)rec::plan_global<float>(*d, nullptr).bytes;
+  if (d->precision == RECNET_PREC_BF16) return (int64_t)rec::plan_global<bf16>(*d, nullptr).bytes;
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_global_fwd(const recnet_global_desc* d, const recnet_global_tensors* w, const float* hiddens, const float* feats,
+                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, float* loss_out, void* stream) {
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32) return rec::global_forward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, loss_out, ST(stream));
+  if (d->precision == RECNET_PREC_BF16) return rec::global_forward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, loss_out, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_global_bwd(const recnet_global_desc* d, const recnet_global_tensors* w, const float* hiddens, const float* feats,
+                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_loss,
+                      const recnet_global_tensors* grads, float* g_hiddens, void* stream) {
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32) return rec::global_backward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_loss, *grads, g_hiddens, ST(stream));
+  if (d->precision == RECNET_PREC_BF16) return rec::global_backward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_loss, *grads, g_hiddens, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+float* recnet_global_outputs(const recnet_global_desc* d, void* workspace) {
+  if (d->precision == RECNET_PREC_FP32) return rec::plan_global<float>(*d, workspace).out;
+  return rec::plan_global<bf16>(*d, workspace).out;
+}
+
+// ---- regulariser -----------------------------------------------------------------------------------------------
+int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor, const int32_t* blk_chunk,
+                           int n_blocks, float* sumsq, float* reg_out, void* stream) {
+  cudaStream_t st = ST(stream);
+  RN_CUDA_OK(cudaMemsetAsync(sumsq, 0, (size_t)n * sizeof(float), st));
+  misc::mt_sumsq_kernel<<<n_blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(ptrs), reinterpret_cast<const long long*>(sizes),
+                                                  blk_tensor, blk_chunk, sumsq);
+  RN_LAUNCH_OK();
+  misc::mt_norm_finalize_kernel<<<1, 256, 0, st>>>(sumsq, n, reg_out);
+  RN_LAUNCH_OK();
+  return 0;
+}
+int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
+                           const int32_t* blk_chunk, int n_blocks, const float* sumsq, const float* g, float lambda, int accumulate,
+                           void* stream) {
+  (void)n;
+  misc::mt_reg_grad_kernel<<<n_blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(ptrs),
+                                                             reinterpret_cast<const long long*>(grad_ptrs),
+                                                             reinterpret_cast<const long long*>(sizes), blk_tensor, blk_chunk, sumsq, g,
+                                                             lambda, accumulate);
+  RN_LAUNCH_OK();
+  return 0;
+}
+}  // extern "C"

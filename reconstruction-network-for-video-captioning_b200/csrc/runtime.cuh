@@ -1,0 +1,127 @@
+// Host-side runtime shared by the sequence drivers: precision dispatch of the GEMM provider, split-K policy,
+// workspace carving.  T = float (RECNET_PREC_FP32, FFMA sgemm) or bf16 (RECNET_PREC_BF16, tcgen05 GEMM).
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "losses.cuh"
+#include "lstm_cell.cuh"
+#include "misc.cuh"
+#include "sgemm.cuh"
+
+namespace rt {
+
+constexpr int NUM_SMS = 148;
+
+struct Bump {
+  uint8_t* base;
+  size_t off;
+  explicit Bump(void* b) : base(reinterpret_cast<uint8_t*>(b)), off(0) {}
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T> struct Prec;
+template <> struct Prec<float> { static constexpr int id = RECNET_PREC_FP32; static constexpr int kpad = 4; };
+template <> struct Prec<bf16> { static constexpr int id = RECNET_PREC_BF16; static constexpr int kpad = 64; };
+
+// ---- split-K / tile policy ---------------------------------------------------------------------------
+struct GemmPlan { int bn; int splits; };
+template <typename T> static inline GemmPlan plan_gemm(int M, int N, int K);
+template <> inline GemmPlan plan_gemm<bf16>(int M, int N, int K) {
+  GemmPlan p;
+  p.bn = (N >= 1024) ? 128 : 64;
+  const int tiles = rn_cdiv(M, tc::BM) * rn_cdiv(N, p.bn);
+  const int nkb = rn_cdiv(K, tc::BK);
+  int s = NUM_SMS / tiles;
+  if (s < 1) s = 1;
+  if (s > nkb) s = nkb;
+  const int kb_per = rn_cdiv(nkb, s);
+  p.splits = rn_cdiv(nkb, kb_per);
+  return p;
+}
+template <> inline GemmPlan plan_gemm<float>(int M, int N, int K) {
+  GemmPlan p;
+  p.bn = 0;
+  const int tiles = rn_cdiv(M, sg::BM) * rn_cdiv(N, sg::BN);
+  int s = (2 * NUM_SMS) / tiles;
+  const int maxs = K / 64 > 0 ? K / 64 : 1;
+  if (s < 1) s = 1;
+  if (s > maxs) s = maxs;
+  const int k_per = rn_cdiv(rn_cdiv(K, s), sg::BK) * sg::BK;
+  p.splits = rn_cdiv(K, k_per);
+  return p;
+}
+
+// ---- raw GEMM provider -----------------------------------------------------------------------------------
+static inline int gemm_raw(const float* A, long long lda, int tA, const float* B, long long ldb, int tB, float* C,
+                           long long ldc, const float* bias, int M, int N, int K, GemmPlan p, long long split_stride,
+                           int accumulate, cudaStream_t st) {
+  return sg::launch(A, lda, tA, B, ldb, tB, C, ldc, bias, M, N, K, p.splits, split_stride, accumulate, st);
+}
+static inline int gemm_raw(const bf16* A, long long lda, int tA, const bf16* B, long long ldb, int tB, float* C,
+                           long long ldc, const float* bias, int M, int N, int K, GemmPlan p, long long split_stride,
+                           int accumulate, cudaStream_t st) {
+  return tc::launch(A, lda, tA, B, ldb, tB, C, ldc, nullptr, 0, bias, M, N, K, p.splits, split_stride, accumulate,
+                    p.bn, st);
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ P, int splits, long long split_stride, long long ldp,
+                                     float* __restrict__ out, long long ldo, int M, int N, const float* __restrict__ bias,
+                                     int accumulate) {
+  const long long total = (long long)M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i % N);
+    float s = bias ? bias[n] : 0.f;
+    for (int k = 0; k < splits; ++k) s += P[k * split_stride + (long long)m * ldp + n];
+    float* o = out + (long long)m * ldo + n;
+    *o = accumulate ? *o + s : s;
+  }
+}
+static inline int splitk_reduce(const float* P, int splits, long long split_stride, long long ldp, float* out,
+                                long long ldo, int M, int N, const float* bias, int accumulate, cudaStream_t st) {
+  const long long total = (long long)M * N;
+  if (total <= 0) return 0;
+  int blocks = (int)min((long long)NUM_SMS * 8, (total + 255) / 256);
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(P, splits, split_stride, ldp, out, ldo, M, N, bias, accumulate);
+  RN_LAUNCH_OK();
+  return 0;
+}
+
+constexpr size_t SPLITK_SCRATCH_FLOATS = (size_t)NUM_SMS * 2 * 128 * 128;   // enough for any plan with splits > 1
+
+// Full GEMM into a dense destination: splits the K loop when the tile grid alone cannot fill the GPU,
+// reducing the partials with one extra pass.  `scratch` holds SPLITK_SCRATCH_FLOATS floats.
+template <typename T>
+static int gemm_full(const T* A, long long lda, int tA, const T* B, long long ldb, int tB, float* C, long long ldc,
+                     const float* bias, int M, int N, int K, int accumulate, float* scratch, cudaStream_t st) {
+  GemmPlan p = plan_gemm<T>(M, N, K);
+  const int Np = round_up(N, 4);
+  if (p.splits > 1 && (size_t)p.splits * M * Np > SPLITK_SCRATCH_FLOATS) p.splits = 1;
+  if (p.splits <= 1) {
+    p.splits = 1;
+    return gemm_raw(A, lda, tA, B, ldb, tB, C, ldc, bias, M, N, K, p, 0, accumulate, st);
+  }
+  RN_TRY(gemm_raw(A, lda, tA, B, ldb, tB, scratch, Np, nullptr, M, N, K, p, (long long)M * Np, 0, st));
+  return splitk_reduce(scratch, p.splits, (long long)M * Np, Np, C, ldc, M, N, bias, accumulate, st);
+}
+
+// Per-step GEMM that leaves split-K partials for the consumer kernel to sum: out [splits][M, N] (ld = N).
+template <typename T>
+static int gemm_partials(const T* A, long long lda, int tA, const T* B, long long ldb, int tB, float* P, int M, int N,
+                         int K, GemmPlan p, cudaStream_t st) {
+  return gemm_raw(A, lda, tA, B, ldb, tB, P, N, nullptr, M, N, K, p, (long long)M * N, 0, st);
+}
+
+template <typename T>
+static int zero_async(T* p, size_t n, cudaStream_t st) {
+  RN_CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+  return 0;
+}
+}  // namespace rt

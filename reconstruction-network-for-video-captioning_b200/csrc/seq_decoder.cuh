@@ -1,0 +1,329 @@
+// Decoder sequence driver: the whole teacher-forced loop of train.forward_decoder (train.py:17-75) over
+// Decoder.forward (models/decoder.py:45-70), forward and BPTT, restructured for B200:
+//   * U.v hoisted out of the loop (the reference recomputes it 31x, decoder.py:54)        -> 1 batched GEMM
+//   * W_ih split into [W_emb | W_ctx]: the embedding half is time-batched (M = L*B)        -> 1 batched GEMM
+//   * per step: [ctx_t ; h_{t-1}] @ [W_ctx | W_hh]^T as ONE K-concatenated tensor-core GEMM (no torch.cat,
+//     decoder.py:64), split-K partials summed inside the fused cell kernel
+//   * vocabulary projection batched over all steps (M = L*B), fused CE forward/backward over stacked logits
+//   * BPTT mirrors it; all weight gradients are batched GEMMs over the stashed operands after the loop.
+#pragma once
+#include "runtime.cuh"
+
+namespace dec {
+using namespace rt;
+
+enum : unsigned { SITE_EMB = 1, SITE_LOGITS = 2 };
+
+template <typename T>
+struct Ws {
+  // geometry
+  int EMBp, KX, Vp, Vld;
+  GemmPlan pl_wh, pl_gate, pl_dx;
+  // operand copies of the weights / inputs (rebuilt every forward: the optimiser changes the masters)
+  T *Wemb, *Wrec, *U, *Wa, *Wout, *feats;
+  // forward state kept for BPTT
+  float* Uv; T* Xe; float* Gx; T* X; float* WhP; float* Wh; float* e; float* P; T* gates; float* c;
+  float *logits, *lse, *row_loss;
+  // backward scratch
+  T* dlogits; float* dHext; T* dG; float* dXp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
+  float* dc; float* dXe; float* splitk;
+  size_t bytes;
+};
+
+template <typename T>
+static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
+  Ws<T> w;
+  const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T;
+  w.EMBp = round_up(d.EMB, Prec<T>::kpad);
+  w.KX = E + H;
+  w.Vp = round_up(V, 8);
+  w.Vld = round_up(V, 4);
+  w.pl_wh = plan_gemm<T>(B, A, H);
+  w.pl_gate = plan_gemm<T>(B, 4 * H, w.KX);
+  w.pl_dx = plan_gemm<T>(B, w.KX, 4 * H);
+  Bump m(base);
+  w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);
+  w.Wrec = m.take<T>((size_t)4 * H * w.KX);
+  w.U = m.take<T>((size_t)A * E);
+  w.Wa = m.take<T>((size_t)A * H);
+  w.Wout = m.take<T>((size_t)V * H);
+  w.feats = m.take<T>((size_t)B * Tn * E);
+  w.Uv = m.take<float>((size_t)B * Tn * A);
+  w.Xe = m.take<T>((size_t)L * B * w.EMBp);
+  w.Gx = m.take<float>((size_t)L * B * 4 * H);
+  w.X = m.take<T>((size_t)(L + 1) * B * w.KX);
+  w.WhP = m.take<float>((size_t)w.pl_wh.splits * B * A);
+  w.Wh = m.take<float>((size_t)L * B * A);
+  w.e = m.take<float>((size_t)L * B * Tn);
+  w.P = m.take<float>((size_t)w.pl_gate.splits * B * 4 * H);
+  w.gates = m.take<T>((size_t)L * B * 4 * H);
+  w.c = m.take<float>((size_t)(L + 1) * B * H);
+  w.logits = m.take<float>((size_t)L * B * w.Vld);
+  w.lse = m.take<float>((size_t)L * B);
+  w.row_loss = m.take<float>((size_t)L * B);
+  w.dlogits = m.take<T>((size_t)L * B * w.Vp);
+  w.dHext = m.take<float>((size_t)L * B * H);
+  w.dG = m.take<T>((size_t)L * B * 4 * H);
+  w.dXp = m.take<float>((size_t)w.pl_dx.splits * B * w.KX);
+  w.dWh = m.take<float>((size_t)L * B * A);
+  w.dWh_op = m.take<T>((size_t)L * B * A);
+  w.dUv = m.take<float>((size_t)B * Tn * A);
+  w.dUv_op = m.take<T>((size_t)B * Tn * A);
+  w.dw_acc = m.take<float>((size_t)B * A);
+  w.dc = m.take<float>((size_t)B * H);
+  w.dXe = m.take<float>((size_t)L * B * w.EMBp);
+  w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.bytes = m.off + 256;
+  return w;
+}
+
+static inline int check(const recnet_decoder_desc& d) {
+  if (d.B < 1 || d.T < 1 || d.L < 1 || d.V < 3 || d.EMB < 1 || d.T > attn::MAX_T) return RECNET_ERR_BAD_SHAPE;
+  const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
+  if (d.E % al || d.H % al || d.A % 4) return RECNET_ERR_ALIGNMENT;
+  return 0;
+}
+
+// Build the operand-typed copies of weights and features.
+template <typename T>
+static int prepare(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, Ws<T>& w, cudaStream_t st) {
+  const int H = d.H, E = d.E, A = d.A, V = d.V, EMB = d.EMB;
+  const long long ldih = EMB + E;
+  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, st));
+  RN_TRY(misc::cast_pad<T>(p.w_ih + EMB, ldih, w.Wrec, w.KX, 4 * H, E, E, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wrec + E, w.KX, 4 * H, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.attn_U, E, w.U, E, A, E, E, st));
+  RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wa, H, A, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
+  if (feats) RN_TRY(misc::cast_pad<T>(feats, E, w.feats, E, (long long)d.B * d.T, E, E, st));
+  return 0;
+}
+
+// one decoder step given X[t] h-slot filled: attention -> gate GEMM -> cell.  Shared by forward and greedy.
+template <typename T>
+static int step(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, Ws<T>& w, int t, const float* gx_t,
+                const float* b1, T* x_t, T* x_next, float* Wh_t, float* e_t, T* gates_t, const float* c_prev,
+                float* c_next, float* h_out, cudaStream_t st) {
+  const int B = d.B, H = d.H, E = d.E, A = d.A, Tn = d.T;
+  int n_whp = 0;
+  if (t > 0) {   // h_{-1} = 0 -> W h = 0, skip the GEMM
+    RN_TRY(gemm_partials<T>(x_t + E, w.KX, 0, w.Wa, H, 0, w.WhP, B, A, H, w.pl_wh, st));
+    n_whp = w.pl_wh.splits;
+  }
+  attn::FwdArgs fa{};
+  fa.WhP = w.WhP; fa.n_whp = n_whp; fa.whp_stride = (long long)B * A;
+  fa.Uv = w.Uv; fa.uv_bs = (long long)Tn * A; fa.uv_ts = A;
+  fa.attn_b = p.attn_b; fa.attn_w = p.attn_w;
+  fa.V = w.feats; fa.v_bs = (long long)Tn * E; fa.v_ts = E;
+  fa.B = B; fa.Tn = Tn; fa.A = A; fa.D = E; fa.inv_T = 1.f / Tn; fa.normalize = 0;
+  fa.Wh_out = Wh_t; fa.e_out = e_t; fa.ctx_out = x_t; fa.ctx_ld = w.KX; fa.p_drop = 0.f;
+  RN_TRY((attn::launch_fwd<T, T>(fa, st)));
+  RN_TRY(gemm_partials<T>(x_t, w.KX, 0, w.Wrec, w.KX, 0, w.P, B, 4 * H, w.KX, w.pl_gate, st));
+  cell::FwdArgs ca{};
+  ca.P = w.P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)B * 4 * H; ca.p_ld = 4 * H;
+  ca.Gx = gx_t; ca.gx_ld = 4 * H; ca.b1 = b1; ca.b2 = p.b_hh; ca.c_prev = c_prev; ca.B = B; ca.H = H;
+  ca.gates_out = gates_t; ca.c_out = c_next; ca.h_out = h_out; ca.h_ld = H;
+  ca.h_op = x_next + E; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
+  RN_TRY((cell::launch_fwd<T, T>(ca, st)));
+  return 0;
+}
+
+template <typename T>
+static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
+                   const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
+                   float* hiddens, float* ce_out, cudaStream_t st) {
+  RN_TRY(check(d));
+  Ws<T> w = plan<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T;
+  const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
+  RN_TRY(prepare<T>(d, p, feats, w, st));
+  // hoisted projections
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, nullptr, B * Tn, A, E, 0, w.splitk, st));
+  misc::embed_gather_kernel<T><<<L * B, 128, 0, st>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, d.EMB, w.EMBp, V,
+                                                      d.embedding_scale, p_emb, rng, SITE_EMB);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk, st));
+  // initial state: h_{-1} = 0 (operand slot of X[0]), c_{-1} = 0
+  RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
+  for (int t = 0; t < L; ++t) {
+    T* x_t = w.X + (size_t)t * B * w.KX;
+    RN_TRY(step<T>(d, p, w, t, w.Gx + (size_t)t * B * 4 * H, nullptr, x_t, x_t + (size_t)B * w.KX,
+                   w.Wh + (size_t)t * B * A, w.e + (size_t)t * B * Tn, w.gates + (size_t)t * B * 4 * H,
+                   w.c + (size_t)t * B * H, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H, st));
+  }
+  // vocabulary projection over all steps, then the masked CE (train.py:54-60,68)
+  RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, L * B, V, H, 0,
+                      w.splitk, st));
+  if (targets && ce_weight && ce_out) {
+    loss::ce_fwd_kernel<<<L * B, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, V, p_out, rng, SITE_LOGITS,
+                                                            w.lse, w.row_loss);
+    RN_LAUNCH_OK();
+    loss::sum_kernel<<<1, 1024, 0, st>>>(w.row_loss, L * B, ce_out, 1.f);
+    RN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <typename T>
+static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
+                    const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
+                    const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors& g, cudaStream_t st) {
+  RN_TRY(check(d));
+  Ws<T> w = plan<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T, EMB = d.EMB;
+  const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
+  const int LB = L * B;
+  const T* Hall = w.X + (size_t)B * w.KX + E;     // h_t rows, ld = KX
+  // ---- CE backward and the vocabulary projection --------------------------------------------------------
+  loss::ce_bwd_kernel<T><<<LB, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, w.lse, g_ce, V, w.Vp, p_out, rng,
+                                                          SITE_LOGITS, w.dlogits, w.Vp);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, w.KX, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk, st));
+  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, st));
+  // ---- BPTT ---------------------------------------------------------------------------------------------
+  for (int t = L - 1; t >= 0; --t) {
+    const bool last = (t == L - 1);
+    cell::BwdArgs cb{};
+    cb.dh_ext = w.dHext + (size_t)t * B * H; cb.dh_ld = H; cb.dh_scale = nullptr;
+    cb.dh_ext2 = g_hiddens ? g_hiddens + (size_t)t * B * H : nullptr; cb.dh2_ld = H;
+    cb.dXp = last ? nullptr : w.dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)B * w.KX; cb.p_ld = w.KX; cb.col0 = E;
+    cb.dQ = last ? nullptr : w.dWh + (size_t)(t + 1) * B * A; cb.Wq = p.attn_W; cb.A = A;
+    cb.dc = w.dc; cb.first = last ? 1 : 0;
+    cb.gates = w.gates + (size_t)t * B * 4 * H;
+    cb.c_prev = w.c + (size_t)t * B * H; cb.c_new = w.c + (size_t)(t + 1) * B * H;
+    cb.B = B; cb.H = H; cb.dG = w.dG + (size_t)t * B * 4 * H; cb.dg_ld = 4 * H;
+    RN_TRY((cell::launch_bwd<T, T>(cb, st)));
+    // d[ctx ; h_{t-1}] = dG_t @ [W_ctx | W_hh]
+    RN_TRY(gemm_partials<T>(w.dG + (size_t)t * B * 4 * H, 4 * H, 0, w.Wrec, w.KX, 1, w.dXp, B, w.KX, 4 * H, w.pl_dx, st));
+    attn::BwdArgs ab{};
+    ab.dXp = w.dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)B * w.KX; ab.p_ld = w.KX;
+    ab.V = w.feats; ab.v_bs = (long long)Tn * E; ab.v_ts = E;
+    ab.Wh = w.Wh + (size_t)t * B * A; ab.Uv = w.Uv; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
+    ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = B; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
+    ab.dWh_out = w.dWh + (size_t)t * B * A; ab.dUv_acc = w.dUv; ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc;
+    ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
+    RN_TRY(attn::launch_bwd<T>(ab, st));
+  }
+  // ---- batched weight gradients over the stashed operands ----------------------------------------------------
+  const long long ldih = EMB + E;
+  RN_TRY(misc::colsum<T>(w.dG, 4 * H, LB, 4 * H, g.b_ih, 0, st));
+  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.X, w.KX, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, LB, 0, w.splitk, st));      // dW_ctx
+  RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.X + E, w.KX, 1, g.w_hh, H, nullptr, 4 * H, H, LB, 0, w.splitk, st));           // dW_hh
+  RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk, st));        // dW_emb
+  RN_TRY(gemm_full<T>(w.dG, 4 * H, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk, st));     // dXe
+  RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), st));
+  misc::embed_scatter_kernel<<<LB, 128, 0, st>>>(g.embedding, tokens_in, w.dXe, w.EMBp, LB, EMB, V, d.embedding_scale, p_emb, rng,
+                                                 SITE_EMB);
+  RN_LAUNCH_OK();
+  // attention parameters
+  RN_TRY(misc::cast_pad<T>(w.dWh, A, w.dWh_op, A, LB, A, A, st));
+  RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + E, w.KX, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk, st));              // dW_a = dWh^T h_{t-1}
+  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)B * Tn, A, A, st));
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.feats, E, 1, g.attn_U, E, nullptr, A, E, B * Tn, 0, w.splitk, st));             // dU = dUv^T v
+  RN_TRY(misc::colsum<float>(w.dWh, A, LB, A, g.attn_b, 0, st));
+  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, st));
+  return 0;
+}
+
+// ---- greedy decoding (eval.py:19-33) ---------------------------------------------------------------------------
+// argmax over the vocabulary (lowest index wins ties, like topk(1)), feeds the id back as next token, all on device.
+__global__ void argmax_feedback_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ ids_out,
+                                       long long* __restrict__ next_tok, int* __restrict__ nonpad_count) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int b = blockIdx.x;
+  const float* z = logits + (long long)b * ld;
+  float best = -INFINITY; int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float x = z[v];
+    if (x > best || (x == best && v < bi)) { best = x; bi = v; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sv[wp] = best; si[wp] = bi; }
+  __syncthreads();
+  if (wp == 0) {
+    best = lane < nw ? sv[lane] : -INFINITY; bi = lane < nw ? si[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      ids_out[b] = bi; next_tok[b] = bi;
+      if (bi != 0) atomicAdd(nonpad_count, 1);
+    }
+  }
+}
+// n_steps = first step (1-based) after which every fed-back token was <PAD> (eval.py:30), else max_steps
+__global__ void greedy_finalize_kernel(const int* __restrict__ nonpad, int max_steps, int* __restrict__ n_steps) {
+  int n = max_steps;
+  for (int t = 0; t < max_steps; ++t) if (nonpad[t] == 0) { n = t + 1; break; }
+  *n_steps = n;
+}
+__global__ void fill_tokens_kernel(long long* tok, int n, long long v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tok[i] = v;
+}
+
+template <typename T>
+struct GreedyWs { Ws<T> w; long long* tok; int* nonpad; float* h_scratch; size_t bytes; };
+
+template <typename T>
+static GreedyWs<T> plan_greedy(const recnet_decoder_desc& d, void* base, int max_steps) {
+  GreedyWs<T> g;
+  recnet_decoder_desc d1 = d; d1.L = 1;
+  g.w = plan<T>(d1, base);
+  Bump m(base); m.off = g.w.bytes;
+  g.tok = m.take<long long>(d.B);
+  g.nonpad = m.take<int>(max_steps);
+  g.h_scratch = m.take<float>((size_t)d.B * d.H);
+  g.bytes = m.off + 256;
+  return g;
+}
+
+template <typename T>
+static int greedy(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p, const float* feats, int max_steps, void* ws,
+                  long long ws_bytes, long long* ids_out, int* n_steps_out, cudaStream_t st) {
+  recnet_decoder_desc d = d0; d.L = 1; d.train = 0;
+  RN_TRY(check(d));
+  GreedyWs<T> g = plan_greedy<T>(d0, ws, max_steps);
+  if ((long long)g.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  Ws<T>& w = g.w;
+  const int B = d.B, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T;
+  RN_TRY(prepare<T>(d, p, feats, w, st));
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, nullptr, B * Tn, A, E, 0, w.splitk, st));
+  RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)2 * B * w.KX * sizeof(T), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)2 * B * H * sizeof(float), st));
+  RN_CUDA_OK(cudaMemsetAsync(g.nonpad, 0, (size_t)max_steps * sizeof(int), st));
+  fill_tokens_kernel<<<rn_cdiv(B, 128), 128, 0, st>>>(g.tok, B, 1 /* <SOS> */);
+  RN_LAUNCH_OK();
+  // ping-pong the two X rows / c rows of the L=1 plan
+  for (int t = 0; t < max_steps; ++t) {
+    T* x_t = w.X + (size_t)(t & 1) * B * w.KX;
+    T* x_n = w.X + (size_t)((t + 1) & 1) * B * w.KX;
+    float* c_p = w.c + (size_t)(t & 1) * B * H;
+    float* c_n = w.c + (size_t)((t + 1) & 1) * B * H;
+    misc::embed_gather_kernel<T><<<B, 128, 0, st>>>(p.embedding, g.tok, w.Xe, w.EMBp, B, d.EMB, w.EMBp, V, d.embedding_scale, 0.f,
+                                                    nullptr, SITE_EMB);
+    RN_LAUNCH_OK();
+    RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, B, 4 * H, w.EMBp, 0, w.splitk, st));
+    RN_TRY(step<T>(d, p, w, t, w.Gx, nullptr, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n, g.h_scratch, st));
+    RN_TRY(gemm_full<T>(x_n + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, B, V, H, 0, w.splitk, st));
+    argmax_feedback_kernel<<<B, 256, 0, st>>>(w.logits, w.Vld, V, ids_out + (size_t)t * B, g.tok, g.nonpad + t);
+    RN_LAUNCH_OK();
+  }
+  greedy_finalize_kernel<<<1, 1, 0, st>>>(g.nonpad, max_steps, n_steps_out);
+  RN_LAUNCH_OK();
+  return 0;
+}
+}  // namespace dec

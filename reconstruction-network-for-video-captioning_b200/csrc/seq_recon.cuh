@@ -1,0 +1,322 @@
+// Reconstructor sequence drivers.
+//  local  : train.forward_local_reconstructor (train.py:108-131) over LocalReconstructor.forward
+//           (models/local_reconstructor.py:37-55): attention over the L decoder states, LSTM(R), Linear(R,R), MSE.
+//  global : train.forward_global_reconstructor (train.py:78-105) over GlobalReconstructor.forward
+//           (models/global_reconstructor.py:30-46): [h_t ; mean-pool] -> LSTM(R) -> Linear(R,R), MSE of means / L.
+// Same restructuring as the decoder: U.hiddens hoisted, [x ; h] K-concatenated gate GEMM per step, output
+// projection and all weight gradients batched over time.  One decoder layer (the reference default).
+#pragma once
+#include "runtime.cuh"
+
+namespace rec {
+using namespace rt;
+
+enum : unsigned { SITE_LOCAL_X = 3, SITE_GLOBAL_MP = 4 };
+
+// ================================================ local =========================================================
+template <typename T>
+struct LocalWs {
+  int KX;
+  GemmPlan pl_wh, pl_gate, pl_dx;
+  T *Wrec, *U, *Wa, *Wout, *Hd;
+  float* Uv; T* X; float* WhP; float* Wh; float* beta; float* P; T* gates; float* c; float* out; float* partial;
+  T* dOut; float* dHext; T* dG; float* dXp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
+  float* dx; float* splitk;
+  size_t bytes;
+};
+constexpr int MSE_BLOCKS = 592;
+
+template <typename T>
+static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
+  LocalWs<T> w;
+  const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
+  w.KX = H + R;
+  w.pl_wh = plan_gemm<T>(B, A, R);
+  w.pl_gate = plan_gemm<T>(B, 4 * R, w.KX);
+  w.pl_dx = plan_gemm<T>(B, w.KX, 4 * R);
+  Bump m(base);
+  w.Wrec = m.take<T>((size_t)4 * R * w.KX);
+  w.U = m.take<T>((size_t)A * H);
+  w.Wa = m.take<T>((size_t)A * R);
+  w.Wout = m.take<T>((size_t)R * R);
+  w.Hd = m.take<T>((size_t)L * B * H);
+  w.Uv = m.take<float>((size_t)L * B * A);
+  w.X = m.take<T>((size_t)(S + 1) * B * w.KX);
+  w.WhP = m.take<float>((size_t)w.pl_wh.splits * B * A);
+  w.Wh = m.take<float>((size_t)S * B * A);
+  w.beta = m.take<float>((size_t)S * B * L);
+  w.P = m.take<float>((size_t)w.pl_gate.splits * B * 4 * R);
+  w.gates = m.take<T>((size_t)S * B * 4 * R);
+  w.c = m.take<float>((size_t)(S + 1) * B * R);
+  w.out = m.take<float>((size_t)S * B * R);
+  w.partial = m.take<float>(MSE_BLOCKS);
+  w.dOut = m.take<T>((size_t)S * B * R);
+  w.dHext = m.take<float>((size_t)S * B * R);
+  w.dG = m.take<T>((size_t)S * B * 4 * R);
+  w.dXp = m.take<float>((size_t)w.pl_dx.splits * B * w.KX);
+  w.dWh = m.take<float>((size_t)S * B * A);
+  w.dWh_op = m.take<T>((size_t)S * B * A);
+  w.dUv = m.take<float>((size_t)L * B * A);
+  w.dUv_op = m.take<T>((size_t)L * B * A);
+  w.dw_acc = m.take<float>((size_t)B * A);
+  w.dc = m.take<float>((size_t)B * R);
+  w.dx = m.take<float>((size_t)S * B * H);
+  w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.bytes = m.off + 256;
+  return w;
+}
+
+static inline int check_local(const recnet_local_desc& d) {
+  if (d.B < 1 || d.S < 1 || d.L < 1 || d.L > attn::MAX_T) return RECNET_ERR_BAD_SHAPE;
+  const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
+  if (d.R % al || d.H % al || d.A % 4) return RECNET_ERR_ALIGNMENT;
+  return 0;
+}
+
+template <typename T>
+static int local_forward(const recnet_local_desc& d, const recnet_local_tensors& p, const float* hiddens, const float* feats,
+                         const unsigned long long* rng, void* ws, long long ws_bytes, float* mse_out, cudaStream_t st) {
+  RN_TRY(check_local(d));
+  LocalWs<T> w = plan_local<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
+  const float p_drop = d.train ? d.p_drop : 0.f;
+  RN_TRY(misc::cast_pad<T>(p.w_ih, H, w.Wrec, w.KX, 4 * R, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Wrec + H, w.KX, 4 * R, R, R, st));
+  RN_TRY(misc::cast_pad<T>(p.attn_U, H, w.U, H, A, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.attn_W, R, w.Wa, R, A, R, R, st));
+  RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
+  RN_TRY(misc::cast_pad<T>(hiddens, H, w.Hd, H, (long long)L * B, H, H, st));
+  RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
+  RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
+  for (int t = 0; t < S; ++t) {
+    T* x_t = w.X + (size_t)t * B * w.KX;
+    T* x_n = x_t + (size_t)B * w.KX;
+    int n_whp = 0;
+    if (t > 0) {
+      RN_TRY(gemm_partials<T>(x_t + H, w.KX, 0, w.Wa, R, 0, w.WhP, B, A, R, w.pl_wh, st));
+      n_whp = w.pl_wh.splits;
+    }
+    attn::FwdArgs fa{};
+    fa.WhP = w.WhP; fa.n_whp = n_whp; fa.whp_stride = (long long)B * A;
+    fa.Uv = w.Uv; fa.uv_bs = A; fa.uv_ts = (long long)B * A;          // Uv is [L,B,A]
+    fa.attn_b = p.attn_b; fa.attn_w = p.attn_w;
+    fa.V = w.Hd; fa.v_bs = H; fa.v_ts = (long long)B * H;             // values = decoder states [L,B,H]
+    fa.B = B; fa.Tn = L; fa.A = A; fa.D = H; fa.inv_T = 1.f / L; fa.normalize = 0;
+    fa.Wh_out = w.Wh + (size_t)t * B * A; fa.e_out = w.beta + (size_t)t * B * L;
+    fa.ctx_out = x_t; fa.ctx_ld = w.KX;
+    fa.p_drop = p_drop; fa.rng = rng; fa.site = SITE_LOCAL_X; fa.drop_base = (long long)t * B * H;
+    RN_TRY((attn::launch_fwd<T, T>(fa, st)));
+    RN_TRY(gemm_partials<T>(x_t, w.KX, 0, w.Wrec, w.KX, 0, w.P, B, 4 * R, w.KX, w.pl_gate, st));
+    cell::FwdArgs ca{};
+    ca.P = w.P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)B * 4 * R; ca.p_ld = 4 * R;
+    ca.Gx = nullptr; ca.b1 = p.b_ih; ca.b2 = p.b_hh; ca.c_prev = w.c + (size_t)t * B * R; ca.B = B; ca.H = R;
+    ca.gates_out = w.gates + (size_t)t * B * 4 * R; ca.c_out = w.c + (size_t)(t + 1) * B * R; ca.h_out = nullptr;
+    ca.h_op = x_n + H; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
+    RN_TRY((cell::launch_fwd<T, T>(ca, st)));
+  }
+  RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + H, w.KX, 0, w.Wout, R, 0, w.out, R, p.out_b, S * B, R, R, 0, w.splitk, st));
+  if (mse_out) {
+    loss::mse_local_fwd_kernel<<<MSE_BLOCKS, 256, 0, st>>>(w.out, feats, S, B, R, w.partial);
+    RN_LAUNCH_OK();
+    loss::sum_kernel<<<1, 1024, 0, st>>>(w.partial, MSE_BLOCKS, mse_out, 1.f / ((float)S * B * R));
+    RN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <typename T>
+static int local_backward(const recnet_local_desc& d, const recnet_local_tensors& p, const float* hiddens, const float* feats,
+                          const unsigned long long* rng, void* ws, long long ws_bytes, const float* g_mse,
+                          const recnet_local_tensors& g, float* g_hiddens, cudaStream_t st) {
+  RN_TRY(check_local(d));
+  LocalWs<T> w = plan_local<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
+  const float p_drop = d.train ? d.p_drop : 0.f;
+  const int SB = S * B;
+  const T* Hr = w.X + (size_t)B * w.KX + H;       // h_t rows, ld = KX
+  loss::mse_local_bwd_kernel<T><<<MSE_BLOCKS, 256, 0, st>>>(w.out, feats, S, B, R, g_mse, 2.f / ((float)S * B * R), w.dOut);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.dOut, R, 0, w.Wout, R, 1, w.dHext, R, nullptr, SB, R, R, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk, st));
+  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, st));
+  for (int t = S - 1; t >= 0; --t) {
+    const bool last = (t == S - 1);
+    cell::BwdArgs cb{};
+    cb.dh_ext = w.dHext + (size_t)t * B * R; cb.dh_ld = R;
+    cb.dXp = last ? nullptr : w.dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)B * w.KX; cb.p_ld = w.KX; cb.col0 = H;
+    cb.dQ = last ? nullptr : w.dWh + (size_t)(t + 1) * B * A; cb.Wq = p.attn_W; cb.A = A;
+    cb.dc = w.dc; cb.first = last ? 1 : 0;
+    cb.gates = w.gates + (size_t)t * B * 4 * R;
+    cb.c_prev = w.c + (size_t)t * B * R; cb.c_new = w.c + (size_t)(t + 1) * B * R;
+    cb.B = B; cb.H = R; cb.dG = w.dG + (size_t)t * B * 4 * R; cb.dg_ld = 4 * R;
+    RN_TRY((cell::launch_bwd<T, T>(cb, st)));
+    RN_TRY(gemm_partials<T>(w.dG + (size_t)t * B * 4 * R, 4 * R, 0, w.Wrec, w.KX, 1, w.dXp, B, w.KX, 4 * R, w.pl_dx, st));
+    attn::BwdArgs ab{};
+    ab.dXp = w.dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)B * w.KX; ab.p_ld = w.KX;
+    ab.V = w.Hd; ab.v_bs = H; ab.v_ts = (long long)B * H;
+    ab.Wh = w.Wh + (size_t)t * B * A; ab.Uv = w.Uv; ab.uv_bs = A; ab.uv_ts = (long long)B * A;
+    ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = B; ab.Tn = L; ab.A = A; ab.D = H; ab.inv_T = 1.f / L;
+    ab.dWh_out = w.dWh + (size_t)t * B * A; ab.dUv_acc = w.dUv; ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc;
+    ab.dctx_out = w.dx + (size_t)t * B * H; ab.de_out = nullptr;
+    ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)t * B * H;
+    RN_TRY(attn::launch_bwd<T>(ab, st));
+  }
+  RN_TRY(misc::colsum<T>(w.dG, 4 * R, SB, 4 * R, g.b_ih, 0, st));
+  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, 4 * R, H, SB, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, 4 * R, R, SB, 0, w.splitk, st));
+  RN_TRY(misc::cast_pad<T>(w.dWh, A, w.dWh_op, A, SB, A, A, st));
+  RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk, st));
+  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, st));
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk, st));
+  RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, st));
+  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, st));
+  // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk, st));
+  {
+    dim3 grid(L, B);
+    attn::attn_dv_kernel<<<grid, 128, (size_t)S * sizeof(float), st>>>(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H,
+                                                                      1.f / L, 1);
+    RN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// ================================================ global ========================================================
+template <typename T>
+struct GlobalWs {
+  GemmPlan pl_gate, pl_dx;
+  T *Wih, *Whh, *Wout; float* mp; T* Xg; float* Gx; T* X; float* P; T* gates; float* c; float* out; float* diff; float* partial;
+  T* dOut; float* dHext; T* dG; float* dXp; float* dc; float* dXg; float* dmp; float* splitk;
+  size_t bytes;
+};
+constexpr int GMSE_THREADS = 256;
+
+template <typename T>
+static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
+  GlobalWs<T> w;
+  const int B = d.B, L = d.L, R = d.R, H = d.H;
+  w.pl_gate = plan_gemm<T>(B, 4 * R, R);
+  w.pl_dx = plan_gemm<T>(B, R, 4 * R);
+  Bump m(base);
+  w.Wih = m.take<T>((size_t)4 * R * 2 * H);
+  w.Whh = m.take<T>((size_t)4 * R * R);
+  w.Wout = m.take<T>((size_t)R * R);
+  w.mp = m.take<float>((size_t)B * H);
+  w.Xg = m.take<T>((size_t)L * B * 2 * H);
+  w.Gx = m.take<float>((size_t)L * B * 4 * R);
+  w.X = m.take<T>((size_t)(L + 1) * B * R);
+  w.P = m.take<float>((size_t)w.pl_gate.splits * B * 4 * R);
+  w.gates = m.take<T>((size_t)L * B * 4 * R);
+  w.c = m.take<float>((size_t)(L + 1) * B * R);
+  w.out = m.take<float>((size_t)L * B * R);
+  w.diff = m.take<float>((size_t)B * R);
+  w.partial = m.take<float>((size_t)rn_cdiv((long long)B * R, GMSE_THREADS));
+  w.dOut = m.take<T>((size_t)L * B * R);
+  w.dHext = m.take<float>((size_t)L * B * R);
+  w.dG = m.take<T>((size_t)L * B * 4 * R);
+  w.dXp = m.take<float>((size_t)w.pl_dx.splits * B * R);
+  w.dc = m.take<float>((size_t)B * R);
+  w.dXg = m.take<float>((size_t)L * B * 2 * H);
+  w.dmp = m.take<float>((size_t)B * H);
+  w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.bytes = m.off + 256;
+  return w;
+}
+static inline int check_global(const recnet_global_desc& d) {
+  if (d.B < 1 || d.L < 1 || d.T < 1) return RECNET_ERR_BAD_SHAPE;
+  const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
+  if (d.R % al || d.H % al) return RECNET_ERR_ALIGNMENT;
+  return 0;
+}
+
+template <typename T>
+static int global_forward(const recnet_global_desc& d, const recnet_global_tensors& p, const float* hiddens, const float* feats,
+                          const unsigned long long* rng, void* ws, long long ws_bytes, float* loss_out, cudaStream_t st) {
+  RN_TRY(check_global(d));
+  GlobalWs<T> w = plan_global<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, L = d.L, R = d.R, H = d.H;
+  const float p_drop = d.train ? d.p_drop : 0.f;
+  RN_TRY(misc::cast_pad<T>(p.w_ih, 2 * H, w.Wih, 2 * H, 4 * R, 2 * H, 2 * H, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Whh, R, 4 * R, R, R, st));
+  RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
+  // mean over time (and the single decoder layer), then / L * caption_max_len  (global_reconstructor.py:33-37)
+  const long long n = (long long)B * H;
+  misc::pool_time_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(hiddens, L, n, d.caption_max_len / ((float)L * L), w.mp);
+  RN_LAUNCH_OK();
+  misc::global_x_kernel<T><<<NUM_SMS * 4, 256, 0, st>>>(hiddens, w.mp, w.Xg, L, B, H, p_drop, rng, SITE_GLOBAL_MP);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.Xg, 2 * H, 0, w.Wih, 2 * H, 0, w.Gx, 4 * R, p.b_ih, L * B, 4 * R, 2 * H, 0, w.splitk, st));
+  RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * R * sizeof(T), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
+  for (int t = 0; t < L; ++t) {
+    T* x_t = w.X + (size_t)t * B * R;
+    int n_p = 0;
+    if (t > 0) {
+      RN_TRY(gemm_partials<T>(x_t, R, 0, w.Whh, R, 0, w.P, B, 4 * R, R, w.pl_gate, st));
+      n_p = w.pl_gate.splits;
+    }
+    cell::FwdArgs ca{};
+    ca.P = w.P; ca.n_p = n_p; ca.p_stride = (long long)B * 4 * R; ca.p_ld = 4 * R;
+    ca.Gx = w.Gx + (size_t)t * B * 4 * R; ca.gx_ld = 4 * R; ca.b1 = nullptr; ca.b2 = p.b_hh;
+    ca.c_prev = w.c + (size_t)t * B * R; ca.B = B; ca.H = R;
+    ca.gates_out = w.gates + (size_t)t * B * 4 * R; ca.c_out = w.c + (size_t)(t + 1) * B * R; ca.h_out = nullptr;
+    ca.h_op = x_t + (size_t)B * R; ca.hop_ld = R; ca.h_op2 = nullptr;
+    RN_TRY((cell::launch_fwd<T, T>(ca, st)));
+  }
+  RN_TRY(gemm_full<T>(w.X + (size_t)B * R, R, 0, w.Wout, R, 0, w.out, R, p.out_b, L * B, R, R, 0, w.splitk, st));
+  if (loss_out) {
+    const int nb = rn_cdiv((long long)B * R, GMSE_THREADS);
+    loss::mse_global_diff_kernel<<<nb, GMSE_THREADS, 0, st>>>(w.out, L, feats, d.T, B, R, w.diff, w.partial);
+    RN_LAUNCH_OK();
+    loss::sum_kernel<<<1, 1024, 0, st>>>(w.partial, nb, loss_out, 1.f / ((float)B * R) / (float)L);
+    RN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <typename T>
+static int global_backward(const recnet_global_desc& d, const recnet_global_tensors& p, const float* hiddens, const float* feats,
+                           const unsigned long long* rng, void* ws, long long ws_bytes, const float* g_loss,
+                           const recnet_global_tensors& g, float* g_hiddens, cudaStream_t st) {
+  RN_TRY(check_global(d));
+  GlobalWs<T> w = plan_global<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, L = d.L, R = d.R, H = d.H;
+  const float p_drop = d.train ? d.p_drop : 0.f;
+  const int LB = L * B;
+  // d loss / d out[t,b,r] = g * 2*diff/(B*R) * (1/L from the mean over t) * (1/L from train.py:100)
+  loss::mse_global_bwd_kernel<T><<<NUM_SMS * 4, 256, 0, st>>>(w.diff, L, B, R, g_loss, 2.f / ((float)B * R) / ((float)L * L), w.dOut);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.dOut, R, 0, w.Wout, R, 1, w.dHext, R, nullptr, LB, R, R, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dOut, R, 1, w.X + (size_t)B * R, R, 1, g.out_w, R, nullptr, R, R, LB, 0, w.splitk, st));
+  RN_TRY(misc::colsum<T>(w.dOut, R, LB, R, g.out_b, 0, st));
+  for (int t = L - 1; t >= 0; --t) {
+    const bool last = (t == L - 1);
+    cell::BwdArgs cb{};
+    cb.dh_ext = w.dHext + (size_t)t * B * R; cb.dh_ld = R;
+    cb.dXp = last ? nullptr : w.dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)B * R; cb.p_ld = R; cb.col0 = 0;
+    cb.dQ = nullptr; cb.dc = w.dc; cb.first = last ? 1 : 0;
+    cb.gates = w.gates + (size_t)t * B * 4 * R;
+    cb.c_prev = w.c + (size_t)t * B * R; cb.c_new = w.c + (size_t)(t + 1) * B * R;
+    cb.B = B; cb.H = R; cb.dG = w.dG + (size_t)t * B * 4 * R; cb.dg_ld = 4 * R;
+    RN_TRY((cell::launch_bwd<T, T>(cb, st)));
+    if (t > 0) RN_TRY(gemm_partials<T>(w.dG + (size_t)t * B * 4 * R, 4 * R, 0, w.Whh, R, 1, w.dXp, B, R, 4 * R, w.pl_dx, st));
+  }
+  RN_TRY(misc::colsum<T>(w.dG, 4 * R, LB, 4 * R, g.b_ih, 0, st));
+  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X, R, 1, g.w_hh, R, nullptr, 4 * R, R, LB, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.Xg, 2 * H, 1, g.w_ih, 2 * H, nullptr, 4 * R, 2 * H, LB, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dG, 4 * R, 0, w.Wih, 2 * H, 1, w.dXg, 2 * H, nullptr, LB, 2 * H, 4 * R, 0, w.splitk, st));
+  const long long n = (long long)B * H;
+  misc::global_x_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dXg, g_hiddens, w.dmp, L, B, H, 0, p_drop, rng, SITE_GLOBAL_MP);
+  RN_LAUNCH_OK();
+  misc::pool_time_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dmp, L, n, d.caption_max_len / ((float)L * L), g_hiddens, 1);
+  RN_LAUNCH_OK();
+  return 0;
+}
+}  // namespace rec

@@ -1,0 +1,264 @@
+"""torch.autograd wrappers over the C ABI (sequence level).
+
+PyTorch supplies device memory, the current stream and the autograd graph; every kernel that runs is ours
+(librecnet_b200.so).  Each Function owns a workspace tensor (raw bytes) that carries the stashed activations
+from forward to backward, exactly like cuDNN's reserve space would for nn.LSTM -- except nothing here calls
+cuDNN.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a float32 CUDA tensor, got {t.dtype} on {t.device} (recnet_b200 has no CPU path)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _pack(struct_cls, tensors: Sequence[torch.Tensor]):
+    s = struct_cls()
+    for name, t in zip(struct_cls.FIELDS, tensors):
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class DecoderSequenceFn(torch.autograd.Function):
+    """Whole teacher-forced decoder loop (train.py:17-75 over models/decoder.py:45-70).
+
+    inputs : meta dict, feats (B,T,E), tokens_in (L,B) i64, targets (L,B) i64, ce_weight (L,B) f32, rng (2,) i64,
+             then the 11 parameters in decoder_tensors.FIELDS order.
+    outputs: ce (scalar: sum_t CE_t / sum_t n_t), hiddens (L,B,H)
+    """
+
+    @staticmethod
+    def forward(ctx, meta: Dict, feats, tokens_in, targets, ce_weight, rng, *params):
+        ce, hiddens, ws, d, nbytes, saved = _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params)
+        ctx.desc, ctx.nbytes = d, nbytes
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(*saved, ws)
+        return ce, hiddens
+
+    @staticmethod
+    def backward(ctx, g_ce, g_hiddens):
+        lib = L.lib()
+        feats, tokens_in, targets, ce_weight, rng, *params, ws = ctx.saved_tensors
+        grads = [torch.empty_like(p) for p in params]
+        if g_ce is None:
+            g_ce = torch.zeros((), dtype=torch.float32, device=feats.device)
+        g_ce = g_ce.contiguous().float()
+        g_hid = g_hiddens.contiguous() if g_hiddens is not None else None
+        w, g = _pack(L.decoder_tensors, params), _pack(L.decoder_tensors, grads)
+        L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
+                                       ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
+                                       _ptr(g_hid), C.byref(g), _stream()), "recnet_decoder_bwd")
+        return (None, None, None, None, None, None, *grads)
+
+
+def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
+    lib = L.lib()
+    L.require_device(feats.device.index if feats.device.index is not None else torch.cuda.current_device())
+    feats = _f32c(feats, "encoder_outputs")
+    params = tuple(_f32c(p, n) for p, n in zip(params, L.decoder_tensors.FIELDS))
+    B, T, E = feats.shape
+    Lsteps = tokens_in.shape[0]
+    d = L.decoder_desc(B=B, T=T, E=E, H=meta["H"], A=meta["A"], EMB=meta["EMB"], V=meta["V"], L=Lsteps,
+                       precision=meta["precision"], train=int(meta["train"]),
+                       embedding_scale=float(meta["embedding_scale"]), p_emb_drop=float(meta["p_emb"]),
+                       p_out_drop=float(meta["p_out"]))
+    nbytes = lib.recnet_decoder_workspace_bytes(C.byref(d))
+    if nbytes < 0:
+        L.check(int(nbytes), "recnet_decoder_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
+    hiddens = torch.empty(Lsteps, B, meta["H"], dtype=torch.float32, device=feats.device)
+    ce = torch.zeros((), dtype=torch.float32, device=feats.device)
+    tokens_in = tokens_in.contiguous()
+    targets = targets.contiguous() if targets is not None else None
+    ce_weight = ce_weight.contiguous() if ce_weight is not None else None
+    w = _pack(L.decoder_tensors, params)
+    L.check(lib.recnet_decoder_fwd(C.byref(d), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), _ptr(targets),
+                                   _ptr(ce_weight), rng.data_ptr(), ws.data_ptr(), nbytes, hiddens.data_ptr(),
+                                   ce.data_ptr(), _stream()), "recnet_decoder_fwd")
+    return ce, hiddens, ws, d, nbytes, (feats, tokens_in, targets, ce_weight, rng, *params)
+
+
+@torch.no_grad()
+def decoder_teacher_forced_logits(meta: Dict, feats, tokens_in, rng, params):
+    """Inference helper: stacked logits (L,B,V) and hiddens (L,B,H) of the teacher-forced loop (no loss)."""
+    ce, hiddens, ws, d, nbytes, _ = _decoder_fwd_raw(meta, feats, tokens_in, None, None, rng, params)
+    ld = C.c_int64()
+    ptr = L.lib().recnet_decoder_logits(C.byref(d), ws.data_ptr(), C.byref(ld))
+    off = ptr - ws.data_ptr()
+    Lsteps, B = tokens_in.shape
+    flat = ws[off: off + Lsteps * B * ld.value * 4].view(torch.float32).view(Lsteps, B, ld.value)
+    return flat[:, :, : meta["V"]], hiddens
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class LocalReconstructorFn(torch.autograd.Function):
+    """train.forward_local_reconstructor (train.py:108-131) over LocalReconstructor.forward.
+    inputs: meta, hiddens (L,B,H), feats (B,S,R), rng, then the 10 parameters in local_tensors.FIELDS order.
+    output: mse (scalar)."""
+
+    @staticmethod
+    def forward(ctx, meta: Dict, hiddens, feats, rng, *params):
+        lib = L.lib()
+        hiddens, feats = _f32c(hiddens, "decoder_hiddens"), _f32c(feats, "encoder_outputs")
+        params = tuple(_f32c(p, n) for p, n in zip(params, L.local_tensors.FIELDS))
+        Lsteps, B, H = hiddens.shape
+        _, S, R = feats.shape
+        d = L.local_desc(B=B, S=S, R=R, H=H, A=meta["A"], L=Lsteps, precision=meta["precision"], train=int(meta["train"]),
+                         p_drop=float(meta["p_drop"]))
+        nbytes = lib.recnet_local_workspace_bytes(C.byref(d))
+        if nbytes < 0:
+            L.check(int(nbytes), "recnet_local_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
+        mse = torch.empty((), dtype=torch.float32, device=feats.device)
+        w = _pack(L.local_tensors, params)
+        L.check(lib.recnet_local_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
+                                     nbytes, mse.data_ptr(), _stream()), "recnet_local_fwd")
+        ctx.desc, ctx.nbytes = d, nbytes
+        ctx.save_for_backward(hiddens, feats, rng, ws, *params)
+        return mse
+
+    @staticmethod
+    def backward(ctx, g_mse):
+        lib = L.lib()
+        hiddens, feats, rng, ws, *params = ctx.saved_tensors
+        grads = [torch.empty_like(p) for p in params]
+        g_hid = torch.empty_like(hiddens)
+        g_mse = g_mse.contiguous().float()
+        w, g = _pack(L.local_tensors, params), _pack(L.local_tensors, grads)
+        L.check(lib.recnet_local_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
+                                     ws.data_ptr(), ctx.nbytes, g_mse.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
+                "recnet_local_bwd")
+        return (None, g_hid, None, None, *grads)
+
+
+class GlobalReconstructorFn(torch.autograd.Function):
+    """train.forward_global_reconstructor (train.py:78-105) over GlobalReconstructor.forward.
+    inputs: meta, hiddens (L,B,H), feats (B,T,R), rng, then the 6 parameters in global_tensors.FIELDS order.
+    output: MSE(mean_t out, mean_tau feats) / L  (scalar)."""
+
+    @staticmethod
+    def forward(ctx, meta: Dict, hiddens, feats, rng, *params):
+        lib = L.lib()
+        hiddens, feats = _f32c(hiddens, "decoder_hiddens"), _f32c(feats, "encoder_outputs")
+        params = tuple(_f32c(p, n) for p, n in zip(params, L.global_tensors.FIELDS))
+        Lsteps, B, H = hiddens.shape
+        _, T, R = feats.shape
+        d = L.global_desc(B=B, L=Lsteps, R=R, H=H, T=T, precision=meta["precision"], train=int(meta["train"]),
+                          p_drop=float(meta["p_drop"]), caption_max_len=float(meta["caption_max_len"]))
+        nbytes = lib.recnet_global_workspace_bytes(C.byref(d))
+        if nbytes < 0:
+            L.check(int(nbytes), "recnet_global_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
+        loss = torch.empty((), dtype=torch.float32, device=feats.device)
+        w = _pack(L.global_tensors, params)
+        L.check(lib.recnet_global_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
+                                      nbytes, loss.data_ptr(), _stream()), "recnet_global_fwd")
+        ctx.desc, ctx.nbytes = d, nbytes
+        ctx.save_for_backward(hiddens, feats, rng, ws, *params)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        lib = L.lib()
+        hiddens, feats, rng, ws, *params = ctx.saved_tensors
+        grads = [torch.empty_like(p) for p in params]
+        g_hid = torch.empty_like(hiddens)
+        g_loss = g_loss.contiguous().float()
+        w, g = _pack(L.global_tensors, params), _pack(L.global_tensors, grads)
+        L.check(lib.recnet_global_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
+                                      ws.data_ptr(), ctx.nbytes, g_loss.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
+                "recnet_global_bwd")
+        return (None, g_hid, None, None, *grads)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _NormTable:
+    """Device-side tables for the multi-tensor norm kernels, cached per parameter list."""
+    CHUNK = 16384
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        dev = params[0].device
+        self.key = tuple((p.data_ptr(), p.numel()) for p in params)
+        self.n = len(params)
+        self.ptrs = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device=dev)
+        self.sizes = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
+        bt, bc = [], []
+        for i, p in enumerate(params):
+            for c in range((p.numel() + self.CHUNK - 1) // self.CHUNK):
+                bt.append(i)
+                bc.append(c)
+        offs, o = [], 0
+        for p in params:
+            offs.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.total = o
+        self.offsets = offs
+        self.offset_bytes = torch.tensor([x * 4 for x in offs], dtype=torch.int64, device=dev)
+        self.blk_tensor = torch.tensor(bt, dtype=torch.int32, device=dev)
+        self.blk_chunk = torch.tensor(bc, dtype=torch.int32, device=dev)
+        self.n_blocks = len(bt)
+
+
+_norm_tables: Dict[tuple, _NormTable] = {}
+
+
+def _table_for(params) -> _NormTable:
+    key = tuple((p.data_ptr(), p.numel()) for p in params)
+    t = _norm_tables.get(key)
+    if t is None:
+        t = _norm_tables[key] = _NormTable(params)
+    return t
+
+
+class ParamNormSumFn(torch.autograd.Function):
+    """reg = sum_p ||p||_2 over a parameter list (train.py:69,101,127); grad_p = g * p / ||p||."""
+
+    @staticmethod
+    def forward(ctx, *params):
+        lib = L.lib()
+        params = tuple(_f32c(p, "parameter") for p in params)
+        tab = _table_for(params)
+        sumsq = torch.empty(tab.n, dtype=torch.float32, device=params[0].device)
+        reg = torch.empty((), dtype=torch.float32, device=params[0].device)
+        L.check(lib.recnet_param_norms_fwd(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(),
+                                           tab.blk_chunk.data_ptr(), tab.n_blocks, sumsq.data_ptr(), reg.data_ptr(), _stream()),
+                "recnet_param_norms_fwd")
+        ctx.tab = tab
+        ctx.save_for_backward(sumsq, *params)
+        return reg
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        sumsq, *params = ctx.saved_tensors
+        tab = ctx.tab
+        flat = torch.empty(tab.total, dtype=torch.float32, device=params[0].device)
+        grads = [flat[o: o + p.numel()].view_as(p) for o, p in zip(tab.offsets, params)]
+        gptrs = tab.offset_bytes + flat.data_ptr()      # device-side add: safe under CUDA-graph capture
+        g = g.contiguous().float()
+        L.check(lib.recnet_param_norms_bwd(tab.ptrs.data_ptr(), gptrs.data_ptr(), tab.sizes.data_ptr(), tab.n,
+                                           tab.blk_tensor.data_ptr(), tab.blk_chunk.data_ptr(), tab.n_blocks, sumsq.data_ptr(),
+                                           g.data_ptr(), 1.0, 0, _stream()), "recnet_param_norms_bwd")
+        return tuple(grads)
+
+
+def param_norm_sum(params: Sequence[torch.Tensor]) -> torch.Tensor:
+    return ParamNormSumFn.apply(*params)

@@ -1,0 +1,141 @@
+"""Step drivers and losses: mirrors of the reference's train.forward_decoder / forward_global_reconstructor /
+forward_local_reconstructor / build_decoder / build_reconstructor (train.py:17-197), same names, same
+arguments, same return values, same module-dict convention {'model','loss','optimizer','lambda_reg'} and the
+same global config object ``C`` -- but each driver is ONE call into the CUDA sequence kernels instead of a
+Python loop of ~400 ATen ops per step.
+"""
+from __future__ import annotations
+
+import random
+
+import torch
+
+from .config import TrainConfig as C
+from .functional import param_norm_sum
+from .models import Decoder, GlobalReconstructor, LocalReconstructor
+
+
+def _num_steps(target_masks: torch.Tensor, caption_max_len: int) -> int:
+    """Loop length of train.py:41,66: stop after step t when masks[t+1] is all False (one host read,
+    the reference does two per step)."""
+    any_t = target_masks.any(dim=1)
+    n = int(any_t[: caption_max_len + 1].sum().item()) if bool(any_t[0]) else 0
+    # masks are prefix-shaped (PAD only after EOS, dataset/MSVD.py:111-117) so the count of non-empty rows is L
+    return max(1, min(n, caption_max_len + 1))
+
+
+def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_forcing_ratio=0., n_steps=None):
+    """train.py:17-75.  Returns (loss, hiddens (L,NL,B,H), output_indices).
+    ``n_steps``: optional static loop length (skips the host read; needed under CUDA-graph capture)."""
+    model = decoder['model']
+    L = n_steps if n_steps is not None else _num_steps(target_masks, C.caption_max_len)
+    B = encoder_outputs.shape[0]
+    sos = torch.full((1, B), C.init_word2idx['<SOS>'], dtype=torch.long, device=encoder_outputs.device)   # train.py:25
+    use_teacher_forcing = random.random() <= teacher_forcing_ratio                                          # train.py:38
+    output_indices = torch.empty(0, dtype=torch.long)
+    if use_teacher_forcing:
+        tokens_in = torch.cat((sos, targets[: L - 1]), dim=0)                                               # train.py:44-45
+    else:
+        # argmax feedback (train.py:47-51): decode greedily on device, then replay those tokens through the
+        # differentiable sequence kernel (identical arithmetic in eval mode, where validation uses it, train.py:329)
+        ids, _ = model.greedy(encoder_outputs, L)
+        tokens_in = torch.cat((sos, ids[: L - 1]), dim=0)
+        output_indices = ids[:L].cpu()
+    m = target_masks[:L].to(torch.float32)
+    n_t = m.sum(dim=1, keepdim=True)                                                                        # train.py:57
+    ce_weight = m / (n_t * n_t.sum())                                                                       # mean over n_t, then / sum n_t (train.py:54-60,68)
+    ce, hiddens = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs)
+    reg_loss = param_norm_sum(list(model.parameters()))                                                    # train.py:69
+    loss = ce + decoder['lambda_reg'] * reg_loss                                                            # train.py:70
+    return loss, hiddens.unsqueeze(1), output_indices                                                       # train.py:73-75
+
+
+def forward_global_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
+    """train.py:78-105."""
+    model = reconstructor['model']
+    loss = model.forward_sequence(decoder_hiddens, encoder_outputs)                                         # includes the /L of train.py:100
+    reg_loss = param_norm_sum(list(model.parameters()))
+    return loss + reconstructor['lambda_reg'] * reg_loss
+
+
+def forward_local_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
+    """train.py:108-131."""
+    model = reconstructor['model']
+    loss = model.forward_sequence(decoder_hiddens, encoder_outputs)
+    reg_loss = param_norm_sum(list(model.parameters()))
+    return loss + reconstructor['lambda_reg'] * reg_loss
+
+
+def build_decoder(n_vocabs):
+    """train.py:134-160."""
+    model = Decoder(
+        model_name=C.decoder_model, n_layers=C.decoder_n_layers, encoder_size=C.encoder_output_size,
+        embedding_size=C.embedding_size, embedding_scale=C.embedding_scale, hidden_size=C.decoder_hidden_size,
+        attn_size=C.decoder_attn_size, output_size=n_vocabs, embedding_dropout=C.embedding_dropout,
+        dropout=C.decoder_dropout, out_dropout=C.decoder_out_dropout, precision=C.precision).to(C.device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=C.decoder_learning_rate, weight_decay=C.decoder_weight_decay,
+                                 amsgrad=C.decoder_use_amsgrad, fused=True, capturable=True)
+    lambda_reg = torch.tensor(0.001, device=C.device)
+    return {'model': model, 'loss': torch.nn.CrossEntropyLoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg}
+
+
+def build_reconstructor():
+    """train.py:163-197."""
+    if C.reconstructor_type == "local":
+        model = LocalReconstructor(
+            model_name=C.reconstructor_model, n_layers=C.reconstructor_n_layers, decoder_hidden_size=C.decoder_hidden_size,
+            hidden_size=C.reconstructor_hidden_size, dropout=C.reconstructor_dropout,
+            decoder_dropout=C.reconstructor_decoder_dropout, attn_size=C.reconstructor_attn_size, precision=C.precision)
+    elif C.reconstructor_type == "global":
+        model = GlobalReconstructor(
+            model_name=C.reconstructor_model, n_layers=C.reconstructor_n_layers, decoder_hidden_size=C.decoder_hidden_size,
+            hidden_size=C.reconstructor_hidden_size, dropout=C.reconstructor_dropout,
+            decoder_dropout=C.reconstructor_decoder_dropout, caption_max_len=C.caption_max_len, precision=C.precision)
+    else:
+        raise NotImplementedError("Unknown reconstructor: {}".format(C.reconstructor_type))
+    model = model.to(C.device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=C.reconstructor_learning_rate,
+                                 weight_decay=C.reconstructor_weight_decay, amsgrad=C.reconstructor_use_amsgrad,
+                                 fused=True, capturable=True)
+    lambda_reg = torch.tensor(0.01, device=C.device)
+    return {'model': model, 'loss': torch.nn.MSELoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg}
+
+
+def forward_reconstructor_for(kind):
+    if kind == "global":
+        return forward_global_reconstructor
+    if kind == "local":
+        return forward_local_reconstructor
+    raise NotImplementedError("Unknown reconstructor type '{}'".format(kind))          # train.py:240
+
+
+def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, lambda_recon=1.0, zero_grad=True,
+               optimizer_step=True, grad_hook=None):
+    """One iteration of the reference's loop body (train.py:243-273): decoder + reconstructor forward, combined
+    loss, backward, clip, two Adam steps.  ``grad_hook`` (if given) runs between backward and clip -- the
+    data-parallel gradient all-reduce plugs in there.  Returns (loss, decoder_loss, recon_loss) device scalars."""
+    target_masks = targets > C.init_word2idx['<PAD>']                                                       # train.py:246
+    decoder['model'].train()
+    dec_loss, hiddens, _ = forward_decoder(decoder, encoder_outputs, targets, target_masks,
+                                           C.decoder_teacher_forcing_ratio, n_steps=n_steps)
+    rec_loss = None
+    if reconstructor is not None:
+        reconstructor['model'].train()
+        rec_loss = forward_reconstructor_for(C.reconstructor_type)(hiddens, encoder_outputs, reconstructor)
+        loss = dec_loss + lambda_recon * rec_loss                                                           # train.py:260
+    else:
+        loss = dec_loss
+    if zero_grad:
+        decoder['optimizer'].zero_grad(set_to_none=True)
+        if reconstructor is not None:
+            reconstructor['optimizer'].zero_grad(set_to_none=True)
+    loss.backward()                                                                                         # train.py:268
+    if grad_hook is not None:
+        grad_hook()
+    if optimizer_step:
+        if C.use_gradient_clip:
+            torch.nn.utils.clip_grad_norm_(decoder['model'].parameters(), C.gradient_clip, foreach=True)    # train.py:269-270
+        decoder['optimizer'].step()
+        if reconstructor is not None:
+            reconstructor['optimizer'].step()
+    return loss, dec_loss, rec_loss

@@ -44,6 +44,15 @@ typedef enum { RECNET_PREC_FP32 = 0, RECNET_PREC_BF16 = 1 } recnet_precision;
 int recnet_abi_version(void);
 int recnet_query_device(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Launch accounting and per-launch device timing (used by bench.py for `gpu_launches` and the roofline leg).
+ * recnet_launch_count: kernels launched by this library so far in this process.
+ * recnet_profile_enable(1, n): record a CUDA-event pair around up to n kernel launches (eager mode only, not under
+ * graph capture); recnet_profile_collect synchronises and writes n x 5 floats (class, M, N, K, ms); classes:
+ * 1 tcgen05 GEMM, 2 fp32 sgemm, 3 attention fwd, 4 attention bwd, 5 cell fwd, 6 cell bwd, 7 CE, 8 split-K reduce. */
+long long recnet_launch_count(void);
+int recnet_profile_enable(int on, int max_records);
+int recnet_profile_collect(float* out, int max_records);
+
 /* ------------------------------------------------------------------------------------------------
  * Operator level (one kernel family each).  Used by the per-step nn.Module.forward mirrors and by
  * the per-kernel parity tests.
@@ -182,9 +191,10 @@ float* recnet_global_outputs(const recnet_global_desc* d, void* workspace);  /* 
 
 /* L2-norm regulariser over a parameter list (train.py:69,101,127): reg = sum_p ||p||_2.
  * ptrs/sizes: device int64 tables of n tensors; blk_tensor/blk_chunk: device int32 tables mapping block ->
- * (tensor, 16384-element chunk); sumsq [n] fp32 scratch kept for the backward. */
+ * (tensor, 16384-element chunk); partial [n_blocks] fp32 scratch (two-stage, fixed-order => bitwise reproducible);
+ * sumsq [n] fp32 kept for the backward. */
 int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
-                           const int32_t* blk_chunk, int n_blocks, float* sumsq, float* reg_out, void* stream);
+                           const int32_t* blk_chunk, int n_blocks, float* partial, float* sumsq, float* reg_out, void* stream);
 /* grad_p (+)= lambda * g * p / ||p|| */
 int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n,
                            const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, const float* sumsq,

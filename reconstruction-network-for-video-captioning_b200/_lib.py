@@ -74,6 +74,9 @@ _p, _i, _l, _f, _u = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 SIGNATURES = {
     "recnet_abi_version": (_i, []),
     "recnet_query_device": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "recnet_launch_count": (C.c_longlong, []),
+    "recnet_profile_enable": (_i, [_i, _i]),
+    "recnet_profile_collect": (_i, [_p, _i]),
     "recnet_gemm": (_i, [_i, _p, _l, _i, _p, _l, _i, _p, _l, _p, _l, _p, _i, _i, _i, _i, _l, _i, _i, _p]),
     "recnet_splitk_reduce": (_i, [_p, _i, _l, _l, _p, _l, _i, _i, _i, _p]),
     "recnet_attn_fwd": (_i, [_i, _p, _i, _l, _p, _l, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _p, _p, _l, _f, _p, _u, _l, _p]),
@@ -97,7 +100,7 @@ SIGNATURES = {
     "recnet_global_bwd": (_i, [C.POINTER(global_desc), C.POINTER(global_tensors), _p, _p, _p, _p, _l, _p,
                                C.POINTER(global_tensors), _p, _p]),
     "recnet_global_outputs": (_p, [C.POINTER(global_desc), _p]),
-    "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
     "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _i, _p]),
 }
 

@@ -197,6 +197,7 @@ static int launch_fwd(FwdArgs a, cudaStream_t st) {
   a.d_slice = slice;
   dim3 grid(slices, a.B);
   const size_t smem = (size_t)(a.A + a.Tn) * sizeof(float);
+  ProfScope prof(KC_ATTN_FWD, a.B, a.Tn, a.D, st);
   attn_fwd_kernel<TV, TO><<<grid, FWD_THREADS, smem, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
@@ -208,6 +209,7 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   constexpr int VN = Vec16<TV>::N;
   if (a.D % VN || a.v_ts % VN || a.v_bs % VN) return RECNET_ERR_ALIGNMENT;
   const size_t smem = (size_t)(a.D + a.Tn) * sizeof(float);
+  ProfScope prof(KC_ATTN_BWD, a.B, a.Tn, a.D, st);
   attn_bwd_kernel<TV><<<a.B, BWD_THREADS, smem, st>>>(a);
   RN_LAUNCH_OK();
   return 0;

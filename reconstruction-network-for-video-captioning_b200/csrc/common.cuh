@@ -15,8 +15,38 @@ typedef __nv_bfloat16 bf16;
     if (_e != cudaSuccess) return (int)_e;                \
   } while (0)
 
+// ---- launch accounting + optional per-launch timing (bench.py's roofline leg) -------------------------------
+// Every kernel launch in the library goes through RN_LAUNCH_OK(), which bumps g_launches.  When profiling is on
+// (recnet_profile_enable), launch sites wrapped in a ProfScope also record a CUDA-event pair on the launching
+// stream, tagged with a kernel class and the problem shape; recnet_profile_collect returns per-launch durations.
+enum KernelClass { KC_OTHER = 0, KC_GEMM_TC = 1, KC_SGEMM = 2, KC_ATTN_FWD = 3, KC_ATTN_BWD = 4, KC_CELL_FWD = 5,
+                   KC_CELL_BWD = 6, KC_CE = 7, KC_REDUCE = 8 };
+struct ProfRecord { int cls, M, N, K; cudaEvent_t e0, e1; };
+struct ProfState {
+  long long launches = 0;
+  int enabled = 0;
+  int n = 0, cap = 0;
+  ProfRecord* rec = nullptr;
+};
+inline ProfState& prof_state() { static ProfState s; return s; }
+
+struct ProfScope {
+  cudaStream_t st; int idx;
+  ProfScope(int cls, int M, int N, int K, cudaStream_t s) : st(s), idx(-1) {
+    ProfState& p = prof_state();
+    if (!p.enabled || p.n >= p.cap) return;
+    idx = p.n++;
+    ProfRecord& r = p.rec[idx];
+    r.cls = cls; r.M = M; r.N = N; r.K = K;
+    if (!r.e0) { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); }
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(prof_state().rec[idx].e1, st); }
+};
+
 #define RN_LAUNCH_OK()                                    \
   do {                                                    \
+    prof_state().launches++;                              \
     cudaError_t _e = cudaGetLastError();                  \
     if (_e != cudaSuccess) return (int)_e;                \
   } while (0)

@@ -290,6 +290,7 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const EpiArg
     attr_set = true;
   }
   dim3 grid(rn_cdiv(N, BN), rn_cdiv(M, BM), splits);
+  ProfScope prof(KC_GEMM_TC, M, N, K, st);
   kern<<<grid, THREADS, L::TOTAL, st>>>(ma, mb, ep, M, N, K, kb_per);
   RN_LAUNCH_OK();
   return 0;

@@ -166,6 +166,7 @@ template <typename TS, typename TO>
 static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   if (a.H % 4 || a.p_ld % 4 || a.p_stride % 4 || (a.Gx && a.gx_ld % 4) || (a.h_out && a.h_ld % 4)) return RECNET_ERR_ALIGNMENT;
   const long long n = (long long)a.B * (a.H / 4);
+  ProfScope prof(KC_CELL_FWD, a.B, a.H, a.n_p, st);
   lstm_cell_fwd_kernel<TS, TO><<<rn_cdiv(n, THREADS), THREADS, 0, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
@@ -176,6 +177,7 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
       (a.dh_ext2 && a.dh2_ld % 4))
     return RECNET_ERR_ALIGNMENT;
   const long long n = (long long)a.B * (a.H / 4);
+  ProfScope prof(KC_CELL_BWD, a.B, a.H, a.dXp ? a.n_p : 0, st);
   lstm_cell_bwd_kernel<TS, TO><<<rn_cdiv(n, THREADS), THREADS, 0, st>>>(a);
   RN_LAUNCH_OK();
   return 0;

@@ -145,7 +145,7 @@ __global__ void global_x_bwd_kernel(const float* __restrict__ dX, float* __restr
 constexpr int MT_CHUNK = 16384;
 // table: ptrs[n] (device addresses), sizes[n]; blk_tensor[nb], blk_chunk[nb] map a block to a chunk of one tensor
 __global__ void mt_sumsq_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes,
-                                const int* __restrict__ blk_tensor, const int* __restrict__ blk_chunk, float* __restrict__ sumsq) {
+                                const int* __restrict__ blk_tensor, const int* __restrict__ blk_chunk, float* __restrict__ partial) {
   __shared__ float red[32];
   const int t = blk_tensor[blockIdx.x];
   const float* p = reinterpret_cast<const float*>(ptrs[t]);
@@ -153,14 +153,21 @@ __global__ void mt_sumsq_kernel(const long long* __restrict__ ptrs, const long l
   float s = 0.f;
   for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float v = p[i]; s += v * v; }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(sumsq + t, s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;          // fixed-order two-stage reduction: bitwise reproducible
 }
-__global__ void mt_norm_finalize_kernel(const float* __restrict__ sumsq, int n, float* __restrict__ out) {
+// one thread per tensor sums that tensor's block partials in block order, then reg = sum_t sqrt(sumsq[t])
+__global__ void mt_norm_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ blk_tensor, int n_blocks,
+                                        float* __restrict__ sumsq, int n, float* __restrict__ out) {
   __shared__ float red[32];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += sqrtf(sumsq[i]);
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) out[0] = s;
+  float r = 0.f;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) if (blk_tensor[b] == t) s += partial[b];
+    sumsq[t] = s;
+    r += sqrtf(s);
+  }
+  r = block_sum(r, red);
+  if (threadIdx.x == 0) out[0] = r;
 }
 __global__ void mt_reg_grad_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ gptrs,
                                    const long long* __restrict__ sizes, const int* __restrict__ blk_tensor,

@@ -9,6 +9,39 @@ extern "C" {
 
 int recnet_abi_version(void) { return 1; }
 
+long long recnet_launch_count(void) { return prof_state().launches; }
+
+int recnet_profile_enable(int on, int max_records) {
+  ProfState& p = prof_state();
+  if (on) {
+    if (max_records > p.cap) {
+      ProfRecord* r = new ProfRecord[max_records]();
+      for (int i = 0; i < p.cap; ++i) r[i] = p.rec[i];
+      delete[] p.rec;
+      p.rec = r; p.cap = max_records;
+    }
+    p.n = 0;
+  }
+  p.enabled = on;
+  return 0;
+}
+
+// out: [n][5] floats = (class, M, N, K, milliseconds); returns the number of records written (after a device sync)
+int recnet_profile_collect(float* out, int max_records) {
+  ProfState& p = prof_state();
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return -(int)e;
+  const int n = p.n < max_records ? p.n : max_records;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.rec[i].e0, p.rec[i].e1);
+    out[5 * i + 0] = (float)p.rec[i].cls; out[5 * i + 1] = (float)p.rec[i].M; out[5 * i + 2] = (float)p.rec[i].N;
+    out[5 * i + 3] = (float)p.rec[i].K; out[5 * i + 4] = ms;
+  }
+  p.n = 0;
+  return n;
+}
+
 int recnet_query_device(int device, int* sm_count, int* cc_major, int* cc_minor) {
   cudaDeviceProp prop;
   RN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -200,13 +233,12 @@ float* recnet_global_outputs(const recnet_global_desc* d, void* workspace) {
 
 // ---- regulariser -----------------------------------------------------------------------------------------------
 int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor, const int32_t* blk_chunk,
-                           int n_blocks, float* sumsq, float* reg_out, void* stream) {
+                           int n_blocks, float* partial, float* sumsq, float* reg_out, void* stream) {
   cudaStream_t st = ST(stream);
-  RN_CUDA_OK(cudaMemsetAsync(sumsq, 0, (size_t)n * sizeof(float), st));
   misc::mt_sumsq_kernel<<<n_blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(ptrs), reinterpret_cast<const long long*>(sizes),
-                                                  blk_tensor, blk_chunk, sumsq);
+                                                  blk_tensor, blk_chunk, partial);
   RN_LAUNCH_OK();
-  misc::mt_norm_finalize_kernel<<<1, 256, 0, st>>>(sumsq, n, reg_out);
+  misc::mt_norm_finalize_kernel<<<1, 32, 0, st>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -89,6 +89,7 @@ static inline int splitk_reduce(const float* P, int splits, long long split_stri
   const long long total = (long long)M * N;
   if (total <= 0) return 0;
   int blocks = (int)min((long long)NUM_SMS * 8, (total + 255) / 256);
+  ProfScope prof(KC_REDUCE, M, N, splits, st);
   splitk_reduce_kernel<<<blocks, 256, 0, st>>>(P, splits, split_stride, ldp, out, ldo, M, N, bias, accumulate);
   RN_LAUNCH_OK();
   return 0;

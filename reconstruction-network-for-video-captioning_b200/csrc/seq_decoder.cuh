@@ -157,6 +157,7 @@ static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
   RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, L * B, V, H, 0,
                       w.splitk, st));
   if (targets && ce_weight && ce_out) {
+    ProfScope prof(KC_CE, L * B, V, 0, st);
     loss::ce_fwd_kernel<<<L * B, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, V, p_out, rng, SITE_LOGITS,
                                                             w.lse, w.row_loss);
     RN_LAUNCH_OK();
@@ -178,8 +179,11 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
   const int LB = L * B;
   const T* Hall = w.X + (size_t)B * w.KX + E;     // h_t rows, ld = KX
   // ---- CE backward and the vocabulary projection --------------------------------------------------------
-  loss::ce_bwd_kernel<T><<<LB, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, w.lse, g_ce, V, w.Vp, p_out, rng,
-                                                          SITE_LOGITS, w.dlogits, w.Vp);
+  {
+    ProfScope prof(KC_CE, LB, V, 1, st);
+    loss::ce_bwd_kernel<T><<<LB, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, w.lse, g_ce, V, w.Vp, p_out, rng,
+                                                            SITE_LOGITS, w.dlogits, w.Vp);
+  }
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, w.KX, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk, st));

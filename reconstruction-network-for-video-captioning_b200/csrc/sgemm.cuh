@@ -89,6 +89,7 @@ static inline int launch(const float* A, long long lda, int transA, const float*
   dim3 grid(rn_cdiv(N, BN), rn_cdiv(M, BM), splits);
   const long long a_rs = transA ? 1 : lda, a_cs = transA ? lda : 1;
   const long long b_rs = transB ? 1 : ldb, b_cs = transB ? ldb : 1;
+  ProfScope prof(KC_SGEMM, M, N, K, st);
   sgemm_kernel<<<grid, THREADS, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, k_per, split_stride,
                                          accumulate);
   RN_LAUNCH_OK();

@@ -2,13 +2,17 @@
 
 PyTorch supplies device memory, the current stream and the autograd graph; every kernel that runs is ours
 (librecnet_b200.so).  Each Function owns a workspace tensor (raw bytes) that carries the stashed activations
-from forward to backward, exactly like cuDNN's reserve space would for nn.LSTM -- except nothing here calls
-cuDNN.
+from forward to backward, like cuDNN's reserve space would for nn.LSTM -- except nothing here calls cuDNN.
+
+Each sequence Function also returns ``reg = sum_p ||p||_2`` over its module's parameters (the reference adds
+``lambda_reg * reg`` to every loss, train.py:69,101,127) and writes ALL parameter gradients of the module --
+BPTT gradients plus the regulariser's g * p / ||p|| -- into ONE flat buffer whose views become ``p.grad``.
+That single contiguous buffer per module is what the data-parallel all-reduce sends (parallel.py).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Sequence
+from typing import Dict, List, Sequence
 
 import torch
 
@@ -36,44 +40,81 @@ def _pack(struct_cls, tensors: Sequence[torch.Tensor]):
     return s
 
 
+# ---- multi-tensor tables for the L2-norm regulariser ------------------------------------------------------------
+class _NormTable:
+    """Device-side (pointer, size, block map) tables for the multi-tensor norm kernels, cached per parameter list."""
+    CHUNK = 16384
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        dev = params[0].device
+        self.n = len(params)
+        self.ptrs = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device=dev)
+        self.sizes = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
+        bt, bc, offs, o = [], [], [], 0
+        for i, p in enumerate(params):
+            for c in range((p.numel() + self.CHUNK - 1) // self.CHUNK):
+                bt.append(i)
+                bc.append(c)
+            offs.append(o)
+            o += (p.numel() + 63) // 64 * 64          # keep every gradient view 256-byte aligned
+        self.total, self.offsets = o, offs
+        self.offset_bytes = torch.tensor([x * 4 for x in offs], dtype=torch.int64, device=dev)
+        self.blk_tensor = torch.tensor(bt, dtype=torch.int32, device=dev)
+        self.blk_chunk = torch.tensor(bc, dtype=torch.int32, device=dev)
+        self.n_blocks = len(bt)
+
+
+_norm_tables: Dict[tuple, _NormTable] = {}
+
+
+def _table_for(params) -> _NormTable:
+    key = tuple((p.data_ptr(), p.numel()) for p in params)
+    t = _norm_tables.get(key)
+    if t is None:
+        t = _norm_tables[key] = _NormTable(params)
+    return t
+
+
+def _norms_fwd(params):
+    tab = _table_for(params)
+    sumsq = torch.empty(tab.n, dtype=torch.float32, device=params[0].device)
+    partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=params[0].device)
+    reg = torch.empty((), dtype=torch.float32, device=params[0].device)
+    L.check(L.lib().recnet_param_norms_fwd(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(),
+                                           tab.blk_chunk.data_ptr(), tab.n_blocks, partial.data_ptr(), sumsq.data_ptr(),
+                                           reg.data_ptr(), _stream()),
+            "recnet_param_norms_fwd")
+    return reg, sumsq
+
+
+def _flat_grads(params) -> (torch.Tensor, List[torch.Tensor], torch.Tensor):
+    """One flat fp32 buffer + per-parameter views + device table of the views' addresses (computed with a device-side
+    add so that it is valid under CUDA-graph capture, where the buffer address is fixed)."""
+    tab = _table_for(params)
+    flat = torch.empty(tab.total, dtype=torch.float32, device=params[0].device)
+    views = [flat[o: o + p.numel()].view_as(p) for o, p in zip(tab.offsets, params)]
+    return flat, views, tab.offset_bytes + flat.data_ptr()
+
+
+def _norms_bwd_into(params, sumsq, g_reg, gptrs, accumulate: bool):
+    tab = _table_for(params)
+    L.check(L.lib().recnet_param_norms_bwd(tab.ptrs.data_ptr(), gptrs.data_ptr(), tab.sizes.data_ptr(), tab.n,
+                                           tab.blk_tensor.data_ptr(), tab.blk_chunk.data_ptr(), tab.n_blocks, sumsq.data_ptr(),
+                                           g_reg.data_ptr(), 1.0, int(accumulate), _stream()), "recnet_param_norms_bwd")
+
+
+def _scalar(g, dev):
+    if g is None:
+        return torch.zeros((), dtype=torch.float32, device=dev)
+    return g.contiguous().float()
+
+
 # ----------------------------------------------------------------------------------------------------------------
-class DecoderSequenceFn(torch.autograd.Function):
-    """Whole teacher-forced decoder loop (train.py:17-75 over models/decoder.py:45-70).
-
-    inputs : meta dict, feats (B,T,E), tokens_in (L,B) i64, targets (L,B) i64, ce_weight (L,B) f32, rng (2,) i64,
-             then the 11 parameters in decoder_tensors.FIELDS order.
-    outputs: ce (scalar: sum_t CE_t / sum_t n_t), hiddens (L,B,H)
-    """
-
-    @staticmethod
-    def forward(ctx, meta: Dict, feats, tokens_in, targets, ce_weight, rng, *params):
-        ce, hiddens, ws, d, nbytes, saved = _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params)
-        ctx.desc, ctx.nbytes = d, nbytes
-        ctx.set_materialize_grads(False)
-        ctx.save_for_backward(*saved, ws)
-        return ce, hiddens
-
-    @staticmethod
-    def backward(ctx, g_ce, g_hiddens):
-        lib = L.lib()
-        feats, tokens_in, targets, ce_weight, rng, *params, ws = ctx.saved_tensors
-        grads = [torch.empty_like(p) for p in params]
-        if g_ce is None:
-            g_ce = torch.zeros((), dtype=torch.float32, device=feats.device)
-        g_ce = g_ce.contiguous().float()
-        g_hid = g_hiddens.contiguous() if g_hiddens is not None else None
-        w, g = _pack(L.decoder_tensors, params), _pack(L.decoder_tensors, grads)
-        L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
-                                       ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
-                                       _ptr(g_hid), C.byref(g), _stream()), "recnet_decoder_bwd")
-        return (None, None, None, None, None, None, *grads)
-
-
 def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
     lib = L.lib()
-    L.require_device(feats.device.index if feats.device.index is not None else torch.cuda.current_device())
     feats = _f32c(feats, "encoder_outputs")
     params = tuple(_f32c(p, n) for p, n in zip(params, L.decoder_tensors.FIELDS))
+    L.require_device(feats.device.index if feats.device.index is not None else torch.cuda.current_device())
     B, T, E = feats.shape
     Lsteps = tokens_in.shape[0]
     d = L.decoder_desc(B=B, T=T, E=E, H=meta["H"], A=meta["A"], EMB=meta["EMB"], V=meta["V"], L=Lsteps,
@@ -96,6 +137,39 @@ def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
     return ce, hiddens, ws, d, nbytes, (feats, tokens_in, targets, ce_weight, rng, *params)
 
 
+class DecoderSequenceFn(torch.autograd.Function):
+    """Whole teacher-forced decoder loop (train.py:17-75 over models/decoder.py:45-70).
+
+    inputs : meta dict, feats (B,T,E), tokens_in (L,B) i64, targets (L,B) i64, ce_weight (L,B) f32, rng (2,) i64,
+             then the 11 parameters in decoder_tensors.FIELDS order.
+    outputs: ce (scalar: sum_t CE_t / sum_t n_t), hiddens (L,B,H), reg (scalar: sum_p ||p||)
+    """
+
+    @staticmethod
+    def forward(ctx, meta: Dict, feats, tokens_in, targets, ce_weight, rng, *params):
+        ce, hiddens, ws, d, nbytes, saved = _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params)
+        reg, sumsq = _norms_fwd(saved[5:])
+        ctx.desc, ctx.nbytes = d, nbytes
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(*saved, ws, sumsq)
+        return ce, hiddens, reg
+
+    @staticmethod
+    def backward(ctx, g_ce, g_hiddens, g_reg):
+        lib = L.lib()
+        feats, tokens_in, targets, ce_weight, rng, *params, ws, sumsq = ctx.saved_tensors
+        flat, grads, gptrs = _flat_grads(params)
+        g_ce = _scalar(g_ce, feats.device)
+        g_hid = g_hiddens.contiguous() if g_hiddens is not None else None
+        w, g = _pack(L.decoder_tensors, params), _pack(L.decoder_tensors, grads)
+        L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
+                                       ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
+                                       _ptr(g_hid), C.byref(g), _stream()), "recnet_decoder_bwd")
+        if g_reg is not None:
+            _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
+        return (None, None, None, None, None, None, *grads)
+
+
 @torch.no_grad()
 def decoder_teacher_forced_logits(meta: Dict, feats, tokens_in, rng, params):
     """Inference helper: stacked logits (L,B,V) and hiddens (L,B,H) of the teacher-forced loop (no loss)."""
@@ -112,7 +186,7 @@ def decoder_teacher_forced_logits(meta: Dict, feats, tokens_in, rng, params):
 class LocalReconstructorFn(torch.autograd.Function):
     """train.forward_local_reconstructor (train.py:108-131) over LocalReconstructor.forward.
     inputs: meta, hiddens (L,B,H), feats (B,S,R), rng, then the 10 parameters in local_tensors.FIELDS order.
-    output: mse (scalar)."""
+    outputs: mse (scalar), reg (scalar)."""
 
     @staticmethod
     def forward(ctx, meta: Dict, hiddens, feats, rng, *params):
@@ -131,28 +205,32 @@ class LocalReconstructorFn(torch.autograd.Function):
         w = _pack(L.local_tensors, params)
         L.check(lib.recnet_local_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
                                      nbytes, mse.data_ptr(), _stream()), "recnet_local_fwd")
+        reg, sumsq = _norms_fwd(params)
         ctx.desc, ctx.nbytes = d, nbytes
-        ctx.save_for_backward(hiddens, feats, rng, ws, *params)
-        return mse
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(hiddens, feats, rng, ws, sumsq, *params)
+        return mse, reg
 
     @staticmethod
-    def backward(ctx, g_mse):
+    def backward(ctx, g_mse, g_reg):
         lib = L.lib()
-        hiddens, feats, rng, ws, *params = ctx.saved_tensors
-        grads = [torch.empty_like(p) for p in params]
+        hiddens, feats, rng, ws, sumsq, *params = ctx.saved_tensors
+        flat, grads, gptrs = _flat_grads(params)
         g_hid = torch.empty_like(hiddens)
-        g_mse = g_mse.contiguous().float()
+        g_mse = _scalar(g_mse, feats.device)
         w, g = _pack(L.local_tensors, params), _pack(L.local_tensors, grads)
         L.check(lib.recnet_local_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
                                      ws.data_ptr(), ctx.nbytes, g_mse.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
                 "recnet_local_bwd")
+        if g_reg is not None:
+            _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
         return (None, g_hid, None, None, *grads)
 
 
 class GlobalReconstructorFn(torch.autograd.Function):
     """train.forward_global_reconstructor (train.py:78-105) over GlobalReconstructor.forward.
     inputs: meta, hiddens (L,B,H), feats (B,T,R), rng, then the 6 parameters in global_tensors.FIELDS order.
-    output: MSE(mean_t out, mean_tau feats) / L  (scalar)."""
+    outputs: MSE(mean_t out, mean_tau feats) / L  (scalar), reg (scalar)."""
 
     @staticmethod
     def forward(ctx, meta: Dict, hiddens, feats, rng, *params):
@@ -171,92 +249,44 @@ class GlobalReconstructorFn(torch.autograd.Function):
         w = _pack(L.global_tensors, params)
         L.check(lib.recnet_global_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
                                       nbytes, loss.data_ptr(), _stream()), "recnet_global_fwd")
+        reg, sumsq = _norms_fwd(params)
         ctx.desc, ctx.nbytes = d, nbytes
-        ctx.save_for_backward(hiddens, feats, rng, ws, *params)
-        return loss
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(hiddens, feats, rng, ws, sumsq, *params)
+        return loss, reg
 
     @staticmethod
-    def backward(ctx, g_loss):
+    def backward(ctx, g_loss, g_reg):
         lib = L.lib()
-        hiddens, feats, rng, ws, *params = ctx.saved_tensors
-        grads = [torch.empty_like(p) for p in params]
+        hiddens, feats, rng, ws, sumsq, *params = ctx.saved_tensors
+        flat, grads, gptrs = _flat_grads(params)
         g_hid = torch.empty_like(hiddens)
-        g_loss = g_loss.contiguous().float()
+        g_loss = _scalar(g_loss, feats.device)
         w, g = _pack(L.global_tensors, params), _pack(L.global_tensors, grads)
         L.check(lib.recnet_global_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
                                       ws.data_ptr(), ctx.nbytes, g_loss.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
                 "recnet_global_bwd")
+        if g_reg is not None:
+            _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
         return (None, g_hid, None, None, *grads)
 
 
 # ----------------------------------------------------------------------------------------------------------------
-class _NormTable:
-    """Device-side tables for the multi-tensor norm kernels, cached per parameter list."""
-    CHUNK = 16384
-
-    def __init__(self, params: Sequence[torch.Tensor]):
-        dev = params[0].device
-        self.key = tuple((p.data_ptr(), p.numel()) for p in params)
-        self.n = len(params)
-        self.ptrs = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device=dev)
-        self.sizes = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
-        bt, bc = [], []
-        for i, p in enumerate(params):
-            for c in range((p.numel() + self.CHUNK - 1) // self.CHUNK):
-                bt.append(i)
-                bc.append(c)
-        offs, o = [], 0
-        for p in params:
-            offs.append(o)
-            o += (p.numel() + 3) // 4 * 4
-        self.total = o
-        self.offsets = offs
-        self.offset_bytes = torch.tensor([x * 4 for x in offs], dtype=torch.int64, device=dev)
-        self.blk_tensor = torch.tensor(bt, dtype=torch.int32, device=dev)
-        self.blk_chunk = torch.tensor(bc, dtype=torch.int32, device=dev)
-        self.n_blocks = len(bt)
-
-
-_norm_tables: Dict[tuple, _NormTable] = {}
-
-
-def _table_for(params) -> _NormTable:
-    key = tuple((p.data_ptr(), p.numel()) for p in params)
-    t = _norm_tables.get(key)
-    if t is None:
-        t = _norm_tables[key] = _NormTable(params)
-    return t
-
-
 class ParamNormSumFn(torch.autograd.Function):
-    """reg = sum_p ||p||_2 over a parameter list (train.py:69,101,127); grad_p = g * p / ||p||."""
+    """Stand-alone reg = sum_p ||p||_2 over a parameter list (train.py:69,101,127); grad_p = g * p / ||p||."""
 
     @staticmethod
     def forward(ctx, *params):
-        lib = L.lib()
         params = tuple(_f32c(p, "parameter") for p in params)
-        tab = _table_for(params)
-        sumsq = torch.empty(tab.n, dtype=torch.float32, device=params[0].device)
-        reg = torch.empty((), dtype=torch.float32, device=params[0].device)
-        L.check(lib.recnet_param_norms_fwd(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(),
-                                           tab.blk_chunk.data_ptr(), tab.n_blocks, sumsq.data_ptr(), reg.data_ptr(), _stream()),
-                "recnet_param_norms_fwd")
-        ctx.tab = tab
+        reg, sumsq = _norms_fwd(params)
         ctx.save_for_backward(sumsq, *params)
         return reg
 
     @staticmethod
     def backward(ctx, g):
-        lib = L.lib()
         sumsq, *params = ctx.saved_tensors
-        tab = ctx.tab
-        flat = torch.empty(tab.total, dtype=torch.float32, device=params[0].device)
-        grads = [flat[o: o + p.numel()].view_as(p) for o, p in zip(tab.offsets, params)]
-        gptrs = tab.offset_bytes + flat.data_ptr()      # device-side add: safe under CUDA-graph capture
-        g = g.contiguous().float()
-        L.check(lib.recnet_param_norms_bwd(tab.ptrs.data_ptr(), gptrs.data_ptr(), tab.sizes.data_ptr(), tab.n,
-                                           tab.blk_tensor.data_ptr(), tab.blk_chunk.data_ptr(), tab.n_blocks, sumsq.data_ptr(),
-                                           g.data_ptr(), 1.0, 0, _stream()), "recnet_param_norms_bwd")
+        flat, grads, gptrs = _flat_grads(params)
+        _norms_bwd_into(params, sumsq, _scalar(g, params[0].device), gptrs, accumulate=False)
         return tuple(grads)
 
 

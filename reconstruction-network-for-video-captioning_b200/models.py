@@ -97,7 +97,7 @@ class Decoder(nn.Module, _RngMixin):
 
     # ---- whole teacher-forced loop: one C call ----
     def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs):
-        """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,B,H))."""
+        """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,B,H), reg = sum_p ||p||)."""
         _require_supported(self.model_name, self.n_layers, "Decoder")
         return Fn.DecoderSequenceFn.apply(self._meta(), encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(),
                                           *self._params())
@@ -137,14 +137,17 @@ class Decoder(nn.Module, _RngMixin):
         h, c = hidden[0][-1], hidden[1][-1]
         emb = torch.nn.functional.embedding(input[0], self.embedding.weight) * self.embedding_scale      # decoder.py:46-47
         emb = torch.nn.functional.dropout(emb, self.embedding_dropout_p, self.training)                   # decoder.py:48
-        # U.v is time-invariant: cache it across the steps of one sequence (the reference recomputes it, decoder.py:54)
-        key = (encoder_outputs.data_ptr(), encoder_outputs._version, self.attn_U.weight._version, tuple(encoder_outputs.shape),
-               torch.is_grad_enabled())
-        if self._uv_cache is None or self._uv_cache[0] != key:
-            B, T, E = encoder_outputs.shape
+        # U.v is time-invariant (the reference recomputes it every step, decoder.py:54).  Without autograd (greedy / beam
+        # loops over this method) it is cached across the steps of one sequence; with autograd it is recomputed so that
+        # every step owns its graph.  The training hot path (forward_sequence) hoists it out of the loop altogether.
+        B, T, E = encoder_outputs.shape
+        need_grad = torch.is_grad_enabled() and self.attn_U.weight.requires_grad
+        key = (encoder_outputs.data_ptr(), encoder_outputs._version, self.attn_U.weight._version, (B, T, E), p)
+        if need_grad or self._uv_cache is None or self._uv_cache[0] != key:
             Uv = ops.linear(encoder_outputs.reshape(B * T, E), self.attn_U.weight, None, p).view(B, T, -1)
-            self._uv_cache = (key, Uv)
-        Uv = self._uv_cache[1]
+            self._uv_cache = None if need_grad else (key, Uv)
+        else:
+            Uv = self._uv_cache[1]
         Wh = ops.linear(h, self.attn_W.weight, None, p)                                                   # decoder.py:51
         ctx = ops.additive_attention(Wh, Uv, self.attn_b, self.attn_w.weight, encoder_outputs, p)          # decoder.py:55-61
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
@@ -178,7 +181,7 @@ class GlobalReconstructor(nn.Module, _RngMixin):
         return (w_ih, w_hh, b_ih, b_hh, self.out.weight, self.out.bias)
 
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
-        """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,T,R) -> MSE(mean_t out, mean_tau feats) / L."""
+        """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||)."""
         _require_supported(self.model_name, self.n_layers, "GlobalReconstructor")
         hid = _squeeze_layers(decoder_hiddens)
         meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p,
@@ -228,7 +231,7 @@ class LocalReconstructor(nn.Module, _RngMixin):
                 self.out.weight, self.out.bias)
 
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
-        """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,S,R) -> MSELoss(outputs^T, encoder_outputs)."""
+        """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||)."""
         _require_supported(self.model_name, self.n_layers, "LocalReconstructor")
         hid = _squeeze_layers(decoder_hiddens)
         meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training,

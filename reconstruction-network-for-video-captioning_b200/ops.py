@@ -46,8 +46,13 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, W, bias, precision):
         dt = _op_dtype(precision)
         xo, Wo = x.contiguous().to(dt), W.contiguous().to(dt)
+        ctx.k = x.shape[1]
+        if precision == L.PREC_BF16 and ctx.k % 8:      # TMA needs 16-byte row pitch: zero-pad K (e.g. 2004 = 468 + 1536)
+            pad = 8 - ctx.k % 8
+            xo, Wo = torch.nn.functional.pad(xo, (0, pad)), torch.nn.functional.pad(Wo, (0, pad))
         ctx.precision = precision
         ctx.has_bias = bias is not None
+        ctx.n = W.shape[0]
         ctx.save_for_backward(xo, Wo)
         return gemm(precision, xo, False, Wo, False, bias=bias.contiguous() if bias is not None else None)
 
@@ -56,10 +61,17 @@ class LinearFn(torch.autograd.Function):
         xo, Wo = ctx.saved_tensors
         p = ctx.precision
         go = gy.contiguous().to(_op_dtype(p))
-        gx = gemm(p, go, False, Wo, True) if ctx.needs_input_grad[0] else None          # [M,N] @ [N,K]
-        gW = gemm(p, go, True, xo, True) if ctx.needs_input_grad[1] else None           # [N,M] @ [M,K]
+        if p == L.PREC_BF16 and go.shape[1] % 8:        # same pitch rule for the N-contiguous operands of the backward GEMMs
+            pad = 8 - go.shape[1] % 8
+            go, Wo = torch.nn.functional.pad(go, (0, pad)), torch.nn.functional.pad(Wo, (0, 0, 0, pad))
+        gx = gemm(p, go, False, Wo, True)[:, :ctx.k] if ctx.needs_input_grad[0] else None              # [M,N] @ [N,K]
+        gW = gemm(p, go, True, xo, True)[:W_rows(ctx, go), :ctx.k] if ctx.needs_input_grad[1] else None  # [N,M] @ [M,K]
         gb = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gx, gW, gb, None
+
+
+def W_rows(ctx, go):
+    return ctx.n
 
 
 def linear(x, W, bias, precision):

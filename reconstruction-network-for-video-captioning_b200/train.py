@@ -11,7 +11,6 @@ import random
 import torch
 
 from .config import TrainConfig as C
-from .functional import param_norm_sum
 from .models import Decoder, GlobalReconstructor, LocalReconstructor
 
 
@@ -43,9 +42,8 @@ def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_for
         output_indices = ids[:L].cpu()
     m = target_masks[:L].to(torch.float32)
     n_t = m.sum(dim=1, keepdim=True)                                                                        # train.py:57
-    ce_weight = m / (n_t * n_t.sum())                                                                       # mean over n_t, then / sum n_t (train.py:54-60,68)
-    ce, hiddens = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs)
-    reg_loss = param_norm_sum(list(model.parameters()))                                                    # train.py:69
+    ce_weight = m / (n_t.clamp_min(1.0) * n_t.sum())                                                                       # mean over n_t, then / sum n_t (train.py:54-60,68)
+    ce, hiddens, reg_loss = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs)     # reg: train.py:69
     loss = ce + decoder['lambda_reg'] * reg_loss                                                            # train.py:70
     return loss, hiddens.unsqueeze(1), output_indices                                                       # train.py:73-75
 
@@ -53,16 +51,14 @@ def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_for
 def forward_global_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
     """train.py:78-105."""
     model = reconstructor['model']
-    loss = model.forward_sequence(decoder_hiddens, encoder_outputs)                                         # includes the /L of train.py:100
-    reg_loss = param_norm_sum(list(model.parameters()))
+    loss, reg_loss = model.forward_sequence(decoder_hiddens, encoder_outputs)                               # includes the /L of train.py:100
     return loss + reconstructor['lambda_reg'] * reg_loss
 
 
 def forward_local_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
     """train.py:108-131."""
     model = reconstructor['model']
-    loss = model.forward_sequence(decoder_hiddens, encoder_outputs)
-    reg_loss = param_norm_sum(list(model.parameters()))
+    loss, reg_loss = model.forward_sequence(decoder_hiddens, encoder_outputs)
     return loss + reconstructor['lambda_reg'] * reg_loss
 
 

@@ -1,0 +1,135 @@
+"""CPU tests of the host-side mirror: module surface (ctor kwargs, state_dict keys/shapes/order, initialiser
+parity with the reference's seeds), config names, loop-length logic, sharding, and the 2-rank gloo path of the
+gradient all-reducer."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import recnet_b200
+from recnet_b200 import train as T
+from recnet_b200.data import shard_range, synthetic_batch
+from recnet_b200.parallel import GradAllReducer
+from oracle import recnet_oracle as O
+from tests.golden_util import load_golden
+
+
+def test_state_dict_matches_reference_fixture_keys_and_shapes():
+    g = load_golden("tiny_lstm")
+    m = g["meta"]
+    dec = recnet_b200.Decoder("LSTM", 1, m["E"], m["EMB"], 1, m["H"], m["A"], m["V"], 0.5, 0.5, 0.5)
+    assert list(dec.state_dict().keys()) == list(g["dec"].keys())          # same keys in the same order
+    dec.load_state_dict({k: v.float() for k, v in g["dec"].items()})
+    loc = recnet_b200.LocalReconstructor("LSTM", 1, m["H"], m["E"], 0.5, 0.5, m["A"])
+    assert list(loc.state_dict().keys()) == list(g["local"].keys())
+    loc.load_state_dict({k: v.float() for k, v in g["local"].items()})
+    glo = recnet_b200.GlobalReconstructor("LSTM", 1, m["H"], m["E"], 0.5, 0.5, m["cap_len"])
+    assert list(glo.state_dict().keys()) == list(g["global"].keys())
+    glo.load_state_dict({k: v.float() for k, v in g["global"].items()})
+
+
+def test_default_shapes_are_the_msvd_ones():
+    dec = recnet_b200.Decoder("LSTM", 1, 1536, 468, 1, 512, 128, 4188, 0.5, 0.5, 0.5)
+    sd = dec.state_dict()
+    assert tuple(sd["rnn.weight_ih_l0"].shape) == (2048, 2004) and tuple(sd["out.weight"].shape) == (4188, 512)
+    assert bool((sd["attn_b"] == 1).all())                                  # decoder.py:27 initialises the bias to ones
+    assert sum(p.numel() for p in dec.parameters()) == 9527692
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference not mounted (GPU box)")
+def test_same_seed_same_initial_weights_as_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_decoder", "/root/reference/models/decoder.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    args = ("LSTM", 1, 64, 20, 1, 32, 16, 101, 0.5, 0.5, 0.5)
+    torch.manual_seed(3)
+    a = ref.Decoder(*args).state_dict()
+    torch.manual_seed(3)
+    b = recnet_b200.Decoder(*args).state_dict()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_config_keeps_reference_attribute_names():
+    C = recnet_b200.TrainConfig
+    for name, val in dict(decoder_model="GRU", reconstructor_model="LSTM", caption_max_len=30, batch_size=100, embedding_size=468,
+                          encoder_output_size=1536, encoder_output_len=28, decoder_hidden_size=512, decoder_attn_size=128,
+                          reconstructor_hidden_size=1536, reconstructor_attn_size=128, decoder_teacher_forcing_ratio=1.0,
+                          gradient_clip=50.0, decoder_learning_rate=1e-5, reconstructor_learning_rate=1e-6).items():
+        assert getattr(C, name) == val
+    assert C.init_word2idx == {'<PAD>': 0, '<SOS>': 1, '<EOS>': 2}
+
+
+def test_unsupported_variants_raise_not_silently_fall_back():
+    gru = recnet_b200.Decoder("GRU", 1, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)
+    assert tuple(gru.state_dict()["rnn.weight_ih_l0"].shape) == (24, 24)    # 3 gates: checkpoint-compatible holder
+    with pytest.raises(NotImplementedError):
+        gru.forward_sequence(None, None, None, None)
+    with pytest.raises(NotImplementedError):
+        T.forward_reconstructor_for("bogus")
+
+
+def test_num_steps_follows_reference_break_rule():
+    feats, targets, masks = synthetic_batch(6, 4, 8, 20, caption_max_len=9, seed=3, full_length_first=False)
+    lens = masks.sum(0)
+    assert T._num_steps(masks, 9) == int(lens.max())                        # loop stops after the last non-empty row
+    feats, targets, masks = synthetic_batch(6, 4, 8, 20, caption_max_len=9, seed=3)
+    assert T._num_steps(masks, 9) == 10
+
+
+def test_synthetic_batch_equals_oracle_generator():
+    a = synthetic_batch(5, 7, 8, 30, 12, seed=99)
+    b = O.synthetic_batch(5, 7, 8, 30, 12, seed=99)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_shard_range_partitions():
+    for n, w in ((800, 8), (100, 3), (7, 8)):
+        got = [shard_range(n, r, w) for r in range(w)]
+        assert got[0][0] == 0 and got[-1][1] == n and all(got[i][1] == got[i + 1][0] for i in range(w - 1))
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = torch.nn.Linear(4, 3)
+    red = GradAllReducer([m])
+    red.start_iteration()
+    # emulate what the sequence Functions do: all gradients of the module are views of ONE flat buffer
+    flat = torch.arange(15, dtype=torch.float32) * (rank + 1)
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, w, b):
+            return (w.sum() + b.sum()) * 0
+
+        @staticmethod
+        def backward(ctx, g):
+            return flat[:12].view(3, 4), flat[12:15]
+
+    Fn.apply(m.weight, m.bias).backward()
+    red.wait()
+    expect = torch.arange(15, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(m.weight.grad.flatten(), expect[:12]) and torch.allclose(m.bias.grad, expect[12:])
+    ok = ok and red.bytes_last == 15 * 4                                     # ONE all-reduce of the flat buffer
+    # per-tensor fallback when grads are not flat views
+    m2 = torch.nn.Linear(2, 2)
+    red2 = GradAllReducer([m2]); red2.start_iteration()
+    m2(torch.ones(1, 2) * (rank + 1)).sum().backward()
+    red2.wait()
+    ok = ok and torch.allclose(m2.bias.grad, torch.ones(2)) and torch.allclose(m2.weight.grad, torch.full((2, 2), (1 + world) / 2))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_grad_allreducer_two_ranks_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(world, 29533, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world)), dict(out)

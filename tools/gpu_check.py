@@ -52,7 +52,7 @@ def check_gemm(prec):
     for (M, N, K) in shapes:
         for tA in (False, True):
             for tB in (False, True):
-                if prec == L.PREC_BF16 and ((tA and M % 8) or (tB and N % 8) or K % 8):
+                if prec == L.PREC_BF16 and (((M if tA else K) % 8) or ((N if tB else K) % 8)):
                     continue
                 A = torch.randn((K, M) if tA else (M, K), generator=g).to(dev).to(dt)
                 B = torch.randn((K, N) if tB else (N, K), generator=g).to(dev).to(dt)

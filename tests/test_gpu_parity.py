@@ -274,8 +274,8 @@ def test_full_size_greedy_bit_exact_fp32_batch1024_shape():
 
 
 def test_samples_are_independent_and_permutation_equivariant_at_full_size():
-    """Size-independent property: the path shards by sample, so permuting the batch permutes hiddens, and the summed
-    gradient over two half-batches (weighted like the loss) equals nothing else's business -- here: permutation."""
+    """Size-independent property at BASELINE sizes: the path shards by sample (no cross-sample arithmetic anywhere),
+    so permuting the batch permutes the decoder states bit-exactly."""
     feats, targets, masks = (t.to(dev()) for t in _full_inputs())
     P = O.init_decoder_params(FULL["V"], FULL["EMB"], FULL["E"], FULL["H"], FULL["A"], seed=0)
     dec, _ = build(FULL, "bf16", "none", P, {})

@@ -87,13 +87,14 @@ int recnet_attn_fwd(int precision, const float* wh_partials, int n_wh, int64_t w
                     int64_t drop_base, void* stream);
 
 /* Fused additive attention, backward (autograd of the same lines).  dctx arrives as n_p split-K partials
- * [n_p][B,p_ld] (columns [0,D)).  Outputs: dwh_out [B,A]; duv_acc (same strides as uv) and dw_acc [B,A]
- * are accumulated across timesteps (first=1 overwrites); dctx_out [B,D] optional (summed, dropout-masked). */
+ * [n_p][B,p_ld] (columns [0,D)).  Outputs: dwh_out [B,A] fp32 and dwh_op [B,A] in operand storage (nullable;
+ * A-operand of the dWh @ attn_W GEMM); duv_acc (same strides as uv) and dw_acc [B,A] are accumulated across
+ * timesteps (first=1 overwrites); dctx_out [B,D] optional (summed, dropout-masked). */
 int recnet_attn_bwd(int precision, const float* dctx_partials, int n_p, int64_t p_stride, int64_t p_ld, const void* v,
                     int64_t v_bs, int64_t v_ts, const float* wh, const float* uv, int64_t uv_bs, int64_t uv_ts,
                     const float* attn_b, const float* attn_w, int B, int Tn, int A, int D, float* dwh_out,
-                    float* duv_acc, float* dw_acc, int first, float* dctx_out, float p_drop, const uint64_t* rng,
-                    uint32_t site, int64_t drop_base, void* stream);
+                    void* dwh_op, float* duv_acc, float* dw_acc, int first, float* dctx_out, float p_drop,
+                    const uint64_t* rng, uint32_t site, int64_t drop_base, void* stream);
 
 /* Fused LSTM gate activation + cell update (the pointwise half of nn.LSTM, decoder.py:66; gate order i,f,g,o).
  *   pre = sum_s partials[s] + gx + b1 + b2.  gates_out [B,4H] (stash, `precision` storage), c_out/h_out fp32,
@@ -103,12 +104,12 @@ int recnet_lstm_cell_fwd(int precision, const float* partials, int n_p, int64_t 
                          void* gates_out, float* c_out, float* h_out, int64_t h_ld, void* h_op, int64_t hop_ld,
                          void* h_op2, int64_t hop2_ld, void* stream);
 
-/* Backward of the same step.  dh = dh_scale*dh_ext + dh_ext2 + sum_s dxp[s][:, col0:col0+H] + dq @ wq
- * (dq [B,A] = d(attention query projection), wq [A,H] = attn_W).  dc is in/out ([B,H]; first=1 -> treated as 0).
- * dg_out [B,4H] in operand storage. */
+/* Backward of the same step.  dh = dh_scale*dh_ext + dh_ext2 + sum_s dxp[s][:, col0:col0+H] + sum_s dqp[s]
+ * (dxp: split-K partials of d[x;h]; dqp [n_q][B,q_ld]: split-K partials of dWh @ attn_W, the attention-query
+ * path).  dc is in/out ([B,H]; first=1 -> treated as 0).  dg_out [B,4H] in operand storage. */
 int recnet_lstm_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const float* dh_scale, const float* dh_ext2,
                          int64_t dh2_ld, const float* dxp, int n_p, int64_t p_stride, int64_t p_ld, int col0,
-                         const float* dq, const float* wq, int A, float* dc, int first, const void* gates,
+                         const float* dqp, int n_q, int64_t q_stride, int64_t q_ld, float* dc, int first, const void* gates,
                          const float* c_prev, const float* c_new, int B, int H, void* dg_out, int64_t dg_ld,
                          void* stream);
 

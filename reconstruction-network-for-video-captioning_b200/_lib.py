@@ -80,9 +80,9 @@ SIGNATURES = {
     "recnet_gemm": (_i, [_i, _p, _l, _i, _p, _l, _i, _p, _l, _p, _l, _p, _i, _i, _i, _i, _l, _i, _i, _p]),
     "recnet_splitk_reduce": (_i, [_p, _i, _l, _l, _p, _l, _i, _i, _i, _p]),
     "recnet_attn_fwd": (_i, [_i, _p, _i, _l, _p, _l, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _p, _p, _l, _f, _p, _u, _l, _p]),
-    "recnet_attn_bwd": (_i, [_i, _p, _i, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _f, _p, _u, _l, _p]),
+    "recnet_attn_bwd": (_i, [_i, _p, _i, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _f, _p, _u, _l, _p]),
     "recnet_lstm_cell_fwd": (_i, [_i, _p, _i, _l, _l, _p, _l, _p, _p, _p, _i, _i, _p, _p, _p, _l, _p, _l, _p, _l, _p]),
-    "recnet_lstm_cell_bwd": (_i, [_i, _p, _l, _p, _p, _l, _p, _i, _l, _l, _i, _p, _p, _i, _p, _i, _p, _p, _p, _i, _i, _p, _l, _p]),
+    "recnet_lstm_cell_bwd": (_i, [_i, _p, _l, _p, _p, _l, _p, _i, _l, _l, _i, _p, _i, _l, _l, _p, _i, _p, _p, _p, _i, _i, _p, _l, _p]),
     "recnet_decoder_workspace_bytes": (_l, [C.POINTER(decoder_desc)]),
     "recnet_decoder_fwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p, _p]),
     "recnet_decoder_bwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p,

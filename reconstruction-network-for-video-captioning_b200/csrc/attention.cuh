@@ -11,9 +11,13 @@
 
 namespace attn {
 
-constexpr int FWD_THREADS = 128;
+constexpr int FWD_THREADS = 256;
 constexpr int BWD_THREADS = 256;
 constexpr int MAX_T = 64;       // frames (28 / 40) or decoder steps (<= 31)
+
+// All three kernels are latency-bound (a few MB that live in L2, ~100 CTAs): every phase issues its loads in
+// batches before the first use so that a thread has 8-28 independent requests in flight (r1 profile: the first
+// version with serial per-frame loops took 13-20 us per launch).
 
 struct FwdArgs {
   const float* WhP; int n_whp; long long whp_stride;   // Wh partials [n_whp][B,A]
@@ -31,21 +35,43 @@ template <typename TV, typename TO>
 __global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
   extern __shared__ float sm[];
   float* Wh = sm;              // [A] (bias folded in)
-  float* e = sm + a.A;         // [Tn]
+  float* wv = sm + a.A;        // [A] attn_w
+  float* e = sm + 2 * a.A;     // [Tn]
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = FWD_THREADS / 32;
   for (int i = tid; i < a.A; i += FWD_THREADS) {
     float s = 0.f;
-    for (int p = 0; p < a.n_whp; ++p) s += a.WhP[p * a.whp_stride + (long long)b * a.A + i];
+    for (int p0 = 0; p0 < a.n_whp; p0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (p0 + k < a.n_whp) ? __ldg(a.WhP + (long long)(p0 + k) * a.whp_stride + (long long)b * a.A + i) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
     Wh[i] = s + a.attn_b[i];
+    wv[i] = a.attn_w[i];
     if (a.Wh_out && blockIdx.x == 0) a.Wh_out[(long long)b * a.A + i] = s;
   }
   __syncthreads();
-  for (int tau = warp; tau < a.Tn; tau += FWD_THREADS / 32) {
-    const float* uv = a.Uv + (long long)b * a.uv_bs + (long long)tau * a.uv_ts;
-    float s = 0.f;
-    for (int i = lane; i < a.A; i += 32) s += a.attn_w[i] * tanhf(Wh[i] + uv[i]);
-    s = warp_sum(s);
-    if (lane == 0) e[tau] = s;
+  // scores: warp w handles frames w, w+NW, ... ; up to 4 frames' Uv rows are loaded before any tanh
+  for (int t0 = warp; t0 < a.Tn; t0 += 4 * NW) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < a.A; i += 32) {
+      float u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int tau = t0 + k * NW;
+        u[k] = (tau < a.Tn) ? __ldg(a.Uv + (long long)b * a.uv_bs + (long long)tau * a.uv_ts + i) : 0.f;
+      }
+      const float whi = Wh[i], wi = wv[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += wi * tanhf(whi + u[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float r = warp_sum(s[k]);
+      if (lane == 0 && t0 + k * NW < a.Tn) e[t0 + k * NW] = r;
+    }
   }
   __syncthreads();
   if (a.normalize) {   // optional softmax over frames (paper variant)
@@ -71,25 +97,20 @@ __global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
     float acc[VN];
 #pragma unroll
     for (int j = 0; j < VN; ++j) acc[j] = 0.f;
-    int tau = 0;
-    for (; tau + 4 <= a.Tn; tau += 4) {
-      Vec16<TV> v0, v1, v2, v3;
-      v0.load(Vb + (long long)(tau + 0) * a.v_ts + d);
-      v1.load(Vb + (long long)(tau + 1) * a.v_ts + d);
-      v2.load(Vb + (long long)(tau + 2) * a.v_ts + d);
-      v3.load(Vb + (long long)(tau + 3) * a.v_ts + d);
-      float f0[VN], f1[VN], f2[VN], f3[VN];
-      v0.get(f0); v1.get(f1); v2.get(f2); v3.get(f3);
-      const float e0 = e[tau], e1 = e[tau + 1], e2 = e[tau + 2], e3 = e[tau + 3];
+    for (int t0 = 0; t0 < a.Tn; t0 += 8) {          // 8 frames (8 x 16 B) in flight per thread
+      Vec16<TV> v[8];
 #pragma unroll
-      for (int j = 0; j < VN; ++j) acc[j] += e0 * f0[j] + e1 * f1[j] + e2 * f2[j] + e3 * f3[j];
-    }
-    for (; tau < a.Tn; ++tau) {
-      Vec16<TV> v0; v0.load(Vb + (long long)tau * a.v_ts + d);
-      float f0[VN]; v0.get(f0);
-      const float e0 = e[tau];
+      for (int k = 0; k < 8; ++k)
+        if (t0 + k < a.Tn) v[k].load(Vb + (long long)(t0 + k) * a.v_ts + d);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) acc[j] += e0 * f0[j];
+      for (int k = 0; k < 8; ++k) {
+        if (t0 + k < a.Tn) {
+          float f[VN]; v[k].get(f);
+          const float ek = e[t0 + k];
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc[j] += ek * f[j];
+        }
+      }
     }
     const float sc = a.normalize ? 1.f : a.inv_T;
 #pragma unroll
@@ -112,7 +133,8 @@ struct BwdArgs {
   const float* Wh; const float* Uv; long long uv_bs, uv_ts;
   const float* attn_b; const float* attn_w;
   int B, Tn, A, D; float inv_T;
-  float* dWh_out;                      // [B,A]
+  float* dWh_out;                      // [B,A] fp32
+  void* dWh_op;                        // [B,A] operand type (nullable): A-operand of the dWh @ attn_W GEMM
   float* dUv_acc; int uv_first;        // same strides as Uv; first => overwrite instead of +=
   float* dw_acc;                       // [B,A] += ; first => overwrite
   float* dctx_out;                     // [B,D] fp32 (nullable): summed/masked dctx, for the deferred dV pass
@@ -120,15 +142,23 @@ struct BwdArgs {
   float p_drop; const unsigned long long* rng; unsigned int site; long long drop_base;
 };
 
-template <typename TV>
+template <typename TV, typename TO>
 __global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
   extern __shared__ float sm[];
   float* dctx = sm;                 // [D]
   float* de = sm + a.D;             // [Tn]
+  float* red = de + a.Tn;           // [2 * BWD_THREADS]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BWD_THREADS / 32;
   for (int d = tid; d < a.D; d += BWD_THREADS) {
     float s = 0.f;
-    for (int p = 0; p < a.n_p; ++p) s += a.dXp[p * a.p_stride + (long long)b * a.p_ld + d];
+    for (int p0 = 0; p0 < a.n_p; p0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (p0 + k < a.n_p) ? __ldg(a.dXp + (long long)(p0 + k) * a.p_stride + (long long)b * a.p_ld + d) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
     if (a.p_drop > 0.f) s *= dropout_scale(a.rng, a.site, (uint64_t)(a.drop_base + (long long)b * a.D + d), a.p_drop);
     dctx[d] = s;
     if (a.dctx_out) a.dctx_out[(long long)b * a.D + d] = s;
@@ -136,34 +166,83 @@ __global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
   __syncthreads();
   constexpr int VN = Vec16<TV>::N;
   const TV* Vb = reinterpret_cast<const TV*>(a.V) + (long long)b * a.v_bs;
-  for (int tau = warp; tau < a.Tn; tau += BWD_THREADS / 32) {
-    const TV* vr = Vb + (long long)tau * a.v_ts;
-    float s = 0.f;
-    for (int d = lane * VN; d < a.D; d += 32 * VN) {
-      Vec16<TV> v; v.load(vr + d);
-      float f[VN]; v.get(f);
+  // de: warp w handles frames w, w+NW, ...; two frames' rows in flight
+  for (int t0 = warp; t0 < a.Tn; t0 += 2 * NW) {
+    float s[2] = {0.f, 0.f};
+    for (int d = lane * VN; d < a.D; d += 32 * VN * 2) {
+      Vec16<TV> v[2][2];
+      bool ok[2][2];
 #pragma unroll
-      for (int j = 0; j < VN; ++j) s += f[j] * dctx[d + j];
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int tau = t0 + k * NW, dd = d + u * 32 * VN;
+          ok[k][u] = tau < a.Tn && dd < a.D;
+          if (ok[k][u]) v[k][u].load(Vb + (long long)tau * a.v_ts + dd);
+        }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (ok[k][u]) {
+            float f[VN]; v[k][u].get(f);
+            const int dd = d + u * 32 * VN;
+#pragma unroll
+            for (int j = 0; j < VN; ++j) s[k] += f[j] * dctx[dd + j];
+          }
     }
-    s = warp_sum(s);
-    if (lane == 0) { de[tau] = s * a.inv_T; if (a.de_out) a.de_out[(long long)b * a.Tn + tau] = s * a.inv_T; }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float r = warp_sum(s[k]) * a.inv_T;
+      const int tau = t0 + k * NW;
+      if (lane == 0 && tau < a.Tn) { de[tau] = r; if (a.de_out) a.de_out[(long long)b * a.Tn + tau] = r; }
+    }
   }
   __syncthreads();
-  for (int i = tid; i < a.A; i += BWD_THREADS) {
-    const float wh = a.Wh[(long long)b * a.A + i] + a.attn_b[i];
-    const float w = a.attn_w[i];
+  // ds: thread (i, part) handles attention unit i and frames part, part+nparts, ... (4 frames in flight)
+  const int nparts = (a.A <= BWD_THREADS && BWD_THREADS % a.A == 0) ? BWD_THREADS / a.A : 1;
+  for (int i0 = 0; i0 < a.A; i0 += BWD_THREADS / nparts) {
+    const int i = i0 + tid % (BWD_THREADS / nparts), part = tid / (BWD_THREADS / nparts);
     float dwh = 0.f, dw = 0.f;
-    for (int tau = 0; tau < a.Tn; ++tau) {
-      const long long off = (long long)b * a.uv_bs + (long long)tau * a.uv_ts + i;
-      const float s = tanhf(wh + a.Uv[off]);
-      const float g = de[tau] * w * (1.f - s * s);
-      dwh += g;
-      dw += de[tau] * s;
-      a.dUv_acc[off] = a.uv_first ? g : a.dUv_acc[off] + g;
+    if (i < a.A) {
+      const float wh = a.Wh[(long long)b * a.A + i] + a.attn_b[i];
+      const float w = a.attn_w[i];
+      for (int t0 = part; t0 < a.Tn; t0 += 4 * nparts) {
+        float u[4], o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tau = t0 + k * nparts;
+          const long long off = (long long)b * a.uv_bs + (long long)tau * a.uv_ts + i;
+          u[k] = (tau < a.Tn) ? __ldg(a.Uv + off) : 0.f;
+          o[k] = (tau < a.Tn && !a.uv_first) ? a.dUv_acc[off] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tau = t0 + k * nparts;
+          if (tau < a.Tn) {
+            const float s = tanhf(wh + u[k]);
+            const float g = de[tau] * w * (1.f - s * s);
+            dwh += g;
+            dw += de[tau] * s;
+            a.dUv_acc[(long long)b * a.uv_bs + (long long)tau * a.uv_ts + i] = o[k] + g;
+          }
+        }
+      }
     }
-    a.dWh_out[(long long)b * a.A + i] = dwh;
-    float* pw = a.dw_acc + (long long)b * a.A + i;
-    *pw = a.uv_first ? dw : *pw + dw;
+    if (nparts > 1) {     // combine the frame partitions
+      red[tid] = dwh; red[BWD_THREADS + tid] = dw;
+      __syncthreads();
+      if (part == 0 && i < a.A) {
+        for (int q = 1; q < nparts; ++q) { dwh += red[q * (BWD_THREADS / nparts) + tid]; dw += red[BWD_THREADS + q * (BWD_THREADS / nparts) + tid]; }
+      }
+      __syncthreads();
+    }
+    if (part == 0 && i < a.A) {
+      a.dWh_out[(long long)b * a.A + i] = dwh;
+      if (a.dWh_op) reinterpret_cast<TO*>(a.dWh_op)[(long long)b * a.A + i] = from_f32<TO>(dwh);
+      float* pw = a.dw_acc + (long long)b * a.A + i;
+      *pw = a.uv_first ? dw : *pw + dw;
+    }
   }
 }
 
@@ -189,28 +268,31 @@ template <typename TV, typename TO>
 static int launch_fwd(FwdArgs a, cudaStream_t st) {
   if (a.Tn > MAX_T || a.Tn < 1) return RECNET_ERR_BAD_SHAPE;
   constexpr int VN = Vec16<TV>::N;
-  if (a.D % VN || a.v_ts % VN || a.v_bs % VN || (sizeof(TO) == 2 && (a.ctx_ld % 2))) return RECNET_ERR_ALIGNMENT;
-  int slices = rn_cdiv(a.D, FWD_THREADS * VN);
-  // keep slice boundaries vector aligned
+  if (a.D % VN || a.v_ts % VN || a.v_bs % VN) return RECNET_ERR_ALIGNMENT;
+  // enough CTAs to cover the SMs (~150), each thread owning at most one 16-byte column group when possible
+  int slices = rn_cdiv(150, a.B);
+  const int min_slices = rn_cdiv(a.D, FWD_THREADS * VN);
+  if (slices < min_slices) slices = min_slices;
+  if (slices > a.D / VN) slices = a.D / VN;
   int slice = rn_cdiv(rn_cdiv(a.D, slices), VN) * VN;
   slices = rn_cdiv(a.D, slice);
   a.d_slice = slice;
   dim3 grid(slices, a.B);
-  const size_t smem = (size_t)(a.A + a.Tn) * sizeof(float);
+  const size_t smem = (size_t)(2 * a.A + a.Tn) * sizeof(float);
   ProfScope prof(KC_ATTN_FWD, a.B, a.Tn, a.D, st);
   attn_fwd_kernel<TV, TO><<<grid, FWD_THREADS, smem, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
 }
 
-template <typename TV>
+template <typename TV, typename TO>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   if (a.Tn > MAX_T || a.Tn < 1) return RECNET_ERR_BAD_SHAPE;
   constexpr int VN = Vec16<TV>::N;
   if (a.D % VN || a.v_ts % VN || a.v_bs % VN) return RECNET_ERR_ALIGNMENT;
-  const size_t smem = (size_t)(a.D + a.Tn) * sizeof(float);
+  const size_t smem = (size_t)(a.D + a.Tn + 2 * BWD_THREADS) * sizeof(float);
   ProfScope prof(KC_ATTN_BWD, a.B, a.Tn, a.D, st);
-  attn_bwd_kernel<TV><<<a.B, BWD_THREADS, smem, st>>>(a);
+  attn_bwd_kernel<TV, TO><<<a.B, BWD_THREADS, smem, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -328,8 +328,13 @@ static inline int launch(const bf16* A, long long lda, int transA, const bf16* B
   if (Cf && ((reinterpret_cast<uintptr_t>(Cf) & 15) || (ldc & 3) || (split_stride & 3))) ep.vec_ok = 0;
   if (Cb && ((reinterpret_cast<uintptr_t>(Cb) & 7) || (ldcb & 3))) ep.vec_ok = 0;
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) ep.vec_ok = 0;
-  if (BN == 64) return launch_bn<64, 8>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
-  if (BN == 128) return launch_bn<128, 6>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
+  // short K loops (the per-step split-K GEMMs) use a shallow ring (<= 97 KB smem) so that two CTAs -- typically of
+  // two different sample chains -- share an SM; long K loops (batched GEMMs) use the deep ring.
+  const bool shallow = kb_per <= 12;
+  if (BN == 64) return shallow ? launch_bn<64, 4>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st)
+                               : launch_bn<64, 8>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
+  if (BN == 128) return shallow ? launch_bn<128, 3>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st)
+                                : launch_bn<128, 6>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
   return launch_bn<256, 4>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
 }
 }  // namespace tc

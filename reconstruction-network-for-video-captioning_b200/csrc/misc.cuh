@@ -59,28 +59,54 @@ __global__ void embed_scatter_kernel(float* __restrict__ demb, const long long* 
   }
 }
 
-// out[n] (+)= sum_m X[m*ld + n]      block = 32 columns x 8 row-lanes
+// out[n] (+)= sum_m X[m*ld + n]      block = 32 columns x 8 row-lanes; blockIdx.y = row chunk (two-stage, fixed order)
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, float* __restrict__ out, int accumulate) {
+__global__ void colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, int rows_per_chunk, float* __restrict__ out,
+                              int accumulate) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
+  const int m_lo = blockIdx.y * rows_per_chunk, m_hi = min(M, m_lo + rows_per_chunk);
   float s = 0.f;
-  if (n < N)
-    for (int m = ty; m < M; m += 8) s += to_f32<T>(X[(long long)m * ld + n]);
+  if (n < N) {
+    int m = m_lo + ty;
+    for (; m + 24 < m_hi; m += 32) {       // 4 independent row loads in flight
+      const float v0 = to_f32<T>(X[(long long)m * ld + n]), v1 = to_f32<T>(X[(long long)(m + 8) * ld + n]);
+      const float v2 = to_f32<T>(X[(long long)(m + 16) * ld + n]), v3 = to_f32<T>(X[(long long)(m + 24) * ld + n]);
+      s += (v0 + v1) + (v2 + v3);
+    }
+    for (; m < m_hi; m += 8) s += to_f32<T>(X[(long long)m * ld + n]);
+  }
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += red[k][tx];
-    out[n] = accumulate ? out[n] + t : t;
+    float* o = out + (long long)blockIdx.y * N + n;
+    *o = (accumulate && gridDim.y == 1) ? *o + t : t;
   }
 }
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += part[(long long)c * N + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+// scratch: >= 64 * N floats (only used when M is large enough to be worth a second stage)
 template <typename T>
-static int colsum(const T* X, long long ld, int M, int N, float* out, int accumulate, cudaStream_t st) {
-  colsum_kernel<T><<<rn_cdiv(N, 32), 256, 0, st>>>(X, ld, M, N, out, accumulate);
+static int colsum(const T* X, long long ld, int M, int N, float* out, int accumulate, float* scratch, cudaStream_t st) {
+  int chunks = (scratch && M >= 512) ? (M + 127) / 128 : 1;
+  if (chunks > 64) chunks = 64;
+  const int rpc = (M + chunks - 1) / chunks;
+  dim3 grid(rn_cdiv(N, 32), chunks);
+  colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, M, N, rpc, chunks > 1 ? scratch : out, accumulate);
   RN_LAUNCH_OK();
+  if (chunks > 1) {
+    colsum_finish_kernel<<<rn_cdiv(N, 256), 256, 0, st>>>(scratch, chunks, N, out, accumulate);
+    RN_LAUNCH_OK();
+  }
   return 0;
 }
 
@@ -155,19 +181,23 @@ __global__ void mt_sumsq_kernel(const long long* __restrict__ ptrs, const long l
   s = block_sum(s, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;          // fixed-order two-stage reduction: bitwise reproducible
 }
-// one thread per tensor sums that tensor's block partials in block order, then reg = sum_t sqrt(sumsq[t])
+// warp t sums tensor t's block partials (lane-strided, fixed order => reproducible), then reg = sum_t sqrt(sumsq[t])
 __global__ void mt_norm_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ blk_tensor, int n_blocks,
                                         float* __restrict__ sumsq, int n, float* __restrict__ out) {
-  __shared__ float red[32];
-  float r = 0.f;
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+  __shared__ float nrm[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t < n; t += nw) {
     float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) if (blk_tensor[b] == t) s += partial[b];
-    sumsq[t] = s;
-    r += sqrtf(s);
+    for (int b = lane; b < n_blocks; b += 32) if (blk_tensor[b] == t) s += partial[b];
+    s = warp_sum(s);
+    if (lane == 0) { sumsq[t] = s; nrm[t & 63] = sqrtf(s); }
   }
-  r = block_sum(r, red);
-  if (threadIdx.x == 0) out[0] = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int t = 0; t < n; ++t) r += nrm[t & 63];
+    out[0] = r;
+  }
 }
 __global__ void mt_reg_grad_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ gptrs,
                                    const long long* __restrict__ sizes, const int* __restrict__ blk_tensor,

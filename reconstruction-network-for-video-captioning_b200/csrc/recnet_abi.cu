@@ -88,17 +88,17 @@ int recnet_attn_fwd(int precision, const float* wh_partials, int n_wh, int64_t w
 
 int recnet_attn_bwd(int precision, const float* dctx_partials, int n_p, int64_t p_stride, int64_t p_ld, const void* v,
                     int64_t v_bs, int64_t v_ts, const float* wh, const float* uv, int64_t uv_bs, int64_t uv_ts,
-                    const float* attn_b, const float* attn_w, int B, int Tn, int A, int D, float* dwh_out, float* duv_acc,
-                    float* dw_acc, int first, float* dctx_out, float p_drop, const uint64_t* rng, uint32_t site,
-                    int64_t drop_base, void* stream) {
+                    const float* attn_b, const float* attn_w, int B, int Tn, int A, int D, float* dwh_out, void* dwh_op,
+                    float* duv_acc, float* dw_acc, int first, float* dctx_out, float p_drop, const uint64_t* rng,
+                    uint32_t site, int64_t drop_base, void* stream) {
   attn::BwdArgs a{};
   a.dXp = dctx_partials; a.n_p = n_p; a.p_stride = p_stride; a.p_ld = p_ld; a.V = v; a.v_bs = v_bs; a.v_ts = v_ts;
   a.Wh = wh; a.Uv = uv; a.uv_bs = uv_bs; a.uv_ts = uv_ts; a.attn_b = attn_b; a.attn_w = attn_w; a.B = B; a.Tn = Tn; a.A = A;
-  a.D = D; a.inv_T = 1.f / Tn; a.dWh_out = dwh_out; a.dUv_acc = duv_acc; a.uv_first = first; a.dw_acc = dw_acc;
+  a.D = D; a.inv_T = 1.f / Tn; a.dWh_out = dwh_out; a.dWh_op = dwh_op; a.dUv_acc = duv_acc; a.uv_first = first; a.dw_acc = dw_acc;
   a.dctx_out = dctx_out; a.de_out = nullptr; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng);
   a.site = site; a.drop_base = drop_base;
-  if (precision == RECNET_PREC_FP32) return attn::launch_bwd<float>(a, ST(stream));
-  if (precision == RECNET_PREC_BF16) return attn::launch_bwd<bf16>(a, ST(stream));
+  if (precision == RECNET_PREC_FP32) return (attn::launch_bwd<float, float>(a, ST(stream)));
+  if (precision == RECNET_PREC_BF16) return (attn::launch_bwd<bf16, bf16>(a, ST(stream)));
   return RECNET_ERR_UNSUPPORTED;
 }
 
@@ -116,12 +116,12 @@ int recnet_lstm_cell_fwd(int precision, const float* partials, int n_p, int64_t 
 }
 
 int recnet_lstm_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const float* dh_scale, const float* dh_ext2,
-                         int64_t dh2_ld, const float* dxp, int n_p, int64_t p_stride, int64_t p_ld, int col0, const float* dq,
-                         const float* wq, int A, float* dc, int first, const void* gates, const float* c_prev,
+                         int64_t dh2_ld, const float* dxp, int n_p, int64_t p_stride, int64_t p_ld, int col0, const float* dqp,
+                         int n_q, int64_t q_stride, int64_t q_ld, float* dc, int first, const void* gates, const float* c_prev,
                          const float* c_new, int B, int H, void* dg_out, int64_t dg_ld, void* stream) {
   cell::BwdArgs a{};
   a.dh_ext = dh_ext; a.dh_ld = dh_ld; a.dh_scale = dh_scale; a.dh_ext2 = dh_ext2; a.dh2_ld = dh2_ld; a.dXp = dxp; a.n_p = n_p;
-  a.p_stride = p_stride; a.p_ld = p_ld; a.col0 = col0; a.dQ = dq; a.Wq = wq; a.A = A; a.dc = dc; a.first = first; a.gates = gates;
+  a.p_stride = p_stride; a.p_ld = p_ld; a.col0 = col0; a.dQp = dqp; a.n_q = n_q; a.q_stride = q_stride; a.q_ld = q_ld; a.dc = dc; a.first = first; a.gates = gates;
   a.c_prev = c_prev; a.c_new = c_new; a.B = B; a.H = H; a.dG = dg_out; a.dg_ld = dg_ld;
   if (precision == RECNET_PREC_FP32) return cell::launch_bwd<float, float>(a, ST(stream));
   if (precision == RECNET_PREC_BF16) return cell::launch_bwd<bf16, bf16>(a, ST(stream));
@@ -238,7 +238,8 @@ int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, con
   misc::mt_sumsq_kernel<<<n_blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(ptrs), reinterpret_cast<const long long*>(sizes),
                                                   blk_tensor, blk_chunk, partial);
   RN_LAUNCH_OK();
-  misc::mt_norm_finalize_kernel<<<1, 32, 0, st>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out);
+  if (n > 64) return RECNET_ERR_BAD_SHAPE;
+  misc::mt_norm_finalize_kernel<<<1, 512, 0, st>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out);
   RN_LAUNCH_OK();
   return 0;
 }

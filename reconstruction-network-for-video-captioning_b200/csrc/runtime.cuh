@@ -8,6 +8,7 @@
 #include "lstm_cell.cuh"
 #include "misc.cuh"
 #include "sgemm.cuh"
+#include <stdlib.h>
 
 namespace rt {
 
@@ -31,26 +32,82 @@ template <typename T> struct Prec;
 template <> struct Prec<float> { static constexpr int id = RECNET_PREC_FP32; static constexpr int kpad = 4; };
 template <> struct Prec<bf16> { static constexpr int id = RECNET_PREC_BF16; static constexpr int kpad = 64; };
 
+// ---- concurrent sample chains --------------------------------------------------------------------------
+// The time loops are latency-bound: each step is a chain of ~4 small dependent kernels that cannot fill 148 SMs.
+// Samples are independent through both loops, so the batch is cut into `n` contiguous sub-batches ("chains")
+// whose loops run concurrently on forked streams (parallel branches of the captured CUDA graph) and share the
+// batched GEMMs before and after the loop.  MEASURED (profiles/r1_b_chains.md): on B200 the graph is bound by
+// per-node launch/dependency overhead, so more chains = more nodes = SLOWER (1: 4.47 ms, 2: 5.11, 4: 5.95, 8: 8.55
+// per step).  Default is therefore 1; RECNET_CHAINS=n keeps the experiment reproducible.
+struct Chains {
+  static constexpr int MAX = 8;
+  cudaStream_t s[MAX];
+  cudaEvent_t fork_ev, join_ev[MAX];
+  bool ready = false;
+  int init() {
+    if (ready) return 0;
+    for (int i = 0; i < MAX; ++i) {
+      RN_CUDA_OK(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+      RN_CUDA_OK(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+    }
+    RN_CUDA_OK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    ready = true;
+    return 0;
+  }
+  int fork(cudaStream_t main, int n) {
+    RN_TRY(init());
+    RN_CUDA_OK(cudaEventRecord(fork_ev, main));
+    for (int i = 0; i < n; ++i) RN_CUDA_OK(cudaStreamWaitEvent(s[i], fork_ev, 0));
+    return 0;
+  }
+  int join(cudaStream_t main, int n) {
+    for (int i = 0; i < n; ++i) {
+      RN_CUDA_OK(cudaEventRecord(join_ev[i], s[i]));
+      RN_CUDA_OK(cudaStreamWaitEvent(main, join_ev[i], 0));
+    }
+    return 0;
+  }
+};
+inline Chains& chains() { static Chains c; return c; }
+
+static inline int num_chains(int B) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("RECNET_CHAINS"); env = e ? atoi(e) : 0; }
+  int n = env > 0 ? env : 1;
+  if (n > Chains::MAX) n = Chains::MAX;
+  if (n > B) n = B;
+  return n < 1 ? 1 : n;
+}
+// rows [lo, lo+cnt) of chain c out of n
+static inline void chain_rows(int B, int n, int c, int* lo, int* cnt) {
+  const int base = B / n, rem = B % n;
+  *lo = c * base + (c < rem ? c : rem);
+  *cnt = base + (c < rem ? 1 : 0);
+}
+static inline int chain_rows_max(int B, int n) { return (B + n - 1) / n; }
+
 // ---- split-K / tile policy ---------------------------------------------------------------------------
 struct GemmPlan { int bn; int splits; };
-template <typename T> static inline GemmPlan plan_gemm(int M, int N, int K);
-template <> inline GemmPlan plan_gemm<bf16>(int M, int N, int K) {
+// target = CTAs one GEMM should spread over: the whole GPU for a single chain, half of it when several chains
+// keep the machine busy (fewer split-K partials for the consumer kernels to sum).
+template <typename T> static inline GemmPlan plan_gemm(int M, int N, int K, int target = NUM_SMS);
+template <> inline GemmPlan plan_gemm<bf16>(int M, int N, int K, int target) {
   GemmPlan p;
   p.bn = (N >= 1024) ? 128 : 64;
   const int tiles = rn_cdiv(M, tc::BM) * rn_cdiv(N, p.bn);
   const int nkb = rn_cdiv(K, tc::BK);
-  int s = NUM_SMS / tiles;
+  int s = target / tiles;
   if (s < 1) s = 1;
   if (s > nkb) s = nkb;
   const int kb_per = rn_cdiv(nkb, s);
   p.splits = rn_cdiv(nkb, kb_per);
   return p;
 }
-template <> inline GemmPlan plan_gemm<float>(int M, int N, int K) {
+template <> inline GemmPlan plan_gemm<float>(int M, int N, int K, int target) {
   GemmPlan p;
   p.bn = 0;
   const int tiles = rn_cdiv(M, sg::BM) * rn_cdiv(N, sg::BN);
-  int s = (2 * NUM_SMS) / tiles;
+  int s = (2 * target) / tiles;
   const int maxs = K / 64 > 0 ? K / 64 : 1;
   if (s < 1) s = 1;
   if (s > maxs) s = maxs;

@@ -18,14 +18,15 @@ template <typename T>
 struct Ws {
   // geometry
   int EMBp, KX, Vp, Vld;
-  GemmPlan pl_wh, pl_gate, pl_dx;
+  int nch, Bc;                       // concurrent sample chains, max rows per chain
+  GemmPlan pl_wh, pl_gate, pl_dx, pl_dq;
   // operand copies of the weights / inputs (rebuilt every forward: the optimiser changes the masters)
   T *Wemb, *Wrec, *U, *Wa, *Wout, *feats;
   // forward state kept for BPTT
   float* Uv; T* Xe; float* Gx; T* X; float* WhP; float* Wh; float* e; float* P; T* gates; float* c;
   float *logits, *lse, *row_loss;
   // backward scratch
-  T* dlogits; float* dHext; T* dG; float* dXp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
+  T* dlogits; float* dHext; T* dG; float* dXp; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
   float* dc; float* dXe; float* splitk;
   size_t bytes;
 };
@@ -38,9 +39,13 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.KX = E + H;
   w.Vp = round_up(V, 8);
   w.Vld = round_up(V, 4);
-  w.pl_wh = plan_gemm<T>(B, A, H);
-  w.pl_gate = plan_gemm<T>(B, 4 * H, w.KX);
-  w.pl_dx = plan_gemm<T>(B, w.KX, 4 * H);
+  w.nch = num_chains(B);
+  w.Bc = chain_rows_max(B, w.nch);
+  const int tgt = w.nch > 1 ? NUM_SMS / 2 : NUM_SMS;
+  w.pl_wh = plan_gemm<T>(w.Bc, A, H, tgt);
+  w.pl_gate = plan_gemm<T>(w.Bc, 4 * H, w.KX, tgt);
+  w.pl_dx = plan_gemm<T>(w.Bc, w.KX, 4 * H, tgt);
+  w.pl_dq = plan_gemm<T>(w.Bc, H, A, tgt);
   Bump m(base);
   w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);
   w.Wrec = m.take<T>((size_t)4 * H * w.KX);
@@ -52,10 +57,10 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.Xe = m.take<T>((size_t)L * B * w.EMBp);
   w.Gx = m.take<float>((size_t)L * B * 4 * H);
   w.X = m.take<T>((size_t)(L + 1) * B * w.KX);
-  w.WhP = m.take<float>((size_t)w.pl_wh.splits * B * A);
+  w.WhP = m.take<float>((size_t)w.nch * w.pl_wh.splits * w.Bc * A);
   w.Wh = m.take<float>((size_t)L * B * A);
   w.e = m.take<float>((size_t)L * B * Tn);
-  w.P = m.take<float>((size_t)w.pl_gate.splits * B * 4 * H);
+  w.P = m.take<float>((size_t)w.nch * w.pl_gate.splits * w.Bc * 4 * H);
   w.gates = m.take<T>((size_t)L * B * 4 * H);
   w.c = m.take<float>((size_t)(L + 1) * B * H);
   w.logits = m.take<float>((size_t)L * B * w.Vld);
@@ -64,7 +69,8 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.dlogits = m.take<T>((size_t)L * B * w.Vp);
   w.dHext = m.take<float>((size_t)L * B * H);
   w.dG = m.take<T>((size_t)L * B * 4 * H);
-  w.dXp = m.take<float>((size_t)w.pl_dx.splits * B * w.KX);
+  w.dXp = m.take<float>((size_t)w.nch * w.pl_dx.splits * w.Bc * w.KX);
+  w.dQp = m.take<float>((size_t)w.nch * w.pl_dq.splits * w.Bc * H);
   w.dWh = m.take<float>((size_t)L * B * A);
   w.dWh_op = m.take<T>((size_t)L * B * A);
   w.dUv = m.take<float>((size_t)B * Tn * A);
@@ -99,31 +105,38 @@ static int prepare(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
   return 0;
 }
 
-// one decoder step given X[t] h-slot filled: attention -> gate GEMM -> cell.  Shared by forward and greedy.
+// one decoder step for the sample rows [b0, b0+nb) of chain `ch`: attention -> gate GEMM -> cell.
+// Pointer arguments are the FULL-batch row-0 addresses of step t; the row offset is applied here.
 template <typename T>
-static int step(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, Ws<T>& w, int t, const float* gx_t,
-                const float* b1, T* x_t, T* x_next, float* Wh_t, float* e_t, T* gates_t, const float* c_prev,
+static int step(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, Ws<T>& w, int t, int ch, int b0, int nb,
+                const float* gx_t, T* x_t, T* x_next, float* Wh_t, float* e_t, T* gates_t, const float* c_prev,
                 float* c_next, float* h_out, cudaStream_t st) {
-  const int B = d.B, H = d.H, E = d.E, A = d.A, Tn = d.T;
+  const int H = d.H, E = d.E, A = d.A, Tn = d.T;
+  float* WhP = w.WhP + (size_t)ch * w.pl_wh.splits * w.Bc * A;
+  float* P = w.P + (size_t)ch * w.pl_gate.splits * w.Bc * 4 * H;
+  T* xr = x_t + (size_t)b0 * w.KX;
   int n_whp = 0;
   if (t > 0) {   // h_{-1} = 0 -> W h = 0, skip the GEMM
-    RN_TRY(gemm_partials<T>(x_t + E, w.KX, 0, w.Wa, H, 0, w.WhP, B, A, H, w.pl_wh, st));
+    RN_TRY(gemm_partials<T>(xr + E, w.KX, 0, w.Wa, H, 0, WhP, nb, A, H, w.pl_wh, st));
     n_whp = w.pl_wh.splits;
   }
   attn::FwdArgs fa{};
-  fa.WhP = w.WhP; fa.n_whp = n_whp; fa.whp_stride = (long long)B * A;
-  fa.Uv = w.Uv; fa.uv_bs = (long long)Tn * A; fa.uv_ts = A;
+  fa.WhP = WhP; fa.n_whp = n_whp; fa.whp_stride = (long long)nb * A;
+  fa.Uv = w.Uv + (size_t)b0 * Tn * A; fa.uv_bs = (long long)Tn * A; fa.uv_ts = A;
   fa.attn_b = p.attn_b; fa.attn_w = p.attn_w;
-  fa.V = w.feats; fa.v_bs = (long long)Tn * E; fa.v_ts = E;
-  fa.B = B; fa.Tn = Tn; fa.A = A; fa.D = E; fa.inv_T = 1.f / Tn; fa.normalize = 0;
-  fa.Wh_out = Wh_t; fa.e_out = e_t; fa.ctx_out = x_t; fa.ctx_ld = w.KX; fa.p_drop = 0.f;
+  fa.V = w.feats + (size_t)b0 * Tn * E; fa.v_bs = (long long)Tn * E; fa.v_ts = E;
+  fa.B = nb; fa.Tn = Tn; fa.A = A; fa.D = E; fa.inv_T = 1.f / Tn; fa.normalize = 0;
+  fa.Wh_out = Wh_t ? Wh_t + (size_t)b0 * A : nullptr; fa.e_out = e_t ? e_t + (size_t)b0 * Tn : nullptr;
+  fa.ctx_out = xr; fa.ctx_ld = w.KX; fa.p_drop = 0.f;
   RN_TRY((attn::launch_fwd<T, T>(fa, st)));
-  RN_TRY(gemm_partials<T>(x_t, w.KX, 0, w.Wrec, w.KX, 0, w.P, B, 4 * H, w.KX, w.pl_gate, st));
+  RN_TRY(gemm_partials<T>(xr, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * H, w.KX, w.pl_gate, st));
   cell::FwdArgs ca{};
-  ca.P = w.P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)B * 4 * H; ca.p_ld = 4 * H;
-  ca.Gx = gx_t; ca.gx_ld = 4 * H; ca.b1 = b1; ca.b2 = p.b_hh; ca.c_prev = c_prev; ca.B = B; ca.H = H;
-  ca.gates_out = gates_t; ca.c_out = c_next; ca.h_out = h_out; ca.h_ld = H;
-  ca.h_op = x_next + E; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
+  ca.P = P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)nb * 4 * H; ca.p_ld = 4 * H;
+  ca.Gx = gx_t + (size_t)b0 * 4 * H; ca.gx_ld = 4 * H; ca.b1 = nullptr; ca.b2 = p.b_hh;
+  ca.c_prev = c_prev + (size_t)b0 * H; ca.B = nb; ca.H = H;
+  ca.gates_out = gates_t ? gates_t + (size_t)b0 * 4 * H : nullptr; ca.c_out = c_next + (size_t)b0 * H;
+  ca.h_out = h_out + (size_t)b0 * H; ca.h_ld = H;
+  ca.h_op = x_next + (size_t)b0 * w.KX + E; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
   RN_TRY((cell::launch_fwd<T, T>(ca, st)));
   return 0;
 }
@@ -147,12 +160,21 @@ static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
   // initial state: h_{-1} = 0 (operand slot of X[0]), c_{-1} = 0
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
+  // time loop: w.nch independent sample chains on forked streams
+  Chains& cs = chains();
+  if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   for (int t = 0; t < L; ++t) {
     T* x_t = w.X + (size_t)t * B * w.KX;
-    RN_TRY(step<T>(d, p, w, t, w.Gx + (size_t)t * B * 4 * H, nullptr, x_t, x_t + (size_t)B * w.KX,
-                   w.Wh + (size_t)t * B * A, w.e + (size_t)t * B * Tn, w.gates + (size_t)t * B * 4 * H,
-                   w.c + (size_t)t * B * H, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H, st));
+    for (int ch = 0; ch < w.nch; ++ch) {
+      int b0, nb;
+      chain_rows(B, w.nch, ch, &b0, &nb);
+      RN_TRY(step<T>(d, p, w, t, ch, b0, nb, w.Gx + (size_t)t * B * 4 * H, x_t, x_t + (size_t)B * w.KX,
+                     w.Wh + (size_t)t * B * A, w.e + (size_t)t * B * Tn, w.gates + (size_t)t * B * 4 * H,
+                     w.c + (size_t)t * B * H, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H,
+                     w.nch > 1 ? cs.s[ch] : st));
+    }
   }
+  if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   // vocabulary projection over all steps, then the masked CE (train.py:54-60,68)
   RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, L * B, V, H, 0,
                       w.splitk, st));
@@ -187,34 +209,48 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, w.KX, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk, st));
-  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, st));
-  // ---- BPTT ---------------------------------------------------------------------------------------------
+  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk, st));
+  // ---- BPTT: the same sample chains, each with private split-K scratch ------------------------------------------
+  Chains& cs = chains();
+  if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
-    cell::BwdArgs cb{};
-    cb.dh_ext = w.dHext + (size_t)t * B * H; cb.dh_ld = H; cb.dh_scale = nullptr;
-    cb.dh_ext2 = g_hiddens ? g_hiddens + (size_t)t * B * H : nullptr; cb.dh2_ld = H;
-    cb.dXp = last ? nullptr : w.dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)B * w.KX; cb.p_ld = w.KX; cb.col0 = E;
-    cb.dQ = last ? nullptr : w.dWh + (size_t)(t + 1) * B * A; cb.Wq = p.attn_W; cb.A = A;
-    cb.dc = w.dc; cb.first = last ? 1 : 0;
-    cb.gates = w.gates + (size_t)t * B * 4 * H;
-    cb.c_prev = w.c + (size_t)t * B * H; cb.c_new = w.c + (size_t)(t + 1) * B * H;
-    cb.B = B; cb.H = H; cb.dG = w.dG + (size_t)t * B * 4 * H; cb.dg_ld = 4 * H;
-    RN_TRY((cell::launch_bwd<T, T>(cb, st)));
-    // d[ctx ; h_{t-1}] = dG_t @ [W_ctx | W_hh]
-    RN_TRY(gemm_partials<T>(w.dG + (size_t)t * B * 4 * H, 4 * H, 0, w.Wrec, w.KX, 1, w.dXp, B, w.KX, 4 * H, w.pl_dx, st));
-    attn::BwdArgs ab{};
-    ab.dXp = w.dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)B * w.KX; ab.p_ld = w.KX;
-    ab.V = w.feats; ab.v_bs = (long long)Tn * E; ab.v_ts = E;
-    ab.Wh = w.Wh + (size_t)t * B * A; ab.Uv = w.Uv; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
-    ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = B; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
-    ab.dWh_out = w.dWh + (size_t)t * B * A; ab.dUv_acc = w.dUv; ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc;
-    ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
-    RN_TRY(attn::launch_bwd<T>(ab, st));
+    for (int ch = 0; ch < w.nch; ++ch) {
+      int b0, nb;
+      chain_rows(B, w.nch, ch, &b0, &nb);
+      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * w.KX;
+      float* dQp = w.dQp + (size_t)ch * w.pl_dq.splits * w.Bc * H;
+      const size_t r = (size_t)t * B + b0;           // first (t, b) row of this chain
+      cell::BwdArgs cb{};
+      cb.dh_ext = w.dHext + r * H; cb.dh_ld = H; cb.dh_scale = nullptr;
+      cb.dh_ext2 = g_hiddens ? g_hiddens + r * H : nullptr; cb.dh2_ld = H;
+      cb.dXp = last ? nullptr : dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)nb * w.KX; cb.p_ld = w.KX; cb.col0 = E;
+      cb.dQp = last ? nullptr : dQp; cb.n_q = w.pl_dq.splits; cb.q_stride = (long long)nb * H; cb.q_ld = H;
+      cb.dc = w.dc + (size_t)b0 * H; cb.first = last ? 1 : 0;
+      cb.gates = w.gates + r * 4 * H;
+      cb.c_prev = w.c + r * H; cb.c_new = w.c + ((size_t)(t + 1) * B + b0) * H;
+      cb.B = nb; cb.H = H; cb.dG = w.dG + r * 4 * H; cb.dg_ld = 4 * H;
+      RN_TRY((cell::launch_bwd<T, T>(cb, cst)));
+      // d[ctx ; h_{t-1}] = dG_t @ [W_ctx | W_hh]
+      RN_TRY(gemm_partials<T>(w.dG + r * 4 * H, 4 * H, 0, w.Wrec, w.KX, 1, dXp, nb, w.KX, 4 * H, w.pl_dx, cst));
+      attn::BwdArgs ab{};
+      ab.dXp = dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)nb * w.KX; ab.p_ld = w.KX;
+      ab.V = w.feats + (size_t)b0 * Tn * E; ab.v_bs = (long long)Tn * E; ab.v_ts = E;
+      ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * Tn * A; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
+      ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
+      ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * Tn * A;
+      ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+      ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
+      RN_TRY((attn::launch_bwd<T, T>(ab, cst)));
+      // attention-query path into h_{t-1}: dWh_t @ attn_W, consumed (as split-K partials) by the next cell backward
+      if (t > 0) RN_TRY(gemm_partials<T>(w.dWh_op + r * A, A, 0, w.Wa, H, 1, dQp, nb, H, A, w.pl_dq, cst));
+    }
   }
+  if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   // ---- batched weight gradients over the stashed operands ----------------------------------------------------
   const long long ldih = EMB + E;
-  RN_TRY(misc::colsum<T>(w.dG, 4 * H, LB, 4 * H, g.b_ih, 0, st));
+  RN_TRY(misc::colsum<T>(w.dG, 4 * H, LB, 4 * H, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.X, w.KX, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, LB, 0, w.splitk, st));      // dW_ctx
   RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.X + E, w.KX, 1, g.w_hh, H, nullptr, 4 * H, H, LB, 0, w.splitk, st));           // dW_hh
@@ -225,12 +261,11 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
                                                  SITE_EMB);
   RN_LAUNCH_OK();
   // attention parameters
-  RN_TRY(misc::cast_pad<T>(w.dWh, A, w.dWh_op, A, LB, A, A, st));
   RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + E, w.KX, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk, st));              // dW_a = dWh^T h_{t-1}
   RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)B * Tn, A, A, st));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.feats, E, 1, g.attn_U, E, nullptr, A, E, B * Tn, 0, w.splitk, st));             // dU = dUv^T v
-  RN_TRY(misc::colsum<float>(w.dWh, A, LB, A, g.attn_b, 0, st));
-  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, st));
+  RN_TRY(misc::colsum<float>(w.dWh, A, LB, A, g.attn_b, 0, w.splitk, st));
+  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
   return 0;
 }
 
@@ -321,7 +356,7 @@ static int greedy(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p
                                                     nullptr, SITE_EMB);
     RN_LAUNCH_OK();
     RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, B, 4 * H, w.EMBp, 0, w.splitk, st));
-    RN_TRY(step<T>(d, p, w, t, w.Gx, nullptr, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n, g.h_scratch, st));
+    RN_TRY(step<T>(d, p, w, t, 0, 0, B, w.Gx, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n, g.h_scratch, st));
     RN_TRY(gemm_full<T>(x_n + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, B, V, H, 0, w.splitk, st));
     argmax_feedback_kernel<<<B, 256, 0, st>>>(w.logits, w.Vld, V, ids_out + (size_t)t * B, g.tok, g.nonpad + t);
     RN_LAUNCH_OK();

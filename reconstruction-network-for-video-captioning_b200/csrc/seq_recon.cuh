@@ -16,11 +16,11 @@ enum : unsigned { SITE_LOCAL_X = 3, SITE_GLOBAL_MP = 4 };
 // ================================================ local =========================================================
 template <typename T>
 struct LocalWs {
-  int KX;
-  GemmPlan pl_wh, pl_gate, pl_dx;
+  int KX, nch, Bc;
+  GemmPlan pl_wh, pl_gate, pl_dx, pl_dq;
   T *Wrec, *U, *Wa, *Wout, *Hd;
   float* Uv; T* X; float* WhP; float* Wh; float* beta; float* P; T* gates; float* c; float* out; float* partial;
-  T* dOut; float* dHext; T* dG; float* dXp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
+  T* dOut; float* dHext; T* dG; float* dXp; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
   float* dx; float* splitk;
   size_t bytes;
 };
@@ -31,9 +31,13 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   LocalWs<T> w;
   const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
   w.KX = H + R;
-  w.pl_wh = plan_gemm<T>(B, A, R);
-  w.pl_gate = plan_gemm<T>(B, 4 * R, w.KX);
-  w.pl_dx = plan_gemm<T>(B, w.KX, 4 * R);
+  w.nch = num_chains(B);
+  w.Bc = chain_rows_max(B, w.nch);
+  const int tgt = w.nch > 1 ? NUM_SMS / 2 : NUM_SMS;
+  w.pl_wh = plan_gemm<T>(w.Bc, A, R, tgt);
+  w.pl_gate = plan_gemm<T>(w.Bc, 4 * R, w.KX, tgt);
+  w.pl_dx = plan_gemm<T>(w.Bc, w.KX, 4 * R, tgt);
+  w.pl_dq = plan_gemm<T>(w.Bc, R, A, tgt);
   Bump m(base);
   w.Wrec = m.take<T>((size_t)4 * R * w.KX);
   w.U = m.take<T>((size_t)A * H);
@@ -42,10 +46,10 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.Hd = m.take<T>((size_t)L * B * H);
   w.Uv = m.take<float>((size_t)L * B * A);
   w.X = m.take<T>((size_t)(S + 1) * B * w.KX);
-  w.WhP = m.take<float>((size_t)w.pl_wh.splits * B * A);
+  w.WhP = m.take<float>((size_t)w.nch * w.pl_wh.splits * w.Bc * A);
   w.Wh = m.take<float>((size_t)S * B * A);
   w.beta = m.take<float>((size_t)S * B * L);
-  w.P = m.take<float>((size_t)w.pl_gate.splits * B * 4 * R);
+  w.P = m.take<float>((size_t)w.nch * w.pl_gate.splits * w.Bc * 4 * R);
   w.gates = m.take<T>((size_t)S * B * 4 * R);
   w.c = m.take<float>((size_t)(S + 1) * B * R);
   w.out = m.take<float>((size_t)S * B * R);
@@ -53,7 +57,8 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.dOut = m.take<T>((size_t)S * B * R);
   w.dHext = m.take<float>((size_t)S * B * R);
   w.dG = m.take<T>((size_t)S * B * 4 * R);
-  w.dXp = m.take<float>((size_t)w.pl_dx.splits * B * w.KX);
+  w.dXp = m.take<float>((size_t)w.nch * w.pl_dx.splits * w.Bc * w.KX);
+  w.dQp = m.take<float>((size_t)w.nch * w.pl_dq.splits * w.Bc * R);
   w.dWh = m.take<float>((size_t)S * B * A);
   w.dWh_op = m.take<T>((size_t)S * B * A);
   w.dUv = m.take<float>((size_t)L * B * A);
@@ -90,32 +95,43 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
+  Chains& cs = chains();
+  if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   for (int t = 0; t < S; ++t) {
-    T* x_t = w.X + (size_t)t * B * w.KX;
-    T* x_n = x_t + (size_t)B * w.KX;
-    int n_whp = 0;
-    if (t > 0) {
-      RN_TRY(gemm_partials<T>(x_t + H, w.KX, 0, w.Wa, R, 0, w.WhP, B, A, R, w.pl_wh, st));
-      n_whp = w.pl_wh.splits;
+    for (int ch = 0; ch < w.nch; ++ch) {
+      int b0, nb;
+      chain_rows(B, w.nch, ch, &b0, &nb);
+      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      float* WhP = w.WhP + (size_t)ch * w.pl_wh.splits * w.Bc * A;
+      float* P = w.P + (size_t)ch * w.pl_gate.splits * w.Bc * 4 * R;
+      const size_t r = (size_t)t * B + b0;
+      T* x_t = w.X + r * w.KX;
+      T* x_n = x_t + (size_t)B * w.KX;
+      int n_whp = 0;
+      if (t > 0) {
+        RN_TRY(gemm_partials<T>(x_t + H, w.KX, 0, w.Wa, R, 0, WhP, nb, A, R, w.pl_wh, cst));
+        n_whp = w.pl_wh.splits;
+      }
+      attn::FwdArgs fa{};
+      fa.WhP = WhP; fa.n_whp = n_whp; fa.whp_stride = (long long)nb * A;
+      fa.Uv = w.Uv + (size_t)b0 * A; fa.uv_bs = A; fa.uv_ts = (long long)B * A;          // Uv is [L,B,A]
+      fa.attn_b = p.attn_b; fa.attn_w = p.attn_w;
+      fa.V = w.Hd + (size_t)b0 * H; fa.v_bs = H; fa.v_ts = (long long)B * H;             // values = decoder states [L,B,H]
+      fa.B = nb; fa.Tn = L; fa.A = A; fa.D = H; fa.inv_T = 1.f / L; fa.normalize = 0;
+      fa.Wh_out = w.Wh + r * A; fa.e_out = w.beta + r * L;
+      fa.ctx_out = x_t; fa.ctx_ld = w.KX;
+      fa.p_drop = p_drop; fa.rng = rng; fa.site = SITE_LOCAL_X; fa.drop_base = (long long)r * H;
+      RN_TRY((attn::launch_fwd<T, T>(fa, cst)));
+      RN_TRY(gemm_partials<T>(x_t, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * R, w.KX, w.pl_gate, cst));
+      cell::FwdArgs ca{};
+      ca.P = P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)nb * 4 * R; ca.p_ld = 4 * R;
+      ca.Gx = nullptr; ca.b1 = p.b_ih; ca.b2 = p.b_hh; ca.c_prev = w.c + r * R; ca.B = nb; ca.H = R;
+      ca.gates_out = w.gates + r * 4 * R; ca.c_out = w.c + ((size_t)(t + 1) * B + b0) * R; ca.h_out = nullptr;
+      ca.h_op = x_n + H; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
+      RN_TRY((cell::launch_fwd<T, T>(ca, cst)));
     }
-    attn::FwdArgs fa{};
-    fa.WhP = w.WhP; fa.n_whp = n_whp; fa.whp_stride = (long long)B * A;
-    fa.Uv = w.Uv; fa.uv_bs = A; fa.uv_ts = (long long)B * A;          // Uv is [L,B,A]
-    fa.attn_b = p.attn_b; fa.attn_w = p.attn_w;
-    fa.V = w.Hd; fa.v_bs = H; fa.v_ts = (long long)B * H;             // values = decoder states [L,B,H]
-    fa.B = B; fa.Tn = L; fa.A = A; fa.D = H; fa.inv_T = 1.f / L; fa.normalize = 0;
-    fa.Wh_out = w.Wh + (size_t)t * B * A; fa.e_out = w.beta + (size_t)t * B * L;
-    fa.ctx_out = x_t; fa.ctx_ld = w.KX;
-    fa.p_drop = p_drop; fa.rng = rng; fa.site = SITE_LOCAL_X; fa.drop_base = (long long)t * B * H;
-    RN_TRY((attn::launch_fwd<T, T>(fa, st)));
-    RN_TRY(gemm_partials<T>(x_t, w.KX, 0, w.Wrec, w.KX, 0, w.P, B, 4 * R, w.KX, w.pl_gate, st));
-    cell::FwdArgs ca{};
-    ca.P = w.P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)B * 4 * R; ca.p_ld = 4 * R;
-    ca.Gx = nullptr; ca.b1 = p.b_ih; ca.b2 = p.b_hh; ca.c_prev = w.c + (size_t)t * B * R; ca.B = B; ca.H = R;
-    ca.gates_out = w.gates + (size_t)t * B * 4 * R; ca.c_out = w.c + (size_t)(t + 1) * B * R; ca.h_out = nullptr;
-    ca.h_op = x_n + H; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
-    RN_TRY((cell::launch_fwd<T, T>(ca, st)));
   }
+  if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + H, w.KX, 0, w.Wout, R, 0, w.out, R, p.out_b, S * B, R, R, 0, w.splitk, st));
   if (mse_out) {
     loss::mse_local_fwd_kernel<<<MSE_BLOCKS, 256, 0, st>>>(w.out, feats, S, B, R, w.partial);
@@ -141,39 +157,51 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dOut, R, 0, w.Wout, R, 1, w.dHext, R, nullptr, SB, R, R, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk, st));
-  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, st));
+  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk, st));
+  Chains& cs = chains();
+  if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   for (int t = S - 1; t >= 0; --t) {
     const bool last = (t == S - 1);
-    cell::BwdArgs cb{};
-    cb.dh_ext = w.dHext + (size_t)t * B * R; cb.dh_ld = R;
-    cb.dXp = last ? nullptr : w.dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)B * w.KX; cb.p_ld = w.KX; cb.col0 = H;
-    cb.dQ = last ? nullptr : w.dWh + (size_t)(t + 1) * B * A; cb.Wq = p.attn_W; cb.A = A;
-    cb.dc = w.dc; cb.first = last ? 1 : 0;
-    cb.gates = w.gates + (size_t)t * B * 4 * R;
-    cb.c_prev = w.c + (size_t)t * B * R; cb.c_new = w.c + (size_t)(t + 1) * B * R;
-    cb.B = B; cb.H = R; cb.dG = w.dG + (size_t)t * B * 4 * R; cb.dg_ld = 4 * R;
-    RN_TRY((cell::launch_bwd<T, T>(cb, st)));
-    RN_TRY(gemm_partials<T>(w.dG + (size_t)t * B * 4 * R, 4 * R, 0, w.Wrec, w.KX, 1, w.dXp, B, w.KX, 4 * R, w.pl_dx, st));
-    attn::BwdArgs ab{};
-    ab.dXp = w.dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)B * w.KX; ab.p_ld = w.KX;
-    ab.V = w.Hd; ab.v_bs = H; ab.v_ts = (long long)B * H;
-    ab.Wh = w.Wh + (size_t)t * B * A; ab.Uv = w.Uv; ab.uv_bs = A; ab.uv_ts = (long long)B * A;
-    ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = B; ab.Tn = L; ab.A = A; ab.D = H; ab.inv_T = 1.f / L;
-    ab.dWh_out = w.dWh + (size_t)t * B * A; ab.dUv_acc = w.dUv; ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc;
-    ab.dctx_out = w.dx + (size_t)t * B * H; ab.de_out = nullptr;
-    ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)t * B * H;
-    RN_TRY(attn::launch_bwd<T>(ab, st));
+    for (int ch = 0; ch < w.nch; ++ch) {
+      int b0, nb;
+      chain_rows(B, w.nch, ch, &b0, &nb);
+      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * w.KX;
+      float* dQp = w.dQp + (size_t)ch * w.pl_dq.splits * w.Bc * R;
+      const size_t r = (size_t)t * B + b0;
+      cell::BwdArgs cb{};
+      cb.dh_ext = w.dHext + r * R; cb.dh_ld = R;
+      cb.dXp = last ? nullptr : dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)nb * w.KX; cb.p_ld = w.KX; cb.col0 = H;
+      cb.dQp = last ? nullptr : dQp; cb.n_q = w.pl_dq.splits; cb.q_stride = (long long)nb * R; cb.q_ld = R;
+      cb.dc = w.dc + (size_t)b0 * R; cb.first = last ? 1 : 0;
+      cb.gates = w.gates + r * 4 * R;
+      cb.c_prev = w.c + r * R; cb.c_new = w.c + ((size_t)(t + 1) * B + b0) * R;
+      cb.B = nb; cb.H = R; cb.dG = w.dG + r * 4 * R; cb.dg_ld = 4 * R;
+      RN_TRY((cell::launch_bwd<T, T>(cb, cst)));
+      RN_TRY(gemm_partials<T>(w.dG + r * 4 * R, 4 * R, 0, w.Wrec, w.KX, 1, dXp, nb, w.KX, 4 * R, w.pl_dx, cst));
+      attn::BwdArgs ab{};
+      ab.dXp = dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)nb * w.KX; ab.p_ld = w.KX;
+      ab.V = w.Hd + (size_t)b0 * H; ab.v_bs = H; ab.v_ts = (long long)B * H;
+      ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * A; ab.uv_bs = A; ab.uv_ts = (long long)B * A;
+      ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = L; ab.A = A; ab.D = H; ab.inv_T = 1.f / L;
+      ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * A;
+      ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+      ab.dctx_out = w.dx + r * H; ab.de_out = nullptr;
+      ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)r * H;
+      RN_TRY((attn::launch_bwd<T, T>(ab, cst)));
+      if (t > 0) RN_TRY(gemm_partials<T>(w.dWh_op + r * A, A, 0, w.Wa, R, 1, dQp, nb, R, A, w.pl_dq, cst));
+    }
   }
-  RN_TRY(misc::colsum<T>(w.dG, 4 * R, SB, 4 * R, g.b_ih, 0, st));
+  if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
+  RN_TRY(misc::colsum<T>(w.dG, 4 * R, SB, 4 * R, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, 4 * R, H, SB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, 4 * R, R, SB, 0, w.splitk, st));
-  RN_TRY(misc::cast_pad<T>(w.dWh, A, w.dWh_op, A, SB, A, A, st));
   RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk, st));
   RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, st));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk, st));
-  RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, st));
-  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, st));
+  RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, w.splitk, st));
+  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
   // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
   RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk, st));
   {
@@ -188,6 +216,7 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
 // ================================================ global ========================================================
 template <typename T>
 struct GlobalWs {
+  int nch, Bc;
   GemmPlan pl_gate, pl_dx;
   T *Wih, *Whh, *Wout; float* mp; T* Xg; float* Gx; T* X; float* P; T* gates; float* c; float* out; float* diff; float* partial;
   T* dOut; float* dHext; T* dG; float* dXp; float* dc; float* dXg; float* dmp; float* splitk;
@@ -199,8 +228,11 @@ template <typename T>
 static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   GlobalWs<T> w;
   const int B = d.B, L = d.L, R = d.R, H = d.H;
-  w.pl_gate = plan_gemm<T>(B, 4 * R, R);
-  w.pl_dx = plan_gemm<T>(B, R, 4 * R);
+  w.nch = num_chains(B);
+  w.Bc = chain_rows_max(B, w.nch);
+  const int tgt = w.nch > 1 ? NUM_SMS / 2 : NUM_SMS;
+  w.pl_gate = plan_gemm<T>(w.Bc, 4 * R, R, tgt);
+  w.pl_dx = plan_gemm<T>(w.Bc, R, 4 * R, tgt);
   Bump m(base);
   w.Wih = m.take<T>((size_t)4 * R * 2 * H);
   w.Whh = m.take<T>((size_t)4 * R * R);
@@ -209,7 +241,7 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   w.Xg = m.take<T>((size_t)L * B * 2 * H);
   w.Gx = m.take<float>((size_t)L * B * 4 * R);
   w.X = m.take<T>((size_t)(L + 1) * B * R);
-  w.P = m.take<float>((size_t)w.pl_gate.splits * B * 4 * R);
+  w.P = m.take<float>((size_t)w.nch * w.pl_gate.splits * w.Bc * 4 * R);
   w.gates = m.take<T>((size_t)L * B * 4 * R);
   w.c = m.take<float>((size_t)(L + 1) * B * R);
   w.out = m.take<float>((size_t)L * B * R);
@@ -218,7 +250,7 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   w.dOut = m.take<T>((size_t)L * B * R);
   w.dHext = m.take<float>((size_t)L * B * R);
   w.dG = m.take<T>((size_t)L * B * 4 * R);
-  w.dXp = m.take<float>((size_t)w.pl_dx.splits * B * R);
+  w.dXp = m.take<float>((size_t)w.nch * w.pl_dx.splits * w.Bc * R);
   w.dc = m.take<float>((size_t)B * R);
   w.dXg = m.take<float>((size_t)L * B * 2 * H);
   w.dmp = m.take<float>((size_t)B * H);
@@ -253,21 +285,31 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
   RN_TRY(gemm_full<T>(w.Xg, 2 * H, 0, w.Wih, 2 * H, 0, w.Gx, 4 * R, p.b_ih, L * B, 4 * R, 2 * H, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * R * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
+  Chains& cs = chains();
+  if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   for (int t = 0; t < L; ++t) {
-    T* x_t = w.X + (size_t)t * B * R;
-    int n_p = 0;
-    if (t > 0) {
-      RN_TRY(gemm_partials<T>(x_t, R, 0, w.Whh, R, 0, w.P, B, 4 * R, R, w.pl_gate, st));
-      n_p = w.pl_gate.splits;
+    for (int ch = 0; ch < w.nch; ++ch) {
+      int b0, nb;
+      chain_rows(B, w.nch, ch, &b0, &nb);
+      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      float* P = w.P + (size_t)ch * w.pl_gate.splits * w.Bc * 4 * R;
+      const size_t r = (size_t)t * B + b0;
+      T* x_t = w.X + r * R;
+      int n_p = 0;
+      if (t > 0) {
+        RN_TRY(gemm_partials<T>(x_t, R, 0, w.Whh, R, 0, P, nb, 4 * R, R, w.pl_gate, cst));
+        n_p = w.pl_gate.splits;
+      }
+      cell::FwdArgs ca{};
+      ca.P = P; ca.n_p = n_p; ca.p_stride = (long long)nb * 4 * R; ca.p_ld = 4 * R;
+      ca.Gx = w.Gx + r * 4 * R; ca.gx_ld = 4 * R; ca.b1 = nullptr; ca.b2 = p.b_hh;
+      ca.c_prev = w.c + r * R; ca.B = nb; ca.H = R;
+      ca.gates_out = w.gates + r * 4 * R; ca.c_out = w.c + ((size_t)(t + 1) * B + b0) * R; ca.h_out = nullptr;
+      ca.h_op = x_t + (size_t)B * R; ca.hop_ld = R; ca.h_op2 = nullptr;
+      RN_TRY((cell::launch_fwd<T, T>(ca, cst)));
     }
-    cell::FwdArgs ca{};
-    ca.P = w.P; ca.n_p = n_p; ca.p_stride = (long long)B * 4 * R; ca.p_ld = 4 * R;
-    ca.Gx = w.Gx + (size_t)t * B * 4 * R; ca.gx_ld = 4 * R; ca.b1 = nullptr; ca.b2 = p.b_hh;
-    ca.c_prev = w.c + (size_t)t * B * R; ca.B = B; ca.H = R;
-    ca.gates_out = w.gates + (size_t)t * B * 4 * R; ca.c_out = w.c + (size_t)(t + 1) * B * R; ca.h_out = nullptr;
-    ca.h_op = x_t + (size_t)B * R; ca.hop_ld = R; ca.h_op2 = nullptr;
-    RN_TRY((cell::launch_fwd<T, T>(ca, st)));
   }
+  if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   RN_TRY(gemm_full<T>(w.X + (size_t)B * R, R, 0, w.Wout, R, 0, w.out, R, p.out_b, L * B, R, R, 0, w.splitk, st));
   if (loss_out) {
     const int nb = rn_cdiv((long long)B * R, GMSE_THREADS);
@@ -294,20 +336,30 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dOut, R, 0, w.Wout, R, 1, w.dHext, R, nullptr, LB, R, R, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dOut, R, 1, w.X + (size_t)B * R, R, 1, g.out_w, R, nullptr, R, R, LB, 0, w.splitk, st));
-  RN_TRY(misc::colsum<T>(w.dOut, R, LB, R, g.out_b, 0, st));
+  RN_TRY(misc::colsum<T>(w.dOut, R, LB, R, g.out_b, 0, w.splitk, st));
+  Chains& cs = chains();
+  if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
-    cell::BwdArgs cb{};
-    cb.dh_ext = w.dHext + (size_t)t * B * R; cb.dh_ld = R;
-    cb.dXp = last ? nullptr : w.dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)B * R; cb.p_ld = R; cb.col0 = 0;
-    cb.dQ = nullptr; cb.dc = w.dc; cb.first = last ? 1 : 0;
-    cb.gates = w.gates + (size_t)t * B * 4 * R;
-    cb.c_prev = w.c + (size_t)t * B * R; cb.c_new = w.c + (size_t)(t + 1) * B * R;
-    cb.B = B; cb.H = R; cb.dG = w.dG + (size_t)t * B * 4 * R; cb.dg_ld = 4 * R;
-    RN_TRY((cell::launch_bwd<T, T>(cb, st)));
-    if (t > 0) RN_TRY(gemm_partials<T>(w.dG + (size_t)t * B * 4 * R, 4 * R, 0, w.Whh, R, 1, w.dXp, B, R, 4 * R, w.pl_dx, st));
+    for (int ch = 0; ch < w.nch; ++ch) {
+      int b0, nb;
+      chain_rows(B, w.nch, ch, &b0, &nb);
+      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * R;
+      const size_t r = (size_t)t * B + b0;
+      cell::BwdArgs cb{};
+      cb.dh_ext = w.dHext + r * R; cb.dh_ld = R;
+      cb.dXp = last ? nullptr : dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)nb * R; cb.p_ld = R; cb.col0 = 0;
+      cb.dQp = nullptr; cb.dc = w.dc + (size_t)b0 * R; cb.first = last ? 1 : 0;
+      cb.gates = w.gates + r * 4 * R;
+      cb.c_prev = w.c + r * R; cb.c_new = w.c + ((size_t)(t + 1) * B + b0) * R;
+      cb.B = nb; cb.H = R; cb.dG = w.dG + r * 4 * R; cb.dg_ld = 4 * R;
+      RN_TRY((cell::launch_bwd<T, T>(cb, cst)));
+      if (t > 0) RN_TRY(gemm_partials<T>(w.dG + r * 4 * R, 4 * R, 0, w.Whh, R, 1, dXp, nb, R, 4 * R, w.pl_dx, cst));
+    }
   }
-  RN_TRY(misc::colsum<T>(w.dG, 4 * R, LB, 4 * R, g.b_ih, 0, st));
+  if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
+  RN_TRY(misc::colsum<T>(w.dG, 4 * R, LB, 4 * R, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X, R, 1, g.w_hh, R, nullptr, 4 * R, R, LB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.Xg, 2 * H, 1, g.w_ih, 2 * H, nullptr, 4 * R, 2 * H, LB, 0, w.splitk, st));

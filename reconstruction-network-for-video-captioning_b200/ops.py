@@ -110,7 +110,7 @@ class AdditiveAttentionFn(torch.autograd.Function):
         dUv = torch.empty_like(Uv)
         dw = torch.empty(B, A, dtype=torch.float32, device=g.device)
         L.check(lib.recnet_attn_bwd(ctx.precision, g.data_ptr(), 1, 0, D, Vo.data_ptr(), Tn * D, D, Wh.data_ptr(), Uv.data_ptr(),
-                                    Tn * A, A, attn_b.data_ptr(), attn_w.data_ptr(), B, Tn, A, D, dWh.data_ptr(), dUv.data_ptr(),
+                                    Tn * A, A, attn_b.data_ptr(), attn_w.data_ptr(), B, Tn, A, D, dWh.data_ptr(), None, dUv.data_ptr(),
                                     dw.data_ptr(), 1, None, 0.0, None, 0, 0, _stream()), "recnet_attn_bwd")
         gV = None
         if ctx.needs_input_grad[4]:
@@ -149,7 +149,7 @@ class LSTMCellFn(torch.autograd.Function):
         gh = gh.contiguous().float() if gh is not None else torch.zeros_like(c)
         dc = gc.contiguous().float().clone() if gc is not None else torch.zeros_like(c)
         dG = torch.empty(B, 4 * H, dtype=_op_dtype(ctx.precision), device=c.device)
-        L.check(lib.recnet_lstm_cell_bwd(ctx.precision, gh.data_ptr(), H, None, None, 0, None, 0, 0, 0, 0, None, None, 0,
+        L.check(lib.recnet_lstm_cell_bwd(ctx.precision, gh.data_ptr(), H, None, None, 0, None, 0, 0, 0, 0, None, 0, 0, 0,
                                          dc.data_ptr(), 0, gates.data_ptr(), c_prev.data_ptr(), c.data_ptr(), B, H, dG.data_ptr(),
                                          4 * H, _stream()), "recnet_lstm_cell_bwd")
         return dG.float(), dc, None

@@ -183,6 +183,11 @@ def algorithmic_work(cls, M, N, K, elt):
     return "hbm", 0.0
 
 
+def dbg(rank, msg):
+    if os.environ.get("RECNET_BENCH_VERBOSE"):
+        print(f"[bench rank {rank} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -203,6 +208,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # whole-step CUDA-graph capture includes the NCCL all-reduces: the process group's watchdog must not poll
+        # events while a capture is open (PyTorch's documented requirement for DDP + graph capture)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     RL.require_device(local_rank)
     s = SHAPE
@@ -237,6 +245,7 @@ def main():
         loss_d.copy_(loss.detach())
 
     lib = RL.lib()
+    dbg(rank, "models built, starting eager warm-up")
     # ---- warm-up (eager), launch count, per-kernel timing leg -------------------------------------------------
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -256,6 +265,7 @@ def main():
         buf = (ctypes.c_float * (4096 * 5))()
         nrec = lib.recnet_profile_collect(ctypes.cast(buf, ctypes.c_void_p), 4096)
     torch.cuda.current_stream().wait_stream(side)
+    dbg(rank, f"eager warm-up + profile leg done ({launches_per_step} launches/step)")
     elt = 2 if args.precision == "bf16" else 4
     agg = {}
     for i in range(max(nrec, 0)):
@@ -274,7 +284,7 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
                 step()
         except Exception as ex:                     # report, never silently change what is measured
             if rank == 0:
@@ -282,6 +292,12 @@ def main():
             graph = None
             torch.cuda.synchronize()
     run = graph.replay if graph is not None else step
+    dbg(rank, f"graph captured: {graph is not None}")
+    if world > 1:      # all ranks must run the same mode, or the collectives would not match up
+        flag = torch.tensor([1 if graph is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0 and graph is not None:
+            graph, run = None, step
 
     def barrier():
         if world > 1:
@@ -304,8 +320,10 @@ def main():
     for _ in range(args.warmup):
         run()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    dbg(rank, "warm-up replays done")
     total_ms = timed(lambda i: run(), args.steps)
     clocks = sampler.stop() if sampler else None
+    dbg(rank, f"timed region done: {total_ms:.2f} ms")
 
     # ---- e2e: host buffers -> H2D -> step -> D2H loss, every step, inside the timed region ------------------------
     losses_h = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
@@ -316,9 +334,12 @@ def main():
         run()
         losses_h[i:i + 1].copy_(loss_d.view(1), non_blocking=True)
 
+    dbg(rank, "clock sampler stopped; e2e warm-up")
     for i in range(2):
         e2e_step(i)
+    dbg(rank, "e2e warm-up issued")
     e2e_ms = timed(e2e_step, args.steps)
+    dbg(rank, f"e2e region done: {e2e_ms:.2f} ms")
     h2d = feats_h.numel() * 4 + targets_h.numel() * 8
     d2h = 4
 
@@ -368,7 +389,12 @@ def main():
         }
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear down without ProcessGroupNCCL's destructor: with NCCL work captured inside a live CUDA graph
+        # destroy_process_group() blocks (observed on the 2-GPU box); everything is flushed, so exit directly
+        sys.stdout.flush(); sys.stderr.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

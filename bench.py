@@ -198,6 +198,11 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    # the contract is ONE JSON line on stdout: park fd 1 on stderr while libraries initialise (NCCL prints its version
+    # banner to stdout) and restore it just before printing the result
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     import recnet_b200
     from recnet_b200 import _lib as RL, train as T
@@ -387,6 +392,8 @@ def main():
             "clocks": clocks, "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
             "allreduce_bytes_per_step": reducer.bytes_last,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         # tear down without ProcessGroupNCCL's destructor: with NCCL work captured inside a live CUDA graph

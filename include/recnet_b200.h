@@ -190,6 +190,19 @@ int recnet_global_bwd(const recnet_global_desc* d, const recnet_global_tensors* 
                       const recnet_global_tensors* grads, float* g_hiddens, void* stream);
 float* recnet_global_outputs(const recnet_global_desc* d, void* workspace);  /* [L,B,R] fp32 */
 
+/* The time loops of the bf16 build run as ONE persistent cooperative "loop kernel" per loop (csrc/mega.cuh).  Its spins
+ * have timeouts; on a protocol failure it raises an int32 flag inside the workspace instead of hanging the GPU.  These
+ * return the flag's byte offset in the workspace (0 = ok, 2 = mbarrier timeout, 3 = grid-barrier timeout). */
+int64_t recnet_decoder_error_offset(const recnet_decoder_desc* d);
+int64_t recnet_local_error_offset(const recnet_local_desc* d);
+int64_t recnet_global_error_offset(const recnet_global_desc* d);
+
+/* developer probe: loop kernel with n_phases empty phases (+ grid barrier each if sync_after); scratch >= n_phases*1024+1024 B */
+int recnet_debug_loop_overhead(int n_phases, int sync_after, void* scratch, void* stream);
+
+/* developer probe: %globaltimer stamp at the start of every loop-kernel phase -> buf (device u64[n_phases + 1]); NULL = off */
+int recnet_debug_set_timeline(void* buf);
+
 /* L2-norm regulariser over a parameter list (train.py:69,101,127): reg = sum_p ||p||_2.
  * ptrs/sizes: device int64 tables of n tensors; blk_tensor/blk_chunk: device int32 tables mapping block ->
  * (tensor, 16384-element chunk); partial [n_blocks] fp32 scratch (two-stage, fixed-order => bitwise reproducible);

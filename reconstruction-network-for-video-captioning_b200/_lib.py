@@ -100,6 +100,11 @@ SIGNATURES = {
     "recnet_global_bwd": (_i, [C.POINTER(global_desc), C.POINTER(global_tensors), _p, _p, _p, _p, _l, _p,
                                C.POINTER(global_tensors), _p, _p]),
     "recnet_global_outputs": (_p, [C.POINTER(global_desc), _p]),
+    "recnet_decoder_error_offset": (_l, [C.POINTER(decoder_desc)]),
+    "recnet_local_error_offset": (_l, [C.POINTER(local_desc)]),
+    "recnet_global_error_offset": (_l, [C.POINTER(global_desc)]),
+    "recnet_debug_loop_overhead": (_i, [_i, _i, _p, _p]),
+    "recnet_debug_set_timeline": (_i, [_p]),
     "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
     "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _i, _p]),
 }

@@ -31,49 +31,98 @@ struct FwdArgs {
   float p_drop; const unsigned long long* rng; unsigned int site; long long drop_base;  // dropout on ctx (train)
 };
 
+// body: one virtual block (bx = D-slice index, b = sample); 256 threads; sm = fwd_smem_floats() floats.
+// Latency structure (each dependent L2 round trip costs ~0.6 us here, r1 timeline): every global load of the block --
+// the V rows for the weighted sum, the Uv rows for the scores, the Wh partials -- is issued at entry, before anything
+// is consumed; the frames of a column group are split over FP threads whose partial sums meet in shared memory.
 template <typename TV, typename TO>
-__global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void attn_fwd_body(const FwdArgs& a, int bx, int b, float* sm, int tid, int bar_id) {
+  constexpr bool FAST = FastMath<TV>::value;
+  constexpr int VN = Vec16<TV>::N, NW = FWD_THREADS / 32, NPRE = 16;
   float* Wh = sm;              // [A] (bias folded in)
   float* wv = sm + a.A;        // [A] attn_w
   float* e = sm + 2 * a.A;     // [Tn]
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = FWD_THREADS / 32;
+  float* red = e + a.Tn;       // [FWD_THREADS * VN] partial context sums (only when FP > 1)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int d_lo = bx * a.d_slice, d_hi = min(a.D, d_lo + a.d_slice);
+  const int G = (d_hi - d_lo) / VN;                    // 16-byte column groups of this slice (<= 256)
+  int FP = 1;
+  while (FP < 8 && G * FP * 2 <= FWD_THREADS) FP *= 2;  // frame partitions per column group
+  const bool active = tid < G * FP;
+  const int cg = active ? tid % G : 0, fp = active ? tid / G : 0;
+  const int d = d_lo + cg * VN;
+  const TV* Vb = reinterpret_cast<const TV*>(a.V) + (long long)b * a.v_bs + d;
+
+  RN_PROBE(20, tid);
+  // ---- issue every load up front ----
+  Vec16<TV> v[NPRE];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int f = fp + k * FP;
+      if (f < a.Tn) v[k].load(Vb + (long long)f * a.v_ts);
+    }
+  }
+  float u[4][4];
+  const float* Ub = a.Uv + (long long)b * a.uv_bs;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int tau = warp + k * NW;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;
+      u[k][q] = (tau < a.Tn && i < a.A) ? __ldg(Ub + (long long)tau * a.uv_ts + i) : 0.f;
+    }
+  }
   for (int i = tid; i < a.A; i += FWD_THREADS) {
     float s = 0.f;
     for (int p0 = 0; p0 < a.n_whp; p0 += 8) {
-      float v[8];
+      float t8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = (p0 + k < a.n_whp) ? __ldg(a.WhP + (long long)(p0 + k) * a.whp_stride + (long long)b * a.A + i) : 0.f;
+      for (int k = 0; k < 8; ++k) t8[k] = (p0 + k < a.n_whp) ? __ldg(a.WhP + (long long)(p0 + k) * a.whp_stride + (long long)b * a.A + i) : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += v[k];
+      for (int k = 0; k < 8; ++k) s += t8[k];
     }
     Wh[i] = s + a.attn_b[i];
     wv[i] = a.attn_w[i];
-    if (a.Wh_out && blockIdx.x == 0) a.Wh_out[(long long)b * a.A + i] = s;
+    if (a.Wh_out && bx == 0) a.Wh_out[(long long)b * a.A + i] = s;
   }
-  __syncthreads();
-  // scores: warp w handles frames w, w+NW, ... ; up to 4 frames' Uv rows are loaded before any tanh
-  for (int t0 = warp; t0 < a.Tn; t0 += 4 * NW) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = lane; i < a.A; i += 32) {
-      float u[4];
+  RN_PROBE(21, tid);
+  blk_sync(bar_id);
+  RN_PROBE(22, tid);
+  // ---- scores: warp w owns frames w, w+8, w+16, w+24 (preloaded); anything beyond 32 frames / 128 units on demand ----
+  {
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int tau = t0 + k * NW;
-        u[k] = (tau < a.Tn) ? __ldg(a.Uv + (long long)b * a.uv_bs + (long long)tau * a.uv_ts + i) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;
+      if (i < a.A) {
+        const float whi = Wh[i], wi = wv[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sc[k] += wi * act_tanh<FAST>(whi + u[k][q]);
       }
+    }
+    for (int i = lane + 128; i < a.A; i += 32) {          // A > 128 (not the reference sizes)
       const float whi = Wh[i], wi = wv[i];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s[k] += wi * tanhf(whi + u[k]);
+      for (int k = 0; k < 4; ++k) {
+        const int tau = warp + k * NW;
+        if (tau < a.Tn) sc[k] += wi * act_tanh<FAST>(whi + __ldg(Ub + (long long)tau * a.uv_ts + i));
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float r = warp_sum(s[k]);
-      if (lane == 0 && t0 + k * NW < a.Tn) e[t0 + k * NW] = r;
+      const float r = warp_sum(sc[k]);
+      if (lane == 0 && warp + k * NW < a.Tn) e[warp + k * NW] = r;
+    }
+    for (int tau = warp + 4 * NW; tau < a.Tn; tau += NW) {  // Tn > 32
+      float s1 = 0.f;
+      for (int i = lane; i < a.A; i += 32) s1 += wv[i] * act_tanh<FAST>(Wh[i] + __ldg(Ub + (long long)tau * a.uv_ts + i));
+      s1 = warp_sum(s1);
+      if (lane == 0) e[tau] = s1;
     }
   }
-  __syncthreads();
+  blk_sync(bar_id);
   if (a.normalize) {   // optional softmax over frames (paper variant)
     if (warp == 0) {
       float m = -INFINITY;
@@ -84,42 +133,64 @@ __global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
       z = warp_sum(z);
       for (int t = lane; t < a.Tn; t += 32) e[t] = __expf(e[t] - m) / z;
     }
-    __syncthreads();
+    blk_sync(bar_id);
   }
-  if (a.e_out && blockIdx.x == 0)
+  if (a.e_out && bx == 0)
     for (int t = tid; t < a.Tn; t += FWD_THREADS) a.e_out[(long long)b * a.Tn + t] = e[t];
 
-  constexpr int VN = Vec16<TV>::N;
-  const int d_lo = blockIdx.x * a.d_slice, d_hi = min(a.D, d_lo + a.d_slice);
-  const TV* Vb = reinterpret_cast<const TV*>(a.V) + (long long)b * a.v_bs;
-  TO* out = reinterpret_cast<TO*>(a.ctx_out) + (long long)b * a.ctx_ld;
-  for (int d = d_lo + tid * VN; d < d_hi; d += FWD_THREADS * VN) {
-    float acc[VN];
+  RN_PROBE(23, tid);
+  // ---- weighted sum over this thread's frames ----
+  float acc[VN];
 #pragma unroll
-    for (int j = 0; j < VN; ++j) acc[j] = 0.f;
-    for (int t0 = 0; t0 < a.Tn; t0 += 8) {          // 8 frames (8 x 16 B) in flight per thread
-      Vec16<TV> v[8];
+  for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+  if (active) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (t0 + k < a.Tn) v[k].load(Vb + (long long)(t0 + k) * a.v_ts + d);
+    for (int k = 0; k < NPRE; ++k) {
+      const int f = fp + k * FP;
+      if (f < a.Tn) {
+        float fv[VN]; v[k].get(fv);
+        const float ek = e[f];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (t0 + k < a.Tn) {
-          float f[VN]; v[k].get(f);
-          const float ek = e[t0 + k];
-#pragma unroll
-          for (int j = 0; j < VN; ++j) acc[j] += ek * f[j];
-        }
+        for (int j = 0; j < VN; ++j) acc[j] += ek * fv[j];
       }
     }
-    const float sc = a.normalize ? 1.f : a.inv_T;
+    for (int f = fp + NPRE * FP; f < a.Tn; f += FP) {       // more than NPRE frames per thread: second round
+      Vec16<TV> vv; vv.load(Vb + (long long)f * a.v_ts);
+      float fv[VN]; vv.get(fv);
+      const float ek = e[f];
 #pragma unroll
-    for (int j = 0; j < VN; ++j) {
-      acc[j] *= sc;
-      if (a.p_drop > 0.f) acc[j] *= dropout_scale(a.rng, a.site, (uint64_t)(a.drop_base + (long long)b * a.D + d + j), a.p_drop);
-      out[d + j] = from_f32<TO>(acc[j]);
+      for (int j = 0; j < VN; ++j) acc[j] += ek * fv[j];
     }
   }
+  if (FP > 1) {
+    if (active && fp > 0) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) red[(fp * G + cg) * VN + j] = acc[j];
+    }
+    blk_sync(bar_id);
+    if (active && fp == 0) {
+      for (int q = 1; q < FP; ++q)
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += red[(q * G + cg) * VN + j];
+    }
+  }
+  if (active && fp == 0) {
+    TO* out = reinterpret_cast<TO*>(a.ctx_out) + (long long)b * a.ctx_ld + d;
+    const float scl = a.normalize ? 1.f : a.inv_T;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      float r = acc[j] * scl;
+      if (a.p_drop > 0.f) r *= dropout_scale(a.rng, a.site, (uint64_t)(a.drop_base + (long long)b * a.D + d + j), a.p_drop);
+      out[j] = from_f32<TO>(r);
+    }
+  }
+  RN_PROBE(24, tid);
+}
+
+template <typename TV, typename TO>
+__global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
+  extern __shared__ float sm[];
+  attn_fwd_body<TV, TO>(a, blockIdx.x, blockIdx.y, sm, threadIdx.x, 0);
 }
 
 // Backward.  One CTA per sample:
@@ -142,100 +213,156 @@ struct BwdArgs {
   float p_drop; const unsigned long long* rng; unsigned int site; long long drop_base;
 };
 
+// body: one virtual block = sample b; sm = (D + Tn + 2*256) floats; 256 threads.
+// Same latency discipline as the forward: the Uv / dUv rows of the score backward and the first V rows of the de dot
+// products are requested at entry; the split-K partial sum of dctx runs as 16-byte loads, all partials in flight.
 template <typename TV, typename TO>
-__global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void attn_bwd_body(const BwdArgs& a, int b, float* sm, int tid, int bar_id) {
+  constexpr bool FAST = FastMath<TV>::value;
+  constexpr int VN = Vec16<TV>::N, NW = BWD_THREADS / 32, MAXP = 12, NF = 14;
   float* dctx = sm;                 // [D]
   float* de = sm + a.D;             // [Tn]
   float* red = de + a.Tn;           // [2 * BWD_THREADS]
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = BWD_THREADS / 32;
-  for (int d = tid; d < a.D; d += BWD_THREADS) {
-    float s = 0.f;
-    for (int p0 = 0; p0 < a.n_p; p0 += 8) {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = (p0 + k < a.n_p) ? __ldg(a.dXp + (long long)(p0 + k) * a.p_stride + (long long)b * a.p_ld + d) : 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += v[k];
-    }
-    if (a.p_drop > 0.f) s *= dropout_scale(a.rng, a.site, (uint64_t)(a.drop_base + (long long)b * a.D + d), a.p_drop);
-    dctx[d] = s;
-    if (a.dctx_out) a.dctx_out[(long long)b * a.D + d] = s;
-  }
-  __syncthreads();
-  constexpr int VN = Vec16<TV>::N;
+  const int lane = tid & 31, warp = tid >> 5;
   const TV* Vb = reinterpret_cast<const TV*>(a.V) + (long long)b * a.v_bs;
-  // de: warp w handles frames w, w+NW, ...; two frames' rows in flight
-  for (int t0 = warp; t0 < a.Tn; t0 += 2 * NW) {
-    float s[2] = {0.f, 0.f};
-    for (int d = lane * VN; d < a.D; d += 32 * VN * 2) {
-      Vec16<TV> v[2][2];
-      bool ok[2][2];
+
+  // ---- prefetch for the score backward: thread (i, part) owns attention unit i and frames part, part+nparts, ... ----
+  const int per = (a.A <= BWD_THREADS && BWD_THREADS % a.A == 0) ? a.A : BWD_THREADS;   // threads per frame partition
+  const int nparts = BWD_THREADS / per;
+  const int i3 = tid % per, part = tid / per;
+  const bool pre3 = (per == a.A);                         // the common case (A divides 256): everything preloaded
+  float u3[NF], o3[NF];
+  const float* Ub = a.Uv + (long long)b * a.uv_bs + i3;
+  float* dUb = a.dUv_acc + (long long)b * a.uv_bs + i3;
+  if (pre3) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int tau = t0 + k * NW, dd = d + u * 32 * VN;
-          ok[k][u] = tau < a.Tn && dd < a.D;
-          if (ok[k][u]) v[k][u].load(Vb + (long long)tau * a.v_ts + dd);
-        }
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (ok[k][u]) {
-            float f[VN]; v[k][u].get(f);
-            const int dd = d + u * 32 * VN;
-#pragma unroll
-            for (int j = 0; j < VN; ++j) s[k] += f[j] * dctx[dd + j];
-          }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float r = warp_sum(s[k]) * a.inv_T;
-      const int tau = t0 + k * NW;
-      if (lane == 0 && tau < a.Tn) { de[tau] = r; if (a.de_out) a.de_out[(long long)b * a.Tn + tau] = r; }
+    for (int k = 0; k < NF; ++k) {
+      const int tau = part + k * nparts;
+      u3[k] = (tau < a.Tn) ? __ldg(Ub + (long long)tau * a.uv_ts) : 0.f;
+      o3[k] = (tau < a.Tn && !a.uv_first) ? dUb[(long long)tau * a.uv_ts] : 0.f;
     }
   }
-  __syncthreads();
-  // ds: thread (i, part) handles attention unit i and frames part, part+nparts, ... (4 frames in flight)
-  const int nparts = (a.A <= BWD_THREADS && BWD_THREADS % a.A == 0) ? BWD_THREADS / a.A : 1;
-  for (int i0 = 0; i0 < a.A; i0 += BWD_THREADS / nparts) {
-    const int i = i0 + tid % (BWD_THREADS / nparts), part = tid / (BWD_THREADS / nparts);
+  // ---- prefetch the V rows of this warp's first two frames (the dot products need dctx, which is not ready yet) ----
+  constexpr int NV = 8;                                    // 16-byte vectors per lane per frame held in registers
+  Vec16<TV> v0[NV], v1[NV];
+  const int tau0 = warp, tau1 = warp + NW;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const int d = (lane + 32 * q) * VN;
+    if (d < a.D) {
+      if (tau0 < a.Tn) v0[q].load(Vb + (long long)tau0 * a.v_ts + d);
+      if (tau1 < a.Tn) v1[q].load(Vb + (long long)tau1 * a.v_ts + d);
+    }
+  }
+  // ---- dctx = sum of split-K partials (x dropout mask), float4 at a time, all partials of a float4 in flight ----
+  const float* Pb = a.dXp + (long long)b * a.p_ld;
+  for (int d4 = tid * 4; d4 < a.D; d4 += BWD_THREADS * 4) {
+    float4 t[MAXP];
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p)
+      t[p] = (p < a.n_p) ? *reinterpret_cast<const float4*>(Pb + (long long)p * a.p_stride + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) { s4.x += t[p].x; s4.y += t[p].y; s4.z += t[p].z; s4.w += t[p].w; }
+    for (int p = MAXP; p < a.n_p; ++p) {
+      const float4 x = *reinterpret_cast<const float4*>(Pb + (long long)p * a.p_stride + d4);
+      s4.x += x.x; s4.y += x.y; s4.z += x.z; s4.w += x.w;
+    }
+    float r[4] = {s4.x, s4.y, s4.z, s4.w};
+    if (a.p_drop > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] *= dropout_scale(a.rng, a.site, (uint64_t)(a.drop_base + (long long)b * a.D + d4 + j), a.p_drop);
+    }
+    *reinterpret_cast<float4*>(dctx + d4) = make_float4(r[0], r[1], r[2], r[3]);
+    if (a.dctx_out) *reinterpret_cast<float4*>(a.dctx_out + (long long)b * a.D + d4) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  blk_sync(bar_id);
+  // ---- de[tau] = inv_T * dctx . V[b,tau,:] ----
+  auto dot_pre = [&](const Vec16<TV>* vv) {
+    float s1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int d = (lane + 32 * q) * VN;
+      if (d < a.D) {
+        float f[VN]; vv[q].get(f);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) s1 += f[j] * dctx[d + j];
+      }
+    }
+    return s1;
+  };
+  auto dot_tail = [&](int tau) {          // columns beyond the NV preloaded vectors per lane (D > 32*NV*VN)
+    float s1 = 0.f;
+    for (int d = (lane + 32 * NV) * VN; d < a.D; d += 32 * VN) {
+      Vec16<TV> x; x.load(Vb + (long long)tau * a.v_ts + d);
+      float f[VN]; x.get(f);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) s1 += f[j] * dctx[d + j];
+    }
+    return s1;
+  };
+  if (tau0 < a.Tn) {
+    const float r = warp_sum(dot_pre(v0) + dot_tail(tau0)) * a.inv_T;
+    if (lane == 0) { de[tau0] = r; if (a.de_out) a.de_out[(long long)b * a.Tn + tau0] = r; }
+  }
+  if (tau1 < a.Tn) {
+    const float r = warp_sum(dot_pre(v1) + dot_tail(tau1)) * a.inv_T;
+    if (lane == 0) { de[tau1] = r; if (a.de_out) a.de_out[(long long)b * a.Tn + tau1] = r; }
+  }
+  for (int t0 = warp + 2 * NW; t0 < a.Tn; t0 += 2 * NW) {     // remaining frames: two rows in flight per round
+    const int t1 = t0 + NW;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int d = (lane + 32 * q) * VN;
+      if (d < a.D) {
+        v0[q].load(Vb + (long long)t0 * a.v_ts + d);
+        if (t1 < a.Tn) v1[q].load(Vb + (long long)t1 * a.v_ts + d);
+      }
+    }
+    const float r0 = warp_sum(dot_pre(v0) + dot_tail(t0)) * a.inv_T;
+    if (lane == 0) { de[t0] = r0; if (a.de_out) a.de_out[(long long)b * a.Tn + t0] = r0; }
+    if (t1 < a.Tn) {
+      const float r1 = warp_sum(dot_pre(v1) + dot_tail(t1)) * a.inv_T;
+      if (lane == 0) { de[t1] = r1; if (a.de_out) a.de_out[(long long)b * a.Tn + t1] = r1; }
+    }
+  }
+  blk_sync(bar_id);
+  // ---- ds / dWh / dUv / dw ----
+  for (int i0 = 0; i0 < a.A; i0 += per) {
+    const int i = i0 + i3;
     float dwh = 0.f, dw = 0.f;
     if (i < a.A) {
       const float wh = a.Wh[(long long)b * a.A + i] + a.attn_b[i];
       const float w = a.attn_w[i];
-      for (int t0 = part; t0 < a.Tn; t0 += 4 * nparts) {
-        float u[4], o[4];
+      if (pre3) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int tau = t0 + k * nparts;
-          const long long off = (long long)b * a.uv_bs + (long long)tau * a.uv_ts + i;
-          u[k] = (tau < a.Tn) ? __ldg(a.Uv + off) : 0.f;
-          o[k] = (tau < a.Tn && !a.uv_first) ? a.dUv_acc[off] : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int tau = t0 + k * nparts;
+        for (int k = 0; k < NF; ++k) {
+          const int tau = part + k * nparts;
           if (tau < a.Tn) {
-            const float s = tanhf(wh + u[k]);
-            const float g = de[tau] * w * (1.f - s * s);
+            const float sv = act_tanh<FAST>(wh + u3[k]);
+            const float g = de[tau] * w * (1.f - sv * sv);
             dwh += g;
-            dw += de[tau] * s;
-            a.dUv_acc[(long long)b * a.uv_bs + (long long)tau * a.uv_ts + i] = o[k] + g;
+            dw += de[tau] * sv;
+            dUb[(long long)tau * a.uv_ts] = o3[k] + g;
           }
         }
+      }
+      for (int tau = pre3 ? part + NF * nparts : part; tau < a.Tn; tau += nparts) {   // not preloaded (odd A or Tn > 14*nparts)
+        const long long off = (long long)b * a.uv_bs + (long long)tau * a.uv_ts + i;
+        const float sv = act_tanh<FAST>(wh + a.Uv[off]);
+        const float g = de[tau] * w * (1.f - sv * sv);
+        dwh += g;
+        dw += de[tau] * sv;
+        a.dUv_acc[off] = a.uv_first ? g : a.dUv_acc[off] + g;
       }
     }
     if (nparts > 1) {     // combine the frame partitions
       red[tid] = dwh; red[BWD_THREADS + tid] = dw;
-      __syncthreads();
+      blk_sync(bar_id);
       if (part == 0 && i < a.A) {
-        for (int q = 1; q < nparts; ++q) { dwh += red[q * (BWD_THREADS / nparts) + tid]; dw += red[BWD_THREADS + q * (BWD_THREADS / nparts) + tid]; }
+        for (int q = 1; q < nparts; ++q) { dwh += red[q * per + tid]; dw += red[BWD_THREADS + q * per + tid]; }
       }
-      __syncthreads();
+      blk_sync(bar_id);
     }
     if (part == 0 && i < a.A) {
       a.dWh_out[(long long)b * a.A + i] = dwh;
@@ -244,6 +371,12 @@ __global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
       *pw = a.uv_first ? dw : *pw + dw;
     }
   }
+}
+
+template <typename TV, typename TO>
+__global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
+  extern __shared__ float sm[];
+  attn_bwd_body<TV, TO>(a, blockIdx.x, sm, threadIdx.x, 0);
 }
 
 // Deferred value-gradient of the local reconstructor's attention (values = decoder hiddens, which need grad):
@@ -264,8 +397,9 @@ __global__ void attn_dv_kernel(const float* __restrict__ beta, const float* __re
   }
 }
 
-template <typename TV, typename TO>
-static int launch_fwd(FwdArgs a, cudaStream_t st) {
+// validates, fills a.d_slice and returns the number of D-slices (grid.x) through *slices_out
+template <typename TV>
+static int prepare_fwd(FwdArgs& a, int* slices_out) {
   if (a.Tn > MAX_T || a.Tn < 1) return RECNET_ERR_BAD_SHAPE;
   constexpr int VN = Vec16<TV>::N;
   if (a.D % VN || a.v_ts % VN || a.v_bs % VN) return RECNET_ERR_ALIGNMENT;
@@ -277,8 +411,18 @@ static int launch_fwd(FwdArgs a, cudaStream_t st) {
   int slice = rn_cdiv(rn_cdiv(a.D, slices), VN) * VN;
   slices = rn_cdiv(a.D, slice);
   a.d_slice = slice;
+  *slices_out = slices;
+  return 0;
+}
+static inline size_t fwd_smem_bytes(const FwdArgs& a) { return (size_t)(2 * a.A + a.Tn + FWD_THREADS * 8) * sizeof(float); }
+static inline size_t bwd_smem_bytes(const BwdArgs& a) { return (size_t)(a.D + a.Tn + 2 * BWD_THREADS) * sizeof(float); }
+
+template <typename TV, typename TO>
+static int launch_fwd(FwdArgs a, cudaStream_t st) {
+  int slices = 1;
+  RN_TRY(prepare_fwd<TV>(a, &slices));
   dim3 grid(slices, a.B);
-  const size_t smem = (size_t)(2 * a.A + a.Tn) * sizeof(float);
+  const size_t smem = fwd_smem_bytes(a);
   ProfScope prof(KC_ATTN_FWD, a.B, a.Tn, a.D, st);
   attn_fwd_kernel<TV, TO><<<grid, FWD_THREADS, smem, st>>>(a);
   RN_LAUNCH_OK();

@@ -20,7 +20,7 @@ typedef __nv_bfloat16 bf16;
 // (recnet_profile_enable), launch sites wrapped in a ProfScope also record a CUDA-event pair on the launching
 // stream, tagged with a kernel class and the problem shape; recnet_profile_collect returns per-launch durations.
 enum KernelClass { KC_OTHER = 0, KC_GEMM_TC = 1, KC_SGEMM = 2, KC_ATTN_FWD = 3, KC_ATTN_BWD = 4, KC_CELL_FWD = 5,
-                   KC_CELL_BWD = 6, KC_CE = 7, KC_REDUCE = 8 };
+                   KC_CELL_BWD = 6, KC_CE = 7, KC_REDUCE = 8, KC_LOOP = 9 };
 struct ProfRecord { int cls, M, N, K; cudaEvent_t e0, e1; };
 struct ProfState {
   long long launches = 0;
@@ -127,7 +127,47 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return r;
 }
 
+// developer timeline (recnet_debug_set_timeline): block 0 / thread 0 appends (tag << 56 | %globaltimer ns) records
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ unsigned int g_timeline_n = 0;
+// (compiled in only with -DRECNET_PROBES for the intra-body points; the loop kernel's phase-level stamps are always on)
+__device__ __forceinline__ void probe(int tag, int tid) {
+  if (g_timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = g_timeline_n++;
+    if (i < 4000) g_timeline[i] = (t & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)tag << 56);
+  }
+}
+
+#ifdef RECNET_PROBES
+#define RN_PROBE(tag, tid) probe(tag, tid)
+#else
+#define RN_PROBE(tag, tid) ((void)0)
+#endif
+
+// sync of one 256-thread (sub-)block: bar 0 = the whole CTA (stand-alone kernels), bar 1..15 = a named barrier shared by
+// the 256 threads of one sub-block of the persistent loop kernel
+__device__ __forceinline__ void blk_sync(int bar_id) {
+  if (bar_id == 0) __syncthreads();
+  else asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Activation math by build: FAST (bf16 build) = one MUFU.TANH per call (tanh.approx.f32, max rel err ~2^-11, far below
+// bf16 operand rounding); accurate libm (fp32 parity build, 1e-3 / bit-exact greedy).  r1 profile: with libm tanhf/expf the
+// cell kernels ran ~570 instructions per element and were issue-bound.
+template <bool FAST> __device__ __forceinline__ float act_tanh(float x) {
+  if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  return tanhf(x);
+}
+template <bool FAST> __device__ __forceinline__ float act_sigmoid(float x) {
+  if (FAST) return fmaf(0.5f, act_tanh<true>(0.5f * x), 0.5f);
+  return 1.f / (1.f + expf(-x));
+}
+template <typename T> struct FastMath { static constexpr bool value = false; };
+template <> struct FastMath<bf16> { static constexpr bool value = true; };
 
 // ---- Philox4x32-10 counter RNG (Salmon et al. 2011), used for in-kernel dropout masks --------
 struct Philox {

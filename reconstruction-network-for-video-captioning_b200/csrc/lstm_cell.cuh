@@ -29,48 +29,46 @@ struct FwdArgs {
   void* h_op2; long long hop2_ld;                                 // second operand-typed copy (nullable)
 };
 
-// sum of n partial buffers at `off`, 4 loads in flight per call site x 4 gates
-__device__ __forceinline__ void sum_partials4(const float* __restrict__ P, int n_p, long long stride, long long off, int H,
-                                              float& s0, float& s1, float& s2, float& s3) {
-  for (int p0 = 0; p0 < n_p; p0 += 4) {
-    float v[4][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool ok = p0 + k < n_p;
-      const float* q = P + (long long)(p0 + k) * stride + off;
-      v[k][0] = ok ? __ldg(q) : 0.f;
-      v[k][1] = ok ? __ldg(q + H) : 0.f;
-      v[k][2] = ok ? __ldg(q + 2 * H) : 0.f;
-      v[k][3] = ok ? __ldg(q + 3 * H) : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { s0 += v[k][0]; s1 += v[k][1]; s2 += v[k][2]; s3 += v[k][3]; }
+// body: virtual block (bx = 256-wide slice of H, b = sample): no integer division, pointer-bump partial loop
+template <typename TS, typename TO>
+__device__ __forceinline__ void lstm_cell_fwd_body(const FwdArgs& a, int bx, int b, int tid) {
+  constexpr bool FAST = FastMath<TO>::value;
+  const int H = a.H, j = bx * THREADS + tid;
+  if (j >= H) return;
+  float pi = 0.f, pf = 0.f, pg = 0.f, po = 0.f;
+  const float cp = a.c_prev[b * H + j];
+  if (a.Gx) { const float* g = a.Gx + b * a.gx_ld + j; pi = g[0]; pf = g[H]; pg = g[2 * H]; po = g[3 * H]; }
+  if (a.b1) { pi += a.b1[j]; pf += a.b1[H + j]; pg += a.b1[2 * H + j]; po += a.b1[3 * H + j]; }
+  if (a.b2) { pi += a.b2[j]; pf += a.b2[H + j]; pg += a.b2[2 * H + j]; po += a.b2[3 * H + j]; }
+  const float* q = a.P + b * a.p_ld + j;
+  int p = 0;
+  for (; p + 4 <= a.n_p; p += 4) {              // 16 independent loads in flight
+    const float* q1 = q + a.p_stride; const float* q2 = q1 + a.p_stride; const float* q3 = q2 + a.p_stride;
+    const float v00 = q[0], v01 = q[H], v02 = q[2 * H], v03 = q[3 * H];
+    const float v10 = q1[0], v11 = q1[H], v12 = q1[2 * H], v13 = q1[3 * H];
+    const float v20 = q2[0], v21 = q2[H], v22 = q2[2 * H], v23 = q2[3 * H];
+    const float v30 = q3[0], v31 = q3[H], v32 = q3[2 * H], v33 = q3[3 * H];
+    pi += (v00 + v10) + (v20 + v30); pf += (v01 + v11) + (v21 + v31);
+    pg += (v02 + v12) + (v22 + v32); po += (v03 + v13) + (v23 + v33);
+    q = q3 + a.p_stride;
   }
+  for (; p < a.n_p; ++p) { pi += q[0]; pf += q[H]; pg += q[2 * H]; po += q[3 * H]; q += a.p_stride; }
+  const float gi = act_sigmoid<FAST>(pi), gf = act_sigmoid<FAST>(pf), gg = act_tanh<FAST>(pg), go = act_sigmoid<FAST>(po);
+  const float cn = fmaf(gf, cp, gi * gg);
+  const float hn = go * act_tanh<FAST>(cn);
+  a.c_out[b * H + j] = cn;
+  if (a.h_out) a.h_out[b * a.h_ld + j] = hn;
+  if (a.gates_out) {
+    TS* g = reinterpret_cast<TS*>(a.gates_out) + b * 4 * H + j;
+    g[0] = from_f32<TS>(gi); g[H] = from_f32<TS>(gf); g[2 * H] = from_f32<TS>(gg); g[3 * H] = from_f32<TS>(go);
+  }
+  if (a.h_op) reinterpret_cast<TO*>(a.h_op)[b * a.hop_ld + j] = from_f32<TO>(hn);
+  if (a.h_op2) reinterpret_cast<TO*>(a.h_op2)[b * a.hop2_ld + j] = from_f32<TO>(hn);
 }
 
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(THREADS) lstm_cell_fwd_kernel(FwdArgs a) {
-  const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
-  if (idx >= (long long)a.B * a.H) return;
-  const int b = (int)(idx / a.H), j = (int)(idx % a.H);
-  const int H = a.H;
-  float pi = 0.f, pf = 0.f, pg = 0.f, po = 0.f;
-  const float cp = a.c_prev[(long long)b * H + j];
-  if (a.Gx) { const float* g = a.Gx + (long long)b * a.gx_ld + j; pi += g[0]; pf += g[H]; pg += g[2 * H]; po += g[3 * H]; }
-  if (a.b1) { pi += a.b1[j]; pf += a.b1[H + j]; pg += a.b1[2 * H + j]; po += a.b1[3 * H + j]; }
-  if (a.b2) { pi += a.b2[j]; pf += a.b2[H + j]; pg += a.b2[2 * H + j]; po += a.b2[3 * H + j]; }
-  sum_partials4(a.P, a.n_p, a.p_stride, (long long)b * a.p_ld + j, H, pi, pf, pg, po);
-  const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf(pg), go = sigmoidf_(po);
-  const float cn = gf * cp + gi * gg;
-  const float hn = go * tanhf(cn);
-  a.c_out[(long long)b * H + j] = cn;
-  if (a.h_out) a.h_out[(long long)b * a.h_ld + j] = hn;
-  if (a.gates_out) {
-    TS* g = reinterpret_cast<TS*>(a.gates_out) + (long long)b * 4 * H + j;
-    g[0] = from_f32<TS>(gi); g[H] = from_f32<TS>(gf); g[2 * H] = from_f32<TS>(gg); g[3 * H] = from_f32<TS>(go);
-  }
-  if (a.h_op) reinterpret_cast<TO*>(a.h_op)[(long long)b * a.hop_ld + j] = from_f32<TO>(hn);
-  if (a.h_op2) reinterpret_cast<TO*>(a.h_op2)[(long long)b * a.hop2_ld + j] = from_f32<TO>(hn);
+  lstm_cell_fwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 // Backward of one step.
@@ -90,37 +88,36 @@ struct BwdArgs {
   void* dG; long long dg_ld;                                       // [B,4H] TO (GEMM operand)
 };
 
-__device__ __forceinline__ float sum_partials1(const float* __restrict__ P, int n_p, long long stride, long long off) {
+__device__ __forceinline__ float sum_partials1(const float* __restrict__ q, int n_p, long long stride) {
   float s = 0.f;
-  for (int p0 = 0; p0 < n_p; p0 += 8) {
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (p0 + k < n_p) ? __ldg(P + (long long)(p0 + k) * stride + off) : 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += v[k];
+  int p = 0;
+  for (; p + 4 <= n_p; p += 4) {
+    const float v0 = q[0], v1 = q[stride], v2 = q[2 * stride], v3 = q[3 * stride];
+    s += (v0 + v1) + (v2 + v3);
+    q += 4 * stride;
   }
+  for (; p < n_p; ++p) { s += q[0]; q += stride; }
   return s;
 }
 
 template <typename TS, typename TO>
-__global__ void __launch_bounds__(THREADS) lstm_cell_bwd_kernel(BwdArgs a) {
-  const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
-  if (idx >= (long long)a.B * a.H) return;
-  const int b = (int)(idx / a.H), j = (int)(idx % a.H);
-  const int H = a.H;
-  const TS* g = reinterpret_cast<const TS*>(a.gates) + (long long)b * 4 * H + j;
+__device__ __forceinline__ void lstm_cell_bwd_body(const BwdArgs& a, int bx, int b, int tid) {
+  constexpr bool FAST = FastMath<TO>::value;
+  const int H = a.H, j = bx * THREADS + tid;
+  if (j >= H) return;
+  const TS* g = reinterpret_cast<const TS*>(a.gates) + b * 4 * H + j;
   const float gi = to_f32<TS>(g[0]), gf = to_f32<TS>(g[H]), gg = to_f32<TS>(g[2 * H]), go = to_f32<TS>(g[3 * H]);
-  const float cp = a.c_prev[(long long)b * H + j], cn = a.c_new[(long long)b * H + j];
-  const float dcn = a.first ? 0.f : a.dc[(long long)b * H + j];
+  const float cp = a.c_prev[b * H + j], cn = a.c_new[b * H + j];
+  const float dcn = a.first ? 0.f : a.dc[b * H + j];
   float dh = 0.f;
-  if (a.dh_ext) dh += (a.dh_scale ? *a.dh_scale : 1.f) * a.dh_ext[(long long)b * a.dh_ld + j];
-  if (a.dh_ext2) dh += a.dh_ext2[(long long)b * a.dh2_ld + j];
-  if (a.dXp) dh += sum_partials1(a.dXp, a.n_p, a.p_stride, (long long)b * a.p_ld + a.col0 + j);
-  if (a.dQp) dh += sum_partials1(a.dQp, a.n_q, a.q_stride, (long long)b * a.q_ld + j);
-  const float tc = tanhf(cn);
-  const float dc = dcn + dh * go * (1.f - tc * tc);
-  a.dc[(long long)b * H + j] = dc * gf;
-  TO* o = reinterpret_cast<TO*>(a.dG) + (long long)b * a.dg_ld + j;
+  if (a.dh_ext) dh = (a.dh_scale ? *a.dh_scale : 1.f) * a.dh_ext[b * a.dh_ld + j];
+  if (a.dh_ext2) dh += a.dh_ext2[b * a.dh2_ld + j];
+  if (a.dXp) dh += sum_partials1(a.dXp + b * a.p_ld + a.col0 + j, a.n_p, a.p_stride);
+  if (a.dQp) dh += sum_partials1(a.dQp + b * a.q_ld + j, a.n_q, a.q_stride);
+  const float tc = act_tanh<FAST>(cn);
+  const float dc = fmaf(dh * go, 1.f - tc * tc, dcn);
+  a.dc[b * H + j] = dc * gf;
+  TO* o = reinterpret_cast<TO*>(a.dG) + b * a.dg_ld + j;
   o[0] = from_f32<TO>(dc * gg * gi * (1.f - gi));
   o[H] = from_f32<TO>(dc * cp * gf * (1.f - gf));
   o[2 * H] = from_f32<TO>(dc * gi * (1.f - gg * gg));
@@ -128,18 +125,21 @@ __global__ void __launch_bounds__(THREADS) lstm_cell_bwd_kernel(BwdArgs a) {
 }
 
 template <typename TS, typename TO>
+__global__ void __launch_bounds__(THREADS) lstm_cell_bwd_kernel(BwdArgs a) {
+  lstm_cell_bwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
+}
+
+template <typename TS, typename TO>
 static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
-  const long long n = (long long)a.B * a.H;
   ProfScope prof(KC_CELL_FWD, a.B, a.H, a.n_p, st);
-  lstm_cell_fwd_kernel<TS, TO><<<rn_cdiv(n, THREADS), THREADS, 0, st>>>(a);
+  lstm_cell_fwd_kernel<TS, TO><<<dim3(rn_cdiv(a.H, THREADS), a.B), THREADS, 0, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
 }
 template <typename TS, typename TO>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
-  const long long n = (long long)a.B * a.H;
   ProfScope prof(KC_CELL_BWD, a.B, a.H, (a.dXp ? a.n_p : 0) + (a.dQp ? a.n_q : 0), st);
-  lstm_cell_bwd_kernel<TS, TO><<<rn_cdiv(n, THREADS), THREADS, 0, st>>>(a);
+  lstm_cell_bwd_kernel<TS, TO><<<dim3(rn_cdiv(a.H, THREADS), a.B), THREADS, 0, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -42,6 +42,32 @@ int recnet_profile_collect(float* out, int max_records) {
   return n;
 }
 
+// developer probe: a loop-kernel launch with n_phases empty phases (grid barrier after each if sync_after) -- measures
+// the per-phase overhead of the persistent loop kernel.  scratch: >= n_phases * 1024 + 1024 bytes of device memory.
+int recnet_debug_loop_overhead(int n_phases, int sync_after, void* scratch, void* stream) {
+  mega::Emitter<bf16> em(true, ST(stream));
+  if (!em.mega) return RECNET_ERR_UNSUPPORTED;
+  for (int i = 0; i < n_phases; ++i) {
+    mega::Phase ph; memset(&ph, 0, sizeof(ph));
+    ph.type = 0; ph.nvb = 0; ph.sync_after = sync_after;
+    em.phases.push_back(ph);
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
+  unsigned* bar = reinterpret_cast<unsigned*>(base);
+  int* err = reinterpret_cast<int*>(base + 256);
+  RN_CUDA_OK(cudaMemsetAsync(base, 0, 512, ST(stream)));
+  return em.flush(base + 1024, (size_t)n_phases * sizeof(mega::Phase), bar, err, 100);
+}
+
+// developer probe: per-phase %globaltimer stamps of the next loop-kernel launches are written to `buf` (device, u64[n+1]); null = off
+int recnet_debug_set_timeline(void* buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  unsigned int zero = 0;
+  RN_CUDA_OK(cudaMemcpyToSymbol(g_timeline_n, &zero, sizeof(zero)));
+  RN_CUDA_OK(cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)));
+  return 0;
+}
+
 int recnet_query_device(int device, int* sm_count, int* cc_major, int* cc_minor) {
   cudaDeviceProp prop;
   RN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -177,6 +203,23 @@ int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_ten
   if (d->precision == RECNET_PREC_BF16)
     return dec::greedy<bf16>(*d, *w, feats, max_steps, workspace, workspace_bytes, reinterpret_cast<long long*>(ids_out), n_steps_out, ST(stream));
   return RECNET_ERR_UNSUPPORTED;
+}
+
+// byte offset of the loop kernel's int32 error flag inside the workspace (0 = ok, 2 = mbarrier timeout, 3 = grid-barrier timeout)
+int64_t recnet_decoder_error_offset(const recnet_decoder_desc* d) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(4096);
+  if (d->precision == RECNET_PREC_FP32) return reinterpret_cast<uint8_t*>(dec::plan<float>(*d, base).err) - base;
+  return reinterpret_cast<uint8_t*>(dec::plan<bf16>(*d, base).err) - base;
+}
+int64_t recnet_local_error_offset(const recnet_local_desc* d) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(4096);
+  if (d->precision == RECNET_PREC_FP32) return reinterpret_cast<uint8_t*>(rec::plan_local<float>(*d, base).err) - base;
+  return reinterpret_cast<uint8_t*>(rec::plan_local<bf16>(*d, base).err) - base;
+}
+int64_t recnet_global_error_offset(const recnet_global_desc* d) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(4096);
+  if (d->precision == RECNET_PREC_FP32) return reinterpret_cast<uint8_t*>(rec::plan_global<float>(*d, base).err) - base;
+  return reinterpret_cast<uint8_t*>(rec::plan_global<bf16>(*d, base).err) - base;
 }
 
 // ---- local reconstructor ---------------------------------------------------------------------------------------

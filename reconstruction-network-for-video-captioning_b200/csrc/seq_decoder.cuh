@@ -7,6 +7,7 @@
 //   * vocabulary projection batched over all steps (M = L*B), fused CE forward/backward over stacked logits
 //   * BPTT mirrors it; all weight gradients are batched GEMMs over the stashed operands after the loop.
 #pragma once
+#include "mega.cuh"
 #include "runtime.cuh"
 
 namespace dec {
@@ -28,6 +29,7 @@ struct Ws {
   // backward scratch
   T* dlogits; float* dHext; T* dG; float* dXp; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
   float* dc; float* dXe; float* splitk;
+  uint8_t* table; size_t table_bytes; unsigned* bar; int* err;     // loop-kernel phase table, grid-barrier counter, error flag
   size_t bytes;
 };
 
@@ -79,6 +81,10 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.dc = m.take<float>((size_t)B * H);
   w.dXe = m.take<float>((size_t)L * B * w.EMBp);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.table_bytes = mega::table_bytes(L);
+  w.table = m.take<uint8_t>(w.table_bytes);
+  w.bar = m.take<unsigned>(64);
+  w.err = m.take<int>(64);
   w.bytes = m.off + 256;
   return w;
 }
@@ -108,16 +114,16 @@ static int prepare(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
 // one decoder step for the sample rows [b0, b0+nb) of chain `ch`: attention -> gate GEMM -> cell.
 // Pointer arguments are the FULL-batch row-0 addresses of step t; the row offset is applied here.
 template <typename T>
-static int step(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, Ws<T>& w, int t, int ch, int b0, int nb,
-                const float* gx_t, T* x_t, T* x_next, float* Wh_t, float* e_t, T* gates_t, const float* c_prev,
-                float* c_next, float* h_out, cudaStream_t st) {
+static int step(mega::Emitter<T>& em, const recnet_decoder_desc& d, const recnet_decoder_tensors& p, Ws<T>& w, int t, int ch,
+                int b0, int nb, const float* gx_t, T* x_t, T* x_next, float* Wh_t, float* e_t, T* gates_t, const float* c_prev,
+                float* c_next, float* h_out) {
   const int H = d.H, E = d.E, A = d.A, Tn = d.T;
   float* WhP = w.WhP + (size_t)ch * w.pl_wh.splits * w.Bc * A;
   float* P = w.P + (size_t)ch * w.pl_gate.splits * w.Bc * 4 * H;
   T* xr = x_t + (size_t)b0 * w.KX;
   int n_whp = 0;
   if (t > 0) {   // h_{-1} = 0 -> W h = 0, skip the GEMM
-    RN_TRY(gemm_partials<T>(xr + E, w.KX, 0, w.Wa, H, 0, WhP, nb, A, H, w.pl_wh, st));
+    RN_TRY(em.gemm_partials(xr + E, w.KX, 0, w.Wa, H, 0, WhP, nb, A, H, w.pl_wh));
     n_whp = w.pl_wh.splits;
   }
   attn::FwdArgs fa{};
@@ -128,8 +134,8 @@ static int step(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, W
   fa.B = nb; fa.Tn = Tn; fa.A = A; fa.D = E; fa.inv_T = 1.f / Tn; fa.normalize = 0;
   fa.Wh_out = Wh_t ? Wh_t + (size_t)b0 * A : nullptr; fa.e_out = e_t ? e_t + (size_t)b0 * Tn : nullptr;
   fa.ctx_out = xr; fa.ctx_ld = w.KX; fa.p_drop = 0.f;
-  RN_TRY((attn::launch_fwd<T, T>(fa, st)));
-  RN_TRY(gemm_partials<T>(xr, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * H, w.KX, w.pl_gate, st));
+  RN_TRY(em.attn_fwd(fa));
+  RN_TRY(em.gemm_partials(xr, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * H, w.KX, w.pl_gate));
   cell::FwdArgs ca{};
   ca.P = P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)nb * 4 * H; ca.p_ld = 4 * H;
   ca.Gx = gx_t + (size_t)b0 * 4 * H; ca.gx_ld = 4 * H; ca.b1 = nullptr; ca.b2 = p.b_hh;
@@ -137,7 +143,7 @@ static int step(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, W
   ca.gates_out = gates_t ? gates_t + (size_t)b0 * 4 * H : nullptr; ca.c_out = c_next + (size_t)b0 * H;
   ca.h_out = h_out + (size_t)b0 * H; ca.h_ld = H;
   ca.h_op = x_next + (size_t)b0 * w.KX + E; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
-  RN_TRY((cell::launch_fwd<T, T>(ca, st)));
+  RN_TRY(em.cell_fwd(ca));
   return 0;
 }
 
@@ -160,19 +166,25 @@ static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
   // initial state: h_{-1} = 0 (operand slot of X[0]), c_{-1} = 0
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
-  // time loop: w.nch independent sample chains on forked streams
+  // time loop.  One chain (default): the whole loop is ONE persistent loop-kernel launch (bf16 build) or one kernel
+  // per phase (fp32 build / RECNET_MEGA=0).  Several chains (RECNET_CHAINS, experimental): forked streams, eager.
+  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
-  for (int t = 0; t < L; ++t) {
-    T* x_t = w.X + (size_t)t * B * w.KX;
-    for (int ch = 0; ch < w.nch; ++ch) {
-      int b0, nb;
-      chain_rows(B, w.nch, ch, &b0, &nb);
-      RN_TRY(step<T>(d, p, w, t, ch, b0, nb, w.Gx + (size_t)t * B * 4 * H, x_t, x_t + (size_t)B * w.KX,
-                     w.Wh + (size_t)t * B * A, w.e + (size_t)t * B * Tn, w.gates + (size_t)t * B * 4 * H,
-                     w.c + (size_t)t * B * H, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H,
-                     w.nch > 1 ? cs.s[ch] : st));
+  {
+    mega::Emitter<T> em0(w.nch == 1, st, (size_t)E + Tn + 8 * attn::BWD_THREADS + 2 * A);
+    for (int t = 0; t < L; ++t) {
+      T* x_t = w.X + (size_t)t * B * w.KX;
+      for (int ch = 0; ch < w.nch; ++ch) {
+        int b0, nb;
+        chain_rows(B, w.nch, ch, &b0, &nb);
+        mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
+        RN_TRY(step<T>(w.nch == 1 ? em0 : emc, d, p, w, t, ch, b0, nb, w.Gx + (size_t)t * B * 4 * H, x_t, x_t + (size_t)B * w.KX,
+                       w.Wh + (size_t)t * B * A, w.e + (size_t)t * B * Tn, w.gates + (size_t)t * B * 4 * H,
+                       w.c + (size_t)t * B * H, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H));
+      }
     }
+    RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 1));
   }
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   // vocabulary projection over all steps, then the masked CE (train.py:54-60,68)
@@ -213,12 +225,14 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
   // ---- BPTT: the same sample chains, each with private split-K scratch ------------------------------------------
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
+  mega::Emitter<T> em0(w.nch == 1, st, (size_t)E + Tn + 8 * attn::BWD_THREADS + 2 * A);
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
       chain_rows(B, w.nch, ch, &b0, &nb);
-      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
+      mega::Emitter<T>& em = w.nch == 1 ? em0 : emc;
       float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * w.KX;
       float* dQp = w.dQp + (size_t)ch * w.pl_dq.splits * w.Bc * H;
       const size_t r = (size_t)t * B + b0;           // first (t, b) row of this chain
@@ -231,9 +245,9 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
       cb.gates = w.gates + r * 4 * H;
       cb.c_prev = w.c + r * H; cb.c_new = w.c + ((size_t)(t + 1) * B + b0) * H;
       cb.B = nb; cb.H = H; cb.dG = w.dG + r * 4 * H; cb.dg_ld = 4 * H;
-      RN_TRY((cell::launch_bwd<T, T>(cb, cst)));
+      RN_TRY(em.cell_bwd(cb));
       // d[ctx ; h_{t-1}] = dG_t @ [W_ctx | W_hh]
-      RN_TRY(gemm_partials<T>(w.dG + r * 4 * H, 4 * H, 0, w.Wrec, w.KX, 1, dXp, nb, w.KX, 4 * H, w.pl_dx, cst));
+      RN_TRY(em.gemm_partials(w.dG + r * 4 * H, 4 * H, 0, w.Wrec, w.KX, 1, dXp, nb, w.KX, 4 * H, w.pl_dx));
       attn::BwdArgs ab{};
       ab.dXp = dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)nb * w.KX; ab.p_ld = w.KX;
       ab.V = w.feats + (size_t)b0 * Tn * E; ab.v_bs = (long long)Tn * E; ab.v_ts = E;
@@ -242,11 +256,12 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
       ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * Tn * A;
       ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
       ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
-      RN_TRY((attn::launch_bwd<T, T>(ab, cst)));
+      RN_TRY(em.attn_bwd(ab));
       // attention-query path into h_{t-1}: dWh_t @ attn_W, consumed (as split-K partials) by the next cell backward
-      if (t > 0) RN_TRY(gemm_partials<T>(w.dWh_op + r * A, A, 0, w.Wa, H, 1, dQp, nb, H, A, w.pl_dq, cst));
+      if (t > 0) RN_TRY(em.gemm_partials(w.dWh_op + r * A, A, 0, w.Wa, H, 1, dQp, nb, H, A, w.pl_dq));
     }
   }
+  RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 2));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   // ---- batched weight gradients over the stashed operands ----------------------------------------------------
   const long long ldih = EMB + E;
@@ -356,7 +371,8 @@ static int greedy(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p
                                                     nullptr, SITE_EMB);
     RN_LAUNCH_OK();
     RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, B, 4 * H, w.EMBp, 0, w.splitk, st));
-    RN_TRY(step<T>(d, p, w, t, 0, 0, B, w.Gx, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n, g.h_scratch, st));
+    mega::Emitter<T> em(false, st);
+    RN_TRY(step<T>(em, d, p, w, t, 0, 0, B, w.Gx, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n, g.h_scratch));
     RN_TRY(gemm_full<T>(x_n + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, B, V, H, 0, w.splitk, st));
     argmax_feedback_kernel<<<B, 256, 0, st>>>(w.logits, w.Vld, V, ids_out + (size_t)t * B, g.tok, g.nonpad + t);
     RN_LAUNCH_OK();

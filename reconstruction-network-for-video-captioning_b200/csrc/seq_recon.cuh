@@ -6,6 +6,7 @@
 // Same restructuring as the decoder: U.hiddens hoisted, [x ; h] K-concatenated gate GEMM per step, output
 // projection and all weight gradients batched over time.  One decoder layer (the reference default).
 #pragma once
+#include "mega.cuh"
 #include "runtime.cuh"
 
 namespace rec {
@@ -22,6 +23,7 @@ struct LocalWs {
   float* Uv; T* X; float* WhP; float* Wh; float* beta; float* P; T* gates; float* c; float* out; float* partial;
   T* dOut; float* dHext; T* dG; float* dXp; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
   float* dx; float* splitk;
+  uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
   size_t bytes;
 };
 constexpr int MSE_BLOCKS = 592;
@@ -67,6 +69,10 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.dc = m.take<float>((size_t)B * R);
   w.dx = m.take<float>((size_t)S * B * H);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.table_bytes = mega::table_bytes(S);
+  w.table = m.take<uint8_t>(w.table_bytes);
+  w.bar = m.take<unsigned>(64);
+  w.err = m.take<int>(64);
   w.bytes = m.off + 256;
   return w;
 }
@@ -95,13 +101,16 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
+  mega::Emitter<T> em0(w.nch == 1, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
   for (int t = 0; t < S; ++t) {
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
       chain_rows(B, w.nch, ch, &b0, &nb);
-      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
+      mega::Emitter<T>& em = w.nch == 1 ? em0 : emc;
       float* WhP = w.WhP + (size_t)ch * w.pl_wh.splits * w.Bc * A;
       float* P = w.P + (size_t)ch * w.pl_gate.splits * w.Bc * 4 * R;
       const size_t r = (size_t)t * B + b0;
@@ -109,7 +118,7 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
       T* x_n = x_t + (size_t)B * w.KX;
       int n_whp = 0;
       if (t > 0) {
-        RN_TRY(gemm_partials<T>(x_t + H, w.KX, 0, w.Wa, R, 0, WhP, nb, A, R, w.pl_wh, cst));
+        RN_TRY(em.gemm_partials(x_t + H, w.KX, 0, w.Wa, R, 0, WhP, nb, A, R, w.pl_wh));
         n_whp = w.pl_wh.splits;
       }
       attn::FwdArgs fa{};
@@ -121,16 +130,17 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
       fa.Wh_out = w.Wh + r * A; fa.e_out = w.beta + r * L;
       fa.ctx_out = x_t; fa.ctx_ld = w.KX;
       fa.p_drop = p_drop; fa.rng = rng; fa.site = SITE_LOCAL_X; fa.drop_base = (long long)r * H;
-      RN_TRY((attn::launch_fwd<T, T>(fa, cst)));
-      RN_TRY(gemm_partials<T>(x_t, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * R, w.KX, w.pl_gate, cst));
+      RN_TRY(em.attn_fwd(fa));
+      RN_TRY(em.gemm_partials(x_t, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * R, w.KX, w.pl_gate));
       cell::FwdArgs ca{};
       ca.P = P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)nb * 4 * R; ca.p_ld = 4 * R;
       ca.Gx = nullptr; ca.b1 = p.b_ih; ca.b2 = p.b_hh; ca.c_prev = w.c + r * R; ca.B = nb; ca.H = R;
       ca.gates_out = w.gates + r * 4 * R; ca.c_out = w.c + ((size_t)(t + 1) * B + b0) * R; ca.h_out = nullptr;
       ca.h_op = x_n + H; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
-      RN_TRY((cell::launch_fwd<T, T>(ca, cst)));
+      RN_TRY(em.cell_fwd(ca));
     }
   }
+  RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 3));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + H, w.KX, 0, w.Wout, R, 0, w.out, R, p.out_b, S * B, R, R, 0, w.splitk, st));
   if (mse_out) {
@@ -160,12 +170,14 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk, st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
+  mega::Emitter<T> em0(w.nch == 1, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
   for (int t = S - 1; t >= 0; --t) {
     const bool last = (t == S - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
       chain_rows(B, w.nch, ch, &b0, &nb);
-      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
+      mega::Emitter<T>& em = w.nch == 1 ? em0 : emc;
       float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * w.KX;
       float* dQp = w.dQp + (size_t)ch * w.pl_dq.splits * w.Bc * R;
       const size_t r = (size_t)t * B + b0;
@@ -177,8 +189,8 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
       cb.gates = w.gates + r * 4 * R;
       cb.c_prev = w.c + r * R; cb.c_new = w.c + ((size_t)(t + 1) * B + b0) * R;
       cb.B = nb; cb.H = R; cb.dG = w.dG + r * 4 * R; cb.dg_ld = 4 * R;
-      RN_TRY((cell::launch_bwd<T, T>(cb, cst)));
-      RN_TRY(gemm_partials<T>(w.dG + r * 4 * R, 4 * R, 0, w.Wrec, w.KX, 1, dXp, nb, w.KX, 4 * R, w.pl_dx, cst));
+      RN_TRY(em.cell_bwd(cb));
+      RN_TRY(em.gemm_partials(w.dG + r * 4 * R, 4 * R, 0, w.Wrec, w.KX, 1, dXp, nb, w.KX, 4 * R, w.pl_dx));
       attn::BwdArgs ab{};
       ab.dXp = dXp; ab.n_p = w.pl_dx.splits; ab.p_stride = (long long)nb * w.KX; ab.p_ld = w.KX;
       ab.V = w.Hd + (size_t)b0 * H; ab.v_bs = H; ab.v_ts = (long long)B * H;
@@ -188,10 +200,11 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
       ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
       ab.dctx_out = w.dx + r * H; ab.de_out = nullptr;
       ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)r * H;
-      RN_TRY((attn::launch_bwd<T, T>(ab, cst)));
-      if (t > 0) RN_TRY(gemm_partials<T>(w.dWh_op + r * A, A, 0, w.Wa, R, 1, dQp, nb, R, A, w.pl_dq, cst));
+      RN_TRY(em.attn_bwd(ab));
+      if (t > 0) RN_TRY(em.gemm_partials(w.dWh_op + r * A, A, 0, w.Wa, R, 1, dQp, nb, R, A, w.pl_dq));
     }
   }
+  RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 4));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   RN_TRY(misc::colsum<T>(w.dG, 4 * R, SB, 4 * R, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -220,6 +233,7 @@ struct GlobalWs {
   GemmPlan pl_gate, pl_dx;
   T *Wih, *Whh, *Wout; float* mp; T* Xg; float* Gx; T* X; float* P; T* gates; float* c; float* out; float* diff; float* partial;
   T* dOut; float* dHext; T* dG; float* dXp; float* dc; float* dXg; float* dmp; float* splitk;
+  uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
   size_t bytes;
 };
 constexpr int GMSE_THREADS = 256;
@@ -255,6 +269,10 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   w.dXg = m.take<float>((size_t)L * B * 2 * H);
   w.dmp = m.take<float>((size_t)B * H);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.table_bytes = mega::table_bytes(L);
+  w.table = m.take<uint8_t>(w.table_bytes);
+  w.bar = m.take<unsigned>(64);
+  w.err = m.take<int>(64);
   w.bytes = m.off + 256;
   return w;
 }
@@ -285,19 +303,22 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
   RN_TRY(gemm_full<T>(w.Xg, 2 * H, 0, w.Wih, 2 * H, 0, w.Gx, 4 * R, p.b_ih, L * B, 4 * R, 2 * H, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * R * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
+  mega::Emitter<T> em0(w.nch == 1, st);
   for (int t = 0; t < L; ++t) {
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
       chain_rows(B, w.nch, ch, &b0, &nb);
-      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
+      mega::Emitter<T>& em = w.nch == 1 ? em0 : emc;
       float* P = w.P + (size_t)ch * w.pl_gate.splits * w.Bc * 4 * R;
       const size_t r = (size_t)t * B + b0;
       T* x_t = w.X + r * R;
       int n_p = 0;
       if (t > 0) {
-        RN_TRY(gemm_partials<T>(x_t, R, 0, w.Whh, R, 0, P, nb, 4 * R, R, w.pl_gate, cst));
+        RN_TRY(em.gemm_partials(x_t, R, 0, w.Whh, R, 0, P, nb, 4 * R, R, w.pl_gate));
         n_p = w.pl_gate.splits;
       }
       cell::FwdArgs ca{};
@@ -306,9 +327,10 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
       ca.c_prev = w.c + r * R; ca.B = nb; ca.H = R;
       ca.gates_out = w.gates + r * 4 * R; ca.c_out = w.c + ((size_t)(t + 1) * B + b0) * R; ca.h_out = nullptr;
       ca.h_op = x_t + (size_t)B * R; ca.hop_ld = R; ca.h_op2 = nullptr;
-      RN_TRY((cell::launch_fwd<T, T>(ca, cst)));
+      RN_TRY(em.cell_fwd(ca));
     }
   }
+  RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 5));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   RN_TRY(gemm_full<T>(w.X + (size_t)B * R, R, 0, w.Wout, R, 0, w.out, R, p.out_b, L * B, R, R, 0, w.splitk, st));
   if (loss_out) {
@@ -339,12 +361,14 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
   RN_TRY(misc::colsum<T>(w.dOut, R, LB, R, g.out_b, 0, w.splitk, st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
+  mega::Emitter<T> em0(w.nch == 1, st);
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
       chain_rows(B, w.nch, ch, &b0, &nb);
-      cudaStream_t cst = w.nch > 1 ? cs.s[ch] : st;
+      mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
+      mega::Emitter<T>& em = w.nch == 1 ? em0 : emc;
       float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * R;
       const size_t r = (size_t)t * B + b0;
       cell::BwdArgs cb{};
@@ -354,10 +378,11 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
       cb.gates = w.gates + r * 4 * R;
       cb.c_prev = w.c + r * R; cb.c_new = w.c + ((size_t)(t + 1) * B + b0) * R;
       cb.B = nb; cb.H = R; cb.dG = w.dG + r * 4 * R; cb.dg_ld = 4 * R;
-      RN_TRY((cell::launch_bwd<T, T>(cb, cst)));
-      if (t > 0) RN_TRY(gemm_partials<T>(w.dG + r * 4 * R, 4 * R, 0, w.Whh, R, 1, dXp, nb, R, 4 * R, w.pl_dx, cst));
+      RN_TRY(em.cell_bwd(cb));
+      if (t > 0) RN_TRY(em.gemm_partials(w.dG + r * 4 * R, 4 * R, 0, w.Whh, R, 1, dXp, nb, R, 4 * R, w.pl_dx));
     }
   }
+  RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 6));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   RN_TRY(misc::colsum<T>(w.dG, 4 * R, LB, 4 * R, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));

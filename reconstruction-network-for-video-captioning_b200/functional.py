@@ -103,6 +103,24 @@ def _norms_bwd_into(params, sumsq, g_reg, gptrs, accumulate: bool):
                                            g_reg.data_ptr(), 1.0, int(accumulate), _stream()), "recnet_param_norms_bwd")
 
 
+# (workspace, byte offset of the loop kernel's error flag) of the most recent sequence calls, for check_loop_status()
+_status_slots = {}
+
+
+def _remember_status(kind: str, ws: torch.Tensor, offset: int):
+    _status_slots[kind] = (ws, int(offset))
+
+
+def check_loop_status() -> None:
+    """Synchronise and raise if any persistent loop kernel reported a protocol timeout (see include/recnet_b200.h)."""
+    torch.cuda.synchronize()
+    for kind, (ws, off) in _status_slots.items():
+        code = int(ws[off: off + 4].view(torch.int32).item())
+        if code != 0:
+            raise RuntimeError(f"recnet_b200 loop kernel ({kind}) failed with device status {code} "
+                               "(2 = mbarrier timeout, 3 = grid-barrier timeout)")
+
+
 def _scalar(g, dev):
     if g is None:
         return torch.zeros((), dtype=torch.float32, device=dev)
@@ -134,6 +152,7 @@ def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
     L.check(lib.recnet_decoder_fwd(C.byref(d), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), _ptr(targets),
                                    _ptr(ce_weight), rng.data_ptr(), ws.data_ptr(), nbytes, hiddens.data_ptr(),
                                    ce.data_ptr(), _stream()), "recnet_decoder_fwd")
+    _remember_status("decoder", ws, lib.recnet_decoder_error_offset(C.byref(d)))
     return ce, hiddens, ws, d, nbytes, (feats, tokens_in, targets, ce_weight, rng, *params)
 
 
@@ -205,6 +224,7 @@ class LocalReconstructorFn(torch.autograd.Function):
         w = _pack(L.local_tensors, params)
         L.check(lib.recnet_local_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
                                      nbytes, mse.data_ptr(), _stream()), "recnet_local_fwd")
+        _remember_status("local", ws, lib.recnet_local_error_offset(C.byref(d)))
         reg, sumsq = _norms_fwd(params)
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.set_materialize_grads(False)
@@ -249,6 +269,7 @@ class GlobalReconstructorFn(torch.autograd.Function):
         w = _pack(L.global_tensors, params)
         L.check(lib.recnet_global_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
                                       nbytes, loss.data_ptr(), _stream()), "recnet_global_fwd")
+        _remember_status("global", ws, lib.recnet_global_error_offset(C.byref(d)))
         reg, sumsq = _norms_fwd(params)
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.set_materialize_grads(False)

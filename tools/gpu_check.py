@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 
 import recnet_b200                                   # noqa: E402
 from recnet_b200 import _lib as L, ops               # noqa: E402
+from recnet_b200 import functional as Fn             # noqa: E402
 from recnet_b200 import train as T                   # noqa: E402
 from oracle import recnet_oracle as O                # noqa: E402
 from tests.golden_util import load_golden            # noqa: E402
@@ -113,6 +114,10 @@ def check_golden(name, precision):
             loss = dloss + 1.0 * rloss
         print(line, flush=True)
         loss.backward()
+        try:
+            Fn.check_loop_status()
+        except RuntimeError as ex:
+            print("   LOOP STATUS:", ex, flush=True)
         worst = 0.0
         for k, ref in g["grads"][kind].items():
             owner, key = k.split(".", 1)
@@ -169,6 +174,10 @@ def check_full(precision, kind="local", B=100):
     rloss = fwd(hiddens, f, rec)
     (dloss + rloss).backward()
     torch.cuda.synchronize()
+    try:
+        Fn.check_loop_status()
+    except RuntimeError as ex:
+        print("   LOOP STATUS:", ex, flush=True)
     print(f"  full {precision} {kind}: dec_loss rel {rel(dloss, dl):.2e} rec_loss rel {rel(rloss, rl):.2e} hiddens rel {rel(hiddens[:, 0], hid[:, 0]):.2e}", flush=True)
     for k, p in dec["model"].named_parameters():
         print(f"      grad dec.{k:28s} rel {rel(p.grad, Pr[k].grad):.2e}", flush=True)

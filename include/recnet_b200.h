@@ -38,6 +38,7 @@ typedef enum {
 } recnet_status;
 
 typedef enum { RECNET_PREC_FP32 = 0, RECNET_PREC_BF16 = 1 } recnet_precision;
+typedef enum { RECNET_CELL_LSTM = 0, RECNET_CELL_GRU = 1 } recnet_cell;   /* models/decoder.py:32-35: anything but "LSTM" is GRU */
 
 /* Library / device checks.  recnet_query_device fails with RECNET_ERR_UNSUPPORTED_ARCH unless the
  * device is compute capability 10.x (sm_100a cubins only; no PTX fallback, no other arch). */
@@ -113,6 +114,20 @@ int recnet_lstm_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, cons
                          const float* c_prev, const float* c_new, int B, int H, void* dg_out, int64_t dg_ld,
                          void* stream);
 
+/* Fused GRU gate activation + state update (the pointwise half of nn.GRU, models/decoder.py:32-40,66; gate order r,z,n).
+ *   gi = sum_s px[s] + gx + b_ih ; gh = sum_s ph[s] + b_hh ; r,z = sigmoid(gi + gh) ; n = tanh(gi_n + r * gh_n) ;
+ *   h' = (1 - z) n + z h.  stash [B,4H] (r, z, n, gh_n) in `precision` storage for BPTT. */
+int recnet_gru_cell_fwd(int precision, const float* px, int n_px, int64_t px_stride, int64_t px_ld, const float* ph,
+                        int n_ph, int64_t ph_stride, int64_t ph_ld, const float* gx, int64_t gx_ld, const float* b_ih,
+                        const float* b_hh, const float* h_prev, int64_t hp_ld, int B, int H, void* stash, float* h_out,
+                        int64_t h_ld, void* h_op, int64_t hop_ld, void* stream);
+/* Backward: dh' = dh_ext + dh_ext2 + carry + sum dhp + sum dqp ; writes dgi / dgh [B,3H] (operand storage) and the new
+ * carry = z * dh' (direct path into h_{t-1}); first=1 treats the incoming carry as 0. */
+int recnet_gru_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const float* dh_ext2, int64_t dh2_ld,
+                        const float* dhp, int n_p, int64_t p_stride, int64_t p_ld, const float* dqp, int n_q,
+                        int64_t q_stride, int64_t q_ld, float* carry, int first, const void* stash, const float* h_prev,
+                        int64_t hp_ld, int B, int H, void* dgi, void* dgh, int64_t dg_ld, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sequence level: whole teacher-forced loops, forward and BPTT, one host call each.
  * ---------------------------------------------------------------------------------------------- */
@@ -123,6 +138,7 @@ typedef struct {
   int32_t precision;                    /* recnet_precision */
   int32_t train;                        /* 1 = apply dropout (embedding, logits) */
   float embedding_scale, p_emb_drop, p_out_drop;
+  int32_t cell;                         /* recnet_cell: LSTM (i,f,g,o; state h,c) or GRU (r,z,n; state h) */
 } recnet_decoder_desc;
 
 typedef struct {                        /* fp32 master weights, reference state_dict layout */
@@ -139,12 +155,12 @@ int64_t recnet_decoder_workspace_bytes(const recnet_decoder_desc* d);
 int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats,
                        const int64_t* tokens_in, const int64_t* targets, const float* ce_weight, const uint64_t* rng,
                        void* workspace, int64_t workspace_bytes, float* hiddens, float* ce_out, void* stream);
-/* g_ce: device scalar dLoss/dCE (nullable = 1); g_hiddens [L,B,H] fp32 (nullable). grads: every field written
- * (overwritten, not accumulated). */
+/* g_ce: device scalar dLoss/dCE (nullable = 1); g_hiddens [L,B,H] fp32 (nullable); hiddens: the forward's fp32 output
+ * (read by the GRU backward, which keeps no separate cell state). grads: every field written (overwritten, not accumulated). */
 int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats,
                        const int64_t* tokens_in, const int64_t* targets, const float* ce_weight, const uint64_t* rng,
                        void* workspace, int64_t workspace_bytes, const float* g_ce, const float* g_hiddens,
-                       const recnet_decoder_tensors* grads, void* stream);
+                       const float* hiddens, const recnet_decoder_tensors* grads, void* stream);
 float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld);
 
 /* Greedy decoding (eval.greedy_search, eval.py:19-33): argmax feedback on device, zero host syncs.

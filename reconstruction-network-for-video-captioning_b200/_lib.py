@@ -41,7 +41,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 class decoder_desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "T", "E", "H", "A", "EMB", "V", "L", "precision", "train")] + \
-               [(n, C.c_float) for n in ("embedding_scale", "p_emb_drop", "p_out_drop")]
+               [(n, C.c_float) for n in ("embedding_scale", "p_emb_drop", "p_out_drop")] + [("cell", C.c_int32)]
+
+
+CELL_LSTM, CELL_GRU = 0, 1
 
 
 class decoder_tensors(C.Structure):
@@ -83,9 +86,11 @@ SIGNATURES = {
     "recnet_attn_bwd": (_i, [_i, _p, _i, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _f, _p, _u, _l, _p]),
     "recnet_lstm_cell_fwd": (_i, [_i, _p, _i, _l, _l, _p, _l, _p, _p, _p, _i, _i, _p, _p, _p, _l, _p, _l, _p, _l, _p]),
     "recnet_lstm_cell_bwd": (_i, [_i, _p, _l, _p, _p, _l, _p, _i, _l, _l, _i, _p, _i, _l, _l, _p, _i, _p, _p, _p, _i, _i, _p, _l, _p]),
+    "recnet_gru_cell_fwd": (_i, [_i, _p, _i, _l, _l, _p, _i, _l, _l, _p, _l, _p, _p, _p, _l, _i, _i, _p, _p, _l, _p, _l, _p]),
+    "recnet_gru_cell_bwd": (_i, [_i, _p, _l, _p, _l, _p, _i, _l, _l, _p, _i, _l, _l, _p, _i, _p, _p, _l, _i, _i, _p, _p, _l, _p]),
     "recnet_decoder_workspace_bytes": (_l, [C.POINTER(decoder_desc)]),
     "recnet_decoder_fwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p, _p]),
-    "recnet_decoder_bwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p,
+    "recnet_decoder_bwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p, _p,
                                 C.POINTER(decoder_tensors), _p]),
     "recnet_decoder_logits": (_p, [C.POINTER(decoder_desc), _p, C.POINTER(_l)]),
     "recnet_greedy_workspace_bytes": (_l, [C.POINTER(decoder_desc)]),

@@ -154,6 +154,32 @@ int recnet_lstm_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, cons
   return RECNET_ERR_UNSUPPORTED;
 }
 
+int recnet_gru_cell_fwd(int precision, const float* px, int n_px, int64_t px_stride, int64_t px_ld, const float* ph, int n_ph,
+                        int64_t ph_stride, int64_t ph_ld, const float* gx, int64_t gx_ld, const float* b_ih, const float* b_hh,
+                        const float* h_prev, int64_t hp_ld, int B, int H, void* stash, float* h_out, int64_t h_ld, void* h_op,
+                        int64_t hop_ld, void* stream) {
+  gru::FwdArgs a{};
+  a.Px = px; a.n_px = n_px; a.px_stride = px_stride; a.px_ld = px_ld; a.Ph = ph; a.n_ph = n_ph; a.ph_stride = ph_stride; a.ph_ld = ph_ld;
+  a.Gx = gx; a.gx_ld = gx_ld; a.b_ih = b_ih; a.b_hh = b_hh; a.h_prev = h_prev; a.hp_ld = hp_ld; a.B = B; a.H = H; a.stash = stash;
+  a.h_out = h_out; a.h_ld = h_ld; a.h_op = h_op; a.hop_ld = hop_ld;
+  if (precision == RECNET_PREC_FP32) return gru::launch_fwd<float, float>(a, ST(stream));
+  if (precision == RECNET_PREC_BF16) return gru::launch_fwd<bf16, bf16>(a, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
+int recnet_gru_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const float* dh_ext2, int64_t dh2_ld, const float* dhp,
+                        int n_p, int64_t p_stride, int64_t p_ld, const float* dqp, int n_q, int64_t q_stride, int64_t q_ld,
+                        float* carry, int first, const void* stash, const float* h_prev, int64_t hp_ld, int B, int H, void* dgi,
+                        void* dgh, int64_t dg_ld, void* stream) {
+  gru::BwdArgs a{};
+  a.dh_ext = dh_ext; a.dh_ld = dh_ld; a.dh_ext2 = dh_ext2; a.dh2_ld = dh2_ld; a.dHp = dhp; a.n_p = n_p; a.p_stride = p_stride; a.p_ld = p_ld;
+  a.dQp = dqp; a.n_q = n_q; a.q_stride = q_stride; a.q_ld = q_ld; a.carry = carry; a.first = first; a.stash = stash; a.h_prev = h_prev;
+  a.hp_ld = hp_ld; a.B = B; a.H = H; a.dGi = dgi; a.dGh = dgh; a.dg_ld = dg_ld;
+  if (precision == RECNET_PREC_FP32) return gru::launch_bwd<float, float>(a, ST(stream));
+  if (precision == RECNET_PREC_BF16) return gru::launch_bwd<bf16, bf16>(a, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
 // ---- decoder ---------------------------------------------------------------------------------------------------
 int64_t recnet_decoder_workspace_bytes(const recnet_decoder_desc* d) {
   if (!d) return RECNET_ERR_BAD_SHAPE;
@@ -175,15 +201,15 @@ int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
 }
 int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
                        const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
-                       int64_t workspace_bytes, const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors* grads,
-                       void* stream) {
+                       int64_t workspace_bytes, const float* g_ce, const float* g_hiddens, const float* hiddens,
+                       const recnet_decoder_tensors* grads, void* stream) {
   const long long* ti = reinterpret_cast<const long long*>(tokens_in);
   const long long* tg = reinterpret_cast<const long long*>(targets);
   const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
   if (d->precision == RECNET_PREC_FP32)
-    return dec::backward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+    return dec::backward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, hiddens, *grads, ST(stream));
   if (d->precision == RECNET_PREC_BF16)
-    return dec::backward<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+    return dec::backward<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, hiddens, *grads, ST(stream));
   return RECNET_ERR_UNSUPPORTED;
 }
 float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld) {

@@ -7,6 +7,7 @@
 //   * vocabulary projection batched over all steps (M = L*B), fused CE forward/backward over stacked logits
 //   * BPTT mirrors it; all weight gradients are batched GEMMs over the stashed operands after the loop.
 #pragma once
+#include "gru_cell.cuh"
 #include "mega.cuh"
 #include "runtime.cuh"
 
@@ -20,14 +21,16 @@ struct Ws {
   // geometry
   int EMBp, KX, Vp, Vld;
   int nch, Bc;                       // concurrent sample chains, max rows per chain
+  int G;                             // gates per unit: 4 (LSTM) or 3 (GRU)
   GemmPlan pl_wh, pl_gate, pl_dx, pl_dq;
+  GemmPlan pl_gx, pl_gh, pl_dxx, pl_dxh;   // GRU: x-part / h-part kept separate (n gate)
   // operand copies of the weights / inputs (rebuilt every forward: the optimiser changes the masters)
   T *Wemb, *Wrec, *U, *Wa, *Wout, *feats;
   // forward state kept for BPTT
-  float* Uv; T* Xe; float* Gx; T* X; float* WhP; float* Wh; float* e; float* P; T* gates; float* c;
+  float* Uv; T* Xe; float* Gx; T* X; float* WhP; float* Wh; float* e; float* P; float* P2; T* gates; float* c;
   float *logits, *lse, *row_loss;
   // backward scratch
-  T* dlogits; float* dHext; T* dG; float* dXp; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
+  T* dlogits; float* dHext; T* dG; T* dG2; float* dXp; float* dXp2; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
   float* dc; float* dXe; float* splitk;
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;     // loop-kernel phase table, grid-barrier counter, error flag
   size_t bytes;
@@ -48,6 +51,12 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.pl_gate = plan_gemm<T>(w.Bc, 4 * H, w.KX, tgt);
   w.pl_dx = plan_gemm<T>(w.Bc, w.KX, 4 * H, tgt);
   w.pl_dq = plan_gemm<T>(w.Bc, H, A, tgt);
+  w.G = d.cell == RECNET_CELL_GRU ? 3 : 4;
+  w.pl_gx = plan_gemm<T>(w.Bc, 3 * H, E, tgt);
+  w.pl_gh = plan_gemm<T>(w.Bc, 3 * H, H, tgt);
+  w.pl_dxx = plan_gemm<T>(w.Bc, E, 3 * H, tgt);
+  w.pl_dxh = plan_gemm<T>(w.Bc, H, 3 * H, tgt);
+  const bool gru_ = d.cell == RECNET_CELL_GRU;
   Bump m(base);
   w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);
   w.Wrec = m.take<T>((size_t)4 * H * w.KX);
@@ -62,7 +71,8 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.WhP = m.take<float>((size_t)w.nch * w.pl_wh.splits * w.Bc * A);
   w.Wh = m.take<float>((size_t)L * B * A);
   w.e = m.take<float>((size_t)L * B * Tn);
-  w.P = m.take<float>((size_t)w.nch * w.pl_gate.splits * w.Bc * 4 * H);
+  w.P = m.take<float>((size_t)w.nch * (gru_ ? w.pl_gx.splits : w.pl_gate.splits) * w.Bc * 4 * H);
+  w.P2 = m.take<float>(gru_ ? (size_t)w.nch * w.pl_gh.splits * w.Bc * 3 * H : 1);
   w.gates = m.take<T>((size_t)L * B * 4 * H);
   w.c = m.take<float>((size_t)(L + 1) * B * H);
   w.logits = m.take<float>((size_t)L * B * w.Vld);
@@ -71,7 +81,9 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.dlogits = m.take<T>((size_t)L * B * w.Vp);
   w.dHext = m.take<float>((size_t)L * B * H);
   w.dG = m.take<T>((size_t)L * B * 4 * H);
-  w.dXp = m.take<float>((size_t)w.nch * w.pl_dx.splits * w.Bc * w.KX);
+  w.dXp = m.take<float>((size_t)w.nch * (gru_ ? w.pl_dxx.splits : w.pl_dx.splits) * w.Bc * w.KX);
+  w.dXp2 = m.take<float>(gru_ ? (size_t)w.nch * w.pl_dxh.splits * w.Bc * H : 1);
+  w.dG2 = m.take<T>(gru_ ? (size_t)L * B * 3 * H : 1);
   w.dQp = m.take<float>((size_t)w.nch * w.pl_dq.splits * w.Bc * H);
   w.dWh = m.take<float>((size_t)L * B * A);
   w.dWh_op = m.take<T>((size_t)L * B * A);
@@ -91,6 +103,7 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
 
 static inline int check(const recnet_decoder_desc& d) {
   if (d.B < 1 || d.T < 1 || d.L < 1 || d.V < 3 || d.EMB < 1 || d.T > attn::MAX_T) return RECNET_ERR_BAD_SHAPE;
+  if (d.cell != RECNET_CELL_LSTM && d.cell != RECNET_CELL_GRU) return RECNET_ERR_UNSUPPORTED;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if (d.E % al || d.H % al || d.A % 4) return RECNET_ERR_ALIGNMENT;
   return 0;
@@ -101,9 +114,10 @@ template <typename T>
 static int prepare(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, Ws<T>& w, cudaStream_t st) {
   const int H = d.H, E = d.E, A = d.A, V = d.V, EMB = d.EMB;
   const long long ldih = EMB + E;
-  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, st));
-  RN_TRY(misc::cast_pad<T>(p.w_ih + EMB, ldih, w.Wrec, w.KX, 4 * H, E, E, st));
-  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wrec + E, w.KX, 4 * H, H, H, st));
+  const int GH = w.G * H;
+  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, GH, EMB, w.EMBp, st));
+  RN_TRY(misc::cast_pad<T>(p.w_ih + EMB, ldih, w.Wrec, w.KX, GH, E, E, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wrec + E, w.KX, GH, H, H, st));
   RN_TRY(misc::cast_pad<T>(p.attn_U, E, w.U, E, A, E, E, st));
   RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wa, H, A, H, H, st));
   RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
@@ -135,6 +149,22 @@ static int step(mega::Emitter<T>& em, const recnet_decoder_desc& d, const recnet
   fa.Wh_out = Wh_t ? Wh_t + (size_t)b0 * A : nullptr; fa.e_out = e_t ? e_t + (size_t)b0 * Tn : nullptr;
   fa.ctx_out = xr; fa.ctx_ld = w.KX; fa.p_drop = 0.f;
   RN_TRY(em.attn_fwd(fa));
+  if (d.cell == RECNET_CELL_GRU) {
+    // x-part: ctx_t @ W_ctx^T (K = E) ; h-part: h_{t-1} @ W_hh^T (K = H): same operand rows, same weight copy, two column ranges
+    float* Px = w.P + (size_t)ch * w.pl_gx.splits * w.Bc * 3 * H;
+    float* Ph = w.P2 + (size_t)ch * w.pl_gh.splits * w.Bc * 3 * H;
+    RN_TRY(em.gemm_partials(xr, w.KX, 0, w.Wrec, w.KX, 0, Px, nb, 3 * H, E, w.pl_gx));
+    if (t > 0) RN_TRY(em.gemm_partials(xr + E, w.KX, 0, w.Wrec + E, w.KX, 0, Ph, nb, 3 * H, H, w.pl_gh));
+    gru::FwdArgs ga{};
+    ga.Px = Px; ga.n_px = w.pl_gx.splits; ga.px_stride = (long long)nb * 3 * H; ga.px_ld = 3 * H;
+    ga.Ph = t > 0 ? Ph : nullptr; ga.n_ph = t > 0 ? w.pl_gh.splits : 0; ga.ph_stride = (long long)nb * 3 * H; ga.ph_ld = 3 * H;
+    ga.Gx = gx_t + (size_t)b0 * 3 * H; ga.gx_ld = 3 * H; ga.b_ih = nullptr; ga.b_hh = p.b_hh;
+    ga.h_prev = c_prev + (size_t)b0 * H; ga.hp_ld = H; ga.B = nb; ga.H = H;
+    ga.stash = gates_t ? gates_t + (size_t)b0 * 4 * H : nullptr;
+    ga.h_out = h_out + (size_t)b0 * H; ga.h_ld = H;
+    ga.h_op = x_next + (size_t)b0 * w.KX + E; ga.hop_ld = w.KX;
+    return gru::launch_fwd<T, T>(ga, em.st);
+  }
   RN_TRY(em.gemm_partials(xr, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * H, w.KX, w.pl_gate));
   cell::FwdArgs ca{};
   ca.P = P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)nb * 4 * H; ca.p_ld = 4 * H;
@@ -162,7 +192,9 @@ static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
   misc::embed_gather_kernel<T><<<L * B, 128, 0, st>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, d.EMB, w.EMBp, V,
                                                       d.embedding_scale, p_emb, rng, SITE_EMB);
   RN_LAUNCH_OK();
-  RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk, st));
+  const int GH = w.G * H;
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, GH, p.b_ih, L * B, GH, w.EMBp, 0, w.splitk, st));
   // initial state: h_{-1} = 0 (operand slot of X[0]), c_{-1} = 0
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
@@ -172,16 +204,18 @@ static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   {
-    mega::Emitter<T> em0(w.nch == 1, st, (size_t)E + Tn + 8 * attn::BWD_THREADS + 2 * A);
+    mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)E + Tn + 8 * attn::BWD_THREADS + 2 * A);
     for (int t = 0; t < L; ++t) {
       T* x_t = w.X + (size_t)t * B * w.KX;
       for (int ch = 0; ch < w.nch; ++ch) {
         int b0, nb;
         chain_rows(B, w.nch, ch, &b0, &nb);
         mega::Emitter<T> emc(false, w.nch > 1 ? cs.s[ch] : st);
-        RN_TRY(step<T>(w.nch == 1 ? em0 : emc, d, p, w, t, ch, b0, nb, w.Gx + (size_t)t * B * 4 * H, x_t, x_t + (size_t)B * w.KX,
+        // LSTM: c_{t-1} -> c_t live in w.c; GRU: the fp32 state is h itself (previous row of `hiddens`, zeros = w.c at t = 0)
+        const float* s_prev = is_gru ? (t == 0 ? w.c : hiddens + (size_t)(t - 1) * B * H) : w.c + (size_t)t * B * H;
+        RN_TRY(step<T>(w.nch == 1 ? em0 : emc, d, p, w, t, ch, b0, nb, w.Gx + (size_t)t * B * GH, x_t, x_t + (size_t)B * w.KX,
                        w.Wh + (size_t)t * B * A, w.e + (size_t)t * B * Tn, w.gates + (size_t)t * B * 4 * H,
-                       w.c + (size_t)t * B * H, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H));
+                       s_prev, w.c + (size_t)(t + 1) * B * H, hiddens + (size_t)t * B * H));
       }
     }
     RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 1));
@@ -204,7 +238,8 @@ static int forward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p
 template <typename T>
 static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
                     const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
-                    const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors& g, cudaStream_t st) {
+                    const float* g_ce, const float* g_hiddens, const float* hiddens_fp32, const recnet_decoder_tensors& g,
+                    cudaStream_t st) {
   RN_TRY(check(d));
   Ws<T> w = plan<T>(d, ws);
   if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
@@ -225,7 +260,9 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
   // ---- BPTT: the same sample chains, each with private split-K scratch ------------------------------------------
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
-  mega::Emitter<T> em0(w.nch == 1, st, (size_t)E + Tn + 8 * attn::BWD_THREADS + 2 * A);
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  const int GH = w.G * H;
+  mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)E + Tn + 8 * attn::BWD_THREADS + 2 * A);
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
@@ -236,6 +273,33 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
       float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * w.KX;
       float* dQp = w.dQp + (size_t)ch * w.pl_dq.splits * w.Bc * H;
       const size_t r = (size_t)t * B + b0;           // first (t, b) row of this chain
+      if (is_gru) {
+        float* dXx = w.dXp + (size_t)ch * w.pl_dxx.splits * w.Bc * w.KX;      // x-part dgrad partials [splits][nb, E]
+        float* dXh = w.dXp2 + (size_t)ch * w.pl_dxh.splits * w.Bc * H;         // h-part dgrad partials [splits][nb, H]
+        gru::BwdArgs gb{};
+        gb.dh_ext = w.dHext + r * H; gb.dh_ld = H;
+        gb.dh_ext2 = g_hiddens ? g_hiddens + r * H : nullptr; gb.dh2_ld = H;
+        gb.dHp = last ? nullptr : dXh; gb.n_p = w.pl_dxh.splits; gb.p_stride = (long long)nb * H; gb.p_ld = H;
+        gb.dQp = last ? nullptr : dQp; gb.n_q = w.pl_dq.splits; gb.q_stride = (long long)nb * H; gb.q_ld = H;
+        gb.carry = w.dc + (size_t)b0 * H; gb.first = last ? 1 : 0;
+        gb.stash = w.gates + r * 4 * H;
+        gb.h_prev = t == 0 ? w.c + (size_t)b0 * H : hiddens_fp32 + ((size_t)(t - 1) * B + b0) * H; gb.hp_ld = H;
+        gb.B = nb; gb.H = H; gb.dGi = w.dG + r * 3 * H; gb.dGh = w.dG2 + r * 3 * H; gb.dg_ld = 3 * H;
+        RN_TRY((gru::launch_bwd<T, T>(gb, em.st)));
+        RN_TRY(em.gemm_partials(w.dG + r * 3 * H, 3 * H, 0, w.Wrec, w.KX, 1, dXx, nb, E, 3 * H, w.pl_dxx));           // dctx = dGi @ W_ctx
+        if (t > 0) RN_TRY(em.gemm_partials(w.dG2 + r * 3 * H, 3 * H, 0, w.Wrec + E, w.KX, 1, dXh, nb, H, 3 * H, w.pl_dxh));  // dh += dGh @ W_hh
+        attn::BwdArgs ab{};
+        ab.dXp = dXx; ab.n_p = w.pl_dxx.splits; ab.p_stride = (long long)nb * E; ab.p_ld = E;
+        ab.V = w.feats + (size_t)b0 * Tn * E; ab.v_bs = (long long)Tn * E; ab.v_ts = E;
+        ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * Tn * A; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
+        ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
+        ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * Tn * A;
+        ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+        ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
+        RN_TRY(em.attn_bwd(ab));
+        if (t > 0) RN_TRY(em.gemm_partials(w.dWh_op + r * A, A, 0, w.Wa, H, 1, dQp, nb, H, A, w.pl_dq));
+        continue;
+      }
       cell::BwdArgs cb{};
       cb.dh_ext = w.dHext + r * H; cb.dh_ld = H; cb.dh_scale = nullptr;
       cb.dh_ext2 = g_hiddens ? g_hiddens + r * H : nullptr; cb.dh2_ld = H;
@@ -265,12 +329,15 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
   // ---- batched weight gradients over the stashed operands ----------------------------------------------------
   const long long ldih = EMB + E;
-  RN_TRY(misc::colsum<T>(w.dG, 4 * H, LB, 4 * H, g.b_ih, 0, w.splitk, st));
-  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.X, w.KX, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, LB, 0, w.splitk, st));      // dW_ctx
-  RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.X + E, w.KX, 1, g.w_hh, H, nullptr, 4 * H, H, LB, 0, w.splitk, st));           // dW_hh
-  RN_TRY(gemm_full<T>(w.dG, 4 * H, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk, st));        // dW_emb
-  RN_TRY(gemm_full<T>(w.dG, 4 * H, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk, st));     // dXe
+  // LSTM: one gate-gradient matrix dG [LB,4H]; GRU: dGi (input side) in w.dG and dGh (hidden side, n column scaled by r) in w.dG2
+  const T* dGh = is_gru ? w.dG2 : w.dG;
+  RN_TRY(misc::colsum<T>(w.dG, GH, LB, GH, g.b_ih, 0, w.splitk, st));
+  if (is_gru) { RN_TRY(misc::colsum<T>(dGh, GH, LB, GH, g.b_hh, 0, w.splitk, st)); }
+  else RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)GH * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(gemm_full<T>(w.dG, GH, 1, w.X, w.KX, 1, g.w_ih + EMB, ldih, nullptr, GH, E, LB, 0, w.splitk, st));            // dW_ctx
+  RN_TRY(gemm_full<T>(dGh, GH, 1, w.X + E, w.KX, 1, g.w_hh, H, nullptr, GH, H, LB, 0, w.splitk, st));                   // dW_hh
+  RN_TRY(gemm_full<T>(w.dG, GH, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, GH, EMB, LB, 0, w.splitk, st));              // dW_emb
+  RN_TRY(gemm_full<T>(w.dG, GH, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, GH, 0, w.splitk, st));           // dXe
   RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), st));
   misc::embed_scatter_kernel<<<LB, 128, 0, st>>>(g.embedding, tokens_in, w.dXe, w.EMBp, LB, EMB, V, d.embedding_scale, p_emb, rng,
                                                  SITE_EMB);
@@ -370,9 +437,11 @@ static int greedy(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p
     misc::embed_gather_kernel<T><<<B, 128, 0, st>>>(p.embedding, g.tok, w.Xe, w.EMBp, B, d.EMB, w.EMBp, V, d.embedding_scale, 0.f,
                                                     nullptr, SITE_EMB);
     RN_LAUNCH_OK();
-    RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, B, 4 * H, w.EMBp, 0, w.splitk, st));
+    RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, w.G * H, p.b_ih, B, w.G * H, w.EMBp, 0, w.splitk, st));
     mega::Emitter<T> em(false, st);
-    RN_TRY(step<T>(em, d, p, w, t, 0, 0, B, w.Gx, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n, g.h_scratch));
+    // GRU keeps its fp32 state h in the c ping-pong rows (h_prev = c_p, h' -> c_n)
+    RN_TRY(step<T>(em, d, p, w, t, 0, 0, B, w.Gx, x_t, x_n, nullptr, nullptr, nullptr, c_p, c_n,
+                   d.cell == RECNET_CELL_GRU ? c_n : g.h_scratch));
     RN_TRY(gemm_full<T>(x_n + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, B, V, H, 0, w.splitk, st));
     argmax_feedback_kernel<<<B, 256, 0, st>>>(w.logits, w.Vld, V, ids_out + (size_t)t * B, g.tok, g.nonpad + t);
     RN_LAUNCH_OK();

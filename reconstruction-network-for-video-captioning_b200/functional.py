@@ -138,7 +138,7 @@ def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
     d = L.decoder_desc(B=B, T=T, E=E, H=meta["H"], A=meta["A"], EMB=meta["EMB"], V=meta["V"], L=Lsteps,
                        precision=meta["precision"], train=int(meta["train"]),
                        embedding_scale=float(meta["embedding_scale"]), p_emb_drop=float(meta["p_emb"]),
-                       p_out_drop=float(meta["p_out"]))
+                       p_out_drop=float(meta["p_out"]), cell=int(meta.get("cell", L.CELL_LSTM)))
     nbytes = lib.recnet_decoder_workspace_bytes(C.byref(d))
     if nbytes < 0:
         L.check(int(nbytes), "recnet_decoder_workspace_bytes")
@@ -170,20 +170,20 @@ class DecoderSequenceFn(torch.autograd.Function):
         reg, sumsq = _norms_fwd(saved[5:])
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(*saved, ws, sumsq)
+        ctx.save_for_backward(*saved, ws, sumsq, hiddens)
         return ce, hiddens, reg
 
     @staticmethod
     def backward(ctx, g_ce, g_hiddens, g_reg):
         lib = L.lib()
-        feats, tokens_in, targets, ce_weight, rng, *params, ws, sumsq = ctx.saved_tensors
+        feats, tokens_in, targets, ce_weight, rng, *params, ws, sumsq, hiddens = ctx.saved_tensors
         flat, grads, gptrs = _flat_grads(params)
         g_ce = _scalar(g_ce, feats.device)
         g_hid = g_hiddens.contiguous() if g_hiddens is not None else None
         w, g = _pack(L.decoder_tensors, params), _pack(L.decoder_tensors, grads)
         L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
                                        ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
-                                       _ptr(g_hid), C.byref(g), _stream()), "recnet_decoder_bwd")
+                                       _ptr(g_hid), hiddens.data_ptr(), C.byref(g), _stream()), "recnet_decoder_bwd")
         if g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
         return (None, None, None, None, None, None, *grads)

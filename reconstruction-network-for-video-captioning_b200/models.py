@@ -8,8 +8,8 @@ reference checkpoint loads with ``load_state_dict``.  The arithmetic runs in lib
 * ``forward_sequence`` (whole teacher-forced loop, what train.forward_* use) -> one C call (``functional.py``)
 
 One extra constructor kwarg, ``precision`` ("bf16" | "fp32"); everything else is positional-compatible.
-Only model_name == "LSTM" with n_layers == 1 is built so far; anything else raises NotImplementedError
-(never a silent fallback).
+Built: Decoder with LSTM or GRU cells (GRU is the reference's default, config.py:31), reconstructors with LSTM cells,
+n_layers == 1.  Anything else raises NotImplementedError (never a silent fallback).
 """
 from __future__ import annotations
 
@@ -47,8 +47,8 @@ class _RngMixin:
         self._rng[1] = 0
 
 
-def _require_supported(model_name: str, n_layers: int, what: str):
-    if model_name != "LSTM":
+def _require_supported(model_name: str, n_layers: int, what: str, gru_ok: bool = False):
+    if model_name != "LSTM" and not gru_ok:
         raise NotImplementedError(f"{what}: model_name={model_name!r} (GRU) is not built yet in recnet_b200; use 'LSTM'")
     if n_layers != 1:
         raise NotImplementedError(f"{what}: n_layers={n_layers} is not built yet in recnet_b200; use 1")
@@ -93,32 +93,33 @@ class Decoder(nn.Module, _RngMixin):
     def _meta(self):
         return dict(H=self.hidden_size, A=self.attn_size, EMB=self.embedding_size, V=self.output_size,
                     precision=_precision_id(self.precision), train=self.training, embedding_scale=self.embedding_scale,
-                    p_emb=self.embedding_dropout_p, p_out=self.out_dropout_p)
+                    p_emb=self.embedding_dropout_p, p_out=self.out_dropout_p,
+                    cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)       # decoder.py:32-35
 
     # ---- whole teacher-forced loop: one C call ----
     def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs):
         """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,B,H), reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "Decoder")
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
         return Fn.DecoderSequenceFn.apply(self._meta(), encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(),
                                           *self._params())
 
     @torch.no_grad()
     def teacher_forced_logits(self, tokens_in, encoder_outputs):
-        _require_supported(self.model_name, self.n_layers, "Decoder")
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
         return Fn.decoder_teacher_forced_logits(self._meta(), encoder_outputs, tokens_in, self._rng, self._params())
 
     @torch.no_grad()
     def greedy(self, encoder_outputs, max_steps):
         """eval.greedy_search (eval.py:19-33) on device: returns (ids (n,B) int64 on device, n)."""
         import ctypes as C
-        _require_supported(self.model_name, self.n_layers, "Decoder")
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
         lib = L.lib()
         feats = Fn._f32c(encoder_outputs, "encoder_outputs")
         B, T, E = feats.shape
         meta = self._meta()
         d = L.decoder_desc(B=B, T=T, E=E, H=meta["H"], A=meta["A"], EMB=meta["EMB"], V=meta["V"], L=1,
                            precision=meta["precision"], train=0, embedding_scale=float(meta["embedding_scale"]),
-                           p_emb_drop=0.0, p_out_drop=0.0)
+                           p_emb_drop=0.0, p_out_drop=0.0, cell=meta["cell"])
         nbytes = lib.recnet_greedy_workspace_bytes(C.byref(d))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
         ids = torch.empty(max_steps, B, dtype=torch.int64, device=feats.device)
@@ -131,10 +132,11 @@ class Decoder(nn.Module, _RngMixin):
 
     # ---- single timestep (reference API) ----
     def forward(self, input, hidden, encoder_outputs):
-        """input (1,B) int64; hidden ((1,B,H),(1,B,H)); encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""
-        _require_supported(self.model_name, self.n_layers, "Decoder")
+        """input (1,B) int64; hidden ((1,B,H),(1,B,H)) [LSTM] or (1,B,H) [GRU]; encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
         p = _precision_id(self.precision)
-        h, c = hidden[0][-1], hidden[1][-1]
+        is_lstm = self.model_name == "LSTM"
+        h, c = (hidden[0][-1], hidden[1][-1]) if is_lstm else (hidden[-1], None)
         emb = torch.nn.functional.embedding(input[0], self.embedding.weight) * self.embedding_scale      # decoder.py:46-47
         emb = torch.nn.functional.dropout(emb, self.embedding_dropout_p, self.training)                   # decoder.py:48
         # U.v is time-invariant (the reference recomputes it every step, decoder.py:54).  Without autograd (greedy / beam
@@ -151,11 +153,14 @@ class Decoder(nn.Module, _RngMixin):
         Wh = ops.linear(h, self.attn_W.weight, None, p)                                                   # decoder.py:51
         ctx = ops.additive_attention(Wh, Uv, self.attn_b, self.attn_w.weight, encoder_outputs, p)          # decoder.py:55-61
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        pre = ops.linear(torch.cat((emb, ctx), dim=1), w_ih, b_ih, p) + ops.linear(h, w_hh, b_hh, p)       # decoder.py:64-66
-        h2, c2 = ops.lstm_cell(pre, c, p)
+        gi, gh = ops.linear(torch.cat((emb, ctx), dim=1), w_ih, b_ih, p), ops.linear(h, w_hh, b_hh, p)     # decoder.py:64-66
+        if is_lstm:
+            h2, c2 = ops.lstm_cell(gi + gh, c, p)
+        else:
+            h2 = ops.gru_cell(gi, gh, h, p)
         logits = ops.linear(h2, self.out.weight, self.out.bias, p)                                        # decoder.py:68
         logits = torch.nn.functional.dropout(logits, self.out_dropout_p, self.training)                    # decoder.py:69
-        return logits, (h2.unsqueeze(0), c2.unsqueeze(0))
+        return logits, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
 
 
 class GlobalReconstructor(nn.Module, _RngMixin):

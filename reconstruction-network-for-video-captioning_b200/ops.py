@@ -157,3 +157,41 @@ class LSTMCellFn(torch.autograd.Function):
 
 def lstm_cell(pre, c_prev, precision):
     return LSTMCellFn.apply(pre, c_prev, precision)
+
+
+class GRUCellFn(torch.autograd.Function):
+    """(gi (B,3H) = x W_ih^T + b_ih, gh (B,3H) = h W_hh^T + b_hh, h (B,H)) -> h'   gate order r,z,n (nn.GRU)."""
+
+    @staticmethod
+    def forward(ctx, gi, gh, h_prev, precision):
+        lib = L.lib()
+        B, H3 = gi.shape
+        H = H3 // 3
+        gi, gh, h_prev = gi.contiguous(), gh.contiguous(), h_prev.contiguous()
+        stash = torch.empty(B, 4 * H, dtype=_op_dtype(precision), device=gi.device)
+        h = torch.empty(B, H, dtype=torch.float32, device=gi.device)
+        L.check(lib.recnet_gru_cell_fwd(precision, gi.data_ptr(), 1, 0, H3, gh.data_ptr(), 1, 0, H3, None, 0, None, None,
+                                        h_prev.data_ptr(), H, B, H, stash.data_ptr(), h.data_ptr(), H, None, 0, _stream()),
+                "recnet_gru_cell_fwd")
+        ctx.precision = precision
+        ctx.save_for_backward(stash, h_prev)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh_out):
+        lib = L.lib()
+        stash, h_prev = ctx.saved_tensors
+        B, H = h_prev.shape
+        g = gh_out.contiguous().float()
+        carry = torch.empty(B, H, dtype=torch.float32, device=g.device)
+        dt = _op_dtype(ctx.precision)
+        dgi = torch.empty(B, 3 * H, dtype=dt, device=g.device)
+        dgh = torch.empty(B, 3 * H, dtype=dt, device=g.device)
+        L.check(lib.recnet_gru_cell_bwd(ctx.precision, g.data_ptr(), H, None, 0, None, 0, 0, 0, None, 0, 0, 0, carry.data_ptr(), 1,
+                                        stash.data_ptr(), h_prev.data_ptr(), H, B, H, dgi.data_ptr(), dgh.data_ptr(), 3 * H,
+                                        _stream()), "recnet_gru_cell_bwd")
+        return dgi.float(), dgh.float(), carry, None
+
+
+def gru_cell(gi, gh, h_prev, precision):
+    return GRUCellFn.apply(gi, gh, h_prev, precision)

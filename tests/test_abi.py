@@ -48,7 +48,7 @@ def test_struct_layouts_match_header_field_order():
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = re.findall(r"\*(\w+)", body)
         assert tuple(fields) == struct.FIELDS
-    assert ctypes.sizeof(L.decoder_desc) == 10 * 4 + 3 * 4
+    assert ctypes.sizeof(L.decoder_desc) == 10 * 4 + 3 * 4 + 4
     assert ctypes.sizeof(L.local_desc) == 8 * 4 + 4
     assert ctypes.sizeof(L.global_desc) == 7 * 4 + 2 * 4
 

@@ -135,6 +135,30 @@ def test_lstm_cell_kernel_fwd_bwd(prec, tol, B, H):
 GOLDEN = [("tiny_lstm", "fp32"), ("tiny_lstm_ragged", "fp32"), ("small_lstm", "fp32"), ("tiny_lstm", "bf16"), ("small_lstm", "bf16")]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gru_decoder_matches_reference_golden(precision):
+    """The reference's DEFAULT decoder cell (config.py:31 decoder_model = "GRU"): loss, hiddens, gradients, greedy ids and
+    the per-step Decoder.forward against the reference-generated fixture."""
+    g = load_golden("tiny_gru")
+    m = dict(g["meta"], rec_model="LSTM")
+    tol = TOL[precision]
+    dec, _ = build(m, precision, "none", g["dec"], {})
+    feats, targets = g["feats"].float().to(dev()), g["targets"].to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, feats, targets, targets > 0, 1.0)
+    assert rel(dloss, torch.tensor(g["dec_loss"])) < tol and rel(hiddens, g["hiddens"]) < tol
+    dloss.backward()
+    for k, ref in g["grads"]["none"].items():
+        assert rel(dict(dec["model"].named_parameters())[k[4:]].grad, ref) < tol, k
+    B, H = feats.shape[0], m["H"]
+    tok = torch.full((1, B), 1, dtype=torch.long, device=dev())
+    with torch.no_grad():
+        logits, h1 = dec["model"](tok, torch.zeros(1, B, H, device=dev()), feats)      # GRU hidden is a single tensor
+    assert h1.shape == (1, B, H) and rel(logits, g["step0_logits"]) < tol
+    if precision == "fp32":
+        ids, n = dec["model"].greedy(feats, m["cap_len"] + 1)
+        assert torch.equal(ids[: int(n)].cpu(), g["greedy_ids"])
+
+
 @pytest.mark.parametrize("kind", ["none", "global", "local"])
 @pytest.mark.parametrize("name,precision", GOLDEN)
 def test_losses_hiddens_grads_match_reference_golden(name, precision, kind):

@@ -190,6 +190,8 @@ __device__ __forceinline__ void attn_fwd_body(const FwdArgs& a, int bx, int b, f
 template <typename TV, typename TO>
 __global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
   extern __shared__ float sm[];
+  pdl_launch_next();
+  pdl_wait();
   attn_fwd_body<TV, TO>(a, blockIdx.x, blockIdx.y, sm, threadIdx.x, 0);
 }
 
@@ -376,6 +378,8 @@ __device__ __forceinline__ void attn_bwd_body(const BwdArgs& a, int b, float* sm
 template <typename TV, typename TO>
 __global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
   extern __shared__ float sm[];
+  pdl_launch_next();
+  pdl_wait();
   attn_bwd_body<TV, TO>(a, blockIdx.x, sm, threadIdx.x, 0);
 }
 
@@ -424,7 +428,7 @@ static int launch_fwd(FwdArgs a, cudaStream_t st) {
   dim3 grid(slices, a.B);
   const size_t smem = fwd_smem_bytes(a);
   ProfScope prof(KC_ATTN_FWD, a.B, a.Tn, a.D, st);
-  attn_fwd_kernel<TV, TO><<<grid, FWD_THREADS, smem, st>>>(a);
+  RN_CUDA_OK(launch_pdl(attn_fwd_kernel<TV, TO>, grid, dim3(FWD_THREADS), smem, st, a));
   RN_LAUNCH_OK();
   return 0;
 }
@@ -436,7 +440,7 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   if (a.D % VN || a.v_ts % VN || a.v_bs % VN) return RECNET_ERR_ALIGNMENT;
   const size_t smem = (size_t)(a.D + a.Tn + 2 * BWD_THREADS) * sizeof(float);
   ProfScope prof(KC_ATTN_BWD, a.B, a.Tn, a.D, st);
-  attn_bwd_kernel<TV, TO><<<a.B, BWD_THREADS, smem, st>>>(a);
+  RN_CUDA_OK(launch_pdl(attn_bwd_kernel<TV, TO>, dim3(a.B), dim3(BWD_THREADS), smem, st, a));
   RN_LAUNCH_OK();
   return 0;
 }

@@ -126,7 +126,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb0 = blockIdx.z * kb_per_split;
   const int nkb = max(0, min(nkb_total, kb0 + kb_per_split) - kb0);
 
+  pdl_launch_next();
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();          // everything above overlapped the previous kernel's tail; operands / outputs are touched only below
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -291,7 +295,7 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const EpiArg
   }
   dim3 grid(rn_cdiv(N, BN), rn_cdiv(M, BM), splits);
   ProfScope prof(KC_GEMM_TC, M, N, K, st);
-  kern<<<grid, THREADS, L::TOTAL, st>>>(ma, mb, ep, M, N, K, kb_per);
+  RN_CUDA_OK(launch_pdl(kern, grid, dim3(THREADS), (size_t)L::TOTAL, st, ma, mb, ep, M, N, K, kb_per));
   RN_LAUNCH_OK();
   return 0;
 }

@@ -58,6 +58,8 @@ __device__ __forceinline__ void gru_cell_fwd_body(const FwdArgs& a, int bx, int 
 }
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(THREADS) gru_cell_fwd_kernel(FwdArgs a) {
+  pdl_launch_next();
+  pdl_wait();
   gru_cell_fwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
@@ -107,20 +109,22 @@ __device__ __forceinline__ void gru_cell_bwd_body(const BwdArgs& a, int bx, int 
 }
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(THREADS) gru_cell_bwd_kernel(BwdArgs a) {
+  pdl_launch_next();
+  pdl_wait();
   gru_cell_bwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 template <typename TS, typename TO>
 static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   ProfScope prof(KC_CELL_FWD, a.B, a.H, a.n_px + a.n_ph, st);
-  gru_cell_fwd_kernel<TS, TO><<<dim3(rn_cdiv(a.H, THREADS), a.B), THREADS, 0, st>>>(a);
+  RN_CUDA_OK(launch_pdl(gru_cell_fwd_kernel<TS, TO>, dim3(rn_cdiv(a.H, THREADS), a.B), dim3(THREADS), 0, st, a));
   RN_LAUNCH_OK();
   return 0;
 }
 template <typename TS, typename TO>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   ProfScope prof(KC_CELL_BWD, a.B, a.H, (a.dHp ? a.n_p : 0) + (a.dQp ? a.n_q : 0), st);
-  gru_cell_bwd_kernel<TS, TO><<<dim3(rn_cdiv(a.H, THREADS), a.B), THREADS, 0, st>>>(a);
+  RN_CUDA_OK(launch_pdl(gru_cell_bwd_kernel<TS, TO>, dim3(rn_cdiv(a.H, THREADS), a.B), dim3(THREADS), 0, st, a));
   RN_LAUNCH_OK();
   return 0;
 }

@@ -401,3 +401,45 @@ def test_whole_train_step_runs_under_cuda_graph_and_updates_weights():
         losses.append(float(out))
     assert all(x == x for x in losses) and len(set(losses)) > 1            # fresh dropout masks every replay
     assert not torch.equal(w0, dec["model"].out.weight)                     # Adam step inside the graph moved the weights
+
+
+class _Vocab:
+    def __init__(self, n):
+        self.n_vocabs = n
+        self.word2idx = {'<PAD>': 0, '<SOS>': 1, '<EOS>': 2}
+
+
+@pytest.mark.parametrize("name", ["tiny_lstm", "tiny_gru"])
+def test_beam_search_matches_oracle_restatement(name):
+    """eval.beam_search (CUDA-only in the reference, eval.py:39,57) against the oracle's CPU restatement of the same
+    algorithm; fp32 build, beam 3 and 5: identical top-1 sequences."""
+    g = load_golden(name)
+    m = dict(g["meta"], rec_model="LSTM")
+    P = {k: v.float() for k, v in g["dec"].items()}
+    P["out.bias"] = P["out.bias"].clone()
+    P["out.bias"][2] += 1.5                      # make <EOS> likely enough that the length-normalisation path is exercised
+    dec, _ = build(m, "fp32", "none", P, {})
+    feats = g["feats"].float().to(dev())
+    B, H = feats.shape[0], m["H"]
+    T.C.batch_size = B
+    for width in (3, 5):
+        ref = O.beam_search(P, g["feats"].float(), width, model_name=m["dec_model"], n_layers=1, caption_max_len=m["cap_len"])
+        tok = torch.full((1, B), 1, dtype=torch.long, device=dev())
+        z = torch.zeros(1, B, H, device=dev())
+        hid = (z, z.clone()) if m["dec_model"] == "LSTM" else z
+        got = E.beam_search(T.C, width, _Vocab(m["V"]), dec["model"], tok, hid, feats)
+        assert got == ref, (width, got, ref)
+
+
+def test_checkpoint_roundtrip_reference_layout(tmp_path):
+    g = load_golden("tiny_lstm")
+    dec, rec = build(g["meta"], "fp32", "local", g["dec"], g["local"])
+    path = str(tmp_path / "5_checkpoint.tar")
+    E.save_checkpoint(path, 5, dec, rec, loss=torch.tensor(1.0), config=None)
+    blob = torch.load(path, weights_only=False)
+    assert set(blob) == {'iteration', 'dec', 'rec', 'dec_opt', 'rec_opt', 'loss', 'config'}       # train.py:404-412
+    dec2, rec2 = build(g["meta"], "fp32", "local", {k: torch.zeros_like(v) for k, v in g["dec"].items()},
+                       {k: torch.zeros_like(v) for k, v in g["local"].items()})
+    assert E.load_checkpoint(path, dec2, rec2) == 5
+    for k, v in dec["model"].state_dict().items():
+        assert torch.equal(v, dec2["model"].state_dict()[k])

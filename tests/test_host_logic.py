@@ -137,3 +137,33 @@ def test_grad_allreducer_two_ranks_gloo():
         out = mgr.dict()
         mp.spawn(_gloo_worker, args=(world, 29533, out), nprocs=world, join=True)
         assert all(out[r] for r in range(world)), dict(out)
+
+
+def test_beam_search_bookkeeping_matches_oracle_on_cpu():
+    """recnet_b200.eval.beam_search's batched bookkeeping (top-k, state gather, <EOS>-length tracking) against the
+    oracle's loop restatement of eval.py:36-120, using the oracle's decoder step as the decoder callable (CPU)."""
+    from recnet_b200 import eval as E
+
+    for name in ("tiny_lstm", "tiny_gru"):
+        g = load_golden(name, dtype=torch.float32)
+        m = g["meta"]
+        P = dict(g["dec"])
+        P["out.bias"] = P["out.bias"].clone()
+        P["out.bias"][2] += 1.5
+
+        class Cfg:
+            caption_max_len, decoder_model = m["cap_len"], m["dec_model"]
+
+        class Vocab:
+            n_vocabs, word2idx = m["V"], {'<PAD>': 0, '<SOS>': 1, '<EOS>': 2}
+
+        def decoder(tok, hid, feats):
+            return O.decoder_step(P, tok, hid, feats, model_name=m["dec_model"], n_layers=1)
+
+        B = g["feats"].shape[0]
+        tok = torch.full((1, B), 1, dtype=torch.long)
+        hid = O.zero_hidden(m["dec_model"], 1, B, m["H"], g["feats"])
+        for width in (2, 5):
+            ref = O.beam_search(P, g["feats"], width, model_name=m["dec_model"], n_layers=1, caption_max_len=m["cap_len"])
+            got = E.beam_search(Cfg, width, Vocab, decoder, tok, hid, g["feats"])
+            assert got == ref, (name, width)

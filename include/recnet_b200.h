@@ -175,6 +175,7 @@ typedef struct {
   int32_t B, S, R, H, A, L;             /* S = encoder_output_len steps, R = hidden (= feature dim), H = decoder hidden */
   int32_t precision, train;
   float p_drop;
+  int32_t cell;                         /* recnet_cell of the reconstructor RNN */
 } recnet_local_desc;
 typedef struct {
   float *attn_W, *attn_U, *attn_b, *attn_w, *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;
@@ -193,6 +194,7 @@ typedef struct {
   int32_t B, L, R, H, T;                /* T = frames of feats (mean target), L = decoder steps */
   int32_t precision, train;
   float p_drop, caption_max_len;
+  int32_t cell;                         /* recnet_cell of the reconstructor RNN */
 } recnet_global_desc;
 typedef struct {
   float *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;

@@ -6,6 +6,7 @@
 // Same restructuring as the decoder: U.hiddens hoisted, [x ; h] K-concatenated gate GEMM per step, output
 // projection and all weight gradients batched over time.  One decoder layer (the reference default).
 #pragma once
+#include "gru_cell.cuh"
 #include "mega.cuh"
 #include "runtime.cuh"
 
@@ -17,11 +18,12 @@ enum : unsigned { SITE_LOCAL_X = 3, SITE_GLOBAL_MP = 4 };
 // ================================================ local =========================================================
 template <typename T>
 struct LocalWs {
-  int KX, nch, Bc;
+  int KX, nch, Bc, G;
   GemmPlan pl_wh, pl_gate, pl_dx, pl_dq;
+  GemmPlan pl_gx, pl_gh, pl_dxx, pl_dxh;      // GRU: input / hidden sides kept separate
   T *Wrec, *U, *Wa, *Wout, *Hd;
-  float* Uv; T* X; float* WhP; float* Wh; float* beta; float* P; T* gates; float* c; float* out; float* partial;
-  T* dOut; float* dHext; T* dG; float* dXp; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
+  float* Uv; T* X; float* WhP; float* Wh; float* beta; float* P; float* P2; T* gates; float* c; float* out; float* partial;
+  T* dOut; float* dHext; T* dG; T* dG2; float* dXp; float* dXp2; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
   float* dx; float* splitk;
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
   size_t bytes;
@@ -40,6 +42,12 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.pl_gate = plan_gemm<T>(w.Bc, 4 * R, w.KX, tgt);
   w.pl_dx = plan_gemm<T>(w.Bc, w.KX, 4 * R, tgt);
   w.pl_dq = plan_gemm<T>(w.Bc, R, A, tgt);
+  const bool gru_ = d.cell == RECNET_CELL_GRU;
+  w.G = gru_ ? 3 : 4;
+  w.pl_gx = plan_gemm<T>(w.Bc, 3 * R, H, tgt);
+  w.pl_gh = plan_gemm<T>(w.Bc, 3 * R, R, tgt);
+  w.pl_dxx = plan_gemm<T>(w.Bc, H, 3 * R, tgt);
+  w.pl_dxh = plan_gemm<T>(w.Bc, R, 3 * R, tgt);
   Bump m(base);
   w.Wrec = m.take<T>((size_t)4 * R * w.KX);
   w.U = m.take<T>((size_t)A * H);
@@ -51,7 +59,8 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.WhP = m.take<float>((size_t)w.nch * w.pl_wh.splits * w.Bc * A);
   w.Wh = m.take<float>((size_t)S * B * A);
   w.beta = m.take<float>((size_t)S * B * L);
-  w.P = m.take<float>((size_t)w.nch * w.pl_gate.splits * w.Bc * 4 * R);
+  w.P = m.take<float>((size_t)w.nch * (gru_ ? w.pl_gx.splits : w.pl_gate.splits) * w.Bc * 4 * R);
+  w.P2 = m.take<float>(gru_ ? (size_t)w.nch * w.pl_gh.splits * w.Bc * 3 * R : 1);
   w.gates = m.take<T>((size_t)S * B * 4 * R);
   w.c = m.take<float>((size_t)(S + 1) * B * R);
   w.out = m.take<float>((size_t)S * B * R);
@@ -59,7 +68,9 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.dOut = m.take<T>((size_t)S * B * R);
   w.dHext = m.take<float>((size_t)S * B * R);
   w.dG = m.take<T>((size_t)S * B * 4 * R);
-  w.dXp = m.take<float>((size_t)w.nch * w.pl_dx.splits * w.Bc * w.KX);
+  w.dXp = m.take<float>((size_t)w.nch * (gru_ ? w.pl_dxx.splits : w.pl_dx.splits) * w.Bc * w.KX);
+  w.dXp2 = m.take<float>(gru_ ? (size_t)w.nch * w.pl_dxh.splits * w.Bc * R : 1);
+  w.dG2 = m.take<T>(gru_ ? (size_t)S * B * 3 * R : 1);
   w.dQp = m.take<float>((size_t)w.nch * w.pl_dq.splits * w.Bc * R);
   w.dWh = m.take<float>((size_t)S * B * A);
   w.dWh_op = m.take<T>((size_t)S * B * A);
@@ -79,6 +90,7 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
 
 static inline int check_local(const recnet_local_desc& d) {
   if (d.B < 1 || d.S < 1 || d.L < 1 || d.L > attn::MAX_T) return RECNET_ERR_BAD_SHAPE;
+  if (d.cell != RECNET_CELL_LSTM && d.cell != RECNET_CELL_GRU) return RECNET_ERR_UNSUPPORTED;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if (d.R % al || d.H % al || d.A % 4) return RECNET_ERR_ALIGNMENT;
   return 0;
@@ -92,8 +104,10 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
   const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
   const float p_drop = d.train ? d.p_drop : 0.f;
-  RN_TRY(misc::cast_pad<T>(p.w_ih, H, w.Wrec, w.KX, 4 * R, H, H, st));
-  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Wrec + H, w.KX, 4 * R, R, R, st));
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  const int GR = w.G * R;
+  RN_TRY(misc::cast_pad<T>(p.w_ih, H, w.Wrec, w.KX, GR, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Wrec + H, w.KX, GR, R, R, st));
   RN_TRY(misc::cast_pad<T>(p.attn_U, H, w.U, H, A, H, H, st));
   RN_TRY(misc::cast_pad<T>(p.attn_W, R, w.Wa, R, A, R, R, st));
   RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
@@ -104,7 +118,7 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
-  mega::Emitter<T> em0(w.nch == 1, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
+  mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
   for (int t = 0; t < S; ++t) {
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
@@ -131,6 +145,21 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
       fa.ctx_out = x_t; fa.ctx_ld = w.KX;
       fa.p_drop = p_drop; fa.rng = rng; fa.site = SITE_LOCAL_X; fa.drop_base = (long long)r * H;
       RN_TRY(em.attn_fwd(fa));
+      if (is_gru) {
+        float* Px = w.P + (size_t)ch * w.pl_gx.splits * w.Bc * 3 * R;
+        float* Ph = w.P2 + (size_t)ch * w.pl_gh.splits * w.Bc * 3 * R;
+        RN_TRY(em.gemm_partials(x_t, w.KX, 0, w.Wrec, w.KX, 0, Px, nb, 3 * R, H, w.pl_gx));
+        if (t > 0) RN_TRY(em.gemm_partials(x_t + H, w.KX, 0, w.Wrec + H, w.KX, 0, Ph, nb, 3 * R, R, w.pl_gh));
+        gru::FwdArgs ga{};
+        ga.Px = Px; ga.n_px = w.pl_gx.splits; ga.px_stride = (long long)nb * 3 * R; ga.px_ld = 3 * R;
+        ga.Ph = t > 0 ? Ph : nullptr; ga.n_ph = t > 0 ? w.pl_gh.splits : 0; ga.ph_stride = (long long)nb * 3 * R; ga.ph_ld = 3 * R;
+        ga.Gx = nullptr; ga.b_ih = p.b_ih; ga.b_hh = p.b_hh;
+        ga.h_prev = w.c + r * R; ga.hp_ld = R; ga.B = nb; ga.H = R;            // fp32 state h lives in the c rows
+        ga.stash = w.gates + r * 4 * R; ga.h_out = w.c + ((size_t)(t + 1) * B + b0) * R; ga.h_ld = R;
+        ga.h_op = x_n + H; ga.hop_ld = w.KX;
+        RN_TRY((gru::launch_fwd<T, T>(ga, em.st)));
+        continue;
+      }
       RN_TRY(em.gemm_partials(x_t, w.KX, 0, w.Wrec, w.KX, 0, P, nb, 4 * R, w.KX, w.pl_gate));
       cell::FwdArgs ca{};
       ca.P = P; ca.n_p = w.pl_gate.splits; ca.p_stride = (long long)nb * 4 * R; ca.p_ld = 4 * R;
@@ -170,7 +199,9 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk, st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
-  mega::Emitter<T> em0(w.nch == 1, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  const int GR = w.G * R;
+  mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
   for (int t = S - 1; t >= 0; --t) {
     const bool last = (t == S - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
@@ -181,6 +212,32 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
       float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * w.KX;
       float* dQp = w.dQp + (size_t)ch * w.pl_dq.splits * w.Bc * R;
       const size_t r = (size_t)t * B + b0;
+      if (is_gru) {
+        float* dXx = w.dXp + (size_t)ch * w.pl_dxx.splits * w.Bc * w.KX;
+        float* dXh = w.dXp2 + (size_t)ch * w.pl_dxh.splits * w.Bc * R;
+        gru::BwdArgs gb{};
+        gb.dh_ext = w.dHext + r * R; gb.dh_ld = R;
+        gb.dHp = last ? nullptr : dXh; gb.n_p = w.pl_dxh.splits; gb.p_stride = (long long)nb * R; gb.p_ld = R;
+        gb.dQp = last ? nullptr : dQp; gb.n_q = w.pl_dq.splits; gb.q_stride = (long long)nb * R; gb.q_ld = R;
+        gb.carry = w.dc + (size_t)b0 * R; gb.first = last ? 1 : 0;
+        gb.stash = w.gates + r * 4 * R; gb.h_prev = w.c + r * R; gb.hp_ld = R;
+        gb.B = nb; gb.H = R; gb.dGi = w.dG + r * 3 * R; gb.dGh = w.dG2 + r * 3 * R; gb.dg_ld = 3 * R;
+        RN_TRY((gru::launch_bwd<T, T>(gb, em.st)));
+        RN_TRY(em.gemm_partials(w.dG + r * 3 * R, 3 * R, 0, w.Wrec, w.KX, 1, dXx, nb, H, 3 * R, w.pl_dxx));
+        if (t > 0) RN_TRY(em.gemm_partials(w.dG2 + r * 3 * R, 3 * R, 0, w.Wrec + H, w.KX, 1, dXh, nb, R, 3 * R, w.pl_dxh));
+        attn::BwdArgs ab{};
+        ab.dXp = dXx; ab.n_p = w.pl_dxx.splits; ab.p_stride = (long long)nb * H; ab.p_ld = H;
+        ab.V = w.Hd + (size_t)b0 * H; ab.v_bs = H; ab.v_ts = (long long)B * H;
+        ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * A; ab.uv_bs = A; ab.uv_ts = (long long)B * A;
+        ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = L; ab.A = A; ab.D = H; ab.inv_T = 1.f / L;
+        ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * A;
+        ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+        ab.dctx_out = w.dx + r * H; ab.de_out = nullptr;
+        ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)r * H;
+        RN_TRY(em.attn_bwd(ab));
+        if (t > 0) RN_TRY(em.gemm_partials(w.dWh_op + r * A, A, 0, w.Wa, R, 1, dQp, nb, R, A, w.pl_dq));
+        continue;
+      }
       cell::BwdArgs cb{};
       cb.dh_ext = w.dHext + r * R; cb.dh_ld = R;
       cb.dXp = last ? nullptr : dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)nb * w.KX; cb.p_ld = w.KX; cb.col0 = H;
@@ -206,10 +263,12 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   }
   RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 4));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
-  RN_TRY(misc::colsum<T>(w.dG, 4 * R, SB, 4 * R, g.b_ih, 0, w.splitk, st));
-  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, 4 * R, H, SB, 0, w.splitk, st));
-  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, 4 * R, R, SB, 0, w.splitk, st));
+  const T* dGh = is_gru ? w.dG2 : w.dG;
+  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st));
+  if (is_gru) { RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st)); }
+  else RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)GR * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(gemm_full<T>(w.dG, GR, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, GR, H, SB, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(dGh, GR, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, GR, R, SB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk, st));
   RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, st));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk, st));
@@ -229,10 +288,10 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
 // ================================================ global ========================================================
 template <typename T>
 struct GlobalWs {
-  int nch, Bc;
+  int nch, Bc, G;
   GemmPlan pl_gate, pl_dx;
   T *Wih, *Whh, *Wout; float* mp; T* Xg; float* Gx; T* X; float* P; T* gates; float* c; float* out; float* diff; float* partial;
-  T* dOut; float* dHext; T* dG; float* dXp; float* dc; float* dXg; float* dmp; float* splitk;
+  T* dOut; float* dHext; T* dG; T* dG2; float* dXp; float* dc; float* dXg; float* dmp; float* splitk;
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
   size_t bytes;
 };
@@ -245,8 +304,10 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   w.nch = num_chains(B);
   w.Bc = chain_rows_max(B, w.nch);
   const int tgt = w.nch > 1 ? NUM_SMS / 2 : NUM_SMS;
-  w.pl_gate = plan_gemm<T>(w.Bc, 4 * R, R, tgt);
-  w.pl_dx = plan_gemm<T>(w.Bc, R, 4 * R, tgt);
+  const bool gru_ = d.cell == RECNET_CELL_GRU;
+  w.G = gru_ ? 3 : 4;
+  w.pl_gate = plan_gemm<T>(w.Bc, w.G * R, R, tgt);
+  w.pl_dx = plan_gemm<T>(w.Bc, R, w.G * R, tgt);
   Bump m(base);
   w.Wih = m.take<T>((size_t)4 * R * 2 * H);
   w.Whh = m.take<T>((size_t)4 * R * R);
@@ -266,6 +327,7 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   w.dG = m.take<T>((size_t)L * B * 4 * R);
   w.dXp = m.take<float>((size_t)w.nch * w.pl_dx.splits * w.Bc * R);
   w.dc = m.take<float>((size_t)B * R);
+  w.dG2 = m.take<T>(gru_ ? (size_t)L * B * 3 * R : 1);
   w.dXg = m.take<float>((size_t)L * B * 2 * H);
   w.dmp = m.take<float>((size_t)B * H);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
@@ -278,6 +340,7 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
 }
 static inline int check_global(const recnet_global_desc& d) {
   if (d.B < 1 || d.L < 1 || d.T < 1) return RECNET_ERR_BAD_SHAPE;
+  if (d.cell != RECNET_CELL_LSTM && d.cell != RECNET_CELL_GRU) return RECNET_ERR_UNSUPPORTED;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if (d.R % al || d.H % al) return RECNET_ERR_ALIGNMENT;
   return 0;
@@ -291,8 +354,10 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
   if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
   const int B = d.B, L = d.L, R = d.R, H = d.H;
   const float p_drop = d.train ? d.p_drop : 0.f;
-  RN_TRY(misc::cast_pad<T>(p.w_ih, 2 * H, w.Wih, 2 * H, 4 * R, 2 * H, 2 * H, st));
-  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Whh, R, 4 * R, R, R, st));
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  const int GR = w.G * R;
+  RN_TRY(misc::cast_pad<T>(p.w_ih, 2 * H, w.Wih, 2 * H, GR, 2 * H, 2 * H, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Whh, R, GR, R, R, st));
   RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
   // mean over time (and the single decoder layer), then / L * caption_max_len  (global_reconstructor.py:33-37)
   const long long n = (long long)B * H;
@@ -300,13 +365,13 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
   RN_LAUNCH_OK();
   misc::global_x_kernel<T><<<NUM_SMS * 4, 256, 0, st>>>(hiddens, w.mp, w.Xg, L, B, H, p_drop, rng, SITE_GLOBAL_MP);
   RN_LAUNCH_OK();
-  RN_TRY(gemm_full<T>(w.Xg, 2 * H, 0, w.Wih, 2 * H, 0, w.Gx, 4 * R, p.b_ih, L * B, 4 * R, 2 * H, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.Xg, 2 * H, 0, w.Wih, 2 * H, 0, w.Gx, GR, p.b_ih, L * B, GR, 2 * H, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * R * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
   RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
-  mega::Emitter<T> em0(w.nch == 1, st);
+  mega::Emitter<T> em0(w.nch == 1 && !is_gru, st);
   for (int t = 0; t < L; ++t) {
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
@@ -318,8 +383,19 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
       T* x_t = w.X + r * R;
       int n_p = 0;
       if (t > 0) {
-        RN_TRY(em.gemm_partials(x_t, R, 0, w.Whh, R, 0, P, nb, 4 * R, R, w.pl_gate));
+        RN_TRY(em.gemm_partials(x_t, R, 0, w.Whh, R, 0, P, nb, GR, R, w.pl_gate));
         n_p = w.pl_gate.splits;
+      }
+      if (is_gru) {
+        gru::FwdArgs ga{};
+        ga.Px = nullptr; ga.n_px = 0;
+        ga.Ph = n_p ? P : nullptr; ga.n_ph = n_p; ga.ph_stride = (long long)nb * 3 * R; ga.ph_ld = 3 * R;
+        ga.Gx = w.Gx + r * 3 * R; ga.gx_ld = 3 * R; ga.b_ih = nullptr; ga.b_hh = p.b_hh;
+        ga.h_prev = w.c + r * R; ga.hp_ld = R; ga.B = nb; ga.H = R;
+        ga.stash = w.gates + r * 4 * R; ga.h_out = w.c + ((size_t)(t + 1) * B + b0) * R; ga.h_ld = R;
+        ga.h_op = x_t + (size_t)B * R; ga.hop_ld = R;
+        RN_TRY((gru::launch_fwd<T, T>(ga, em.st)));
+        continue;
       }
       cell::FwdArgs ca{};
       ca.P = P; ca.n_p = n_p; ca.p_stride = (long long)nb * 4 * R; ca.p_ld = 4 * R;
@@ -361,7 +437,9 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
   RN_TRY(misc::colsum<T>(w.dOut, R, LB, R, g.out_b, 0, w.splitk, st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
-  mega::Emitter<T> em0(w.nch == 1, st);
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  const int GR = w.G * R;
+  mega::Emitter<T> em0(w.nch == 1 && !is_gru, st);
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
@@ -371,6 +449,17 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
       mega::Emitter<T>& em = w.nch == 1 ? em0 : emc;
       float* dXp = w.dXp + (size_t)ch * w.pl_dx.splits * w.Bc * R;
       const size_t r = (size_t)t * B + b0;
+      if (is_gru) {
+        gru::BwdArgs gb{};
+        gb.dh_ext = w.dHext + r * R; gb.dh_ld = R;
+        gb.dHp = last ? nullptr : dXp; gb.n_p = w.pl_dx.splits; gb.p_stride = (long long)nb * R; gb.p_ld = R;
+        gb.dQp = nullptr; gb.carry = w.dc + (size_t)b0 * R; gb.first = last ? 1 : 0;
+        gb.stash = w.gates + r * 4 * R; gb.h_prev = w.c + r * R; gb.hp_ld = R;
+        gb.B = nb; gb.H = R; gb.dGi = w.dG + r * 3 * R; gb.dGh = w.dG2 + r * 3 * R; gb.dg_ld = 3 * R;
+        RN_TRY((gru::launch_bwd<T, T>(gb, em.st)));
+        if (t > 0) RN_TRY(em.gemm_partials(w.dG2 + r * 3 * R, 3 * R, 0, w.Whh, R, 1, dXp, nb, R, 3 * R, w.pl_dx));
+        continue;
+      }
       cell::BwdArgs cb{};
       cb.dh_ext = w.dHext + r * R; cb.dh_ld = R;
       cb.dXp = last ? nullptr : dXp; cb.n_p = w.pl_dx.splits; cb.p_stride = (long long)nb * R; cb.p_ld = R; cb.col0 = 0;
@@ -384,11 +473,13 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
   }
   RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 6));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
-  RN_TRY(misc::colsum<T>(w.dG, 4 * R, LB, 4 * R, g.b_ih, 0, w.splitk, st));
-  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.X, R, 1, g.w_hh, R, nullptr, 4 * R, R, LB, 0, w.splitk, st));
-  RN_TRY(gemm_full<T>(w.dG, 4 * R, 1, w.Xg, 2 * H, 1, g.w_ih, 2 * H, nullptr, 4 * R, 2 * H, LB, 0, w.splitk, st));
-  RN_TRY(gemm_full<T>(w.dG, 4 * R, 0, w.Wih, 2 * H, 1, w.dXg, 2 * H, nullptr, LB, 2 * H, 4 * R, 0, w.splitk, st));
+  const T* dGh = is_gru ? w.dG2 : w.dG;
+  RN_TRY(misc::colsum<T>(w.dG, GR, LB, GR, g.b_ih, 0, w.splitk, st));
+  if (is_gru) { RN_TRY(misc::colsum<T>(dGh, GR, LB, GR, g.b_hh, 0, w.splitk, st)); }
+  else RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)GR * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(gemm_full<T>(dGh, GR, 1, w.X, R, 1, g.w_hh, R, nullptr, GR, R, LB, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dG, GR, 1, w.Xg, 2 * H, 1, g.w_ih, 2 * H, nullptr, GR, 2 * H, LB, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dG, GR, 0, w.Wih, 2 * H, 1, w.dXg, 2 * H, nullptr, LB, 2 * H, GR, 0, w.splitk, st));
   const long long n = (long long)B * H;
   misc::global_x_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dXg, g_hiddens, w.dmp, L, B, H, 0, p_drop, rng, SITE_GLOBAL_MP);
   RN_LAUNCH_OK();

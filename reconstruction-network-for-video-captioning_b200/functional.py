@@ -215,7 +215,7 @@ class LocalReconstructorFn(torch.autograd.Function):
         Lsteps, B, H = hiddens.shape
         _, S, R = feats.shape
         d = L.local_desc(B=B, S=S, R=R, H=H, A=meta["A"], L=Lsteps, precision=meta["precision"], train=int(meta["train"]),
-                         p_drop=float(meta["p_drop"]))
+                         p_drop=float(meta["p_drop"]), cell=int(meta.get("cell", L.CELL_LSTM)))
         nbytes = lib.recnet_local_workspace_bytes(C.byref(d))
         if nbytes < 0:
             L.check(int(nbytes), "recnet_local_workspace_bytes")
@@ -260,7 +260,8 @@ class GlobalReconstructorFn(torch.autograd.Function):
         Lsteps, B, H = hiddens.shape
         _, T, R = feats.shape
         d = L.global_desc(B=B, L=Lsteps, R=R, H=H, T=T, precision=meta["precision"], train=int(meta["train"]),
-                          p_drop=float(meta["p_drop"]), caption_max_len=float(meta["caption_max_len"]))
+                          p_drop=float(meta["p_drop"]), caption_max_len=float(meta["caption_max_len"]),
+                          cell=int(meta.get("cell", L.CELL_LSTM)))
         nbytes = lib.recnet_global_workspace_bytes(C.byref(d))
         if nbytes < 0:
             L.check(int(nbytes), "recnet_global_workspace_bytes")

@@ -8,7 +8,7 @@ reference checkpoint loads with ``load_state_dict``.  The arithmetic runs in lib
 * ``forward_sequence`` (whole teacher-forced loop, what train.forward_* use) -> one C call (``functional.py``)
 
 One extra constructor kwarg, ``precision`` ("bf16" | "fp32"); everything else is positional-compatible.
-Built: Decoder with LSTM or GRU cells (GRU is the reference's default, config.py:31), reconstructors with LSTM cells,
+Built: Decoder and both reconstructors with LSTM or GRU cells (GRU is the reference's default decoder, config.py:31),
 n_layers == 1.  Anything else raises NotImplementedError (never a silent fallback).
 """
 from __future__ import annotations
@@ -187,25 +187,30 @@ class GlobalReconstructor(nn.Module, _RngMixin):
 
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
         """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "GlobalReconstructor")
+        _require_supported(self.model_name, self.n_layers, "GlobalReconstructor", gru_ok=True)
         hid = _squeeze_layers(decoder_hiddens)
         meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p,
-                    caption_max_len=self.caption_max_len)
+                    caption_max_len=self.caption_max_len, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.GlobalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
     def forward(self, input, hidden, decoder_hiddens):
-        """input (1,B,H) = decoder_hiddens[t]; hidden ((1,B,R),(1,B,R)); decoder_hiddens (L,1,B,H)."""
-        _require_supported(self.model_name, self.n_layers, "GlobalReconstructor")
+        """input (1,B,H) = decoder_hiddens[t]; hidden ((1,B,R),(1,B,R)) [LSTM] or (1,B,R) [GRU]; decoder_hiddens (L,1,B,H)."""
+        _require_supported(self.model_name, self.n_layers, "GlobalReconstructor", gru_ok=True)
         p = _precision_id(self.precision)
+        is_lstm = self.model_name == "LSTM"
+        h_prev = hidden[0][-1] if is_lstm else hidden[-1]
         Lsteps = decoder_hiddens.size(0)
         mp = decoder_hiddens.mean(0).mean(0) / Lsteps * self.caption_max_len            # global_reconstructor.py:33-37
         mp = torch.nn.functional.dropout(mp, self.decoder_dropout_p, self.training)      # :38
         x = torch.cat((input[0], mp), 1)                                                 # :40
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        pre = ops.linear(x, w_ih, b_ih, p) + ops.linear(hidden[0][-1], w_hh, b_hh, p)    # :43
-        h2, c2 = ops.lstm_cell(pre, hidden[1][-1], p)
+        gi, gh = ops.linear(x, w_ih, b_ih, p), ops.linear(h_prev, w_hh, b_hh, p)         # :43
+        if is_lstm:
+            h2, c2 = ops.lstm_cell(gi + gh, hidden[1][-1], p)
+        else:
+            h2 = ops.gru_cell(gi, gh, h_prev, p)
         out = ops.linear(h2, self.out.weight, self.out.bias, p)                          # :45
-        return out, (h2.unsqueeze(0), c2.unsqueeze(0))
+        return out, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
 
 
 class LocalReconstructor(nn.Module, _RngMixin):
@@ -237,27 +242,32 @@ class LocalReconstructor(nn.Module, _RngMixin):
 
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
         """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "LocalReconstructor")
+        _require_supported(self.model_name, self.n_layers, "LocalReconstructor", gru_ok=True)
         hid = _squeeze_layers(decoder_hiddens)
         meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training,
-                    p_drop=self.decoder_dropout_p)
+                    p_drop=self.decoder_dropout_p, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.LocalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
     def forward(self, hidden, decoder_hiddens):
-        """hidden ((1,B,R),(1,B,R)); decoder_hiddens (L,1,B,H) -> (out (B,R), hidden)."""
-        _require_supported(self.model_name, self.n_layers, "LocalReconstructor")
+        """hidden ((1,B,R),(1,B,R)) [LSTM] or (1,B,R) [GRU]; decoder_hiddens (L,1,B,H) -> (out (B,R), hidden)."""
+        _require_supported(self.model_name, self.n_layers, "LocalReconstructor", gru_ok=True)
         p = _precision_id(self.precision)
+        is_lstm = self.model_name == "LSTM"
+        h_prev = hidden[0][-1] if is_lstm else hidden[-1]
         hid = _squeeze_layers(decoder_hiddens)                                           # (L,B,H)
         Lsteps, B, H = hid.shape
         Uv = ops.linear(hid.reshape(Lsteps * B, H), self.attn_U.weight, None, p).view(Lsteps, B, -1).transpose(0, 1)
-        Wh = ops.linear(hidden[0][-1], self.attn_W.weight, None, p)                      # local_reconstructor.py:39
+        Wh = ops.linear(h_prev, self.attn_W.weight, None, p)                             # local_reconstructor.py:39
         x = ops.additive_attention(Wh, Uv.contiguous(), self.attn_b, self.attn_w.weight, hid.transpose(0, 1).contiguous(), p)
         x = torch.nn.functional.dropout(x, self.decoder_dropout_p, self.training)        # :50
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        pre = ops.linear(x, w_ih, b_ih, p) + ops.linear(hidden[0][-1], w_hh, b_hh, p)    # :52
-        h2, c2 = ops.lstm_cell(pre, hidden[1][-1], p)
+        gi, gh = ops.linear(x, w_ih, b_ih, p), ops.linear(h_prev, w_hh, b_hh, p)         # :52
+        if is_lstm:
+            h2, c2 = ops.lstm_cell(gi + gh, hidden[1][-1], p)
+        else:
+            h2 = ops.gru_cell(gi, gh, h_prev, p)
         out = ops.linear(h2, self.out.weight, self.out.bias, p)                          # :54
-        return out, (h2.unsqueeze(0), c2.unsqueeze(0))
+        return out, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
 
 
 def _squeeze_layers(decoder_hiddens: torch.Tensor) -> torch.Tensor:

@@ -403,6 +403,24 @@ def test_whole_train_step_runs_under_cuda_graph_and_updates_weights():
     assert not torch.equal(w0, dec["model"].out.weight)                     # Adam step inside the graph moved the weights
 
 
+@pytest.mark.parametrize("kind", ["global", "local"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gru_decoder_plus_gru_reconstructor_match_reference_golden(precision, kind):
+    """GRU everywhere (decoder_model = reconstructor_model = "GRU"): joint loss and every gradient against the fixture."""
+    g = load_golden("tiny_gru")
+    tol = TOL[precision]
+    dec, rec = build(g["meta"], precision, kind, g["dec"], g[kind])
+    feats, targets = g["feats"].float().to(dev()), g["targets"].to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, feats, targets, targets > 0, 1.0)
+    rloss = T.forward_reconstructor_for(kind)(hiddens, feats, rec)
+    assert rel(rloss, torch.tensor(g[kind + "_loss"])) < tol
+    (dloss + rloss).backward()
+    for k, ref in g["grads"][kind].items():
+        owner, key = k.split(".", 1)
+        p = dict((dec if owner == "dec" else rec)["model"].named_parameters())[key]
+        assert rel(p.grad, ref) < tol, k
+
+
 class _Vocab:
     def __init__(self, n):
         self.n_vocabs = n

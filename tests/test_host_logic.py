@@ -66,7 +66,7 @@ def test_config_keeps_reference_attribute_names():
 def test_unsupported_variants_raise_not_silently_fall_back():
     gru = recnet_b200.Decoder("GRU", 1, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)
     assert tuple(gru.state_dict()["rnn.weight_ih_l0"].shape) == (24, 24)    # 3 gates: checkpoint-compatible holder
-    rec = recnet_b200.LocalReconstructor("GRU", 1, 8, 16, 0.5, 0.5, 8)          # GRU reconstructors: not built yet -> must raise
+    rec = recnet_b200.LocalReconstructor("LSTM", 2, 8, 16, 0.5, 0.5, 8)         # multi-layer reconstructors: not built yet -> must raise
     with pytest.raises(NotImplementedError):
         rec.forward_sequence(torch.zeros(3, 2, 8), torch.zeros(2, 4, 16))
     two = recnet_b200.Decoder("LSTM", 2, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)

@@ -1,16 +1,19 @@
 """Data-parallel plumbing: one process per GPU, batch sharded, weights replicated, ONE gradient
-all-reduce (average) per module per iteration over NCCL / NVLink, overlapped with the rest of backward.
+all-reduce (average) per iteration over NCCL / NVLink.
 
 The reference has no distributed code at all.  The path shards cleanly: samples are independent through both
 loops, only parameter gradients couple the replicas, so the only collective is the gradient all-reduce.
 
-Overlap: every sequence Function writes its module's gradients into one flat buffer (functional.py).  The
-reconstructor's backward finishes before the decoder's BPTT starts, so its buffer (61 MB fp32 for the local
-reconstructor) is all-reduced on NCCL's stream WHILE the decoder BPTT kernels run; the decoder's buffer (38 MB)
-follows and is waited on just before clip + Adam.
+Every sequence Function writes its module's gradients into one flat buffer (functional.py); after backward the two
+buffers (61 MB local reconstructor + 38 MB decoder, fp32) go out as ONE fused NCCL group (ncclGroupStart/End), i.e.
+one rank synchronisation per step, then clip + Adam.  Measured on 2 x B200 (profiles/r1_d_dp.md): fused, after
+backward 4.67 ms/step; per-module all-reduces launched from grad hooks to overlap the decoder BPTT 5.00 ms/step --
+the NCCL CTAs slow the latency-bound BPTT chain as much as they hide, and a second collective is a second rank
+sync -- so overlap is opt-in (RECNET_DP_OVERLAP=1).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
 import torch
@@ -30,7 +33,8 @@ class GradAllReducer:
         self._handles = []
         self.modules = list(modules)
         self.bytes_last = 0
-        if self.world > 1:
+        self.overlap = os.environ.get("RECNET_DP_OVERLAP", "0") == "1"
+        if self.world > 1 and self.overlap:
             for mi, m in enumerate(self.modules):
                 params = [p for p in m.parameters() if p.requires_grad]
                 for p in params:
@@ -49,6 +53,10 @@ class GradAllReducer:
 
     def _launch(self, buf: torch.Tensor):
         self.bytes_last += buf.numel() * buf.element_size()
+        if os.environ.get("RECNET_DP_DRYRUN") == "1":      # developer probe: everything but the collective itself
+            return
+        if os.environ.get("RECNET_DP_DRYRUN") == "2":      # developer probe: synchronise the ranks, move no data
+            buf = buf.view(-1)[:1]
         if self.backend == "nccl":
             self.pending.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         else:                                  # gloo (CPU tests): no AVG
@@ -62,11 +70,25 @@ class GradAllReducer:
         """Join the outstanding all-reduces; modules whose grads were not flat views are reduced tensor by tensor."""
         if self.world <= 1:
             return
+        late = []
         for mi, m in enumerate(self.modules):
             if self._fired.get(mi) is None:
-                for p in m.parameters():
-                    if p.grad is not None:
-                        self._launch(p.grad)
+                grads = [p.grad for p in m.parameters() if p.grad is not None]
+                bases = {id(g._base): g._base for g in grads if g._base is not None}
+                if len(bases) == 1 and all(g._base is not None for g in grads):
+                    late.append(next(iter(bases.values())))          # still ONE flat buffer per module
+                else:
+                    late.extend(grads)
+        if len(late) > 1 and self.backend == "nccl" and os.environ.get("RECNET_DP_DRYRUN") is None:
+            # one NCCL group (ncclGroupStart/End): all buffers in a single fused collective launch -> one rank sync per step
+            with dist._coalescing_manager(group=self.group, device=late[0].device, async_ops=True) as cm:
+                for buf in late:
+                    self.bytes_last += buf.numel() * buf.element_size()
+                    dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+            self.pending.append(cm)
+        else:
+            for buf in late:
+                self._launch(buf)
         for w in self.pending:
             if isinstance(w, tuple):
                 w[0].wait()

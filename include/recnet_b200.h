@@ -38,6 +38,7 @@ typedef enum {
 } recnet_status;
 
 typedef enum { RECNET_PREC_FP32 = 0, RECNET_PREC_BF16 = 1 } recnet_precision;
+#define RECNET_MAX_LAYERS 4
 typedef enum { RECNET_CELL_LSTM = 0, RECNET_CELL_GRU = 1 } recnet_cell;   /* models/decoder.py:32-35: anything but "LSTM" is GRU */
 
 /* Library / device checks.  recnet_query_device fails with RECNET_ERR_UNSUPPORTED_ARCH unless the
@@ -139,17 +140,21 @@ typedef struct {
   int32_t train;                        /* 1 = apply dropout (embedding, logits) */
   float embedding_scale, p_emb_drop, p_out_drop;
   int32_t cell;                         /* recnet_cell: LSTM (i,f,g,o; state h,c) or GRU (r,z,n; state h) */
+  int32_t n_layers;                     /* stacked decoder layers (decoder.py:36-40), 0/1 = one; > 1: LSTM only */
+  float p_layer_drop;                   /* nn.LSTM(dropout=) between layers, train mode only */
 } recnet_decoder_desc;
 
 typedef struct {                        /* fp32 master weights, reference state_dict layout */
   float *embedding, *attn_W, *attn_U, *attn_b, *attn_w, *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;
+  /* layers 1 .. n_layers-1 (index l-1): rnn.weight_ih_l{l} [4H,H], rnn.weight_hh_l{l} [4H,H], biases [4H]; NULL when absent */
+  float *w_ih_x[RECNET_MAX_LAYERS - 1], *w_hh_x[RECNET_MAX_LAYERS - 1], *b_ih_x[RECNET_MAX_LAYERS - 1], *b_hh_x[RECNET_MAX_LAYERS - 1];
 } recnet_decoder_tensors;
 
 /* bytes of caller-provided workspace that must stay alive from fwd to bwd */
 int64_t recnet_decoder_workspace_bytes(const recnet_decoder_desc* d);
 
 /* tokens_in [L,B] int64 (SOS then targets[t-1], train.py:25,44-45); targets [L,B] int64; ce_weight [L,B] fp32 =
- * mask/(n_t * sum n_t) (train.py:54-60,68).  Outputs: hiddens [L,B,H] fp32 (train.py:61-64,73), ce_out[1] =
+ * mask/(n_t * sum n_t) (train.py:54-60,68).  Outputs: hiddens [L,NL,B,H] fp32 (train.py:61-64,73), ce_out[1] =
  * sum_t CE_t / sum_t n_t, logits_out [L*B, ld = round_up(V,4)] lives inside the workspace
  * (recnet_decoder_logits returns it). */
 int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats,

@@ -41,15 +41,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 class decoder_desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "T", "E", "H", "A", "EMB", "V", "L", "precision", "train")] + \
-               [(n, C.c_float) for n in ("embedding_scale", "p_emb_drop", "p_out_drop")] + [("cell", C.c_int32)]
+               [(n, C.c_float) for n in ("embedding_scale", "p_emb_drop", "p_out_drop")] + \
+               [("cell", C.c_int32), ("n_layers", C.c_int32), ("p_layer_drop", C.c_float)]
 
 
 CELL_LSTM, CELL_GRU = 0, 1
 
 
+MAX_LAYERS = 4
+
+
 class decoder_tensors(C.Structure):
     FIELDS = ("embedding", "attn_W", "attn_U", "attn_b", "attn_w", "w_ih", "w_hh", "b_ih", "b_hh", "out_w", "out_b")
-    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+    EXTRA = ("w_ih_x", "w_hh_x", "b_ih_x", "b_hh_x")          # per extra layer l = 1.., in this order in the flat parameter list
+    _fields_ = [(n, C.c_void_p) for n in FIELDS] + [(n, C.c_void_p * (MAX_LAYERS - 1)) for n in EXTRA]
 
 
 class local_desc(C.Structure):

@@ -27,6 +27,8 @@ struct FwdArgs {
   float* h_out; long long h_ld;                                   // fp32 h' (nullable)
   void* h_op; long long hop_ld;                                   // operand-typed h' (nullable)
   void* h_op2; long long hop2_ld;                                 // second operand-typed copy (nullable)
+  // inter-layer dropout (nn.LSTM(dropout=p), train mode): applied to the h_op2 copy only (the next layer's input)
+  float op2_drop; const unsigned long long* rng; unsigned int site; long long drop_base;
 };
 
 // body: virtual block (bx = 256-wide slice of H, b = sample): no integer division, pointer-bump partial loop
@@ -63,7 +65,11 @@ __device__ __forceinline__ void lstm_cell_fwd_body(const FwdArgs& a, int bx, int
     g[0] = from_f32<TS>(gi); g[H] = from_f32<TS>(gf); g[2 * H] = from_f32<TS>(gg); g[3 * H] = from_f32<TS>(go);
   }
   if (a.h_op) reinterpret_cast<TO*>(a.h_op)[b * a.hop_ld + j] = from_f32<TO>(hn);
-  if (a.h_op2) reinterpret_cast<TO*>(a.h_op2)[b * a.hop2_ld + j] = from_f32<TO>(hn);
+  if (a.h_op2) {
+    float hd = hn;
+    if (a.op2_drop > 0.f) hd *= dropout_scale(a.rng, a.site, (uint64_t)(a.drop_base + (long long)b * H + j), a.op2_drop);
+    reinterpret_cast<TO*>(a.h_op2)[b * a.hop2_ld + j] = from_f32<TO>(hd);
+  }
 }
 
 template <typename TS, typename TO>
@@ -82,6 +88,7 @@ struct BwdArgs {
   const float* dh_ext2; long long dh2_ld;                          // second external term (nullable)
   const float* dXp; int n_p; long long p_stride; long long p_ld; int col0;   // nullable
   const float* dQp; int n_q; long long q_stride; long long q_ld;   // nullable
+  float q_drop; const unsigned long long* rng; unsigned int q_site; long long q_base;   // dropout mask on the dQp term (inter-layer path)
   float* dc;                                                       // [B,H] in/out (dc_next -> dc_prev); first => treated as 0
   int first;
   const void* gates;                                               // [B,4H] TS
@@ -115,7 +122,11 @@ __device__ __forceinline__ void lstm_cell_bwd_body(const BwdArgs& a, int bx, int
   if (a.dh_ext) dh = (a.dh_scale ? *a.dh_scale : 1.f) * a.dh_ext[b * a.dh_ld + j];
   if (a.dh_ext2) dh += a.dh_ext2[b * a.dh2_ld + j];
   if (a.dXp) dh += sum_partials1(a.dXp + b * a.p_ld + a.col0 + j, a.n_p, a.p_stride);
-  if (a.dQp) dh += sum_partials1(a.dQp + b * a.q_ld + j, a.n_q, a.q_stride);
+  if (a.dQp) {
+    float q = sum_partials1(a.dQp + b * a.q_ld + j, a.n_q, a.q_stride);
+    if (a.q_drop > 0.f) q *= dropout_scale(a.rng, a.q_site, (uint64_t)(a.q_base + (long long)b * H + j), a.q_drop);
+    dh += q;
+  }
   const float tc = act_tanh<FAST>(cn);
   const float dc = fmaf(dh * go, 1.f - tc * tc, dcn);
   a.dc[b * H + j] = dc * gf;

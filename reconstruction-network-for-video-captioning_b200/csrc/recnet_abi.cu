@@ -1,6 +1,7 @@
 // extern "C" entry points of librecnet_b200.so (declared in include/recnet_b200.h).
 #include "runtime.cuh"
 #include "seq_decoder.cuh"
+#include "seq_decoder_ml.cuh"
 #include "seq_recon.cuh"
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -193,6 +194,13 @@ int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
   const long long* ti = reinterpret_cast<const long long*>(tokens_in);
   const long long* tg = reinterpret_cast<const long long*>(targets);
   const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->n_layers > 1) {
+    if (d->precision == RECNET_PREC_FP32)
+      return dec::forward_ml<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
+    if (d->precision == RECNET_PREC_BF16)
+      return dec::forward_ml<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
+    return RECNET_ERR_UNSUPPORTED;
+  }
   if (d->precision == RECNET_PREC_FP32)
     return dec::forward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
   if (d->precision == RECNET_PREC_BF16)
@@ -206,6 +214,13 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
   const long long* ti = reinterpret_cast<const long long*>(tokens_in);
   const long long* tg = reinterpret_cast<const long long*>(targets);
   const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->n_layers > 1) {
+    if (d->precision == RECNET_PREC_FP32)
+      return dec::backward_ml<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+    if (d->precision == RECNET_PREC_BF16)
+      return dec::backward_ml<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+    return RECNET_ERR_UNSUPPORTED;
+  }
   if (d->precision == RECNET_PREC_FP32)
     return dec::backward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, hiddens, *grads, ST(stream));
   if (d->precision == RECNET_PREC_BF16)

@@ -33,6 +33,11 @@ struct Ws {
   T* dlogits; float* dHext; T* dG; T* dG2; float* dXp; float* dXp2; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc;
   float* dc; float* dXe; float* splitk;
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;     // loop-kernel phase table, grid-barrier counter, error flag
+  // layers 1 .. NL-1 of a stacked decoder (index l-1): operand rows X_l[t] = [h^{l-1}_t ; h^l_{t-1}], K = 2H
+  int NL;
+  GemmPlan pl_gate_x, pl_dx_x;
+  T* Wrec_x[RECNET_MAX_LAYERS - 1]; T* X_x[RECNET_MAX_LAYERS - 1]; T* gates_x[RECNET_MAX_LAYERS - 1]; float* c_x[RECNET_MAX_LAYERS - 1];
+  T* dG_x[RECNET_MAX_LAYERS - 1]; float* dXp_x[RECNET_MAX_LAYERS - 1]; float* dc_x[RECNET_MAX_LAYERS - 1];
   size_t bytes;
 };
 
@@ -71,7 +76,7 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.WhP = m.take<float>((size_t)w.nch * w.pl_wh.splits * w.Bc * A);
   w.Wh = m.take<float>((size_t)L * B * A);
   w.e = m.take<float>((size_t)L * B * Tn);
-  w.P = m.take<float>((size_t)w.nch * (gru_ ? w.pl_gx.splits : w.pl_gate.splits) * w.Bc * 4 * H);
+  w.P = m.take<float>((size_t)w.nch * (gru_ ? w.pl_gx.splits : w.pl_gate.splits) * w.Bc * 4 * H + (size_t)16 * B * 4 * H);
   w.P2 = m.take<float>(gru_ ? (size_t)w.nch * w.pl_gh.splits * w.Bc * 3 * H : 1);
   w.gates = m.take<T>((size_t)L * B * 4 * H);
   w.c = m.take<float>((size_t)(L + 1) * B * H);
@@ -97,6 +102,18 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
   w.table = m.take<uint8_t>(w.table_bytes);
   w.bar = m.take<unsigned>(64);
   w.err = m.take<int>(64);
+  w.NL = d.n_layers < 1 ? 1 : d.n_layers;
+  w.pl_gate_x = plan_gemm<T>(w.Bc, 4 * H, 2 * H, tgt);
+  w.pl_dx_x = plan_gemm<T>(w.Bc, 2 * H, 4 * H, tgt);
+  for (int l = 1; l < w.NL && l < RECNET_MAX_LAYERS; ++l) {
+    w.Wrec_x[l - 1] = m.take<T>((size_t)4 * H * 2 * H);
+    w.X_x[l - 1] = m.take<T>((size_t)(L + 1) * B * 2 * H);
+    w.gates_x[l - 1] = m.take<T>((size_t)L * B * 4 * H);
+    w.c_x[l - 1] = m.take<float>((size_t)(L + 1) * B * H);
+    w.dG_x[l - 1] = m.take<T>((size_t)L * B * 4 * H);
+    w.dXp_x[l - 1] = m.take<float>((size_t)w.pl_dx_x.splits * B * 2 * H);
+    w.dc_x[l - 1] = m.take<float>((size_t)B * H);
+  }
   w.bytes = m.off + 256;
   return w;
 }
@@ -104,6 +121,8 @@ static Ws<T> plan(const recnet_decoder_desc& d, void* base) {
 static inline int check(const recnet_decoder_desc& d) {
   if (d.B < 1 || d.T < 1 || d.L < 1 || d.V < 3 || d.EMB < 1 || d.T > attn::MAX_T) return RECNET_ERR_BAD_SHAPE;
   if (d.cell != RECNET_CELL_LSTM && d.cell != RECNET_CELL_GRU) return RECNET_ERR_UNSUPPORTED;
+  if (d.n_layers > RECNET_MAX_LAYERS) return RECNET_ERR_UNSUPPORTED;
+  if (d.n_layers > 1 && d.cell != RECNET_CELL_LSTM) return RECNET_ERR_UNSUPPORTED;      // stacked GRU: not built
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if (d.E % al || d.H % al || d.A % 4) return RECNET_ERR_ALIGNMENT;
   return 0;

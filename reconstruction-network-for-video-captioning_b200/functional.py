@@ -34,9 +34,18 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def _pack(struct_cls, tensors: Sequence[torch.Tensor]):
+    """Fill a C tensor-table struct.  Decoder: the first 11 tensors are layer 0 (+ embedding / attention / out); every
+    further group of 4 is (weight_ih, weight_hh, bias_ih, bias_hh) of one extra stacked layer."""
     s = struct_cls()
+    nbase = len(struct_cls.FIELDS)
     for name, t in zip(struct_cls.FIELDS, tensors):
         setattr(s, name, t.data_ptr())
+    extra = tensors[nbase:]
+    if extra:
+        assert hasattr(struct_cls, "EXTRA") and len(extra) % 4 == 0 and len(extra) // 4 <= L.MAX_LAYERS - 1
+        for li in range(len(extra) // 4):
+            for k, name in enumerate(struct_cls.EXTRA):
+                getattr(s, name)[li] = extra[4 * li + k].data_ptr()
     return s
 
 
@@ -131,19 +140,21 @@ def _scalar(g, dev):
 def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
     lib = L.lib()
     feats = _f32c(feats, "encoder_outputs")
-    params = tuple(_f32c(p, n) for p, n in zip(params, L.decoder_tensors.FIELDS))
+    params = tuple(_f32c(p, f"decoder parameter {i}") for i, p in enumerate(params))
+    NL = 1 + (len(params) - len(L.decoder_tensors.FIELDS)) // 4
     L.require_device(feats.device.index if feats.device.index is not None else torch.cuda.current_device())
     B, T, E = feats.shape
     Lsteps = tokens_in.shape[0]
     d = L.decoder_desc(B=B, T=T, E=E, H=meta["H"], A=meta["A"], EMB=meta["EMB"], V=meta["V"], L=Lsteps,
                        precision=meta["precision"], train=int(meta["train"]),
                        embedding_scale=float(meta["embedding_scale"]), p_emb_drop=float(meta["p_emb"]),
-                       p_out_drop=float(meta["p_out"]), cell=int(meta.get("cell", L.CELL_LSTM)))
+                       p_out_drop=float(meta["p_out"]), cell=int(meta.get("cell", L.CELL_LSTM)), n_layers=NL,
+                       p_layer_drop=float(meta.get("p_layer", 0.0)))
     nbytes = lib.recnet_decoder_workspace_bytes(C.byref(d))
     if nbytes < 0:
         L.check(int(nbytes), "recnet_decoder_workspace_bytes")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
-    hiddens = torch.empty(Lsteps, B, meta["H"], dtype=torch.float32, device=feats.device)
+    hiddens = torch.empty(Lsteps, NL, B, meta["H"], dtype=torch.float32, device=feats.device)     # train.py:61-64,73
     ce = torch.zeros((), dtype=torch.float32, device=feats.device)
     tokens_in = tokens_in.contiguous()
     targets = targets.contiguous() if targets is not None else None
@@ -161,7 +172,7 @@ class DecoderSequenceFn(torch.autograd.Function):
 
     inputs : meta dict, feats (B,T,E), tokens_in (L,B) i64, targets (L,B) i64, ce_weight (L,B) f32, rng (2,) i64,
              then the 11 parameters in decoder_tensors.FIELDS order.
-    outputs: ce (scalar: sum_t CE_t / sum_t n_t), hiddens (L,B,H), reg (scalar: sum_p ||p||)
+    outputs: ce (scalar: sum_t CE_t / sum_t n_t), hiddens (L,NL,B,H), reg (scalar: sum_p ||p||)
     """
 
     @staticmethod

@@ -47,11 +47,11 @@ class _RngMixin:
         self._rng[1] = 0
 
 
-def _require_supported(model_name: str, n_layers: int, what: str, gru_ok: bool = False):
+def _require_supported(model_name: str, n_layers: int, what: str, gru_ok: bool = False, max_layers: int = 1):
     if model_name != "LSTM" and not gru_ok:
         raise NotImplementedError(f"{what}: model_name={model_name!r} (GRU) is not built yet in recnet_b200; use 'LSTM'")
-    if n_layers != 1:
-        raise NotImplementedError(f"{what}: n_layers={n_layers} is not built yet in recnet_b200; use 1")
+    if n_layers > max_layers or (n_layers > 1 and model_name != "LSTM"):
+        raise NotImplementedError(f"{what}: n_layers={n_layers} with {model_name} cells is not built yet in recnet_b200")
 
 
 class Decoder(nn.Module, _RngMixin):
@@ -87,32 +87,52 @@ class Decoder(nn.Module, _RngMixin):
     # ---- helpers ----
     def _params(self):
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        return (self.embedding.weight, self.attn_W.weight, self.attn_U.weight, self.attn_b, self.attn_w.weight,
+        base = (self.embedding.weight, self.attn_W.weight, self.attn_U.weight, self.attn_b, self.attn_w.weight,
                 w_ih, w_hh, b_ih, b_hh, self.out.weight, self.out.bias)
+        extra = tuple(t for l in range(1, self.n_layers) for t in self.rnn.layer(l))       # stacked layers 1..NL-1
+        return base + extra
 
     def _meta(self):
         return dict(H=self.hidden_size, A=self.attn_size, EMB=self.embedding_size, V=self.output_size,
                     precision=_precision_id(self.precision), train=self.training, embedding_scale=self.embedding_scale,
-                    p_emb=self.embedding_dropout_p, p_out=self.out_dropout_p,
+                    p_emb=self.embedding_dropout_p, p_out=self.out_dropout_p, p_layer=self.dropout_p,
                     cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)       # decoder.py:32-35
 
     # ---- whole teacher-forced loop: one C call ----
     def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs):
-        """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,B,H), reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
+        """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,NL,B,H), reg = sum_p ||p||)."""
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
         return Fn.DecoderSequenceFn.apply(self._meta(), encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(),
                                           *self._params())
 
     @torch.no_grad()
     def teacher_forced_logits(self, tokens_in, encoder_outputs):
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
         return Fn.decoder_teacher_forced_logits(self._meta(), encoder_outputs, tokens_in, self._rng, self._params())
 
     @torch.no_grad()
     def greedy(self, encoder_outputs, max_steps):
         """eval.greedy_search (eval.py:19-33) on device: returns (ids (n,B) int64 on device, n)."""
         import ctypes as C
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
+        if self.n_layers > 1:       # stacked decoder: step-by-step through Decoder.forward (our kernels), feedback on device
+            B = encoder_outputs.shape[0]
+            dev = encoder_outputs.device
+            z = lambda: torch.zeros(self.n_layers, B, self.hidden_size, device=dev)
+            hid, tok = (z(), z()), torch.ones(1, B, dtype=torch.long, device=dev)
+            was_training = self.training
+            self.eval()
+            ids = torch.zeros(max_steps, B, dtype=torch.long, device=dev)
+            n = max_steps
+            for t in range(max_steps):
+                logits, hid = self.forward(tok, hid, encoder_outputs)
+                tok = logits.argmax(dim=1).view(1, -1)
+                ids[t] = tok[0]
+                if bool((tok == 0).all()):
+                    n = t + 1
+                    break
+            self.train(was_training)
+            return ids, torch.tensor([n], dtype=torch.int32, device=dev)
         lib = L.lib()
         feats = Fn._f32c(encoder_outputs, "encoder_outputs")
         B, T, E = feats.shape
@@ -132,8 +152,8 @@ class Decoder(nn.Module, _RngMixin):
 
     # ---- single timestep (reference API) ----
     def forward(self, input, hidden, encoder_outputs):
-        """input (1,B) int64; hidden ((1,B,H),(1,B,H)) [LSTM] or (1,B,H) [GRU]; encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True)
+        """input (1,B) int64; hidden ((NL,B,H),(NL,B,H)) [LSTM] or (1,B,H) [GRU]; encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""
+        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
         p = _precision_id(self.precision)
         is_lstm = self.model_name == "LSTM"
         h, c = (hidden[0][-1], hidden[1][-1]) if is_lstm else (hidden[-1], None)
@@ -154,6 +174,17 @@ class Decoder(nn.Module, _RngMixin):
         ctx = ops.additive_attention(Wh, Uv, self.attn_b, self.attn_w.weight, encoder_outputs, p)          # decoder.py:55-61
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
         gi, gh = ops.linear(torch.cat((emb, ctx), dim=1), w_ih, b_ih, p), ops.linear(h, w_hh, b_hh, p)     # decoder.py:64-66
+        if self.n_layers > 1:          # stacked LSTM: layer 0 takes [emb ; ctx], layer l the (dropped-out) output of layer l-1
+            hs, cs, x = [], [], torch.cat((emb, ctx), dim=1)
+            for l in range(self.n_layers):
+                w_ih, w_hh, b_ih, b_hh = self.rnn.layer(l)
+                pre = ops.linear(x, w_ih, b_ih, p) + ops.linear(hidden[0][l], w_hh, b_hh, p)
+                hl, cl = ops.lstm_cell(pre, hidden[1][l], p)
+                hs.append(hl); cs.append(cl)
+                x = torch.nn.functional.dropout(hl, self.dropout_p, self.training) if l < self.n_layers - 1 else hl
+            logits = ops.linear(hs[-1], self.out.weight, self.out.bias, p)
+            logits = torch.nn.functional.dropout(logits, self.out_dropout_p, self.training)
+            return logits, (torch.stack(hs), torch.stack(cs))
         if is_lstm:
             h2, c2 = ops.lstm_cell(gi + gh, c, p)
         else:

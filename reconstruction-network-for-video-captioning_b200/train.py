@@ -45,7 +45,7 @@ def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_for
     ce_weight = m / (n_t.clamp_min(1.0) * n_t.sum())                                                                       # mean over n_t, then / sum n_t (train.py:54-60,68)
     ce, hiddens, reg_loss = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs)     # reg: train.py:69
     loss = ce + decoder['lambda_reg'] * reg_loss                                                            # train.py:70
-    return loss, hiddens.unsqueeze(1), output_indices                                                       # train.py:73-75
+    return loss, hiddens, output_indices                                                                    # (L,NL,B,H), train.py:73-75
 
 
 def forward_global_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):

@@ -41,14 +41,15 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_struct_layouts_match_header_field_order():
-    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     for cname, struct in (("recnet_decoder_tensors", L.decoder_tensors), ("recnet_local_tensors", L.local_tensors),
                           ("recnet_global_tensors", L.global_tensors)):
         body = re.search(r"typedef struct \{([^}]*)\}\s*" + cname, src, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = re.findall(r"\*(\w+)", body)
-        assert tuple(fields) == struct.FIELDS
-    assert ctypes.sizeof(L.decoder_desc) == 10 * 4 + 3 * 4 + 4
+        assert tuple(fields) == struct.FIELDS + getattr(struct, "EXTRA", ())
+    assert ctypes.sizeof(L.decoder_desc) == 10 * 4 + 3 * 4 + 4 + 8
+    assert ctypes.sizeof(L.decoder_tensors) == (11 + 4 * 3) * 8
     assert ctypes.sizeof(L.local_desc) == 8 * 4 + 4 + 4
     assert ctypes.sizeof(L.global_desc) == 7 * 4 + 2 * 4 + 4
 

@@ -421,6 +421,32 @@ def test_gru_decoder_plus_gru_reconstructor_match_reference_golden(precision, ki
         assert rel(p.grad, ref) < tol, k
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_two_layer_decoder_matches_reference_golden(precision):
+    """Stacked decoder (decoder_n_layers = 2, BASELINE config 5 family): loss, hiddens (L,2,B,H), gradients of every layer,
+    greedy ids and the per-step forward against the reference-generated fixture."""
+    g = load_golden("tiny_lstm_2layer")
+    m = g["meta"]
+    tol = TOL[precision]
+    dec, _ = build(m, precision, "none", g["dec"], {})
+    feats, targets = g["feats"].float().to(dev()), g["targets"].to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, feats, targets, targets > 0, 1.0)
+    assert hiddens.shape == g["hiddens"].shape
+    assert rel(dloss, torch.tensor(g["dec_loss"])) < tol and rel(hiddens, g["hiddens"]) < tol
+    dloss.backward()
+    for k, ref in g["grads"]["none"].items():
+        assert rel(dict(dec["model"].named_parameters())[k[4:]].grad, ref) < tol, k
+    B, H = feats.shape[0], m["H"]
+    tok = torch.full((1, B), 1, dtype=torch.long, device=dev())
+    z = torch.zeros(2, B, H, device=dev())
+    with torch.no_grad():
+        logits, (h1, c1) = dec["model"](tok, (z, z.clone()), feats)
+    assert h1.shape == (2, B, H) and rel(logits, g["step0_logits"]) < tol
+    if precision == "fp32":
+        ids, n = dec["model"].greedy(feats, m["cap_len"] + 1)
+        assert torch.equal(ids[: int(n)].cpu(), g["greedy_ids"])
+
+
 class _Vocab:
     def __init__(self, n):
         self.n_vocabs = n

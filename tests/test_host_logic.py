@@ -69,7 +69,7 @@ def test_unsupported_variants_raise_not_silently_fall_back():
     rec = recnet_b200.LocalReconstructor("LSTM", 2, 8, 16, 0.5, 0.5, 8)         # multi-layer reconstructors: not built yet -> must raise
     with pytest.raises(NotImplementedError):
         rec.forward_sequence(torch.zeros(3, 2, 8), torch.zeros(2, 4, 16))
-    two = recnet_b200.Decoder("LSTM", 2, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)
+    two = recnet_b200.Decoder("GRU", 2, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)      # stacked GRU: not built yet -> must raise
     with pytest.raises(NotImplementedError):
         two.forward_sequence(None, None, None, None)
     with pytest.raises(NotImplementedError):

@@ -181,6 +181,7 @@ typedef struct {
   int32_t precision, train;
   float p_drop;
   int32_t cell;                         /* recnet_cell of the reconstructor RNN */
+  int32_t dec_layers;                   /* decoder layers NLd: hiddens is (L, NLd, B, H) and every outer step runs NLd pseudo-steps */
 } recnet_local_desc;
 typedef struct {
   float *attn_W, *attn_U, *attn_b, *attn_w, *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;
@@ -200,6 +201,7 @@ typedef struct {
   int32_t precision, train;
   float p_drop, caption_max_len;
   int32_t cell;                         /* recnet_cell of the reconstructor RNN */
+  int32_t dec_layers;                   /* decoder layers NLd: hiddens is (L, NLd, B, H); 0/1 = one */
 } recnet_global_desc;
 typedef struct {
   float *w_ih, *w_hh, *b_ih, *b_hh, *out_w, *out_b;

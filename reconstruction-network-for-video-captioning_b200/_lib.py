@@ -58,7 +58,7 @@ class decoder_tensors(C.Structure):
 
 
 class local_desc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "S", "R", "H", "A", "L", "precision", "train")] + [("p_drop", C.c_float), ("cell", C.c_int32)]
+    _fields_ = [(n, C.c_int32) for n in ("B", "S", "R", "H", "A", "L", "precision", "train")] + [("p_drop", C.c_float), ("cell", C.c_int32), ("dec_layers", C.c_int32)]
 
 
 class local_tensors(C.Structure):
@@ -68,7 +68,7 @@ class local_tensors(C.Structure):
 
 class global_desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "L", "R", "H", "T", "precision", "train")] + \
-               [("p_drop", C.c_float), ("caption_max_len", C.c_float), ("cell", C.c_int32)]
+               [("p_drop", C.c_float), ("caption_max_len", C.c_float), ("cell", C.c_int32), ("dec_layers", C.c_int32)]
 
 
 class global_tensors(C.Structure):

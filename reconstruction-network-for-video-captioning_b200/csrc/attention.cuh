@@ -209,7 +209,8 @@ struct BwdArgs {
   float* dWh_out;                      // [B,A] fp32
   void* dWh_op;                        // [B,A] operand type (nullable): A-operand of the dWh @ attn_W GEMM
   float* dUv_acc; int uv_first;        // same strides as Uv; first => overwrite instead of +=
-  float* dw_acc;                       // [B,A] += ; first => overwrite
+  float* dw_acc; int dw_first;         // [B,A] += ; dw_first => overwrite
+  int dwh_acc;                         // dWh_out += (several attentions share one query: stacked-decoder pseudo-steps)
   float* dctx_out;                     // [B,D] fp32 (nullable): summed/masked dctx, for the deferred dV pass
   float* de_out;                       // [B,Tn] (nullable)
   float p_drop; const unsigned long long* rng; unsigned int site; long long drop_base;
@@ -367,10 +368,11 @@ __device__ __forceinline__ void attn_bwd_body(const BwdArgs& a, int b, float* sm
       blk_sync(bar_id);
     }
     if (part == 0 && i < a.A) {
+      if (a.dwh_acc) dwh += a.dWh_out[(long long)b * a.A + i];
       a.dWh_out[(long long)b * a.A + i] = dwh;
       if (a.dWh_op) reinterpret_cast<TO*>(a.dWh_op)[(long long)b * a.A + i] = from_f32<TO>(dwh);
       float* pw = a.dw_acc + (long long)b * a.A + i;
-      *pw = a.uv_first ? dw : *pw + dw;
+      *pw = a.dw_first ? dw : *pw + dw;
     }
   }
 }
@@ -386,15 +388,17 @@ __global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
 // Deferred value-gradient of the local reconstructor's attention (values = decoder hiddens, which need grad):
 //   dV[l,b,:] (+)= inv_T * sum_t beta_t[b,l] * dx_t[b,:]        one pass after the time loop instead of Tsteps RMWs
 // beta [S,B,Tn] fp32, dx [S,B,D] fp32, dV[b*dv_bs + l*dv_ts + d] fp32.
+// step_mul / step_off: stash row of outer step t is t * step_mul + step_off (pseudo-steps of a stacked decoder)
 __global__ void attn_dv_kernel(const float* __restrict__ beta, const float* __restrict__ dx, float* __restrict__ dV,
-                               long long dv_bs, long long dv_ts, int S, int B, int Tn, int D, float inv_T, int accumulate) {
+                               long long dv_bs, long long dv_ts, int S, int B, int Tn, int D, float inv_T, int accumulate,
+                               int step_mul, int step_off) {
   const int b = blockIdx.y, l = blockIdx.x;
   extern __shared__ float bt[];   // [S]
-  for (int t = threadIdx.x; t < S; t += blockDim.x) bt[t] = beta[((long long)t * B + b) * Tn + l];
+  for (int t = threadIdx.x; t < S; t += blockDim.x) bt[t] = beta[((long long)(t * step_mul + step_off) * B + b) * Tn + l];
   __syncthreads();
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float s = 0.f;
-    for (int t = 0; t < S; ++t) s += bt[t] * dx[((long long)t * B + b) * D + d];
+    for (int t = 0; t < S; ++t) s += bt[t] * dx[((long long)(t * step_mul + step_off) * B + b) * D + d];
     float* p = dV + (long long)b * dv_bs + (long long)l * dv_ts + d;
     s *= inv_T;
     *p = accumulate ? *p + s : s;

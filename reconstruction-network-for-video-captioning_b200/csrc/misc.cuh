@@ -131,16 +131,18 @@ __global__ void pool_time_bwd_kernel(const float* __restrict__ dmp, int L, long 
 }
 
 // Global reconstructor operand rows: Xg[t,b,:] = [Hd[t,b,:], mp[b,:] * dropmask(t,b,:)]   (TO)
+// Hd is (L, NLd, B, H): the per-step input is the LAYER-0 state (global_reconstructor.py:40 `input[0]`)
 template <typename TO>
 __global__ void global_x_kernel(const float* __restrict__ Hd, const float* __restrict__ mp, TO* __restrict__ X, int L, int B,
-                                int H, float p_drop, const unsigned long long* rng, unsigned int site) {
+                                int H, int NLd, float p_drop, const unsigned long long* rng, unsigned int site) {
   const long long total = (long long)L * B * 2 * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (2 * H));
     const long long tb = i / (2 * H);
     const int b = (int)(tb % B);
+    const long long t = tb / B;
     float v;
-    if (c < H) v = Hd[tb * H + c];
+    if (c < H) v = Hd[((t * NLd) * B + b) * H + c];
     else {
       v = mp[(long long)b * H + (c - H)];
       if (p_drop > 0.f) v *= dropout_scale(rng, site, (uint64_t)(tb * H + (c - H)), p_drop);
@@ -150,7 +152,7 @@ __global__ void global_x_kernel(const float* __restrict__ Hd, const float* __res
 }
 // dmp[b,j] = sum_t dXg[t,b,H+j] * dropmask ; dHd[t,b,j] (+)= dXg[t,b,j]
 __global__ void global_x_bwd_kernel(const float* __restrict__ dX, float* __restrict__ dHd, float* __restrict__ dmp, int L, int B,
-                                    int H, int accumulate, float p_drop, const unsigned long long* rng, unsigned int site) {
+                                    int H, int NLd, int accumulate, float p_drop, const unsigned long long* rng, unsigned int site) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * H) return;
   const int b = (int)(i / H), j = (int)(i % H);
@@ -160,9 +162,11 @@ __global__ void global_x_bwd_kernel(const float* __restrict__ dX, float* __restr
     float g = dX[tb * 2 * H + H + j];
     if (p_drop > 0.f) g *= dropout_scale(rng, site, (uint64_t)(tb * H + j), p_drop);
     s += g;
-    float* p = dHd + tb * H + j;
+    float* p = dHd + (((long long)t * NLd) * B + b) * H + j;          // layer-0 slice of (L, NLd, B, H)
     const float d = dX[tb * 2 * H + j];
     *p = accumulate ? *p + d : d;
+    if (!accumulate)
+      for (int l = 1; l < NLd; ++l) dHd[(((long long)t * NLd + l) * B + b) * H + j] = 0.f;   // other layers: only the pooled term
   }
   dmp[i] = s;
 }

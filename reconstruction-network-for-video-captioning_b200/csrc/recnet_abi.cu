@@ -3,6 +3,7 @@
 #include "seq_decoder.cuh"
 #include "seq_decoder_ml.cuh"
 #include "seq_recon.cuh"
+#include "seq_recon_ml.cuh"
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -121,7 +122,7 @@ int recnet_attn_bwd(int precision, const float* dctx_partials, int n_p, int64_t 
   attn::BwdArgs a{};
   a.dXp = dctx_partials; a.n_p = n_p; a.p_stride = p_stride; a.p_ld = p_ld; a.V = v; a.v_bs = v_bs; a.v_ts = v_ts;
   a.Wh = wh; a.Uv = uv; a.uv_bs = uv_bs; a.uv_ts = uv_ts; a.attn_b = attn_b; a.attn_w = attn_w; a.B = B; a.Tn = Tn; a.A = A;
-  a.D = D; a.inv_T = 1.f / Tn; a.dWh_out = dwh_out; a.dWh_op = dwh_op; a.dUv_acc = duv_acc; a.uv_first = first; a.dw_acc = dw_acc;
+  a.D = D; a.inv_T = 1.f / Tn; a.dWh_out = dwh_out; a.dWh_op = dwh_op; a.dUv_acc = duv_acc; a.uv_first = first; a.dw_first = first; a.dw_acc = dw_acc;
   a.dctx_out = dctx_out; a.de_out = nullptr; a.p_drop = p_drop; a.rng = reinterpret_cast<const unsigned long long*>(rng);
   a.site = site; a.drop_base = drop_base;
   if (precision == RECNET_PREC_FP32) return (attn::launch_bwd<float, float>(a, ST(stream)));
@@ -272,6 +273,11 @@ int64_t recnet_local_workspace_bytes(const recnet_local_desc* d) {
 int recnet_local_fwd(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, float* mse_out, void* stream) {
   const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->dec_layers > 1) {
+    if (d->precision == RECNET_PREC_FP32) return rec::local_forward_ml<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, mse_out, ST(stream));
+    if (d->precision == RECNET_PREC_BF16) return rec::local_forward_ml<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, mse_out, ST(stream));
+    return RECNET_ERR_UNSUPPORTED;
+  }
   if (d->precision == RECNET_PREC_FP32) return rec::local_forward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, mse_out, ST(stream));
   if (d->precision == RECNET_PREC_BF16) return rec::local_forward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, mse_out, ST(stream));
   return RECNET_ERR_UNSUPPORTED;
@@ -280,6 +286,11 @@ int recnet_local_bwd(const recnet_local_desc* d, const recnet_local_tensors* w, 
                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
                      const recnet_local_tensors* grads, float* g_hiddens, void* stream) {
   const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->dec_layers > 1) {
+    if (d->precision == RECNET_PREC_FP32) return rec::local_backward_ml<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
+    if (d->precision == RECNET_PREC_BF16) return rec::local_backward_ml<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
+    return RECNET_ERR_UNSUPPORTED;
+  }
   if (d->precision == RECNET_PREC_FP32) return rec::local_backward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
   if (d->precision == RECNET_PREC_BF16) return rec::local_backward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
   return RECNET_ERR_UNSUPPORTED;

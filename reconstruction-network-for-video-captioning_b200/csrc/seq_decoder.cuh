@@ -313,7 +313,7 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
         ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * Tn * A; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
         ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
         ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * Tn * A;
-        ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+        ab.uv_first = last ? 1 : 0; ab.dw_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
         ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
         RN_TRY(em.attn_bwd(ab));
         if (t > 0) RN_TRY(em.gemm_partials(w.dWh_op + r * A, A, 0, w.Wa, H, 1, dQp, nb, H, A, w.pl_dq));
@@ -337,7 +337,7 @@ static int backward(const recnet_decoder_desc& d, const recnet_decoder_tensors& 
       ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * Tn * A; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
       ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
       ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * Tn * A;
-      ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+      ab.uv_first = last ? 1 : 0; ab.dw_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
       ab.dctx_out = nullptr; ab.de_out = nullptr; ab.p_drop = 0.f;
       RN_TRY(em.attn_bwd(ab));
       // attention-query path into h_{t-1}: dWh_t @ attn_W, consumed (as split-K partials) by the next cell backward

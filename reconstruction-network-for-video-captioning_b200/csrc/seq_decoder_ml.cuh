@@ -31,6 +31,7 @@ static int forward_ml(const recnet_decoder_desc& d, const recnet_decoder_tensors
   RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   for (int l = 1; l < NL; ++l) {
     RN_CUDA_OK(cudaMemsetAsync(w.X_x[l - 1], 0, (size_t)B * 2 * H * sizeof(T), st));
     RN_CUDA_OK(cudaMemsetAsync(w.c_x[l - 1], 0, (size_t)B * H * sizeof(float), st));
@@ -139,7 +140,7 @@ static int backward_ml(const recnet_decoder_desc& d, const recnet_decoder_tensor
     ab.Wh = w.Wh + (size_t)t * B * A; ab.Uv = w.Uv; ab.uv_bs = (long long)Tn * A; ab.uv_ts = A;
     ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = B; ab.Tn = Tn; ab.A = A; ab.D = E; ab.inv_T = 1.f / Tn;
     ab.dWh_out = w.dWh + (size_t)t * B * A; ab.dWh_op = w.dWh_op + (size_t)t * B * A; ab.dUv_acc = w.dUv;
-    ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc;
+    ab.uv_first = last ? 1 : 0; ab.dw_first = last ? 1 : 0; ab.dw_acc = w.dw_acc;
     RN_TRY(em.attn_bwd(ab));
     if (t > 0) RN_TRY(em.gemm_partials(w.dWh_op + (size_t)t * B * A, A, 0, w.Wa, H, 1, w.dQp, B, H, A, w.pl_dq));
   }

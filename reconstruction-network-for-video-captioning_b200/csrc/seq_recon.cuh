@@ -26,6 +26,7 @@ struct LocalWs {
   T* dOut; float* dHext; T* dG; T* dG2; float* dXp; float* dXp2; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
   float* dx; float* splitk;
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
+  T* Hout; T* Hq;                 // stacked decoder only: compact rows of h after pseudo-step (t,0) / at the start of outer step t
   size_t bytes;
 };
 constexpr int MSE_BLOCKS = 592;
@@ -33,7 +34,9 @@ constexpr int MSE_BLOCKS = 592;
 template <typename T>
 static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   LocalWs<T> w;
-  const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
+  const int NLd = d.dec_layers < 1 ? 1 : d.dec_layers;
+  // with a stacked decoder every outer step runs NLd pseudo-steps and the hiddens carry a layer axis: size by S*NLd / L*NLd
+  const int B = d.B, S = d.S * NLd, R = d.R, H = d.H, A = d.A, L = d.L * NLd;
   w.KX = H + R;
   w.nch = num_chains(B);
   w.Bc = chain_rows_max(B, w.nch);
@@ -84,6 +87,8 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.table = m.take<uint8_t>(w.table_bytes);
   w.bar = m.take<unsigned>(64);
   w.err = m.take<int>(64);
+  w.Hout = m.take<T>(NLd > 1 ? (size_t)d.S * B * R : 1);
+  w.Hq = m.take<T>(NLd > 1 ? (size_t)d.S * B * R : 1);
   w.bytes = m.off + 256;
   return w;
 }
@@ -91,6 +96,7 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
 static inline int check_local(const recnet_local_desc& d) {
   if (d.B < 1 || d.S < 1 || d.L < 1 || d.L > attn::MAX_T) return RECNET_ERR_BAD_SHAPE;
   if (d.cell != RECNET_CELL_LSTM && d.cell != RECNET_CELL_GRU) return RECNET_ERR_UNSUPPORTED;
+  if (d.dec_layers > 1 && d.cell != RECNET_CELL_LSTM) return RECNET_ERR_UNSUPPORTED;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if (d.R % al || d.H % al || d.A % 4) return RECNET_ERR_ALIGNMENT;
   return 0;
@@ -231,7 +237,7 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
         ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * A; ab.uv_bs = A; ab.uv_ts = (long long)B * A;
         ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = L; ab.A = A; ab.D = H; ab.inv_T = 1.f / L;
         ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * A;
-        ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+        ab.uv_first = last ? 1 : 0; ab.dw_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
         ab.dctx_out = w.dx + r * H; ab.de_out = nullptr;
         ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)r * H;
         RN_TRY(em.attn_bwd(ab));
@@ -254,7 +260,7 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
       ab.Wh = w.Wh + r * A; ab.Uv = w.Uv + (size_t)b0 * A; ab.uv_bs = A; ab.uv_ts = (long long)B * A;
       ab.attn_b = p.attn_b; ab.attn_w = p.attn_w; ab.B = nb; ab.Tn = L; ab.A = A; ab.D = H; ab.inv_T = 1.f / L;
       ab.dWh_out = w.dWh + r * A; ab.dWh_op = w.dWh_op + r * A; ab.dUv_acc = w.dUv + (size_t)b0 * A;
-      ab.uv_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
+      ab.uv_first = last ? 1 : 0; ab.dw_first = last ? 1 : 0; ab.dw_acc = w.dw_acc + (size_t)b0 * A;
       ab.dctx_out = w.dx + r * H; ab.de_out = nullptr;
       ab.p_drop = p_drop; ab.rng = rng; ab.site = SITE_LOCAL_X; ab.drop_base = (long long)r * H;
       RN_TRY(em.attn_bwd(ab));
@@ -279,7 +285,7 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   {
     dim3 grid(L, B);
     attn::attn_dv_kernel<<<grid, 128, (size_t)S * sizeof(float), st>>>(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H,
-                                                                      1.f / L, 1);
+                                                                      1.f / L, 1, 1, 0);
     RN_LAUNCH_OK();
   }
   return 0;
@@ -361,9 +367,10 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
   RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
   // mean over time (and the single decoder layer), then / L * caption_max_len  (global_reconstructor.py:33-37)
   const long long n = (long long)B * H;
-  misc::pool_time_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(hiddens, L, n, d.caption_max_len / ((float)L * L), w.mp);
+  const int NLd = d.dec_layers < 1 ? 1 : d.dec_layers;      // hiddens is (L, NLd, B, H); mean over time AND layers (global_reconstructor.py:33-36)
+  misc::pool_time_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(hiddens, L * NLd, n, d.caption_max_len / ((float)L * NLd * L), w.mp);
   RN_LAUNCH_OK();
-  misc::global_x_kernel<T><<<NUM_SMS * 4, 256, 0, st>>>(hiddens, w.mp, w.Xg, L, B, H, p_drop, rng, SITE_GLOBAL_MP);
+  misc::global_x_kernel<T><<<NUM_SMS * 4, 256, 0, st>>>(hiddens, w.mp, w.Xg, L, B, H, NLd, p_drop, rng, SITE_GLOBAL_MP);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.Xg, 2 * H, 0, w.Wih, 2 * H, 0, w.Gx, GR, p.b_ih, L * B, GR, 2 * H, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * R * sizeof(T), st));
@@ -481,9 +488,10 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
   RN_TRY(gemm_full<T>(w.dG, GR, 1, w.Xg, 2 * H, 1, g.w_ih, 2 * H, nullptr, GR, 2 * H, LB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dG, GR, 0, w.Wih, 2 * H, 1, w.dXg, 2 * H, nullptr, LB, 2 * H, GR, 0, w.splitk, st));
   const long long n = (long long)B * H;
-  misc::global_x_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dXg, g_hiddens, w.dmp, L, B, H, 0, p_drop, rng, SITE_GLOBAL_MP);
+  const int NLd = d.dec_layers < 1 ? 1 : d.dec_layers;
+  misc::global_x_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dXg, g_hiddens, w.dmp, L, B, H, NLd, 0, p_drop, rng, SITE_GLOBAL_MP);
   RN_LAUNCH_OK();
-  misc::pool_time_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dmp, L, n, d.caption_max_len / ((float)L * L), g_hiddens, 1);
+  misc::pool_time_bwd_kernel<<<rn_cdiv(n, 256), 256, 0, st>>>(w.dmp, L * NLd, n, d.caption_max_len / ((float)L * NLd * L), g_hiddens, 1);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -212,10 +212,19 @@ def decoder_teacher_forced_logits(meta: Dict, feats, tokens_in, rng, params):
     return flat[:, :, : meta["V"]], hiddens
 
 
+def _layered_shape(hiddens):
+    """decoder hiddens are (L,B,H) or, from a stacked decoder, (L,NLdec,B,H) -> (L, NLdec, B, H) sizes."""
+    if hiddens.dim() == 4:
+        return tuple(hiddens.shape)
+    if hiddens.dim() != 3:
+        raise ValueError(f"decoder_hiddens must be (L,B,H) or (L,n_layers,B,H), got {tuple(hiddens.shape)}")
+    return hiddens.shape[0], 1, hiddens.shape[1], hiddens.shape[2]
+
+
 # ----------------------------------------------------------------------------------------------------------------
 class LocalReconstructorFn(torch.autograd.Function):
     """train.forward_local_reconstructor (train.py:108-131) over LocalReconstructor.forward.
-    inputs: meta, hiddens (L,B,H), feats (B,S,R), rng, then the 10 parameters in local_tensors.FIELDS order.
+    inputs: meta, hiddens (L,B,H) or (L,NLdec,B,H), feats (B,S,R), rng, then the 10 parameters in local_tensors.FIELDS order.
     outputs: mse (scalar), reg (scalar)."""
 
     @staticmethod
@@ -223,10 +232,10 @@ class LocalReconstructorFn(torch.autograd.Function):
         lib = L.lib()
         hiddens, feats = _f32c(hiddens, "decoder_hiddens"), _f32c(feats, "encoder_outputs")
         params = tuple(_f32c(p, n) for p, n in zip(params, L.local_tensors.FIELDS))
-        Lsteps, B, H = hiddens.shape
+        Lsteps, NLd, B, H = _layered_shape(hiddens)
         _, S, R = feats.shape
         d = L.local_desc(B=B, S=S, R=R, H=H, A=meta["A"], L=Lsteps, precision=meta["precision"], train=int(meta["train"]),
-                         p_drop=float(meta["p_drop"]), cell=int(meta.get("cell", L.CELL_LSTM)))
+                         p_drop=float(meta["p_drop"]), cell=int(meta.get("cell", L.CELL_LSTM)), dec_layers=NLd)
         nbytes = lib.recnet_local_workspace_bytes(C.byref(d))
         if nbytes < 0:
             L.check(int(nbytes), "recnet_local_workspace_bytes")
@@ -260,7 +269,7 @@ class LocalReconstructorFn(torch.autograd.Function):
 
 class GlobalReconstructorFn(torch.autograd.Function):
     """train.forward_global_reconstructor (train.py:78-105) over GlobalReconstructor.forward.
-    inputs: meta, hiddens (L,B,H), feats (B,T,R), rng, then the 6 parameters in global_tensors.FIELDS order.
+    inputs: meta, hiddens (L,B,H) or (L,NLdec,B,H), feats (B,T,R), rng, then the 6 parameters in global_tensors.FIELDS order.
     outputs: MSE(mean_t out, mean_tau feats) / L  (scalar), reg (scalar)."""
 
     @staticmethod
@@ -268,11 +277,11 @@ class GlobalReconstructorFn(torch.autograd.Function):
         lib = L.lib()
         hiddens, feats = _f32c(hiddens, "decoder_hiddens"), _f32c(feats, "encoder_outputs")
         params = tuple(_f32c(p, n) for p, n in zip(params, L.global_tensors.FIELDS))
-        Lsteps, B, H = hiddens.shape
+        Lsteps, NLd, B, H = _layered_shape(hiddens)
         _, T, R = feats.shape
         d = L.global_desc(B=B, L=Lsteps, R=R, H=H, T=T, precision=meta["precision"], train=int(meta["train"]),
                           p_drop=float(meta["p_drop"]), caption_max_len=float(meta["caption_max_len"]),
-                          cell=int(meta.get("cell", L.CELL_LSTM)))
+                          cell=int(meta.get("cell", L.CELL_LSTM)), dec_layers=NLd)
         nbytes = lib.recnet_global_workspace_bytes(C.byref(d))
         if nbytes < 0:
             L.check(int(nbytes), "recnet_global_workspace_bytes")

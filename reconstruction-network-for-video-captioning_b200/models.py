@@ -219,7 +219,7 @@ class GlobalReconstructor(nn.Module, _RngMixin):
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
         """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||)."""
         _require_supported(self.model_name, self.n_layers, "GlobalReconstructor", gru_ok=True)
-        hid = _squeeze_layers(decoder_hiddens)
+        hid = _sequence_hiddens(decoder_hiddens, self.model_name)
         meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p,
                     caption_max_len=self.caption_max_len, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.GlobalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
@@ -274,7 +274,7 @@ class LocalReconstructor(nn.Module, _RngMixin):
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
         """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||)."""
         _require_supported(self.model_name, self.n_layers, "LocalReconstructor", gru_ok=True)
-        hid = _squeeze_layers(decoder_hiddens)
+        hid = _sequence_hiddens(decoder_hiddens, self.model_name)
         meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training,
                     p_drop=self.decoder_dropout_p, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.LocalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
@@ -301,9 +301,18 @@ class LocalReconstructor(nn.Module, _RngMixin):
         return out, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
 
 
+def _sequence_hiddens(decoder_hiddens: torch.Tensor, model_name: str) -> torch.Tensor:
+    """(L,1,B,H) -> (L,B,H); a stacked decoder's (L,NLdec,B,H) passes through (LSTM reconstructor cells only)."""
+    if decoder_hiddens.dim() == 4 and decoder_hiddens.size(1) != 1:
+        if model_name != "LSTM":
+            raise NotImplementedError("GRU reconstructors over a stacked decoder are not built in recnet_b200")
+        return decoder_hiddens
+    return _squeeze_layers(decoder_hiddens)
+
+
 def _squeeze_layers(decoder_hiddens: torch.Tensor) -> torch.Tensor:
     if decoder_hiddens.dim() == 4:
         if decoder_hiddens.size(1) != 1:
-            raise NotImplementedError("multi-layer decoder hiddens are not built yet in recnet_b200")
+            raise NotImplementedError("per-step reconstructor forward over a stacked decoder is not built in recnet_b200; use forward_sequence")
         return decoder_hiddens[:, 0]
     return decoder_hiddens

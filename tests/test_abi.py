@@ -50,8 +50,8 @@ def test_struct_layouts_match_header_field_order():
         assert tuple(fields) == struct.FIELDS + getattr(struct, "EXTRA", ())
     assert ctypes.sizeof(L.decoder_desc) == 10 * 4 + 3 * 4 + 4 + 8
     assert ctypes.sizeof(L.decoder_tensors) == (11 + 4 * 3) * 8
-    assert ctypes.sizeof(L.local_desc) == 8 * 4 + 4 + 4
-    assert ctypes.sizeof(L.global_desc) == 7 * 4 + 2 * 4 + 4
+    assert ctypes.sizeof(L.local_desc) == 8 * 4 + 4 + 4 + 4
+    assert ctypes.sizeof(L.global_desc) == 7 * 4 + 2 * 4 + 4 + 4
 
 
 def test_workspace_size_queries_run_on_cpu():

@@ -447,6 +447,28 @@ def test_two_layer_decoder_matches_reference_golden(precision):
         assert torch.equal(ids[: int(n)].cpu(), g["greedy_ids"])
 
 
+@pytest.mark.parametrize("kind", ["global", "local"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_reconstructors_over_two_layer_decoder_match_reference_golden(precision, kind):
+    """Reconstructors fed by a stacked decoder's (L,2,B,H) hiddens: the global one pools over time AND layers and reads
+    layer 0 (global_reconstructor.py:33-40); the local one runs one LSTM pseudo-step per decoder layer and projects the
+    first (local_reconstructor.py:42-54).  Joint loss and every gradient (decoder layers included)."""
+    g = load_golden("tiny_lstm_2layer")
+    tol = TOL[precision]
+    dec, rec = build(g["meta"], precision, kind, g["dec"], g[kind])
+    feats, targets = g["feats"].float().to(dev()), g["targets"].to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, feats, targets, targets > 0, 1.0)
+    assert hiddens.shape[1] == 2
+    rloss = T.forward_reconstructor_for(kind)(hiddens, feats, rec)
+    assert rel(rloss, torch.tensor(g[kind + "_loss"])) < tol
+    (dloss + rloss).backward()
+    Fn.check_loop_status()
+    for k, ref in g["grads"][kind].items():
+        owner, key = k.split(".", 1)
+        p = dict((dec if owner == "dec" else rec)["model"].named_parameters())[key]
+        assert rel(p.grad, ref) < tol, k
+
+
 class _Vocab:
     def __init__(self, n):
         self.n_vocabs = n

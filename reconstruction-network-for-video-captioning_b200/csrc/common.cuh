@@ -21,7 +21,7 @@ typedef __nv_bfloat16 bf16;
 // (recnet_profile_enable), launch sites wrapped in a ProfScope also record a CUDA-event pair on the launching
 // stream, tagged with a kernel class and the problem shape; recnet_profile_collect returns per-launch durations.
 enum KernelClass { KC_OTHER = 0, KC_GEMM_TC = 1, KC_SGEMM = 2, KC_ATTN_FWD = 3, KC_ATTN_BWD = 4, KC_CELL_FWD = 5,
-                   KC_CELL_BWD = 6, KC_CE = 7, KC_REDUCE = 8, KC_LOOP = 9 };
+                   KC_CELL_BWD = 6, KC_CE = 7, KC_REDUCE = 8, KC_LOOP = 9, KC_PF_FWD = 10, KC_PF_BWD = 11 };
 struct ProfRecord { int cls, M, N, K; cudaEvent_t e0, e1; };
 struct ProfState {
   long long launches = 0;

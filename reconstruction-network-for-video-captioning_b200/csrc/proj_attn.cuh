@@ -1,0 +1,508 @@
+// Projected-feature attention fused with the LSTM cell (decoder hot path, models/decoder.py:50-66).
+//
+// The reference's attention has NO softmax: ctx_t[b] = (1/T) sum_tau e_t[b,tau] * v[b,tau]  (decoder.py:57-62) and the
+// context only ever enters the step through the LSTM input projection ctx_t W_ctx^T (decoder.py:64-66).  Both are
+// linear, so    ctx_t[b] W_ctx^T = (1/T) sum_tau e_t[b,tau] * (v[b,tau] W_ctx^T) = (1/T) sum_tau e_t[b,tau] * VW[b,tau]
+// with VW = feats W_ctx^T computed ONCE per sequence (one 2800 x 2048 x 1536 tensor-core GEMM) instead of a
+// [100 x 1536] x [1536 x 2048] GEMM in every one of the 31 steps.  What is left per step:
+//   K1  h_{t-1} [W_a ; W_hh]^T          one split-K tcgen05 GEMM, K = H = 512 (attention query + recurrent gates together)
+//   K2  pf_fwd_kernel                   scores e_t, the 28-frame weighted sum of VW, gate activations, c_t, h_t  (this file)
+// and in BPTT
+//   K3  pf_bwd_kernel                   cell backward -> dG_t, d e_t = <dG_t, VW>, score backward -> dWh_t, dUv, dw
+//   K4  [dWh_t | dG_t] [W_a ; W_hh]     one split-K GEMM, K = A + 4H -> dh_{t-1}
+// i.e. 2 + 2 dependent kernels per step instead of 4 + 4, and the per-step weight traffic drops from 8.4 MB to 2.2 MB.
+// dW_ctx = dVW^T feats with dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b] (pf_dvw_kernel, once after the loop).
+//
+// VW and the gate stash are stored "unit-interleaved": [.., H, 4] (the 4 gate columns i,f,g,o of one hidden unit
+// adjacent) so that one thread fetches its unit's 4 columns of a frame with ONE 8-byte (bf16) / 16-byte (fp32) load.
+#pragma once
+#include "common.cuh"
+
+namespace pf {
+constexpr int THREADS = 256;
+constexpr int UPB = 128;        // hidden units per forward CTA (2 frame-halves x 128 units = 256 threads)
+constexpr int MAX_T = 64;       // frames
+constexpr int MAX_A = 256;      // attention size (<= 2 float4 chunks per lane)
+constexpr int NW = THREADS / 32;
+
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  float4 r;
+  __device__ __forceinline__ void load(const float* p) { r = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void get(float* f) const { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
+  static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  }
+};
+template <> struct Quad<bf16> {
+  uint2 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void get(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(bf16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// Split-K partial sums.  These kernels are latency-bound: every load of a batch is issued before the first add
+// (a plain `for (s) acc += q[s * stride]` loop costs one L2 round trip PER SPLIT -- measured 17 us for 17 splits).
+__device__ __forceinline__ float sum_splits(const float* __restrict__ q, int n, long long stride) {
+  float s = 0.f;
+  int p = 0;
+  for (; p + 8 <= n; p += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = q[i * stride];
+    s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    q += 8 * stride;
+  }
+  if (p + 4 <= n) {
+    const float v0 = q[0], v1 = q[stride], v2 = q[2 * stride], v3 = q[3 * stride];
+    s += (v0 + v1) + (v2 + v3);
+    q += 4 * stride; p += 4;
+  }
+  if (p + 2 <= n) { const float v0 = q[0], v1 = q[stride]; s += v0 + v1; q += 2 * stride; p += 2; }
+  if (p < n) s += q[0];
+  return s;
+}
+__device__ __forceinline__ float4 sum_splits4(const float* __restrict__ q, int n, long long stride) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int p = 0;
+  for (; p + 4 <= n; p += 4) {
+    const float4 v0 = *reinterpret_cast<const float4*>(q), v1 = *reinterpret_cast<const float4*>(q + stride);
+    const float4 v2 = *reinterpret_cast<const float4*>(q + 2 * stride), v3 = *reinterpret_cast<const float4*>(q + 3 * stride);
+    s = f4_add(s, f4_add(f4_add(v0, v1), f4_add(v2, v3)));
+    q += 4 * stride;
+  }
+  for (; p < n; ++p) { s = f4_add(s, *reinterpret_cast<const float4*>(q)); q += stride; }
+  return s;
+}
+
+// ---- forward -----------------------------------------------------------------------------------------------------
+struct FwdArgs {
+  const float* P; int n_p; long long p_stride; int NP;   // split-K partials of h_{t-1} [W_a ; W_hh]^T: [n_p][B, NP = A + 4H]; n_p = 0 at t = 0
+  const float* Uv;                                        // [B, Tn, A]   hoisted U v
+  const float* attn_b; const float* attn_w;               // [A]
+  const void* VW;                                         // [B, Tn, H, 4] TV   hoisted v W_ctx^T, unit-interleaved
+  const float* Gx;                                        // [B, 4H]  hoisted embedding projection + b_ih (gate-block order)
+  const float* b_hh;                                      // [4H]
+  const float* c_prev;                                    // [B, H]
+  int B, Tn, A, H; float inv_T;
+  float* Wh_out; float* e_out;                            // [B, A], [B, Tn]  stash for BPTT (nullable)
+  void* gates_out;                                        // [B, H, 4] TO      activated gates, unit-interleaved (nullable)
+  float* c_out; float* h_out;                             // [B, H] fp32
+  void* h_op;                                             // [B, H] TO: next step's GEMM operand row / vocabulary-projection row
+};
+
+// NCH = float4 chunks of the attention axis per lane: 1 (A <= 128) or 2 (A <= 256)
+template <typename TV, typename TO, int NCH>
+__global__ void __launch_bounds__(THREADS, NCH == 1 ? 3 : 2) pf_fwd_kernel(FwdArgs a) {
+  constexpr bool FAST = FastMath<TO>::value;
+  __shared__ float e_s[MAX_T];
+  __shared__ float4 red[UPB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, u = tid & (UPB - 1), half = tid >> 7;
+  const int Tn = a.Tn, H = a.H, A = a.A;
+  const int j = blockIdx.x * UPB + u;
+  const bool unit_ok = j < H;
+  // (1) this thread's projected-feature quads of the first 32 frames (frames 2k + half): issued before anything else
+  // (loads are UNCONDITIONAL on clamped indices: a predicated `if (ok) v[k].load()` compiles to load-into-temp + predicated
+  //  move and ptxas then keeps only two loads in flight -- measured 18 us instead of 5 for the backward kernel)
+  const TV* vw = reinterpret_cast<const TV*>(a.VW) + ((long long)b * Tn * H + (unit_ok ? j : H - 1)) * 4;
+  Quad<TV> v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k].load(vw + (long long)min(2 * k + half, Tn - 1) * 4 * H);
+  // (2) the unit's gate pre-activations that do not depend on the attention: half 0 (which owns the cell update) fetches
+  //     the hoisted embedding projection, bias and c_{t-1}; half 1 sums the split-K partials of h_{t-1} W_hh^T
+  float pre[4] = {0.f, 0.f, 0.f, 0.f};
+  float cp = 0.f;
+  if (unit_ok) {
+    if (half == 0) {
+      const float* gx = a.Gx + (long long)b * 4 * H + j;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pre[g] = gx[g * H] + a.b_hh[g * H + j];
+      cp = a.c_prev[(long long)b * H + j];
+    } else {
+      const float* q = a.P + (long long)b * a.NP + A + j;
+      int s = 0;
+      for (; s + 4 <= a.n_p; s += 4) {             // 16 independent loads in flight
+        float x[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) x[i][g] = q[i * a.p_stride + g * H];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[g] += (x[0][g] + x[1][g]) + (x[2][g] + x[3][g]);
+        q += 4 * a.p_stride;
+      }
+      for (; s < a.n_p; ++s) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[g] += q[g * H];
+        q += a.p_stride;
+      }
+    }
+  }
+  // (3) scores e[tau] = w . tanh(W h + U v_tau + b): warp w takes frames w, w + 8, ..; a lane takes float4 chunks lane, lane + 32 of A
+  const int nchunk = A >> 2;
+  const float* uvb = a.Uv + (long long)b * Tn * A;
+  float4 uv[4][NCH];
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+      uv[f][i] = reinterpret_cast<const float4*>(uvb + (long long)min(warp + f * NW, Tn - 1) * A)[min(lane + 32 * i, nchunk - 1)];
+  float4 wh[NCH], bb[NCH], ww[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    wh[i] = bb[i] = ww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nchunk) {
+      bb[i] = reinterpret_cast<const float4*>(a.attn_b)[c];
+      ww[i] = reinterpret_cast<const float4*>(a.attn_w)[c];
+      wh[i] = sum_splits4(a.P + (long long)b * a.NP + 4 * c, a.n_p, a.p_stride);
+      if (blockIdx.x == 0 && warp == 0 && a.Wh_out) reinterpret_cast<float4*>(a.Wh_out + (long long)b * A)[c] = wh[i];
+      wh[i] = f4_add(wh[i], bb[i]);
+    }
+  }
+  for (int f0 = 0;;) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int tau = warp + (f0 + f) * NW;
+      if (tau < Tn) {               // warp-uniform
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          if (lane + 32 * i < nchunk) {
+            const float4 x = uv[f][i];
+            s = fmaf(ww[i].x, act_tanh<FAST>(wh[i].x + x.x), s);
+            s = fmaf(ww[i].y, act_tanh<FAST>(wh[i].y + x.y), s);
+            s = fmaf(ww[i].z, act_tanh<FAST>(wh[i].z + x.z), s);
+            s = fmaf(ww[i].w, act_tanh<FAST>(wh[i].w + x.w), s);
+          }
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+          e_s[tau] = s;
+          if (blockIdx.x == 0 && a.e_out) a.e_out[(long long)b * Tn + tau] = s;
+        }
+      }
+    }
+    f0 += 4;
+    if (warp + f0 * NW >= Tn) break;
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+        uv[f][i] = reinterpret_cast<const float4*>(uvb + (long long)min(warp + (f0 + f) * NW, Tn - 1) * A)[min(lane + 32 * i, nchunk - 1)];
+  }
+  __syncthreads();
+  // (4) weighted sum over this thread's frames
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t0 = 0;;) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int tau = t0 + 2 * k + half;
+      if (tau < Tn) {
+        float f[4];
+        v[k].get(f);
+        const float e = e_s[tau];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[g] = fmaf(e, f[g], acc[g]);
+      }
+    }
+    t0 += 32;
+    if (t0 >= Tn) break;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k].load(vw + (long long)min(t0 + 2 * k + half, Tn - 1) * 4 * H);
+  }
+  if (half == 1)
+    red[u] = make_float4(fmaf(acc[0], a.inv_T, pre[0]), fmaf(acc[1], a.inv_T, pre[1]), fmaf(acc[2], a.inv_T, pre[2]),
+                         fmaf(acc[3], a.inv_T, pre[3]));
+  __syncthreads();
+  if (half == 0 && unit_ok) {
+    const float4 o = red[u];
+    const float pi = fmaf(acc[0], a.inv_T, pre[0]) + o.x, pf_ = fmaf(acc[1], a.inv_T, pre[1]) + o.y;
+    const float pg = fmaf(acc[2], a.inv_T, pre[2]) + o.z, po = fmaf(acc[3], a.inv_T, pre[3]) + o.w;
+    const float gi = act_sigmoid<FAST>(pi), gf = act_sigmoid<FAST>(pf_), gg = act_tanh<FAST>(pg), go = act_sigmoid<FAST>(po);
+    const float cn = fmaf(gf, cp, gi * gg);
+    const float hn = go * act_tanh<FAST>(cn);
+    const long long o1 = (long long)b * H + j;
+    a.c_out[o1] = cn;
+    a.h_out[o1] = hn;
+    reinterpret_cast<TO*>(a.h_op)[o1] = from_f32<TO>(hn);
+    if (a.gates_out) Quad<TO>::store(reinterpret_cast<TO*>(a.gates_out) + o1 * 4, gi, gf, gg, go);
+  }
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float* dh_ext; const float* dh_ext2;            // [B, H] each (nullable): vocabulary-projection path, reconstructor path
+  const float* dhP; int n_p; long long p_stride;        // split-K partials of [dWh | dG]_{t+1} [W_a ; W_hh]: [n_p][B, H] (nullable at the last step)
+  float* dc; int first;                                 // [B, H] in/out; first => treated as 0
+  const void* gates;                                    // [B, H, 4] TO
+  const float* c_prev; const float* c_new;              // [B, H]
+  const void* VW;                                       // [B, Tn, H, 4] TV
+  const float* Wh; const float* Uv; const float* attn_b; const float* attn_w;
+  int B, Tn, A, H; float inv_T;
+  void* dGW; long long dgw_ld;                          // [B, A + 4H] TO: [dWh | dG (gate-block order)]  -> operand of K4 and of the weight-gradient GEMMs
+  float* dWh_out;                                       // [B, A] fp32 (attn_b gradient)
+  float* dUv_acc; int uv_first;                         // [B, Tn, A] accumulated over steps
+  float* dw_acc; int dw_first;                          // [B, A]     accumulated over steps
+};
+
+// sum over the 32 lanes of v[k] for every k; lane l ends up with the total of v[l] (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// one CTA per sample; dynamic shared memory: 4H floats (this sample's gate gradients)
+template <typename TV, typename TO, int NCH>
+__global__ void __launch_bounds__(THREADS) pf_bwd_kernel(BwdArgs a) {
+  constexpr bool FAST = FastMath<TO>::value;
+  extern __shared__ float4 dg_s[];                      // [H]
+  __shared__ float de_w[NW][MAX_T];
+  __shared__ float de_s[MAX_T];
+  __shared__ float part[2][NW][MAX_A];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, Tn = a.Tn, H = a.H, A = a.A;
+  const TV* vwb = reinterpret_cast<const TV*>(a.VW) + (long long)b * Tn * H * 4;
+  // first unit's quads of the first 32 frames: in flight while the cell backward runs
+  Quad<TV> v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(k, Tn - 1) * H + min(tid, H - 1)) * 4);   // unconditional, clamped
+  // ---- LSTM cell backward of this sample (same math as cell::lstm_cell_bwd_body)
+  for (int j = tid; j < H; j += THREADS) {
+    const long long o1 = (long long)b * H + j;
+    Quad<TO> gq;
+    gq.load(reinterpret_cast<const TO*>(a.gates) + o1 * 4);
+    float g[4];
+    gq.get(g);
+    const float cp = a.c_prev[o1], cn = a.c_new[o1];
+    const float dcn = a.first ? 0.f : a.dc[o1];
+    float dh = 0.f;
+    if (a.dh_ext) dh = a.dh_ext[o1];
+    if (a.dh_ext2) dh += a.dh_ext2[o1];
+    if (a.dhP) dh += sum_splits(a.dhP + o1, a.n_p, a.p_stride);
+    const float tc = act_tanh<FAST>(cn);
+    const float dc = fmaf(dh * g[3], 1.f - tc * tc, dcn);
+    a.dc[o1] = dc * g[1];
+    const float di = dc * g[2] * g[0] * (1.f - g[0]);
+    const float df = dc * cp * g[1] * (1.f - g[1]);
+    const float dgg = dc * g[0] * (1.f - g[2] * g[2]);
+    const float dO = dh * tc * g[3] * (1.f - g[3]);
+    TO* o = reinterpret_cast<TO*>(a.dGW) + (long long)b * a.dgw_ld + A + j;
+    const TO r0 = from_f32<TO>(di), r1 = from_f32<TO>(df), r2 = from_f32<TO>(dgg), r3 = from_f32<TO>(dO);
+    o[0] = r0; o[H] = r1; o[2 * H] = r2; o[3 * H] = r3;
+    // the score gradient below sees exactly what the GEMMs see: the operand-rounded values
+    dg_s[j] = make_float4(to_f32<TO>(r0), to_f32<TO>(r1), to_f32<TO>(r2), to_f32<TO>(r3));
+  }
+  // ---- d e[tau] = (1/T) <dG, VW[tau]>  (each thread re-reads only the dg_s entries it wrote: no barrier needed)
+  for (int t0 = 0; t0 < Tn; t0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    for (int j = tid; j < H; j += THREADS) {
+      if (t0 != 0 || j != tid) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(t0 + k, Tn - 1) * H + j) * 4);
+      }
+      const float4 dg = dg_s[j];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (t0 + k < Tn) {
+          float f[4];
+          v[k].get(f);
+          acc[k] = fmaf(dg.x, f[0], fmaf(dg.y, f[1], fmaf(dg.z, f[2], fmaf(dg.w, f[3], acc[k]))));
+        }
+      }
+    }
+    const float tot = warp_transpose_sum32(acc, lane);
+    if (t0 + lane < MAX_T) de_w[warp][t0 + lane] = tot;
+  }
+  __syncthreads();
+  if (tid < Tn) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += de_w[w][tid];
+    de_s[tid] = s * a.inv_T;
+  }
+  __syncthreads();
+  // ---- score backward: ds = de * w * (1 - tanh^2); dWh = sum_tau ds; dUv[tau] += ds; dw += de * tanh
+  const int nchunk = A >> 2;
+  float4 wh[NCH], ww[NCH], dwh[NCH], dww[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    dwh[i] = dww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cc = min(c, nchunk - 1);
+    wh[i] = f4_add(reinterpret_cast<const float4*>(a.Wh + (long long)b * A)[cc], reinterpret_cast<const float4*>(a.attn_b)[cc]);
+    ww[i] = reinterpret_cast<const float4*>(a.attn_w)[cc];
+  }
+  for (int f0 = 0; warp + f0 * NW < Tn; f0 += 4) {
+    float4 uv[4][NCH], old[4][NCH];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const long long off = ((long long)b * Tn + min(warp + (f0 + f) * NW, Tn - 1)) * A;
+        uv[f][i] = reinterpret_cast<const float4*>(a.Uv + off)[min(lane + 32 * i, nchunk - 1)];
+      }
+    if (a.uv_first) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) old[f][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const long long off = ((long long)b * Tn + min(warp + (f0 + f) * NW, Tn - 1)) * A;
+          old[f][i] = reinterpret_cast<const float4*>(a.dUv_acc + off)[min(lane + 32 * i, nchunk - 1)];
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int tau = warp + (f0 + f) * NW;
+      if (tau < Tn) {
+        const float g = de_s[tau];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c = lane + 32 * i;
+          if (c < nchunk) {
+            const float4 x = uv[f][i];
+            const float tx = act_tanh<FAST>(wh[i].x + x.x), ty = act_tanh<FAST>(wh[i].y + x.y);
+            const float tz = act_tanh<FAST>(wh[i].z + x.z), tw = act_tanh<FAST>(wh[i].w + x.w);
+            const float4 ds = make_float4(g * ww[i].x * (1.f - tx * tx), g * ww[i].y * (1.f - ty * ty), g * ww[i].z * (1.f - tz * tz),
+                                          g * ww[i].w * (1.f - tw * tw));
+            dwh[i] = f4_add(dwh[i], ds);
+            dww[i] = f4_add(dww[i], make_float4(g * tx, g * ty, g * tz, g * tw));
+            reinterpret_cast<float4*>(a.dUv_acc + ((long long)b * Tn + tau) * A)[c] = f4_add(ds, old[f][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      reinterpret_cast<float4*>(&part[0][warp][0])[c] = dwh[i];
+      reinterpret_cast<float4*>(&part[1][warp][0])[c] = dww[i];
+    }
+  }
+  __syncthreads();
+  for (int x = tid; x < A; x += THREADS) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { s0 += part[0][w][x]; s1 += part[1][w][x]; }
+    a.dWh_out[(long long)b * A + x] = s0;
+    reinterpret_cast<TO*>(a.dGW)[(long long)b * a.dgw_ld + x] = from_f32<TO>(s0);
+    float* pw = a.dw_acc + (long long)b * A + x;
+    *pw = a.dw_first ? s1 : *pw + s1;
+  }
+}
+
+// dVW[b, tau, n] = (1/T) sum_t e[t, b, tau] * dG[t, b, n]   (n in gate-block order = the row order of W_ctx)
+// grid (ceil(N / 512), B), 256 threads x 2 adjacent columns, dynamic smem L * round_up(Tn, 4) floats (float4 broadcast reads:
+// the first version read e one float at a time and was LDS-issue bound, 53 us)
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ void store(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+};
+template <> struct Pair<bf16> {
+  static __device__ __forceinline__ float2 load(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+  static __device__ __forceinline__ void store(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+};
+template <typename TO>
+__global__ void __launch_bounds__(256) pf_dvw_kernel(const float* __restrict__ e, const TO* __restrict__ dGW, long long ld, int col0,
+                                                     TO* __restrict__ dVW, int L, int B, int Tn, int N, float inv_T) {
+  extern __shared__ float4 e_sm4[];                     // [L][Tnp / 4]
+  float* e_sm = reinterpret_cast<float*>(e_sm4);
+  const int Tnp = (Tn + 3) & ~3;
+  const int b = blockIdx.y, n = (blockIdx.x * 256 + threadIdx.x) * 2;
+  for (int i = threadIdx.x; i < L * Tnp; i += 256) {
+    const int t = i / Tnp, k = i % Tnp;
+    e_sm[i] = k < Tn ? e[((long long)t * B + b) * Tn + k] : 0.f;
+  }
+  __syncthreads();
+  if (n >= N) return;
+  for (int t0 = 0; t0 < Tn; t0 += 32) {
+    float acc[32][2];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k][0] = acc[k][1] = 0.f;
+#pragma unroll 2
+    for (int t = 0; t < L; ++t) {
+      const float2 dg = Pair<TO>::load(dGW + ((long long)t * B + b) * ld + col0 + n);
+      const float4* er = e_sm4 + (t * Tnp + t0) / 4;
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        if (t0 + 4 * k4 < Tn) {
+          const float4 e4 = er[k4];
+          acc[4 * k4 + 0][0] = fmaf(e4.x, dg.x, acc[4 * k4 + 0][0]); acc[4 * k4 + 0][1] = fmaf(e4.x, dg.y, acc[4 * k4 + 0][1]);
+          acc[4 * k4 + 1][0] = fmaf(e4.y, dg.x, acc[4 * k4 + 1][0]); acc[4 * k4 + 1][1] = fmaf(e4.y, dg.y, acc[4 * k4 + 1][1]);
+          acc[4 * k4 + 2][0] = fmaf(e4.z, dg.x, acc[4 * k4 + 2][0]); acc[4 * k4 + 2][1] = fmaf(e4.z, dg.y, acc[4 * k4 + 2][1]);
+          acc[4 * k4 + 3][0] = fmaf(e4.w, dg.x, acc[4 * k4 + 3][0]); acc[4 * k4 + 3][1] = fmaf(e4.w, dg.y, acc[4 * k4 + 3][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (t0 + k < Tn) Pair<TO>::store(dVW + ((long long)b * Tn + t0 + k) * N + n, acc[k][0] * inv_T, acc[k][1] * inv_T);
+  }
+}
+
+// dst[(4j + g), :] = (TO) src[(g H + j), :]   -- W_ctx rows in unit-interleaved order (makes the VW GEMM emit [.., H, 4])
+template <typename TO>
+__global__ void interleave_rows_kernel(const float* __restrict__ src, long long ld_src, TO* __restrict__ dst, int H, int cols) {
+  const long long total = (long long)4 * H * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const int j = r >> 2, g = r & 3;
+    dst[i] = from_f32<TO>(src[((long long)g * H + j) * ld_src + c]);
+  }
+}
+
+static inline int check_shape(int Tn, int A, int H) {
+  if (Tn < 1 || Tn > MAX_T || A < 4 || A > MAX_A || (A & 3) || H < 1) return RECNET_ERR_BAD_SHAPE;
+  return 0;
+}
+
+template <typename TV, typename TO>
+static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
+  RN_TRY(check_shape(a.Tn, a.A, a.H));
+  ProfScope prof(KC_PF_FWD, a.B, a.Tn, a.H, st);
+  if (a.A <= 128) pf_fwd_kernel<TV, TO, 1><<<dim3(rn_cdiv(a.H, UPB), a.B), THREADS, 0, st>>>(a);
+  else pf_fwd_kernel<TV, TO, 2><<<dim3(rn_cdiv(a.H, UPB), a.B), THREADS, 0, st>>>(a);
+  RN_LAUNCH_OK();
+  return 0;
+}
+template <typename TV, typename TO>
+static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+  RN_TRY(check_shape(a.Tn, a.A, a.H));
+  const size_t smem = (size_t)a.H * sizeof(float4);
+  if (smem > 40 * 1024) return RECNET_ERR_BAD_SHAPE;     // + ~19 KB static: stays under the 48 KB default limit
+  ProfScope prof(KC_PF_BWD, a.B, a.Tn, a.H, st);
+  if (a.A <= 128) pf_bwd_kernel<TV, TO, 1><<<a.B, THREADS, smem, st>>>(a);
+  else pf_bwd_kernel<TV, TO, 2><<<a.B, THREADS, smem, st>>>(a);
+  RN_LAUNCH_OK();
+  return 0;
+}
+}  // namespace pf

@@ -2,6 +2,7 @@
 #include "runtime.cuh"
 #include "seq_decoder.cuh"
 #include "seq_decoder_ml.cuh"
+#include "seq_decoder_pf.cuh"
 #include "seq_recon.cuh"
 #include "seq_recon_ml.cuh"
 
@@ -185,6 +186,11 @@ int recnet_gru_cell_bwd(int precision, const float* dh_ext, int64_t dh_ld, const
 // ---- decoder ---------------------------------------------------------------------------------------------------
 int64_t recnet_decoder_workspace_bytes(const recnet_decoder_desc* d) {
   if (!d) return RECNET_ERR_BAD_SHAPE;
+  if (dec::pf_ok(*d)) {
+    if (d->precision == RECNET_PREC_FP32) return (int64_t)dec::plan_pf<float>(*d, nullptr).bytes;
+    if (d->precision == RECNET_PREC_BF16) return (int64_t)dec::plan_pf<bf16>(*d, nullptr).bytes;
+    return RECNET_ERR_UNSUPPORTED;
+  }
   if (d->precision == RECNET_PREC_FP32) return (int64_t)dec::plan<float>(*d, nullptr).bytes;
   if (d->precision == RECNET_PREC_BF16) return (int64_t)dec::plan<bf16>(*d, nullptr).bytes;
   return RECNET_ERR_UNSUPPORTED;
@@ -200,6 +206,13 @@ int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
       return dec::forward_ml<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
     if (d->precision == RECNET_PREC_BF16)
       return dec::forward_ml<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
+    return RECNET_ERR_UNSUPPORTED;
+  }
+  if (dec::pf_ok(*d)) {
+    if (d->precision == RECNET_PREC_FP32)
+      return dec::forward_pf<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
+    if (d->precision == RECNET_PREC_BF16)
+      return dec::forward_pf<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
     return RECNET_ERR_UNSUPPORTED;
   }
   if (d->precision == RECNET_PREC_FP32)
@@ -222,6 +235,13 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
       return dec::backward_ml<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
     return RECNET_ERR_UNSUPPORTED;
   }
+  if (dec::pf_ok(*d)) {
+    if (d->precision == RECNET_PREC_FP32)
+      return dec::backward_pf<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+    if (d->precision == RECNET_PREC_BF16)
+      return dec::backward_pf<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream));
+    return RECNET_ERR_UNSUPPORTED;
+  }
   if (d->precision == RECNET_PREC_FP32)
     return dec::backward<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, hiddens, *grads, ST(stream));
   if (d->precision == RECNET_PREC_BF16)
@@ -229,6 +249,10 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
   return RECNET_ERR_UNSUPPORTED;
 }
 float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld) {
+  if (dec::pf_ok(*d)) {
+    if (d->precision == RECNET_PREC_FP32) { auto w = dec::plan_pf<float>(*d, workspace); if (ld) *ld = w.Vld; return w.logits; }
+    auto w = dec::plan_pf<bf16>(*d, workspace); if (ld) *ld = w.Vld; return w.logits;
+  }
   if (d->precision == RECNET_PREC_FP32) { auto w = dec::plan<float>(*d, workspace); if (ld) *ld = w.Vld; return w.logits; }
   auto w = dec::plan<bf16>(*d, workspace); if (ld) *ld = w.Vld; return w.logits;
 }
@@ -250,6 +274,10 @@ int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_ten
 // byte offset of the loop kernel's int32 error flag inside the workspace (0 = ok, 2 = mbarrier timeout, 3 = grid-barrier timeout)
 int64_t recnet_decoder_error_offset(const recnet_decoder_desc* d) {
   uint8_t* base = reinterpret_cast<uint8_t*>(4096);
+  if (dec::pf_ok(*d)) {
+    if (d->precision == RECNET_PREC_FP32) return reinterpret_cast<uint8_t*>(dec::plan_pf<float>(*d, base).err) - base;
+    return reinterpret_cast<uint8_t*>(dec::plan_pf<bf16>(*d, base).err) - base;
+  }
   if (d->precision == RECNET_PREC_FP32) return reinterpret_cast<uint8_t*>(dec::plan<float>(*d, base).err) - base;
   return reinterpret_cast<uint8_t*>(dec::plan<bf16>(*d, base).err) - base;
 }

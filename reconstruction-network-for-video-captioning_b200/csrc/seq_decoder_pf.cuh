@@ -1,0 +1,221 @@
+// Decoder sequence driver, projected-feature formulation (single-layer LSTM decoder -- the BASELINE benchmark config).
+// Same contract as dec::forward / dec::backward (train.py:17-75 over models/decoder.py:45-70); see proj_attn.cuh for
+// the algebra.  Per step: ONE split-K GEMM on h_{t-1} (K = H) + ONE fused attention/cell kernel; BPTT: one fused
+// cell/attention backward kernel + ONE split-K GEMM (K = A + 4H).
+//   hoisted once per sequence: U v, VW = feats W_ctx^T (unit-interleaved, operand precision), embedding projection Gx
+//   after the loop: vocabulary projection + CE (forward); dVW, all weight gradients as batched GEMMs (backward)
+#pragma once
+#include "proj_attn.cuh"
+#include "seq_decoder.cuh"
+
+namespace dec {
+
+template <typename T>
+struct PfWs {
+  int EMBp, Vp, Vld, NP;
+  GemmPlan pl_h, pl_dh;
+  T *Wemb, *WctxI, *Wcat, *U, *Wout, *feats;
+  float* Uv; T* VW; T* Xe; float* Gx; T* Hop; float* P; float* Wh; float* e; T* gates; float* c;
+  float *logits, *lse, *row_loss;
+  T* dlogits; float* dHext; T* dGW; float* dhP; float* dWh; float* dUv; T* dUv_op; float* dw_acc; float* dc; float* dXe; T* dVW;
+  float* splitk; int* err;
+  size_t bytes;
+};
+
+// eligibility of the projected-feature path; everything else runs the general drivers (seq_decoder.cuh / seq_decoder_ml.cuh)
+static inline bool pf_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RECNET_PF"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+static inline bool pf_ok(const recnet_decoder_desc& d) {
+  if (!pf_enabled() || d.cell != RECNET_CELL_LSTM || d.n_layers > 1) return false;
+  if (num_chains(d.B) != 1 || mega::mega_enabled()) return false;
+  const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
+  return d.T >= 1 && d.T <= pf::MAX_T && d.A >= 4 && d.A <= pf::MAX_A && d.A % al == 0 && d.H % al == 0 && d.H <= 2560;
+}
+
+template <typename T>
+static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
+  PfWs<T> w;
+  const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T;
+  w.EMBp = round_up(d.EMB, Prec<T>::kpad);
+  w.Vp = round_up(V, 8);
+  w.Vld = round_up(V, 4);
+  w.NP = A + 4 * H;
+  w.pl_h = plan_gemm<T>(B, w.NP, H, NUM_SMS);
+  w.pl_dh = plan_gemm<T>(B, H, w.NP, NUM_SMS);
+  if (Prec<T>::id == RECNET_PREC_BF16) {
+    // K = H is only 8 k-blocks: 64-wide N tiles x few splits (34 x 4 CTAs at H = 512) instead of 128-wide x 8 -- half the
+    // partial traffic for the fused kernel to sum
+    w.pl_h.bn = 64;
+    const int tiles = rn_cdiv(B, tc::BM) * rn_cdiv(w.NP, 64), nkb = rn_cdiv(H, tc::BK);
+    int sp = NUM_SMS / tiles; if (sp < 1) sp = 1; if (sp > nkb) sp = nkb;
+    w.pl_h.splits = rn_cdiv(nkb, rn_cdiv(nkb, sp));
+  }
+  Bump m(base);
+  w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);
+  w.WctxI = m.take<T>((size_t)4 * H * E);
+  w.Wcat = m.take<T>((size_t)w.NP * H);
+  w.U = m.take<T>((size_t)A * E);
+  w.Wout = m.take<T>((size_t)V * H);
+  w.feats = m.take<T>((size_t)B * Tn * E);
+  w.Uv = m.take<float>((size_t)B * Tn * A);
+  w.VW = m.take<T>((size_t)B * Tn * 4 * H);
+  w.Xe = m.take<T>((size_t)L * B * w.EMBp);
+  w.Gx = m.take<float>((size_t)L * B * 4 * H);
+  w.Hop = m.take<T>((size_t)(L + 1) * B * H);
+  w.P = m.take<float>((size_t)w.pl_h.splits * B * w.NP);
+  w.Wh = m.take<float>((size_t)L * B * A);
+  w.e = m.take<float>((size_t)L * B * Tn);
+  w.gates = m.take<T>((size_t)L * B * 4 * H);
+  w.c = m.take<float>((size_t)(L + 1) * B * H);
+  w.logits = m.take<float>((size_t)L * B * w.Vld);
+  w.lse = m.take<float>((size_t)L * B);
+  w.row_loss = m.take<float>((size_t)L * B);
+  w.dlogits = m.take<T>((size_t)L * B * w.Vp);
+  w.dHext = m.take<float>((size_t)L * B * H);
+  w.dGW = m.take<T>((size_t)L * B * w.NP);
+  w.dhP = m.take<float>((size_t)w.pl_dh.splits * B * H);
+  w.dWh = m.take<float>((size_t)L * B * A);
+  w.dUv = m.take<float>((size_t)B * Tn * A);
+  w.dUv_op = m.take<T>((size_t)B * Tn * A);
+  w.dw_acc = m.take<float>((size_t)B * A);
+  w.dc = m.take<float>((size_t)B * H);
+  w.dXe = m.take<float>((size_t)L * B * w.EMBp);
+  w.dVW = m.take<T>((size_t)B * Tn * 4 * H);
+  w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.err = m.take<int>(64);
+  w.bytes = m.off + 256;
+  return w;
+}
+
+// C (operand type) = A B^T, written straight in the operand precision
+static inline int gemm_to_operand(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M,
+                                  int N, int K, float* scratch, cudaStream_t st) {
+  return gemm_full<float>(A, lda, 0, B, ldb, 0, C, ldc, nullptr, M, N, K, 0, scratch, st);
+}
+static inline int gemm_to_operand(const bf16* A, long long lda, const bf16* B, long long ldb, bf16* C, long long ldc, int M, int N,
+                                  int K, float*, cudaStream_t st) {
+  return tc::launch(A, lda, 0, B, ldb, 0, nullptr, 0, C, ldc, nullptr, M, N, K, 1, 0, 0, 128, st);
+}
+
+template <typename T>
+static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
+                      const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
+                      float* hiddens, float* ce_out, cudaStream_t st) {
+  RN_TRY(check(d));
+  PfWs<T> w = plan_pf<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T, EMB = d.EMB;
+  const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
+  const long long ldih = EMB + E;
+  // operand copies of the weights / features (the optimiser changes the fp32 masters every step)
+  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, st));
+  pf::interleave_rows_kernel<T><<<NUM_SMS * 8, 256, 0, st>>>(p.w_ih + EMB, ldih, w.WctxI, H, E);
+  RN_LAUNCH_OK();
+  RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wcat, H, A, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.attn_U, E, w.U, E, A, E, E, st));
+  RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
+  RN_TRY(misc::cast_pad<T>(feats, E, w.feats, E, (long long)B * Tn, E, E, st));
+  // hoisted projections
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, nullptr, B * Tn, A, E, 0, w.splitk, st));
+  RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
+  misc::embed_gather_kernel<T><<<L * B, 128, 0, st>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
+                                                      p_emb, rng, SITE_EMB);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk, st));
+  RN_CUDA_OK(cudaMemsetAsync(w.Hop, 0, (size_t)B * H * sizeof(T), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
+  for (int t = 0; t < L; ++t) {
+    const size_t r = (size_t)t * B;
+    if (t > 0)      // h_{-1} = 0: no query, no recurrent term
+      RN_TRY(gemm_partials<T>(w.Hop + r * H, H, 0, w.Wcat, H, 0, w.P, B, w.NP, H, w.pl_h, st));
+    pf::FwdArgs fa{};
+    fa.P = w.P; fa.n_p = t > 0 ? w.pl_h.splits : 0; fa.p_stride = (long long)B * w.NP; fa.NP = w.NP;
+    fa.Uv = w.Uv; fa.attn_b = p.attn_b; fa.attn_w = p.attn_w; fa.VW = w.VW;
+    fa.Gx = w.Gx + r * 4 * H; fa.b_hh = p.b_hh; fa.c_prev = w.c + r * H;
+    fa.B = B; fa.Tn = Tn; fa.A = A; fa.H = H; fa.inv_T = 1.f / Tn;
+    fa.Wh_out = w.Wh + r * A; fa.e_out = w.e + r * Tn; fa.gates_out = w.gates + r * 4 * H;
+    fa.c_out = w.c + (r + B) * H; fa.h_out = hiddens + r * H; fa.h_op = w.Hop + (r + B) * H;
+    RN_TRY((pf::launch_fwd<T, T>(fa, st)));
+  }
+  // vocabulary projection over all steps, then the masked CE (train.py:54-60,68)
+  RN_TRY(gemm_full<T>(w.Hop + (size_t)B * H, H, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, L * B, V, H, 0, w.splitk, st));
+  if (targets && ce_weight && ce_out) {
+    ProfScope prof(KC_CE, L * B, V, 0, st);
+    loss::ce_fwd_kernel<<<L * B, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, V, p_out, rng, SITE_LOGITS, w.lse,
+                                                            w.row_loss);
+    RN_LAUNCH_OK();
+    loss::sum_kernel<<<1, 1024, 0, st>>>(w.row_loss, L * B, ce_out, 1.f);
+    RN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <typename T>
+static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
+                       const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
+                       const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors& g, cudaStream_t st) {
+  RN_TRY(check(d));
+  PfWs<T> w = plan_pf<T>(d, ws);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T, EMB = d.EMB;
+  const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
+  const int LB = L * B, NP = w.NP;
+  const T* Hall = w.Hop + (size_t)B * H;          // h_t rows
+  // ---- CE backward and the vocabulary projection
+  {
+    ProfScope prof(KC_CE, LB, V, 1, st);
+    loss::ce_bwd_kernel<T><<<LB, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, w.lse, g_ce, V, w.Vp, p_out, rng,
+                                                            SITE_LOGITS, w.dlogits, w.Vp);
+  }
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk, st));
+  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk, st));
+  // ---- BPTT
+  for (int t = L - 1; t >= 0; --t) {
+    const bool last = (t == L - 1);
+    const size_t r = (size_t)t * B;
+    pf::BwdArgs ba{};
+    ba.dh_ext = w.dHext + r * H; ba.dh_ext2 = g_hiddens ? g_hiddens + r * H : nullptr;
+    ba.dhP = last ? nullptr : w.dhP; ba.n_p = w.pl_dh.splits; ba.p_stride = (long long)B * H;
+    ba.dc = w.dc; ba.first = last ? 1 : 0;
+    ba.gates = w.gates + r * 4 * H; ba.c_prev = w.c + r * H; ba.c_new = w.c + (r + B) * H;
+    ba.VW = w.VW; ba.Wh = w.Wh + r * A; ba.Uv = w.Uv; ba.attn_b = p.attn_b; ba.attn_w = p.attn_w;
+    ba.B = B; ba.Tn = Tn; ba.A = A; ba.H = H; ba.inv_T = 1.f / Tn;
+    ba.dGW = w.dGW + r * NP; ba.dgw_ld = NP; ba.dWh_out = w.dWh + r * A;
+    ba.dUv_acc = w.dUv; ba.uv_first = last ? 1 : 0; ba.dw_acc = w.dw_acc; ba.dw_first = last ? 1 : 0;
+    RN_TRY((pf::launch_bwd<T, T>(ba, st)));
+    // dh_{t-1} = [dWh_t | dG_t] [W_a ; W_hh]  (attention-query path and recurrent path in one K-concatenated GEMM)
+    if (t > 0) RN_TRY(gemm_partials<T>(w.dGW + r * NP, NP, 0, w.Wcat, H, 1, w.dhP, B, H, NP, w.pl_dh, st));
+  }
+  // ---- batched weight gradients over the stashed operands
+  const long long ldih = EMB + E;
+  const T* dG = w.dGW + A;                       // [LB, 4H] gate gradients, ld = NP
+  RN_TRY(misc::colsum<T>(dG, NP, LB, 4 * H, g.b_ih, 0, w.splitk, st));
+  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // dW_ctx = dVW^T feats,  dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b]
+  pf::pf_dvw_kernel<T><<<dim3(rn_cdiv(4 * H, 512), B), 256, (size_t)L * round_up(Tn, 4) * sizeof(float), st>>>(w.e, w.dGW, NP, A, w.dVW,
+                                                                                                          L, B, Tn, 4 * H, 1.f / Tn);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.dVW, 4 * H, 1, w.feats, E, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, B * Tn, 0, w.splitk, st));   // dW_ctx
+  RN_TRY(gemm_full<T>(dG, NP, 1, w.Hop, H, 1, g.w_hh, H, nullptr, 4 * H, H, LB, 0, w.splitk, st));                        // dW_hh = dG^T h_{t-1}
+  RN_TRY(gemm_full<T>(dG, NP, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk, st));               // dW_emb
+  RN_TRY(gemm_full<T>(dG, NP, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk, st));            // dXe
+  RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), st));
+  misc::embed_scatter_kernel<<<LB, 128, 0, st>>>(g.embedding, tokens_in, w.dXe, w.EMBp, LB, EMB, V, d.embedding_scale, p_emb, rng,
+                                                 SITE_EMB);
+  RN_LAUNCH_OK();
+  // attention parameters
+  RN_TRY(gemm_full<T>(w.dGW, NP, 1, w.Hop, H, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk, st));                       // dW_a = dWh^T h_{t-1}
+  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)B * Tn, A, A, st));
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.feats, E, 1, g.attn_U, E, nullptr, A, E, B * Tn, 0, w.splitk, st));               // dU = dUv^T v
+  RN_TRY(misc::colsum<float>(w.dWh, A, LB, A, g.attn_b, 0, w.splitk, st));
+  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
+  return 0;
+}
+}  // namespace dec

@@ -425,8 +425,13 @@ static int prepare_fwd(FwdArgs& a, int* slices_out) {
 static inline size_t fwd_smem_bytes(const FwdArgs& a) { return (size_t)(2 * a.A + a.Tn + FWD_THREADS * 8) * sizeof(float); }
 static inline size_t bwd_smem_bytes(const BwdArgs& a) { return (size_t)(a.D + a.Tn + 2 * BWD_THREADS) * sizeof(float); }
 
+}  // namespace attn
+#include "attention_lean.cuh"
+namespace attn {
+
 template <typename TV, typename TO>
 static int launch_fwd(FwdArgs a, cudaStream_t st) {
+  if (!a.normalize && lean_ok<TV>(a.Tn, a.A, a.D, a.v_bs, a.v_ts, a.uv_bs, a.uv_ts)) return launch_lean_fwd<TV, TO>(a, st);
   int slices = 1;
   RN_TRY(prepare_fwd<TV>(a, &slices));
   dim3 grid(slices, a.B);
@@ -439,6 +444,8 @@ static int launch_fwd(FwdArgs a, cudaStream_t st) {
 
 template <typename TV, typename TO>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+  if (lean_ok<TV>(a.Tn, a.A, a.D, a.v_bs, a.v_ts, a.uv_bs, a.uv_ts) && a.p_ld % 2 == 0 && a.p_stride % 2 == 0 && a.D <= 6144)
+    return launch_lean_bwd<TV, TO>(a, st);
   if (a.Tn > MAX_T || a.Tn < 1) return RECNET_ERR_BAD_SHAPE;
   constexpr int VN = Vec16<TV>::N;
   if (a.D % VN || a.v_ts % VN || a.v_bs % VN) return RECNET_ERR_ALIGNMENT;

@@ -271,7 +271,62 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   return v[0];
 }
 
-// one CTA per sample; dynamic shared memory: 4H floats (this sample's gate gradients)
+constexpr int MAXS = 12;        // split-K partials summed with one batch of loads (the drivers plan <= MAXS splits)
+
+// operands of one hidden unit's cell backward, all fetched before the first use
+template <typename TO>
+struct CellIn {
+  Quad<TO> gq; float cp, cn, dcn, dhe, dhe2; float part[MAXS];
+  __device__ __forceinline__ void load(const BwdArgs& a, long long o1) {
+    gq.load(reinterpret_cast<const TO*>(a.gates) + o1 * 4);
+    cp = a.c_prev[o1]; cn = a.c_new[o1];
+    dcn = a.first ? 0.f : a.dc[o1];
+    dhe = a.dh_ext ? a.dh_ext[o1] : 0.f;
+    dhe2 = a.dh_ext2 ? a.dh_ext2[o1] : 0.f;
+    if (a.dhP) {                                     // uniform branch; clamped split index -> unconditional loads
+#pragma unroll
+      for (int s = 0; s < MAXS; ++s) part[s] = a.dhP[o1 + (long long)min(s, a.n_p - 1) * a.p_stride];
+    } else {
+#pragma unroll
+      for (int s = 0; s < MAXS; ++s) part[s] = 0.f;
+    }
+  }
+  __device__ __forceinline__ float dh(const BwdArgs& a, long long o1) const {
+    float d = dhe + dhe2;
+    if (a.dhP) {
+#pragma unroll
+      for (int s = 0; s < MAXS; ++s) d += (s < a.n_p) ? part[s] : 0.f;
+      if (a.n_p > MAXS) d += sum_splits(a.dhP + o1 + (long long)MAXS * a.p_stride, a.n_p - MAXS, a.p_stride);
+    }
+    return d;
+  }
+};
+
+// cell backward of one unit (same math as cell::lstm_cell_bwd_body); returns the operand-rounded gate gradients
+template <typename TO, bool FAST>
+__device__ __forceinline__ float4 cell_bwd_unit(const BwdArgs& a, const CellIn<TO>& in, int b, int j, bool ok) {
+  const long long o1 = (long long)b * a.H + j;
+  float g[4];
+  in.gq.get(g);
+  const float dh = in.dh(a, o1);
+  const float tc = act_tanh<FAST>(in.cn);
+  const float dc = fmaf(dh * g[3], 1.f - tc * tc, in.dcn);
+  const float di = dc * g[2] * g[0] * (1.f - g[0]);
+  const float df = dc * in.cp * g[1] * (1.f - g[1]);
+  const float dgg = dc * g[0] * (1.f - g[2] * g[2]);
+  const float dO = dh * tc * g[3] * (1.f - g[3]);
+  const TO r0 = from_f32<TO>(di), r1 = from_f32<TO>(df), r2 = from_f32<TO>(dgg), r3 = from_f32<TO>(dO);
+  if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+  a.dc[o1] = dc * g[1];
+  TO* o = reinterpret_cast<TO*>(a.dGW) + (long long)b * a.dgw_ld + a.A + j;
+  o[0] = r0; o[a.H] = r1; o[2 * a.H] = r2; o[3 * a.H] = r3;
+  // the score gradient sees exactly what the GEMMs see: the operand-rounded values
+  return make_float4(to_f32<TO>(r0), to_f32<TO>(r1), to_f32<TO>(r2), to_f32<TO>(r3));
+}
+
+// one CTA per sample, two hidden units per thread and pass; dynamic shared memory: 4H floats (gate gradients, only re-read
+// when Tn > 32).  The kernel is latency-bound (114 KB of VW per CTA, ~10 dependent steps), so every independent load --
+// both units' cell operands and split-K partials, the first unit's 28 VW quads, the score operands -- is issued up front.
 template <typename TV, typename TO, int NCH>
 __global__ void __launch_bounds__(THREADS) pf_bwd_kernel(BwdArgs a) {
   constexpr bool FAST = FastMath<TO>::value;
@@ -281,54 +336,73 @@ __global__ void __launch_bounds__(THREADS) pf_bwd_kernel(BwdArgs a) {
   __shared__ float part[2][NW][MAX_A];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, Tn = a.Tn, H = a.H, A = a.A;
+  const int nchunk = A >> 2;
   const TV* vwb = reinterpret_cast<const TV*>(a.VW) + (long long)b * Tn * H * 4;
-  // first unit's quads of the first 32 frames: in flight while the cell backward runs
   Quad<TV> v[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(k, Tn - 1) * H + min(tid, H - 1)) * 4);   // unconditional, clamped
-  // ---- LSTM cell backward of this sample (same math as cell::lstm_cell_bwd_body)
-  for (int j = tid; j < H; j += THREADS) {
-    const long long o1 = (long long)b * H + j;
-    Quad<TO> gq;
-    gq.load(reinterpret_cast<const TO*>(a.gates) + o1 * 4);
-    float g[4];
-    gq.get(g);
-    const float cp = a.c_prev[o1], cn = a.c_new[o1];
-    const float dcn = a.first ? 0.f : a.dc[o1];
-    float dh = 0.f;
-    if (a.dh_ext) dh = a.dh_ext[o1];
-    if (a.dh_ext2) dh += a.dh_ext2[o1];
-    if (a.dhP) dh += sum_splits(a.dhP + o1, a.n_p, a.p_stride);
-    const float tc = act_tanh<FAST>(cn);
-    const float dc = fmaf(dh * g[3], 1.f - tc * tc, dcn);
-    a.dc[o1] = dc * g[1];
-    const float di = dc * g[2] * g[0] * (1.f - g[0]);
-    const float df = dc * cp * g[1] * (1.f - g[1]);
-    const float dgg = dc * g[0] * (1.f - g[2] * g[2]);
-    const float dO = dh * tc * g[3] * (1.f - g[3]);
-    TO* o = reinterpret_cast<TO*>(a.dGW) + (long long)b * a.dgw_ld + A + j;
-    const TO r0 = from_f32<TO>(di), r1 = from_f32<TO>(df), r2 = from_f32<TO>(dgg), r3 = from_f32<TO>(dO);
-    o[0] = r0; o[H] = r1; o[2 * H] = r2; o[3 * H] = r3;
-    // the score gradient below sees exactly what the GEMMs see: the operand-rounded values
-    dg_s[j] = make_float4(to_f32<TO>(r0), to_f32<TO>(r1), to_f32<TO>(r2), to_f32<TO>(r3));
+  CellIn<TO> in1, in2;
+  in1.load(a, (long long)b * H + min(tid, H - 1));
+  in2.load(a, (long long)b * H + min(tid + THREADS, H - 1));
+  // score operands of this warp's first four frames
+  float4 wh[NCH], ww[NCH], dwh[NCH], dww[NCH], uv[4][NCH], old[4][NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    dwh[i] = dww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cc = min(lane + 32 * i, nchunk - 1);
+    wh[i] = f4_add(reinterpret_cast<const float4*>(a.Wh + (long long)b * A)[cc], reinterpret_cast<const float4*>(a.attn_b)[cc]);
+    ww[i] = reinterpret_cast<const float4*>(a.attn_w)[cc];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const long long off = ((long long)b * Tn + min(warp + f * NW, Tn - 1)) * A;
+      uv[f][i] = reinterpret_cast<const float4*>(a.Uv + off)[cc];
+      old[f][i] = a.uv_first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.dUv_acc + off)[cc];
+    }
   }
-  // ---- d e[tau] = (1/T) <dG, VW[tau]>  (each thread re-reads only the dg_s entries it wrote: no barrier needed)
+  // ---- d e[tau] = (1/T) <dG, VW[tau]> with the LSTM cell backward folded into the first pass
   for (int t0 = 0; t0 < Tn; t0 += 32) {
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-    for (int j = tid; j < H; j += THREADS) {
-      if (t0 != 0 || j != tid) {
+    for (int j0 = 0; j0 < H; j0 += 2 * THREADS) {
+      const int j1 = j0 + tid, j2 = j1 + THREADS;
+      const bool ok1 = j1 < H, ok2 = j2 < H;
+      if (t0 != 0 || j0 != 0) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(t0 + k, Tn - 1) * H + j) * 4);
+        for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(t0 + k, Tn - 1) * H + min(j1, H - 1)) * 4);
       }
-      const float4 dg = dg_s[j];
+      float4 dg1, dg2;
+      if (t0 == 0) {
+        if (j0 != 0) {
+          in1.load(a, (long long)b * H + min(j1, H - 1));
+          in2.load(a, (long long)b * H + min(j2, H - 1));
+        }
+        dg1 = cell_bwd_unit<TO, FAST>(a, in1, b, min(j1, H - 1), ok1);
+        dg2 = cell_bwd_unit<TO, FAST>(a, in2, b, min(j2, H - 1), ok2);
+        if (ok1) dg_s[j1] = dg1;
+        if (ok2) dg_s[j2] = dg2;
+      } else {                                        // own entries only: no barrier needed
+        dg1 = ok1 ? dg_s[j1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        dg2 = ok2 ? dg_s[j2] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         if (t0 + k < Tn) {
           float f[4];
           v[k].get(f);
-          acc[k] = fmaf(dg.x, f[0], fmaf(dg.y, f[1], fmaf(dg.z, f[2], fmaf(dg.w, f[3], acc[k]))));
+          acc[k] = fmaf(dg1.x, f[0], fmaf(dg1.y, f[1], fmaf(dg1.z, f[2], fmaf(dg1.w, f[3], acc[k]))));
+        }
+      }
+      if (j0 + THREADS < H) {                         // uniform
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(t0 + k, Tn - 1) * H + min(j2, H - 1)) * 4);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          if (t0 + k < Tn) {
+            float f[4];
+            v[k].get(f);
+            acc[k] = fmaf(dg2.x, f[0], fmaf(dg2.y, f[1], fmaf(dg2.z, f[2], fmaf(dg2.w, f[3], acc[k]))));
+          }
         }
       }
     }
@@ -344,37 +418,16 @@ __global__ void __launch_bounds__(THREADS) pf_bwd_kernel(BwdArgs a) {
   }
   __syncthreads();
   // ---- score backward: ds = de * w * (1 - tanh^2); dWh = sum_tau ds; dUv[tau] += ds; dw += de * tanh
-  const int nchunk = A >> 2;
-  float4 wh[NCH], ww[NCH], dwh[NCH], dww[NCH];
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int c = lane + 32 * i;
-    dwh[i] = dww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int cc = min(c, nchunk - 1);
-    wh[i] = f4_add(reinterpret_cast<const float4*>(a.Wh + (long long)b * A)[cc], reinterpret_cast<const float4*>(a.attn_b)[cc]);
-    ww[i] = reinterpret_cast<const float4*>(a.attn_w)[cc];
-  }
   for (int f0 = 0; warp + f0 * NW < Tn; f0 += 4) {
-    float4 uv[4][NCH], old[4][NCH];
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const long long off = ((long long)b * Tn + min(warp + (f0 + f) * NW, Tn - 1)) * A;
-        uv[f][i] = reinterpret_cast<const float4*>(a.Uv + off)[min(lane + 32 * i, nchunk - 1)];
-      }
-    if (a.uv_first) {
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) old[f][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
+    if (f0 != 0) {
 #pragma unroll
       for (int f = 0; f < 4; ++f)
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
           const long long off = ((long long)b * Tn + min(warp + (f0 + f) * NW, Tn - 1)) * A;
-          old[f][i] = reinterpret_cast<const float4*>(a.dUv_acc + off)[min(lane + 32 * i, nchunk - 1)];
+          const int cc = min(lane + 32 * i, nchunk - 1);
+          uv[f][i] = reinterpret_cast<const float4*>(a.Uv + off)[cc];
+          old[f][i] = a.uv_first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.dUv_acc + off)[cc];
         }
     }
 #pragma unroll

@@ -52,6 +52,9 @@ static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
     const int tiles = rn_cdiv(B, tc::BM) * rn_cdiv(w.NP, 64), nkb = rn_cdiv(H, tc::BK);
     int sp = NUM_SMS / tiles; if (sp < 1) sp = 1; if (sp > nkb) sp = nkb;
     w.pl_h.splits = rn_cdiv(nkb, rn_cdiv(nkb, sp));
+    // dh GEMM (N = H, K = A + 4H): at most pf::MAXS splits so the fused backward kernel sums them with one batch of loads
+    const int nkb2 = rn_cdiv(w.NP, tc::BK);
+    if (w.pl_dh.splits > pf::MAXS) w.pl_dh.splits = rn_cdiv(nkb2, rn_cdiv(nkb2, pf::MAXS));
   }
   Bump m(base);
   w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);

@@ -42,6 +42,10 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.Bc = chain_rows_max(B, w.nch);
   const int tgt = w.nch > 1 ? NUM_SMS / 2 : NUM_SMS;
   w.pl_wh = plan_gemm<T>(w.Bc, A, R, tgt);
+  if (w.pl_wh.splits > 8) {      // the attention kernel sums these partials with one batch of 8 loads per lane
+    const int nkb = rn_cdiv(R, 64);
+    w.pl_wh.splits = rn_cdiv(nkb, rn_cdiv(nkb, 8));
+  }
   w.pl_gate = plan_gemm<T>(w.Bc, 4 * R, w.KX, tgt);
   w.pl_dx = plan_gemm<T>(w.Bc, w.KX, 4 * R, tgt);
   w.pl_dq = plan_gemm<T>(w.Bc, R, A, tgt);

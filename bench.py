@@ -399,7 +399,7 @@ def main():
                         "traffic": None, "kernel": top["kernel"], "shape_MNK": top["shape"], "avg_us": top["avg_us"],
                         "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy)")}
         cpu = None
-        if world == 1:
+        if world == 1 and args.cpu_iters > 0:
             sps, sec = cpu_oracle_samples_per_s(args.recon, args.cpu_iters)
             cores = os.cpu_count() or 1
             cpu = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",

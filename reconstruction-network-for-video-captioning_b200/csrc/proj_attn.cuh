@@ -87,8 +87,8 @@ __device__ __forceinline__ float4 sum_splits4(const float* __restrict__ q, int n
 // ---- forward -----------------------------------------------------------------------------------------------------
 struct FwdArgs {
   const float* P; int n_p; long long p_stride; int NP;   // split-K partials of h_{t-1} [W_a ; W_hh]^T: [n_p][B, NP = A + 4H]; n_p = 0 at t = 0
-  const float* Uv;                                        // [B, Tn, A]   hoisted U v
-  const float* attn_b; const float* attn_w;               // [A]
+  const float* Uv;                                        // [B, Tn, A]   hoisted U v + attn_b
+  const float* attn_w;                                    // [A]
   const void* VW;                                         // [B, Tn, H, 4] TV   hoisted v W_ctx^T, unit-interleaved
   const float* Gx;                                        // [B, 4H]  hoisted embedding projection + b_ih (gate-block order)
   const float* b_hh;                                      // [4H]
@@ -100,85 +100,83 @@ struct FwdArgs {
   void* h_op;                                             // [B, H] TO: next step's GEMM operand row / vocabulary-projection row
 };
 
-// NCH = float4 chunks of the attention axis per lane: 1 (A <= 128) or 2 (A <= 256)
-template <typename TV, typename TO, int NCH>
-__global__ void __launch_bounds__(THREADS, NCH == 1 ? 3 : 2) pf_fwd_kernel(FwdArgs a) {
+// NCH = float4 chunks of the attention axis per lane: 1 (A <= 128) or 2 (A <= 256).
+// Index math is 32-bit unsigned on purpose (r1 ncu: 42% of the first version's instructions were 64-bit address arithmetic);
+// the drivers check that every tensor has < 2^31 elements.  `Uv` already contains the attention bias (folded in at the hoist).
+template <typename TV, typename TO, int NCH, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) pf_fwd_kernel(FwdArgs a) {
   constexpr bool FAST = FastMath<TO>::value;
-  __shared__ float e_s[MAX_T];
+  __shared__ __align__(16) float e_s[2][MAX_T / 2];     // e_s[tau & 1][tau >> 1]; zero for tau >= Tn
   __shared__ float4 red[UPB];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, u = tid & (UPB - 1), half = tid >> 7;
-  const int Tn = a.Tn, H = a.H, A = a.A;
-  const int j = blockIdx.x * UPB + u;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned b = blockIdx.y, u = tid & (UPB - 1), half = tid >> 7;
+  const unsigned Tn = a.Tn, H = a.H, A = a.A, row = 4u * H;
+  const unsigned j = blockIdx.x * UPB + u;
   const bool unit_ok = j < H;
-  // (1) this thread's projected-feature quads of the first 32 frames (frames 2k + half): issued before anything else
+  const unsigned jc = unit_ok ? j : H - 1;
+  // (1) this thread's projected-feature quads of the first 32 frames (frames 2k + half): issued before anything else.
   // (loads are UNCONDITIONAL on clamped indices: a predicated `if (ok) v[k].load()` compiles to load-into-temp + predicated
   //  move and ptxas then keeps only two loads in flight -- measured 18 us instead of 5 for the backward kernel)
-  const TV* vw = reinterpret_cast<const TV*>(a.VW) + ((long long)b * Tn * H + (unit_ok ? j : H - 1)) * 4;
+  const TV* vw = reinterpret_cast<const TV*>(a.VW) + ((size_t)b * Tn * H + jc) * 4;
   Quad<TV> v[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) v[k].load(vw + (long long)min(2 * k + half, Tn - 1) * 4 * H);
+  for (unsigned k = 0; k < 16; ++k) v[k].load(vw + min(2 * k + half, Tn - 1) * row);
+  if (tid < MAX_T && tid >= Tn) e_s[tid & 1][tid >> 1] = 0.f;
   // (2) the unit's gate pre-activations that do not depend on the attention: half 0 (which owns the cell update) fetches
   //     the hoisted embedding projection, bias and c_{t-1}; half 1 sums the split-K partials of h_{t-1} W_hh^T
   float pre[4] = {0.f, 0.f, 0.f, 0.f};
   float cp = 0.f;
-  if (unit_ok) {
-    if (half == 0) {
-      const float* gx = a.Gx + (long long)b * 4 * H + j;
+  if (half == 0) {
+    const float* gx = a.Gx + (size_t)b * row + jc;
+    const float* bh = a.b_hh + jc;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) pre[g] = gx[g * H] + a.b_hh[g * H + j];
-      cp = a.c_prev[(long long)b * H + j];
-    } else {
-      const float* q = a.P + (long long)b * a.NP + A + j;
-      int s = 0;
-      for (; s + 4 <= a.n_p; s += 4) {             // 16 independent loads in flight
-        float x[4][4];
+    for (unsigned g = 0; g < 4; ++g) pre[g] = gx[g * H] + bh[g * H];
+    cp = a.c_prev[b * H + jc];
+  } else {
+    const float* q = a.P + (size_t)b * a.NP + A + jc;
+    const unsigned ps = (unsigned)a.p_stride;
+    int s = 0;
+    for (; s + 4 <= a.n_p; s += 4) {             // 16 independent loads in flight
+      float x[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (unsigned i = 0; i < 4; ++i)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) x[i][g] = q[i * a.p_stride + g * H];
+        for (unsigned g = 0; g < 4; ++g) x[i][g] = q[i * ps + g * H];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pre[g] += (x[0][g] + x[1][g]) + (x[2][g] + x[3][g]);
-        q += 4 * a.p_stride;
-      }
-      for (; s < a.n_p; ++s) {
+      for (int g = 0; g < 4; ++g) pre[g] += (x[0][g] + x[1][g]) + (x[2][g] + x[3][g]);
+      q += 4 * ps;
+    }
+    for (; s < a.n_p; ++s) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pre[g] += q[g * H];
-        q += a.p_stride;
-      }
+      for (unsigned g = 0; g < 4; ++g) pre[g] += q[g * H];
+      q += ps;
     }
   }
-  // (3) scores e[tau] = w . tanh(W h + U v_tau + b): warp w takes frames w, w + 8, ..; a lane takes float4 chunks lane, lane + 32 of A
-  const int nchunk = A >> 2;
-  const float* uvb = a.Uv + (long long)b * Tn * A;
+  // (3) scores e[tau] = w . tanh(W h + (U v_tau + b)): warp w takes frames w, w + 8, ..; a lane takes float4 chunks lane, lane + 32 of A
+  const unsigned nchunk = A >> 2;
+  const float4* uvb = reinterpret_cast<const float4*>(a.Uv + (size_t)b * Tn * A);
   float4 uv[4][NCH];
 #pragma unroll
-  for (int f = 0; f < 4; ++f)
+  for (unsigned f = 0; f < 4; ++f)
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
-      uv[f][i] = reinterpret_cast<const float4*>(uvb + (long long)min(warp + f * NW, Tn - 1) * A)[min(lane + 32 * i, nchunk - 1)];
-  float4 wh[NCH], bb[NCH], ww[NCH];
+    for (unsigned i = 0; i < NCH; ++i) uv[f][i] = uvb[min(warp + f * NW, Tn - 1) * nchunk + min(lane + 32 * i, nchunk - 1)];
+  float4 wh[NCH], ww[NCH];
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int c = lane + 32 * i;
-    wh[i] = bb[i] = ww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < nchunk) {
-      bb[i] = reinterpret_cast<const float4*>(a.attn_b)[c];
-      ww[i] = reinterpret_cast<const float4*>(a.attn_w)[c];
-      wh[i] = sum_splits4(a.P + (long long)b * a.NP + 4 * c, a.n_p, a.p_stride);
-      if (blockIdx.x == 0 && warp == 0 && a.Wh_out) reinterpret_cast<float4*>(a.Wh_out + (long long)b * A)[c] = wh[i];
-      wh[i] = f4_add(wh[i], bb[i]);
-    }
+  for (unsigned i = 0; i < NCH; ++i) {
+    const unsigned c = min(lane + 32 * i, nchunk - 1);
+    ww[i] = reinterpret_cast<const float4*>(a.attn_w)[c];
+    wh[i] = sum_splits4(a.P + (size_t)b * a.NP + 4 * c, a.n_p, a.p_stride);
+    if (blockIdx.x == 0 && warp == 0 && a.Wh_out && lane + 32 * i < nchunk) reinterpret_cast<float4*>(a.Wh_out + (size_t)b * A)[c] = wh[i];
   }
-  for (int f0 = 0;;) {
+  for (unsigned f0 = 0;;) {
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int tau = warp + (f0 + f) * NW;
+    for (unsigned f = 0; f < 4; ++f) {
+      const unsigned tau = warp + (f0 + f) * NW;
       if (tau < Tn) {               // warp-uniform
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          if (lane + 32 * i < nchunk) {
+        for (unsigned i = 0; i < NCH; ++i) {
+          if (NCH == 1 || lane + 32 * i < nchunk) {
             const float4 x = uv[f][i];
             s = fmaf(ww[i].x, act_tanh<FAST>(wh[i].x + x.x), s);
             s = fmaf(ww[i].y, act_tanh<FAST>(wh[i].y + x.y), s);
@@ -186,40 +184,42 @@ __global__ void __launch_bounds__(THREADS, NCH == 1 ? 3 : 2) pf_fwd_kernel(FwdAr
             s = fmaf(ww[i].w, act_tanh<FAST>(wh[i].w + x.w), s);
           }
         }
+        if (NCH == 1 && lane >= nchunk) s = 0.f;
         s = warp_sum(s);
         if (lane == 0) {
-          e_s[tau] = s;
-          if (blockIdx.x == 0 && a.e_out) a.e_out[(long long)b * Tn + tau] = s;
+          e_s[tau & 1][tau >> 1] = s;
+          if (blockIdx.x == 0 && a.e_out) a.e_out[b * Tn + tau] = s;
         }
       }
     }
     f0 += 4;
     if (warp + f0 * NW >= Tn) break;
 #pragma unroll
-    for (int f = 0; f < 4; ++f)
+    for (unsigned f = 0; f < 4; ++f)
 #pragma unroll
-      for (int i = 0; i < NCH; ++i)
-        uv[f][i] = reinterpret_cast<const float4*>(uvb + (long long)min(warp + (f0 + f) * NW, Tn - 1) * A)[min(lane + 32 * i, nchunk - 1)];
+      for (unsigned i = 0; i < NCH; ++i) uv[f][i] = uvb[min(warp + (f0 + f) * NW, Tn - 1) * nchunk + min(lane + 32 * i, nchunk - 1)];
   }
   __syncthreads();
-  // (4) weighted sum over this thread's frames
+  // (4) weighted sum over this thread's frames (weights of frames >= Tn are zero, their clamped quads are finite)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t0 = 0;;) {
+  for (unsigned t0 = 0;;) {
+    const float4* e4 = reinterpret_cast<const float4*>(&e_s[half][t0 >> 1]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int tau = t0 + 2 * k + half;
-      if (tau < Tn) {
+    for (unsigned k4 = 0; k4 < 4; ++k4) {
+      const float4 e = e4[k4];
+      const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+      for (unsigned kk = 0; kk < 4; ++kk) {
         float f[4];
-        v[k].get(f);
-        const float e = e_s[tau];
+        v[4 * k4 + kk].get(f);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) acc[g] = fmaf(e, f[g], acc[g]);
+        for (int g = 0; g < 4; ++g) acc[g] = fmaf(ev[kk], f[g], acc[g]);
       }
     }
     t0 += 32;
     if (t0 >= Tn) break;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) v[k].load(vw + (long long)min(t0 + 2 * k + half, Tn - 1) * 4 * H);
+    for (unsigned k = 0; k < 16; ++k) v[k].load(vw + min(t0 + 2 * k + half, Tn - 1) * row);
   }
   if (half == 1)
     red[u] = make_float4(fmaf(acc[0], a.inv_T, pre[0]), fmaf(acc[1], a.inv_T, pre[1]), fmaf(acc[2], a.inv_T, pre[2]),
@@ -232,11 +232,11 @@ __global__ void __launch_bounds__(THREADS, NCH == 1 ? 3 : 2) pf_fwd_kernel(FwdAr
     const float gi = act_sigmoid<FAST>(pi), gf = act_sigmoid<FAST>(pf_), gg = act_tanh<FAST>(pg), go = act_sigmoid<FAST>(po);
     const float cn = fmaf(gf, cp, gi * gg);
     const float hn = go * act_tanh<FAST>(cn);
-    const long long o1 = (long long)b * H + j;
+    const unsigned o1 = b * H + j;
     a.c_out[o1] = cn;
     a.h_out[o1] = hn;
     reinterpret_cast<TO*>(a.h_op)[o1] = from_f32<TO>(hn);
-    if (a.gates_out) Quad<TO>::store(reinterpret_cast<TO*>(a.gates_out) + o1 * 4, gi, gf, gg, go);
+    if (a.gates_out) Quad<TO>::store(reinterpret_cast<TO*>(a.gates_out) + (size_t)o1 * 4, gi, gf, gg, go);
   }
 }
 
@@ -248,7 +248,7 @@ struct BwdArgs {
   const void* gates;                                    // [B, H, 4] TO
   const float* c_prev; const float* c_new;              // [B, H]
   const void* VW;                                       // [B, Tn, H, 4] TV
-  const float* Wh; const float* Uv; const float* attn_b; const float* attn_w;
+  const float* Wh; const float* Uv; const float* attn_w;  // Uv = hoisted U v + attn_b
   int B, Tn, A, H; float inv_T;
   void* dGW; long long dgw_ld;                          // [B, A + 4H] TO: [dWh | dG (gate-block order)]  -> operand of K4 and of the weight-gradient GEMMs
   float* dWh_out;                                       // [B, A] fp32 (attn_b gradient)
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(THREADS) pf_bwd_kernel(BwdArgs a) {
   for (int i = 0; i < NCH; ++i) {
     dwh[i] = dww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int cc = min(lane + 32 * i, nchunk - 1);
-    wh[i] = f4_add(reinterpret_cast<const float4*>(a.Wh + (long long)b * A)[cc], reinterpret_cast<const float4*>(a.attn_b)[cc]);
+    wh[i] = reinterpret_cast<const float4*>(a.Wh + (long long)b * A)[cc];          // Uv already contains attn_b
     ww[i] = reinterpret_cast<const float4*>(a.attn_w)[cc];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
@@ -542,8 +542,12 @@ template <typename TV, typename TO>
 static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   RN_TRY(check_shape(a.Tn, a.A, a.H));
   ProfScope prof(KC_PF_FWD, a.B, a.Tn, a.H, st);
-  if (a.A <= 128) pf_fwd_kernel<TV, TO, 1><<<dim3(rn_cdiv(a.H, UPB), a.B), THREADS, 0, st>>>(a);
-  else pf_fwd_kernel<TV, TO, 2><<<dim3(rn_cdiv(a.H, UPB), a.B), THREADS, 0, st>>>(a);
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("RECNET_PF_MINB"); minb = e ? atoi(e) : 3; }
+  const dim3 grid(rn_cdiv(a.H, UPB), a.B);
+  if (a.A <= 128 && minb == 3) pf_fwd_kernel<TV, TO, 1, 3><<<grid, THREADS, 0, st>>>(a);
+  else if (a.A <= 128) pf_fwd_kernel<TV, TO, 1, 2><<<grid, THREADS, 0, st>>>(a);
+  else pf_fwd_kernel<TV, TO, 2, 2><<<grid, THREADS, 0, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -32,6 +32,7 @@ static inline bool pf_ok(const recnet_decoder_desc& d) {
   if (!pf_enabled() || d.cell != RECNET_CELL_LSTM || d.n_layers > 1) return false;
   if (num_chains(d.B) != 1 || mega::mega_enabled()) return false;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
+  if ((long long)d.B * d.T * 4 * d.H >= (1ll << 31) || (long long)d.L * d.B * (d.A + 4 * d.H) >= (1ll << 31)) return false;   // 32-bit index math
   return d.T >= 1 && d.T <= pf::MAX_T && d.A >= 4 && d.A <= pf::MAX_A && d.A % al == 0 && d.H % al == 0 && d.H <= 2560;
 }
 
@@ -55,6 +56,14 @@ static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
     // dh GEMM (N = H, K = A + 4H): at most pf::MAXS splits so the fused backward kernel sums them with one batch of loads
     const int nkb2 = rn_cdiv(w.NP, tc::BK);
     if (w.pl_dh.splits > pf::MAXS) w.pl_dh.splits = rn_cdiv(nkb2, rn_cdiv(nkb2, pf::MAXS));
+    // tuning overrides (tools/ sweeps): RECNET_PF_SPLITS_H / RECNET_PF_SPLITS_DH / RECNET_PF_BN_H
+    static int eh = -1, edh = -1, ebn = -1;
+    if (eh < 0) { const char* e = getenv("RECNET_PF_SPLITS_H"); eh = e ? atoi(e) : 0; }
+    if (edh < 0) { const char* e = getenv("RECNET_PF_SPLITS_DH"); edh = e ? atoi(e) : 0; }
+    if (ebn < 0) { const char* e = getenv("RECNET_PF_BN_H"); ebn = e ? atoi(e) : 0; }
+    if (ebn == 64 || ebn == 128) w.pl_h.bn = ebn;
+    if (eh > 0) w.pl_h.splits = rn_cdiv(nkb, rn_cdiv(nkb, eh > nkb ? nkb : eh));
+    if (edh > 0) w.pl_dh.splits = rn_cdiv(nkb2, rn_cdiv(nkb2, edh > nkb2 ? nkb2 : edh));
   }
   Bump m(base);
   w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);
@@ -123,7 +132,7 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
   RN_TRY(misc::cast_pad<T>(feats, E, w.feats, E, (long long)B * Tn, E, E, st));
   // hoisted projections
-  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, nullptr, B * Tn, A, E, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, p.attn_b, B * Tn, A, E, 0, w.splitk, st));      // U v + b (bias folded in)
   RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
   misc::embed_gather_kernel<T><<<L * B, 128, 0, st>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
                                                       p_emb, rng, SITE_EMB);
@@ -138,7 +147,7 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
       RN_TRY(gemm_partials<T>(w.Hop + r * H, H, 0, w.Wcat, H, 0, w.P, B, w.NP, H, w.pl_h, st));
     pf::FwdArgs fa{};
     fa.P = w.P; fa.n_p = t > 0 ? w.pl_h.splits : 0; fa.p_stride = (long long)B * w.NP; fa.NP = w.NP;
-    fa.Uv = w.Uv; fa.attn_b = p.attn_b; fa.attn_w = p.attn_w; fa.VW = w.VW;
+    fa.Uv = w.Uv; fa.attn_w = p.attn_w; fa.VW = w.VW;
     fa.Gx = w.Gx + r * 4 * H; fa.b_hh = p.b_hh; fa.c_prev = w.c + r * H;
     fa.B = B; fa.Tn = Tn; fa.A = A; fa.H = H; fa.inv_T = 1.f / Tn;
     fa.Wh_out = w.Wh + r * A; fa.e_out = w.e + r * Tn; fa.gates_out = w.gates + r * 4 * H;
@@ -188,7 +197,7 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
     ba.dhP = last ? nullptr : w.dhP; ba.n_p = w.pl_dh.splits; ba.p_stride = (long long)B * H;
     ba.dc = w.dc; ba.first = last ? 1 : 0;
     ba.gates = w.gates + r * 4 * H; ba.c_prev = w.c + r * H; ba.c_new = w.c + (r + B) * H;
-    ba.VW = w.VW; ba.Wh = w.Wh + r * A; ba.Uv = w.Uv; ba.attn_b = p.attn_b; ba.attn_w = p.attn_w;
+    ba.VW = w.VW; ba.Wh = w.Wh + r * A; ba.Uv = w.Uv; ba.attn_w = p.attn_w;
     ba.B = B; ba.Tn = Tn; ba.A = A; ba.H = H; ba.inv_T = 1.f / Tn;
     ba.dGW = w.dGW + r * NP; ba.dgw_ld = NP; ba.dWh_out = w.dWh + r * A;
     ba.dUv_acc = w.dUv; ba.uv_first = last ? 1 : 0; ba.dw_acc = w.dw_acc; ba.dw_first = last ? 1 : 0;

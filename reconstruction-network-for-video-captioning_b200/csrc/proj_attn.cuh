@@ -324,150 +324,126 @@ __device__ __forceinline__ float4 cell_bwd_unit(const BwdArgs& a, const CellIn<T
   return make_float4(to_f32<TO>(r0), to_f32<TO>(r1), to_f32<TO>(r2), to_f32<TO>(r3));
 }
 
-// one CTA per sample, two hidden units per thread and pass; dynamic shared memory: 4H floats (gate gradients, only re-read
-// when Tn > 32).  The kernel is latency-bound (114 KB of VW per CTA, ~10 dependent steps), so every independent load --
-// both units' cell operands and split-K partials, the first unit's 28 VW quads, the score operands -- is issued up front.
-template <typename TV, typename TO, int NCH>
-__global__ void __launch_bounds__(THREADS) pf_bwd_kernel(BwdArgs a) {
+// One CTA of 512 threads per sample.  r1 ncu of the first version (256 threads, thread-owns-unit, 28 partial sums per
+// thread transposed across the warp): 2600 instructions per warp at 2 warps per scheduler -> instruction-latency bound,
+// 10 us.  Now: (A) the cell backward runs one unit per thread and leaves the (operand-rounded) gate gradients in shared
+// memory; (B) warp w owns the frames w, w + 16, ..: its lanes stream whole VW rows against the shared gate gradients, one
+// warp_sum per frame gives d e[tau] in every lane, and (C) the same warp does the score backward of its frames.  Every
+// load that does not depend on a previous phase is issued at kernel entry.
+// dynamic shared memory: H float4 (gate gradients) + 2 * BNW * A floats (per-warp dWh / dw partials)
+constexpr int BTHREADS = 512;
+constexpr int BNW = BTHREADS / 32;
+template <typename TV, typename TO, int NF, int NCH>
+__global__ void __launch_bounds__(BTHREADS) pf_bwd_kernel(BwdArgs a) {
   constexpr bool FAST = FastMath<TO>::value;
+  constexpr int QP = 32 / NF;                           // VW quads per lane, frame and pass (32 quads = 64 registers in flight)
   extern __shared__ float4 dg_s[];                      // [H]
-  __shared__ float de_w[NW][MAX_T];
-  __shared__ float de_s[MAX_T];
-  __shared__ float part[2][NW][MAX_A];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x, Tn = a.Tn, H = a.H, A = a.A;
-  const int nchunk = A >> 2;
-  const TV* vwb = reinterpret_cast<const TV*>(a.VW) + (long long)b * Tn * H * 4;
-  Quad<TV> v[32];
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned b = blockIdx.x, Tn = a.Tn, H = a.H, A = a.A, row = 4u * H, nchunk = A >> 2;
+  float* part = reinterpret_cast<float*>(dg_s + H);     // [2][BNW][A]
+  const TV* vwb = reinterpret_cast<const TV*>(a.VW) + (size_t)b * Tn * row;
+  unsigned tauc[NF];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(k, Tn - 1) * H + min(tid, H - 1)) * 4);   // unconditional, clamped
-  CellIn<TO> in1, in2;
-  in1.load(a, (long long)b * H + min(tid, H - 1));
-  in2.load(a, (long long)b * H + min(tid + THREADS, H - 1));
-  // score operands of this warp's first four frames
-  float4 wh[NCH], ww[NCH], dwh[NCH], dww[NCH], uv[4][NCH], old[4][NCH];
+  for (unsigned f = 0; f < NF; ++f) tauc[f] = min(warp + f * BNW, Tn - 1);
+  // ---- issue: cell operands of unit tid, the first VW pass of this warp's frames, the score operands
+  CellIn<TO> in;
+  in.load(a, (long long)(b * H + min(tid, H - 1)));
+  Quad<TV> v[NF][QP];
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    dwh[i] = dww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int cc = min(lane + 32 * i, nchunk - 1);
-    wh[i] = reinterpret_cast<const float4*>(a.Wh + (long long)b * A)[cc];          // Uv already contains attn_b
+  for (unsigned f = 0; f < NF; ++f)
+#pragma unroll
+    for (unsigned q = 0; q < QP; ++q) v[f][q].load(vwb + tauc[f] * row + min(lane + 32 * q, H - 1) * 4);
+  const float4* uvb = reinterpret_cast<const float4*>(a.Uv + (size_t)b * Tn * A);
+  float4* dub = reinterpret_cast<float4*>(a.dUv_acc + (size_t)b * Tn * A);
+  float4 uv[NF][NCH], old[NF][NCH], wh[NCH], ww[NCH];
+#pragma unroll
+  for (unsigned i = 0; i < NCH; ++i) {
+    const unsigned cc = min(lane + 32 * i, nchunk - 1);
+    wh[i] = reinterpret_cast<const float4*>(a.Wh + (size_t)b * A)[cc];          // Uv already contains attn_b
     ww[i] = reinterpret_cast<const float4*>(a.attn_w)[cc];
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const long long off = ((long long)b * Tn + min(warp + f * NW, Tn - 1)) * A;
-      uv[f][i] = reinterpret_cast<const float4*>(a.Uv + off)[cc];
-      old[f][i] = a.uv_first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.dUv_acc + off)[cc];
-    }
+    for (unsigned f = 0; f < NF; ++f) uv[f][i] = uvb[tauc[f] * nchunk + cc];
   }
-  // ---- d e[tau] = (1/T) <dG, VW[tau]> with the LSTM cell backward folded into the first pass
-  for (int t0 = 0; t0 < Tn; t0 += 32) {
-    float acc[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-    for (int j0 = 0; j0 < H; j0 += 2 * THREADS) {
-      const int j1 = j0 + tid, j2 = j1 + THREADS;
-      const bool ok1 = j1 < H, ok2 = j2 < H;
-      if (t0 != 0 || j0 != 0) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(t0 + k, Tn - 1) * H + min(j1, H - 1)) * 4);
-      }
-      float4 dg1, dg2;
-      if (t0 == 0) {
-        if (j0 != 0) {
-          in1.load(a, (long long)b * H + min(j1, H - 1));
-          in2.load(a, (long long)b * H + min(j2, H - 1));
-        }
-        dg1 = cell_bwd_unit<TO, FAST>(a, in1, b, min(j1, H - 1), ok1);
-        dg2 = cell_bwd_unit<TO, FAST>(a, in2, b, min(j2, H - 1), ok2);
-        if (ok1) dg_s[j1] = dg1;
-        if (ok2) dg_s[j2] = dg2;
-      } else {                                        // own entries only: no barrier needed
-        dg1 = ok1 ? dg_s[j1] : make_float4(0.f, 0.f, 0.f, 0.f);
-        dg2 = ok2 ? dg_s[j2] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        if (t0 + k < Tn) {
-          float f[4];
-          v[k].get(f);
-          acc[k] = fmaf(dg1.x, f[0], fmaf(dg1.y, f[1], fmaf(dg1.z, f[2], fmaf(dg1.w, f[3], acc[k]))));
-        }
-      }
-      if (j0 + THREADS < H) {                         // uniform
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k].load(vwb + ((long long)min(t0 + k, Tn - 1) * H + min(j2, H - 1)) * 4);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          if (t0 + k < Tn) {
-            float f[4];
-            v[k].get(f);
-            acc[k] = fmaf(dg2.x, f[0], fmaf(dg2.y, f[1], fmaf(dg2.z, f[2], fmaf(dg2.w, f[3], acc[k]))));
-          }
-        }
-      }
-    }
-    const float tot = warp_transpose_sum32(acc, lane);
-    if (t0 + lane < MAX_T) de_w[warp][t0 + lane] = tot;
+  // ---- (A) LSTM cell backward, one unit per thread and pass
+  for (unsigned j0 = 0; j0 < H; j0 += BTHREADS) {
+    const unsigned j = j0 + tid;
+    if (j0 != 0) in.load(a, (long long)(b * H + min(j, H - 1)));
+    const float4 dg = cell_bwd_unit<TO, FAST>(a, in, b, min(j, H - 1), j < H);
+    if (j < H) dg_s[j] = dg;
   }
+#pragma unroll
+  for (unsigned i = 0; i < NCH; ++i)
+#pragma unroll
+    for (unsigned f = 0; f < NF; ++f)
+      old[f][i] = a.uv_first ? make_float4(0.f, 0.f, 0.f, 0.f) : dub[tauc[f] * nchunk + min(lane + 32 * i, nchunk - 1)];
   __syncthreads();
-  if (tid < Tn) {
-    float s = 0.f;
+  // ---- (B) d e[tau] = (1/T) <dG, VW[tau]> for this warp's frames
+  float de[NF];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) s += de_w[w][tid];
-    de_s[tid] = s * a.inv_T;
-  }
-  __syncthreads();
-  // ---- score backward: ds = de * w * (1 - tanh^2); dWh = sum_tau ds; dUv[tau] += ds; dw += de * tanh
-  for (int f0 = 0; warp + f0 * NW < Tn; f0 += 4) {
-    if (f0 != 0) {
+  for (unsigned f = 0; f < NF; ++f) de[f] = 0.f;
+  for (unsigned q0 = 0; q0 < H; q0 += 32 * QP) {
+    if (q0 != 0) {
 #pragma unroll
-      for (int f = 0; f < 4; ++f)
+      for (unsigned f = 0; f < NF; ++f)
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          const long long off = ((long long)b * Tn + min(warp + (f0 + f) * NW, Tn - 1)) * A;
-          const int cc = min(lane + 32 * i, nchunk - 1);
-          uv[f][i] = reinterpret_cast<const float4*>(a.Uv + off)[cc];
-          old[f][i] = a.uv_first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.dUv_acc + off)[cc];
-        }
+        for (unsigned q = 0; q < QP; ++q) v[f][q].load(vwb + tauc[f] * row + min(q0 + lane + 32 * q, H - 1) * 4);
     }
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int tau = warp + (f0 + f) * NW;
-      if (tau < Tn) {
-        const float g = de_s[tau];
+    for (unsigned q = 0; q < QP; ++q) {
+      const unsigned unit = q0 + lane + 32 * q;
+      float4 dg = dg_s[min(unit, H - 1)];
+      if (unit >= H) dg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          const int c = lane + 32 * i;
-          if (c < nchunk) {
-            const float4 x = uv[f][i];
-            const float tx = act_tanh<FAST>(wh[i].x + x.x), ty = act_tanh<FAST>(wh[i].y + x.y);
-            const float tz = act_tanh<FAST>(wh[i].z + x.z), tw = act_tanh<FAST>(wh[i].w + x.w);
-            const float4 ds = make_float4(g * ww[i].x * (1.f - tx * tx), g * ww[i].y * (1.f - ty * ty), g * ww[i].z * (1.f - tz * tz),
-                                          g * ww[i].w * (1.f - tw * tw));
-            dwh[i] = f4_add(dwh[i], ds);
-            dww[i] = f4_add(dww[i], make_float4(g * tx, g * ty, g * tz, g * tw));
-            reinterpret_cast<float4*>(a.dUv_acc + ((long long)b * Tn + tau) * A)[c] = f4_add(ds, old[f][i]);
-          }
+      for (unsigned f = 0; f < NF; ++f) {
+        float x[4];
+        v[f][q].get(x);
+        de[f] = fmaf(dg.x, x[0], fmaf(dg.y, x[1], fmaf(dg.z, x[2], fmaf(dg.w, x[3], de[f]))));
+      }
+    }
+  }
+#pragma unroll
+  for (unsigned f = 0; f < NF; ++f) de[f] = warp_sum(de[f]) * a.inv_T;
+  // ---- (C) score backward of the same frames: ds = de * w * (1 - tanh^2); dWh = sum_tau ds; dUv[tau] += ds; dw += de * tanh
+  float4 dwh[NCH], dww[NCH];
+#pragma unroll
+  for (unsigned i = 0; i < NCH; ++i) dwh[i] = dww[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (unsigned f = 0; f < NF; ++f) {
+    const unsigned tau = warp + f * BNW;
+    if (tau < Tn) {                                     // warp-uniform
+      const float g = de[f];
+#pragma unroll
+      for (unsigned i = 0; i < NCH; ++i) {
+        const unsigned c = lane + 32 * i;
+        if (c < nchunk) {
+          const float4 x = uv[f][i];
+          const float tx = act_tanh<FAST>(wh[i].x + x.x), ty = act_tanh<FAST>(wh[i].y + x.y);
+          const float tz = act_tanh<FAST>(wh[i].z + x.z), tw = act_tanh<FAST>(wh[i].w + x.w);
+          const float4 ds = make_float4(g * ww[i].x * (1.f - tx * tx), g * ww[i].y * (1.f - ty * ty), g * ww[i].z * (1.f - tz * tz),
+                                        g * ww[i].w * (1.f - tw * tw));
+          dwh[i] = f4_add(dwh[i], ds);
+          dww[i] = f4_add(dww[i], make_float4(g * tx, g * ty, g * tz, g * tw));
+          dub[tau * nchunk + c] = f4_add(ds, old[f][i]);
         }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int c = lane + 32 * i;
+  for (unsigned i = 0; i < NCH; ++i) {
+    const unsigned c = lane + 32 * i;
     if (c < nchunk) {
-      reinterpret_cast<float4*>(&part[0][warp][0])[c] = dwh[i];
-      reinterpret_cast<float4*>(&part[1][warp][0])[c] = dww[i];
+      reinterpret_cast<float4*>(part + warp * A)[c] = dwh[i];
+      reinterpret_cast<float4*>(part + (BNW + warp) * A)[c] = dww[i];
     }
   }
   __syncthreads();
-  for (int x = tid; x < A; x += THREADS) {
+  for (unsigned x = tid; x < A; x += BTHREADS) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) { s0 += part[0][w][x]; s1 += part[1][w][x]; }
-    a.dWh_out[(long long)b * A + x] = s0;
-    reinterpret_cast<TO*>(a.dGW)[(long long)b * a.dgw_ld + x] = from_f32<TO>(s0);
-    float* pw = a.dw_acc + (long long)b * A + x;
+    for (unsigned w = 0; w < BNW; ++w) { s0 += part[w * A + x]; s1 += part[(BNW + w) * A + x]; }
+    a.dWh_out[b * A + x] = s0;
+    reinterpret_cast<TO*>(a.dGW)[(size_t)b * a.dgw_ld + x] = from_f32<TO>(s0);
+    float* pw = a.dw_acc + b * A + x;
     *pw = a.dw_first ? s1 : *pw + s1;
   }
 }
@@ -551,14 +527,18 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   RN_LAUNCH_OK();
   return 0;
 }
+static inline size_t bwd_smem_bytes(int H, int A) { return (size_t)H * sizeof(float4) + (size_t)2 * BNW * A * sizeof(float); }
 template <typename TV, typename TO>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   RN_TRY(check_shape(a.Tn, a.A, a.H));
-  const size_t smem = (size_t)a.H * sizeof(float4);
-  if (smem > 40 * 1024) return RECNET_ERR_BAD_SHAPE;     // + ~19 KB static: stays under the 48 KB default limit
+  const size_t smem = bwd_smem_bytes(a.H, a.A);
+  if (smem > 46 * 1024) return RECNET_ERR_BAD_SHAPE;
+  const bool nf2 = a.Tn <= 2 * BNW, ch1 = a.A <= 128;
   ProfScope prof(KC_PF_BWD, a.B, a.Tn, a.H, st);
-  if (a.A <= 128) pf_bwd_kernel<TV, TO, 1><<<a.B, THREADS, smem, st>>>(a);
-  else pf_bwd_kernel<TV, TO, 2><<<a.B, THREADS, smem, st>>>(a);
+  if (nf2 && ch1) pf_bwd_kernel<TV, TO, 2, 1><<<a.B, BTHREADS, smem, st>>>(a);
+  else if (nf2) pf_bwd_kernel<TV, TO, 2, 2><<<a.B, BTHREADS, smem, st>>>(a);
+  else if (ch1) pf_bwd_kernel<TV, TO, 4, 1><<<a.B, BTHREADS, smem, st>>>(a);
+  else pf_bwd_kernel<TV, TO, 4, 2><<<a.B, BTHREADS, smem, st>>>(a);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -33,7 +33,8 @@ static inline bool pf_ok(const recnet_decoder_desc& d) {
   if (num_chains(d.B) != 1 || mega::mega_enabled()) return false;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if ((long long)d.B * d.T * 4 * d.H >= (1ll << 31) || (long long)d.L * d.B * (d.A + 4 * d.H) >= (1ll << 31)) return false;   // 32-bit index math
-  return d.T >= 1 && d.T <= pf::MAX_T && d.A >= 4 && d.A <= pf::MAX_A && d.A % al == 0 && d.H % al == 0 && d.H <= 2560;
+  return d.T >= 1 && d.T <= pf::MAX_T && d.A >= 4 && d.A <= pf::MAX_A && d.A % al == 0 && d.H % al == 0 &&
+         pf::bwd_smem_bytes(d.H, d.A) <= 46 * 1024;
 }
 
 template <typename T>

@@ -405,6 +405,66 @@ __global__ void attn_dv_kernel(const float* __restrict__ beta, const float* __re
   }
 }
 
+// Same result, one pass over dx: a block owns (sample b, 256 columns) and accumulates ALL Tn frames in registers; the S step
+// values of a column are fetched with independent loads up front (the kernel above re-reads dx once per frame: 31 x 5.7 MB of
+// L2 traffic, 37 us).  grid (ceil(D / 256), B), 256 threads, dynamic smem round_up(S, 32) * round_up(Tn, 4) floats.  Tn <= 64.
+__global__ void __launch_bounds__(256) attn_dv2_kernel(const float* __restrict__ beta, const float* __restrict__ dx, float* __restrict__ dV,
+                                                       long long dv_bs, long long dv_ts, int S, int B, int Tn, int D, float inv_T,
+                                                       int accumulate, int step_mul, int step_off) {
+  extern __shared__ float4 bt4[];
+  float* bt = reinterpret_cast<float*>(bt4);
+  const int Tnp = (Tn + 3) & ~3, Sp = (S + 31) & ~31;
+  const int b = blockIdx.y, d = blockIdx.x * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < Sp * Tnp; i += 256) {        // zero rows beyond S / columns beyond Tn
+    const int t = i / Tnp, l = i - t * Tnp;
+    bt[i] = (t < S && l < Tn) ? beta[((long long)(t * step_mul + step_off) * B + b) * Tn + l] : 0.f;
+  }
+  __syncthreads();
+  if (d >= D) return;
+  for (int l0 = 0; l0 < Tn; l0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    for (int t0 = 0; t0 < S; t0 += 32) {
+      float g[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) g[k] = dx[((long long)(min(t0 + k, S - 1) * step_mul + step_off) * B + b) * D + d];
+#pragma unroll
+      for (int tt = 0; tt < 32; ++tt) {                        // rows >= S carry zero weights
+        const float4* br = bt4 + ((t0 + tt) * Tnp + l0) / 4;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          if (l0 + 4 * k4 < Tn) {
+            const float4 e4 = br[k4];
+            acc[4 * k4 + 0] = fmaf(e4.x, g[tt], acc[4 * k4 + 0]);
+            acc[4 * k4 + 1] = fmaf(e4.y, g[tt], acc[4 * k4 + 1]);
+            acc[4 * k4 + 2] = fmaf(e4.z, g[tt], acc[4 * k4 + 2]);
+            acc[4 * k4 + 3] = fmaf(e4.w, g[tt], acc[4 * k4 + 3]);
+          }
+        }
+      }
+    }
+    float old[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) old[k] = accumulate ? dV[(long long)b * dv_bs + (long long)min(l0 + k, Tn - 1) * dv_ts + d] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (l0 + k < Tn) dV[(long long)b * dv_bs + (long long)(l0 + k) * dv_ts + d] = fmaf(acc[k], inv_T, old[k]);
+  }
+}
+// picks the one-pass kernel when its alignment requirements hold
+static inline int launch_dv(const float* beta, const float* dx, float* dV, long long dv_bs, long long dv_ts, int S, int B, int Tn, int D,
+                            float inv_T, int accumulate, int step_mul, int step_off, cudaStream_t st) {
+  const size_t smem2 = (size_t)((S + 31) & ~31) * ((Tn + 3) & ~3) * sizeof(float);
+  if (Tn <= 64 && smem2 <= 40 * 1024) {
+    attn_dv2_kernel<<<dim3(rn_cdiv(D, 256), B), 256, smem2, st>>>(beta, dx, dV, dv_bs, dv_ts, S, B, Tn, D, inv_T, accumulate, step_mul, step_off);
+  } else {
+    attn_dv_kernel<<<dim3(Tn, B), 128, (size_t)S * sizeof(float), st>>>(beta, dx, dV, dv_bs, dv_ts, S, B, Tn, D, inv_T, accumulate, step_mul, step_off);
+  }
+  RN_LAUNCH_OK();
+  return 0;
+}
+
 // validates, fills a.d_slice and returns the number of D-slices (grid.x) through *slices_out
 template <typename TV>
 static int prepare_fwd(FwdArgs& a, int* slices_out) {

@@ -221,3 +221,12 @@ __device__ __forceinline__ float dropout_scale(const unsigned long long* rng, ui
   const float u = (float)(w >> 8) * (1.0f / 16777216.0f);
   return (u >= p) ? 1.f / (1.f - p) : 0.f;
 }
+// the four scales of elements idx4 .. idx4 + 3 (idx4 a multiple of 4) from ONE Philox call; identical to dropout_scale()
+__device__ __forceinline__ float4 dropout_scale4(const unsigned long long* rng, uint32_t site, uint64_t idx4, float p) {
+  if (p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
+  Philox ph(rng[0]);
+  const uint4 r = ph(idx4 >> 2, (rng[1] << 8) | site);
+  const float k = 1.f / (1.f - p), sc = 1.0f / 16777216.0f;
+  return make_float4(((float)(r.x >> 8) * sc >= p) ? k : 0.f, ((float)(r.y >> 8) * sc >= p) ? k : 0.f,
+                     ((float)(r.z >> 8) * sc >= p) ? k : 0.f, ((float)(r.w >> 8) * sc >= p) ? k : 0.f);
+}

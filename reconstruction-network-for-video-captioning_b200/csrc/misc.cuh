@@ -17,13 +17,43 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long ld_src,
     dst[r * ld_dst + c] = from_f32<TO>(c < cols ? src[r * ld_src + c] : 0.f);
   }
 }
+template <typename TO> struct Store4;
+template <> struct Store4<float> {
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Store4<bf16> {
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+// 4 elements per thread, 32-bit index math (r1 launch list: the scalar version with a 64-bit divide per element ran at
+// 1.9 TB/s on the 6144 x 1536 recurrent weight; these casts re-stage ~29 M weights every step)
+template <typename TO>
+__global__ void cast_pad4_kernel(const float* __restrict__ src, unsigned ld_src, TO* __restrict__ dst, unsigned ld_dst,
+                                 unsigned total4, unsigned cols4, unsigned cp4) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / cp4, c4 = i - r * cp4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < cols4) v = *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + 4 * c4);
+    Store4<TO>::st(dst + (size_t)r * ld_dst + 4 * c4, v);
+  }
+}
 template <typename TO>
 static int cast_pad(const float* src, long long ld_src, TO* dst, long long ld_dst, long long rows, int cols, int cols_pad,
                     cudaStream_t st) {
   const long long total = rows * cols_pad;
   if (total == 0) return 0;
-  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  cast_pad_kernel<TO><<<blocks, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols, cols_pad);
+  const bool vec = !(cols & 3) && !(cols_pad & 3) && !(ld_src & 3) && !(ld_dst & 3) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
+                   !(reinterpret_cast<uintptr_t>(dst) & 15) && total / 4 < (1ll << 31) && ld_src < (1ll << 31) && ld_dst < (1ll << 31);
+  if (vec) {
+    const unsigned total4 = (unsigned)(total / 4);
+    const int blocks = (int)min((long long)148 * 16, ((long long)total4 + 255) / 256);
+    cast_pad4_kernel<TO><<<blocks, 256, 0, st>>>(src, (unsigned)ld_src, dst, (unsigned)ld_dst, total4, (unsigned)cols / 4, (unsigned)cols_pad / 4);
+  } else {
+    int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+    cast_pad_kernel<TO><<<blocks, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols, cols_pad);
+  }
   RN_LAUNCH_OK();
   return 0;
 }
@@ -181,7 +211,16 @@ __global__ void mt_sumsq_kernel(const long long* __restrict__ ptrs, const long l
   const float* p = reinterpret_cast<const float*>(ptrs[t]);
   const long long n = sizes[t], lo = (long long)blk_chunk[blockIdx.x] * MT_CHUNK, hi = min(n, lo + MT_CHUNK);
   float s = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float v = p[i]; s += v * v; }
+  if (!(reinterpret_cast<uintptr_t>(p) & 15)) {           // chunk offsets are multiples of 4 elements: 16-byte loads
+    const long long hi4 = lo + ((hi - lo) & ~3ll);
+    for (long long i = lo + 4 * threadIdx.x; i < hi4; i += 4 * blockDim.x) {
+      const float4 v = *reinterpret_cast<const float4*>(p + i);
+      s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    for (long long i = hi4 + threadIdx.x; i < hi; i += blockDim.x) { const float v = p[i]; s += v * v; }
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float v = p[i]; s += v * v; }
+  }
   s = block_sum(s, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;          // fixed-order two-stage reduction: bitwise reproducible
 }
@@ -213,6 +252,17 @@ __global__ void mt_reg_grad_kernel(const long long* __restrict__ ptrs, const lon
   const long long n = sizes[t], lo = (long long)blk_chunk[blockIdx.x] * MT_CHUNK, hi = min(n, lo + MT_CHUNK);
   const float nrm = sqrtf(sumsq[t]);
   const float k = (nrm > 0.f) ? lambda * (gscale ? *gscale : 1.f) / nrm : 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) g[i] = (accumulate ? g[i] : 0.f) + k * p[i];
+  if (!((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15)) {
+    const long long hi4 = lo + ((hi - lo) & ~3ll);
+    for (long long i = lo + 4 * threadIdx.x; i < hi4; i += 4 * blockDim.x) {
+      const float4 v = *reinterpret_cast<const float4*>(p + i);
+      float4 o = accumulate ? *reinterpret_cast<const float4*>(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = fmaf(k, v.x, o.x); o.y = fmaf(k, v.y, o.y); o.z = fmaf(k, v.z, o.z); o.w = fmaf(k, v.w, o.w);
+      *reinterpret_cast<float4*>(g + i) = o;
+    }
+    for (long long i = hi4 + threadIdx.x; i < hi; i += blockDim.x) g[i] = fmaf(k, p[i], accumulate ? g[i] : 0.f);
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) g[i] = fmaf(k, p[i], accumulate ? g[i] : 0.f);
+  }
 }
 }  // namespace misc

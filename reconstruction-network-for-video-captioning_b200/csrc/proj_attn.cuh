@@ -463,13 +463,13 @@ template <> struct Pair<bf16> {
 template <typename TO>
 __global__ void __launch_bounds__(256) pf_dvw_kernel(const float* __restrict__ e, const TO* __restrict__ dGW, long long ld, int col0,
                                                      TO* __restrict__ dVW, int L, int B, int Tn, int N, float inv_T) {
-  extern __shared__ float4 e_sm4[];                     // [L][Tnp / 4]
+  extern __shared__ float4 e_sm4[];                     // [round_up(L, 32)][Tnp / 4], zero beyond L / Tn
   float* e_sm = reinterpret_cast<float*>(e_sm4);
-  const int Tnp = (Tn + 3) & ~3;
+  const int Tnp = (Tn + 3) & ~3, Lp = (L + 31) & ~31;
   const int b = blockIdx.y, n = (blockIdx.x * 256 + threadIdx.x) * 2;
-  for (int i = threadIdx.x; i < L * Tnp; i += 256) {
-    const int t = i / Tnp, k = i % Tnp;
-    e_sm[i] = k < Tn ? e[((long long)t * B + b) * Tn + k] : 0.f;
+  for (int i = threadIdx.x; i < Lp * Tnp; i += 256) {
+    const int t = i / Tnp, k = i - t * Tnp;
+    e_sm[i] = (t < L && k < Tn) ? e[((long long)t * B + b) * Tn + k] : 0.f;
   }
   __syncthreads();
   if (n >= N) return;
@@ -477,18 +477,22 @@ __global__ void __launch_bounds__(256) pf_dvw_kernel(const float* __restrict__ e
     float acc[32][2];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k][0] = acc[k][1] = 0.f;
-#pragma unroll 2
-    for (int t = 0; t < L; ++t) {
-      const float2 dg = Pair<TO>::load(dGW + ((long long)t * B + b) * ld + col0 + n);
-      const float4* er = e_sm4 + (t * Tnp + t0) / 4;
+    for (int s0 = 0; s0 < L; s0 += 16) {
+      float2 dg[16];                                    // 16 steps of this column pair in flight at once
 #pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        if (t0 + 4 * k4 < Tn) {
-          const float4 e4 = er[k4];
-          acc[4 * k4 + 0][0] = fmaf(e4.x, dg.x, acc[4 * k4 + 0][0]); acc[4 * k4 + 0][1] = fmaf(e4.x, dg.y, acc[4 * k4 + 0][1]);
-          acc[4 * k4 + 1][0] = fmaf(e4.y, dg.x, acc[4 * k4 + 1][0]); acc[4 * k4 + 1][1] = fmaf(e4.y, dg.y, acc[4 * k4 + 1][1]);
-          acc[4 * k4 + 2][0] = fmaf(e4.z, dg.x, acc[4 * k4 + 2][0]); acc[4 * k4 + 2][1] = fmaf(e4.z, dg.y, acc[4 * k4 + 2][1]);
-          acc[4 * k4 + 3][0] = fmaf(e4.w, dg.x, acc[4 * k4 + 3][0]); acc[4 * k4 + 3][1] = fmaf(e4.w, dg.y, acc[4 * k4 + 3][1]);
+      for (int k = 0; k < 16; ++k) dg[k] = Pair<TO>::load(dGW + ((long long)min(s0 + k, L - 1) * B + b) * ld + col0 + n);
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) {                 // steps >= L carry zero weights
+        const float4* er = e_sm4 + ((s0 + tt) * Tnp + t0) / 4;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          if (t0 + 4 * k4 < Tn) {
+            const float4 e4 = er[k4];
+            acc[4 * k4 + 0][0] = fmaf(e4.x, dg[tt].x, acc[4 * k4 + 0][0]); acc[4 * k4 + 0][1] = fmaf(e4.x, dg[tt].y, acc[4 * k4 + 0][1]);
+            acc[4 * k4 + 1][0] = fmaf(e4.y, dg[tt].x, acc[4 * k4 + 1][0]); acc[4 * k4 + 1][1] = fmaf(e4.y, dg[tt].y, acc[4 * k4 + 1][1]);
+            acc[4 * k4 + 2][0] = fmaf(e4.z, dg[tt].x, acc[4 * k4 + 2][0]); acc[4 * k4 + 2][1] = fmaf(e4.z, dg[tt].y, acc[4 * k4 + 2][1]);
+            acc[4 * k4 + 3][0] = fmaf(e4.w, dg[tt].x, acc[4 * k4 + 3][0]); acc[4 * k4 + 3][1] = fmaf(e4.w, dg[tt].y, acc[4 * k4 + 3][1]);
+          }
         }
       }
     }
@@ -499,13 +503,19 @@ __global__ void __launch_bounds__(256) pf_dvw_kernel(const float* __restrict__ e
 }
 
 // dst[(4j + g), :] = (TO) src[(g H + j), :]   -- W_ctx rows in unit-interleaved order (makes the VW GEMM emit [.., H, 4])
+// one block per destination row, float4 groups per thread when cols % 4 == 0 (grid = 4H blocks)
 template <typename TO>
 __global__ void interleave_rows_kernel(const float* __restrict__ src, long long ld_src, TO* __restrict__ dst, int H, int cols) {
-  const long long total = (long long)4 * H * cols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i % cols);
-    const int j = r >> 2, g = r & 3;
-    dst[i] = from_f32<TO>(src[((long long)g * H + j) * ld_src + c]);
+  const int r = blockIdx.x, j = r >> 2, g = r & 3;
+  const float* s = src + ((long long)g * H + j) * ld_src;
+  TO* d = dst + (long long)r * cols;
+  if (!(cols & 3) && !(ld_src & 3) && !(reinterpret_cast<uintptr_t>(src) & 15)) {
+    for (int c4 = threadIdx.x; c4 < (cols >> 2); c4 += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(s)[c4];
+      Quad<TO>::store(d + 4 * c4, v.x, v.y, v.z, v.w);
+    }
+  } else {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) d[c] = from_f32<TO>(s[c]);
   }
 }
 

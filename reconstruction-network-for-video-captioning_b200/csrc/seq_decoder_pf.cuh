@@ -125,7 +125,7 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   const long long ldih = EMB + E;
   // operand copies of the weights / features (the optimiser changes the fp32 masters every step)
   RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, st));
-  pf::interleave_rows_kernel<T><<<NUM_SMS * 8, 256, 0, st>>>(p.w_ih + EMB, ldih, w.WctxI, H, E);
+  pf::interleave_rows_kernel<T><<<4 * H, 128, 0, st>>>(p.w_ih + EMB, ldih, w.WctxI, H, E);
   RN_LAUNCH_OK();
   RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wcat, H, A, H, H, st));
   RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H, st));
@@ -212,7 +212,7 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   RN_TRY(misc::colsum<T>(dG, NP, LB, 4 * H, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // dW_ctx = dVW^T feats,  dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b]
-  pf::pf_dvw_kernel<T><<<dim3(rn_cdiv(4 * H, 512), B), 256, (size_t)L * round_up(Tn, 4) * sizeof(float), st>>>(w.e, w.dGW, NP, A, w.dVW,
+  pf::pf_dvw_kernel<T><<<dim3(rn_cdiv(4 * H, 512), B), 256, (size_t)round_up(L, 32) * round_up(Tn, 4) * sizeof(float), st>>>(w.e, w.dGW, NP, A, w.dVW,
                                                                                                           L, B, Tn, 4 * H, 1.f / Tn);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dVW, 4 * H, 1, w.feats, E, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, B * Tn, 0, w.splitk, st));   // dW_ctx

@@ -286,12 +286,7 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
   // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
   RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk, st));
-  {
-    dim3 grid(L, B);
-    attn::attn_dv_kernel<<<grid, 128, (size_t)S * sizeof(float), st>>>(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H,
-                                                                      1.f / L, 1, 1, 0);
-    RN_LAUNCH_OK();
-  }
+  RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H, 1.f / L, 1, 1, 0, st));
   return 0;
 }
 

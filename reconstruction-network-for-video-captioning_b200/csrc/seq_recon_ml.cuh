@@ -139,12 +139,8 @@ static int local_backward_ml(const recnet_local_desc& d, const recnet_local_tens
   RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, w.splitk, st));
   RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * NLd * B, H, A, 0, w.splitk, st));
-  for (int l = 0; l < NLd; ++l) {
-    dim3 grid(L, B);
-    attn::attn_dv_kernel<<<grid, 128, (size_t)S * sizeof(float), st>>>(w.beta, w.dx, g_hiddens + (size_t)l * B * H, H, (long long)NLd * B * H,
-                                                                      S, B, L, H, 1.f / L, 1, NLd, l);
-    RN_LAUNCH_OK();
-  }
+  for (int l = 0; l < NLd; ++l)
+    RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens + (size_t)l * B * H, H, (long long)NLd * B * H, S, B, L, H, 1.f / L, 1, NLd, l, st));
   return 0;
 }
 }  // namespace rec

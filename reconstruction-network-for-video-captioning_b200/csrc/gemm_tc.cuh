@@ -127,12 +127,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nkb = max(0, min(nkb_total, kb0 + kb_per_split) - kb0);
 
   pdl_launch_next();
+  // one producer step: expect-tx + the TMA boxes of k-block i into ring slot i % STAGES
+  auto produce = [&](int i) {
+    const int s = i % STAGES;
+    mbar_expect_tx(bar_full + 8 * s, L::STAGE_BYTES);
+    const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+    const int k = (kb0 + i) * BK;
+    if (!TA) {
+      tma_load_2d(sa, &tmA, bar_full + 8 * s, k, m0);                       // box {64 k, 128 m}
+    } else {
+#pragma unroll
+      for (int j = 0; j < BM / 64; ++j)                                     // boxes {64 m, 64 k}
+        tma_load_2d(sa + j * (BK * 128), &tmA, bar_full + 8 * s, m0 + j * 64, k);
+    }
+    if (!TB) {
+      tma_load_2d(sb, &tmB, bar_full + 8 * s, k, n0);                       // box {64 k, BN n}
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)                                     // boxes {64 n, 64 k}
+        tma_load_2d(sb + j * (BK * 128), &tmB, bar_full + 8 * s, n0 + j * 64, k);
+    }
+  };
+  const int n_early = nkb < STAGES ? nkb : STAGES;
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // The per-step GEMMs have 1-11 k-blocks and are pure latency chains (launch -> TMA -> UMMA -> tcgen05.ld -> store): the
+    // first pass through the ring needs no empty-slot wait, so its loads are issued right here, by the thread that just
+    // initialised the barriers, while warp 1 is still allocating TMEM and the CTA has not yet met at the barrier below.
+    pdl_wait();
+    for (int i = 0; i < n_early; ++i) produce(i);
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);
   tc_fence_before();
@@ -144,27 +171,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = n_early; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        mbar_expect_tx(bar_full + 8 * s, L::STAGE_BYTES);
-        const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-        const int k = (kb0 + i) * BK;
-        if (!TA) {
-          tma_load_2d(sa, &tmA, bar_full + 8 * s, k, m0);                       // box {64 k, 128 m}
-        } else {
-#pragma unroll
-          for (int j = 0; j < BM / 64; ++j)                                     // boxes {64 m, 64 k}
-            tma_load_2d(sa + j * (BK * 128), &tmA, bar_full + 8 * s, m0 + j * 64, k);
-        }
-        if (!TB) {
-          tma_load_2d(sb, &tmB, bar_full + 8 * s, k, n0);                       // box {64 k, BN n}
-        } else {
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j)                                     // boxes {64 n, 64 k}
-            tma_load_2d(sb + j * (BK * 128), &tmB, bar_full + 8 * s, n0 + j * 64, k);
-        }
+        produce(i);
       }
     }
   } else if (warp == 1) {

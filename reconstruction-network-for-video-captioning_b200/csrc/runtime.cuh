@@ -94,6 +94,23 @@ template <typename T> static inline GemmPlan plan_gemm(int M, int N, int K, int 
 template <> inline GemmPlan plan_gemm<bf16>(int M, int N, int K, int target) {
   GemmPlan p;
   p.bn = (N >= 1024) ? 128 : 64;
+  const int nkb0 = rn_cdiv(K, tc::BK);
+  static int big_bn = -1;
+  if (big_bn < 0) { const char* e = getenv("RECNET_GEMM_COSTMODEL"); big_bn = e ? atoi(e) : 1; }
+  if (big_bn && nkb0 >= 16 && rn_cdiv(M, tc::BM) * rn_cdiv(N, 64) >= 2 * target) {
+    // Batched GEMMs (weight gradients, hoisted projections).  r1 ncu: the main loop is bound by what one SM can pull from L2
+    // (~50 B/clk), not by the tensor pipe, so wider N tiles (fewer A re-reads per MMA) win unless they cost a whole extra wave.
+    // cost per k-block ~ max(MMA cycles = 2 bn, (A 12.8 KB + B 128 bn bytes) / 50 B/clk); total ~ waves * cost.
+    float best = 1e30f;
+    for (int bn = 64; bn <= 256; bn *= 2) {
+      const int tiles = rn_cdiv(M, tc::BM) * rn_cdiv(N, bn);
+      const float per = fmaxf(2.f * bn, (12800.f + 128.f * bn) / 50.f);
+      const float cost = (float)rn_cdiv(tiles, target) * per;
+      if (cost < best * 0.97f) { best = cost; p.bn = bn; }
+    }
+    p.splits = 1;
+    return p;
+  }
   const int tiles = rn_cdiv(M, tc::BM) * rn_cdiv(N, p.bn);
   const int nkb = rn_cdiv(K, tc::BK);
   int s = target / tiles;

@@ -288,6 +288,42 @@ def test_full_size_parity_against_oracle(full_oracle, precision, kind):
     assert rel(logits, o["logits"]) < tol
 
 
+# shape variants that walk the generic branches of the fused decoder kernels and the lean attention kernels:
+#   msrvtt : 40 frames x 3584-d (BASELINE config 5 feature shape) -> second frame chunk / NF = 4 frame groups, 3584-wide VW GEMM
+#   wide_a : attention size 256 -> two float4 chunks per lane (NCH = 2)
+#   odd_h  : hidden 328 (not a multiple of the 128-unit tile), 19 frames, short captions
+VARIANTS = {
+    "msrvtt": dict(B=12, T=40, E=3584, H=512, A=128, EMB=468, V=1000, cap_len=12),
+    "wide_a": dict(B=9, T=28, E=256, H=256, A=256, EMB=64, V=400, cap_len=8),
+    "odd_h": dict(B=7, T=19, E=264, H=328, A=72, EMB=52, V=333, cap_len=6),
+}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_shape_variants_against_oracle(variant, precision):
+    m = dict(VARIANTS[variant], dec_layers=1, rec_layers=1, dec_model="LSTM", rec_model="LSTM")
+    feats, targets, masks = O.synthetic_batch(m["B"], m["T"], m["E"], m["V"], m["cap_len"], seed=5)
+    P = O.init_decoder_params(m["V"], m["EMB"], m["E"], m["H"], m["A"], seed=2)
+    Q = O.init_reconstructor_params("local", m["H"], m["E"], m["A"], seed=3)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    Qr = {k: v.clone().requires_grad_(True) for k, v in Q.items()}
+    dl, hid, _, _ = O.forward_decoder(Pr, feats, targets, masks, caption_max_len=m["cap_len"])
+    rl, _ = O.forward_local_reconstructor(Qr, hid, feats)
+    (dl + rl).backward()
+    dec, rec = build(m, precision, "local", P, Q)
+    tol = TOL[precision]
+    f, t, k = feats.to(dev()), targets.to(dev()), masks.to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, f, t, k, 1.0)
+    rloss = T.forward_local_reconstructor(hiddens, f, rec)
+    (dloss + rloss).backward()
+    assert rel(dloss, dl.detach()) < tol and rel(rloss, rl.detach()) < tol and rel(hiddens, hid.detach()) < tol
+    for name, p in dec["model"].named_parameters():
+        assert rel(p.grad, Pr[name].grad) < tol, name
+    for name, p in rec["model"].named_parameters():
+        assert rel(p.grad, Qr[name].grad) < tol, name
+
+
 def test_full_size_greedy_bit_exact_fp32_batch1024_shape():
     """BASELINE config 4 shape family (greedy, decoder-only, 28 frames, max len 30); B=256 keeps the CPU oracle in seconds."""
     B = 256

@@ -193,6 +193,30 @@ def algorithmic_work(cls, M, N, K, elt):
     return "hbm", 0.0
 
 
+# ncu --set full captures committed under profiles/ (tools/collect_profiles.sh + tools/summarise_profiles.py): DRAM traffic per
+# launch of the hot-loop kernels, keyed by the (kernel class, shape) the live profile reports
+NCU_KEYS = {("gemm_tcgen05", (100, 6144, 2048)): "gate_gemm_warm", ("proj_attn_cell_fwd", (100, 28, 512)): "pf_fwd_kernel",
+            ("proj_attn_cell_bwd", (100, 28, 512)): "pf_bwd_kernel", ("attn_fwd", (100, 31, 512)): "lean_fwd_kernel",
+            ("attn_bwd", (100, 31, 512)): "lean_bwd_kernel", ("lstm_cell_fwd", (100, 1536, 3)): "lstm_cell_fwd_kernel",
+            ("lstm_cell_bwd", (100, 1536, 11)): "lstm_cell_bwd_kernel"}
+
+
+def ncu_traffic(kernel, shape):
+    """(steady-state traffic bytes, cold-cache traffic bytes or None, source file) from the newest committed ncu summary."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_ncu_kernels.json")))
+    key = NCU_KEYS.get((kernel, tuple(shape)))
+    if not files or key is None:
+        return None, None, None
+    try:
+        d = json.load(open(files[-1]))
+        warm = d.get(key, {}).get("traffic_bytes")
+        cold = d.get(key.replace("_warm", "_cold"), {}).get("traffic_bytes") if key.endswith("_warm") else None
+        return warm, cold, os.path.basename(files[-1])
+    except Exception:
+        return None, None, None
+
+
 def dbg(rank, msg):
     if os.environ.get("RECNET_BENCH_VERBOSE"):
         print(f"[bench rank {rank} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
@@ -445,9 +469,13 @@ def main():
         top = kernels[0] if kernels else None
         roofline = None
         if top:
+            tr_warm, tr_cold, tr_src = ncu_traffic(top["kernel"], top["shape"])
             roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                        "traffic": None, "kernel": top["kernel"], "shape_MNK": top["shape"], "avg_us": top["avg_us"],
-                        "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy)")}
+                        "traffic": tr_warm, "traffic_cold_cache": tr_cold, "traffic_source": tr_src,
+                        "kernel": top["kernel"], "shape_MNK": top["shape"], "avg_us": top["avg_us"],
+                        "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy)"),
+                        "note": "avg_us is a per-launch CUDA-event pair in an eager step (adds ~4 us to every launch); traffic = dram bytes of one "
+                                "ncu --set full launch in steady state (operands L2-resident), traffic_cold_cache = same kernel after an L2 flush"}
         cpu = None
         if world == 1 and args.cpu_iters > 0:
             sps, sec = cpu_oracle_samples_per_s(args.recon, args.cpu_iters)

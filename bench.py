@@ -327,8 +327,13 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            dump = os.environ.get("RECNET_GRAPH_DUMP")           # developer probe: DOT file of the captured step graph
+            if dump:
+                graph.enable_debug_mode()
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
                 step()
+            if dump and rank == 0:
+                graph.debug_dump(dump)
         except Exception as ex:                     # report, never silently change what is measured
             if rank == 0:
                 print(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {ex}); timing eager launches", file=sys.stderr)

@@ -114,7 +114,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": round(sps, 3), "unit": "samples/s", "n_gpus": args.gpus, "steps": iters,
         "warmup": 1, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"RecNet decoder + {args.recon} reconstructor, MSVD shape (28x1536 feats, cap 30, emb 468, attn 128), batch 100, CPU oracle port"},
+        "config": {"workload": workload_text(args.recon, SHAPE["B"]), "global_batch": SHAPE["B"], "parallelism": "cpu",
+                   "implementation": "oracle/recnet_oracle.py (CPU restatement of the reference, pinned to reference-generated fixtures); "
+                                     "dropout is evaluated in eval mode (p = 0) by the oracle"},
         "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -215,6 +217,11 @@ def ncu_traffic(kernel, shape):
         return warm, cold, os.path.basename(files[-1])
     except Exception:
         return None, None, None
+
+
+def workload_text(recon, batch):
+    return (f"RecNet decoder + {recon} reconstructor train step (fwd+bwd+clip+Adam), MSVD shape: 28x1536 InceptionV4 feats, "
+            f"caption len 30 (L=31 steps), emb 468, attn 128, hidden 512, rec hidden 1536, vocab 4188, batch {batch} per GPU, dropout on")
 
 
 def dbg(rank, msg):
@@ -492,8 +499,7 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"RecNet decoder + {args.recon} reconstructor train step (fwd+bwd+clip+Adam), MSVD shape: 28x1536 InceptionV4 feats, "
-                                   f"caption len 30 (L=31 steps), emb 468, attn 128, hidden 512, rec hidden 1536, vocab 4188, batch {s['B']} per GPU, dropout on",
+            "config": {"workload": workload_text(args.recon, s["B"]),
                        "global_batch": s["B"] * world, "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                        "l2": "no explicit flush: every step streams ~0.9 GB of weights/optimizer state/activation stash, >> 126 MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

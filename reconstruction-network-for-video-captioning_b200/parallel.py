@@ -34,6 +34,11 @@ class GradAllReducer:
         self.modules = list(modules)
         self.bytes_last = 0
         self.overlap = os.environ.get("RECNET_DP_OVERLAP", "0") == "1"
+        # symmetric-memory all-reduce over NVLink peer / NVSwitch multicast memory instead of an NCCL collective:
+        # "multimem" (in-switch reduction, multimem.ld_reduce / multimem.st), "two_shot" (P2P reduce-scatter + all-gather), "" = NCCL
+        self.symm = os.environ.get("RECNET_DP_SYMM", "")
+        self._symm_buf = None
+        self._symm_group_name = None
         if self.world > 1 and self.overlap:
             for mi, m in enumerate(self.modules):
                 params = [p for p in m.parameters() if p.requires_grad]
@@ -79,7 +84,9 @@ class GradAllReducer:
                     late.append(next(iter(bases.values())))          # still ONE flat buffer per module
                 else:
                     late.extend(grads)
-        if len(late) > 1 and self.backend == "nccl" and os.environ.get("RECNET_DP_DRYRUN") is None:
+        if late and self.symm and self.backend == "nccl" and all(b.dtype == torch.float32 for b in late):
+            self._symm_allreduce(late)
+        elif len(late) > 1 and self.backend == "nccl" and os.environ.get("RECNET_DP_DRYRUN") is None:
             # one NCCL group (ncclGroupStart/End): all buffers in a single fused collective launch -> one rank sync per step
             with dist._coalescing_manager(group=self.group, device=late[0].device, async_ops=True) as cm:
                 for buf in late:
@@ -96,6 +103,42 @@ class GradAllReducer:
             else:
                 w.wait()
         self.pending = []
+
+    def _symm_allreduce(self, bufs):
+        """Average `bufs` across ranks through ONE symmetric-memory buffer: pack -> all-reduce kernel over peer memory -> unpack * 1/N.
+        The buffer is allocated and rendezvous-ed on first use (must happen outside CUDA-graph capture: run one eager step first)."""
+        import torch.distributed._symmetric_memory as sm
+        if torch.cuda.is_current_stream_capturing():
+            # measured on 2 x B200: correct and 421 us per 99 MB eagerly (tools/dp_check.py), but the captured step graph never
+            # completed its first replay (signal-pad barrier vs graph replay); refuse rather than hang
+            raise RuntimeError("GradAllReducer: RECNET_DP_SYMM is an eager-mode experiment; it is not usable under CUDA-graph capture")
+        group = self.group if self.group is not None else dist.group.WORLD
+        total = sum(b.numel() for b in bufs)
+        padded = (total + 4095) // 4096 * 4096
+        if self._symm_buf is None or self._symm_buf.numel() < padded:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("GradAllReducer: the symmetric buffer must be created before graph capture (run an eager step first)")
+            self._symm_buf = sm.empty(padded, dtype=torch.float32, device=bufs[0].device)
+            self._symm_buf.zero_()
+            sm.rendezvous(self._symm_buf, group.group_name)
+            self._symm_group_name = group.group_name
+        off = 0
+        for b in bufs:
+            n = b.numel()
+            self._symm_buf[off:off + n].copy_(b.reshape(-1))
+            off += n
+            self.bytes_last += n * 4
+        if self.symm == "two_shot":
+            torch.ops.symm_mem.two_shot_all_reduce_(self._symm_buf, "sum", self._symm_group_name)
+        elif self.symm == "one_shot":
+            self._symm_buf.copy_(torch.ops.symm_mem.one_shot_all_reduce(self._symm_buf, "sum", self._symm_group_name))
+        else:
+            torch.ops.symm_mem.multimem_all_reduce_(self._symm_buf, "sum", self._symm_group_name)
+        off = 0
+        for b in bufs:
+            n = b.numel()
+            torch.mul(self._symm_buf[off:off + n], 1.0 / self.world, out=b.reshape(-1))
+            off += n
 
     def remove(self):
         for h in self._handles:

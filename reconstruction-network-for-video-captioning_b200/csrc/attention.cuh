@@ -190,8 +190,8 @@ __device__ __forceinline__ void attn_fwd_body(const FwdArgs& a, int bx, int b, f
 template <typename TV, typename TO>
 __global__ void __launch_bounds__(FWD_THREADS) attn_fwd_kernel(FwdArgs a) {
   extern __shared__ float sm[];
-  pdl_launch_next();
-  pdl_wait();
+  pdl_wait();            // prerequisites complete ...
+  pdl_launch_next();     // ... only then let the NEXT kernel be scheduled (depth-1 look-ahead, no cascade of resident waiters)
   attn_fwd_body<TV, TO>(a, blockIdx.x, blockIdx.y, sm, threadIdx.x, 0);
 }
 
@@ -380,8 +380,8 @@ __device__ __forceinline__ void attn_bwd_body(const BwdArgs& a, int b, float* sm
 template <typename TV, typename TO>
 __global__ void __launch_bounds__(BWD_THREADS) attn_bwd_kernel(BwdArgs a) {
   extern __shared__ float sm[];
-  pdl_launch_next();
-  pdl_wait();
+  pdl_wait();            // prerequisites complete ...
+  pdl_launch_next();     // ... only then let the NEXT kernel be scheduled (depth-1 look-ahead, no cascade of resident waiters)
   attn_bwd_body<TV, TO>(a, blockIdx.x, sm, threadIdx.x, 0);
 }
 

@@ -42,6 +42,8 @@ template <typename TV, typename TO, int NF, int NCH>
 __global__ void __launch_bounds__(LEAN_THREADS) lean_fwd_kernel(FwdArgs a) {
   constexpr bool FAST = FastMath<TV>::value;
   constexpr int VN = Vec16<TV>::N;
+  pdl_wait();
+  pdl_launch_next();
   __shared__ float red[LEAN_NW][32 * VN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, Tn = a.Tn, A = a.A, D = a.D;
@@ -113,6 +115,8 @@ template <typename TV, typename TO, int NF, int NCH>
 __global__ void __launch_bounds__(LEAN_THREADS) lean_bwd_kernel(BwdArgs a) {
   constexpr bool FAST = FastMath<TV>::value;
   constexpr int VN = Vec16<TV>::N;
+  pdl_wait();
+  pdl_launch_next();
   extern __shared__ float dx_s[];                       // [D]
   __shared__ float part[2][LEAN_NW][LEAN_MAX_A];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -253,10 +257,10 @@ static int launch_lean_fwd(const FwdArgs& a, cudaStream_t st) {
   const dim3 grid(rn_cdiv(a.D, 32 * VN), a.B);
   const bool nf4 = a.Tn <= 4 * LEAN_NW, ch1 = a.A <= 128;
   ProfScope prof(KC_ATTN_FWD, a.B, a.Tn, a.D, st);
-  if (nf4 && ch1) lean_fwd_kernel<TV, TO, 4, 1><<<grid, LEAN_THREADS, 0, st>>>(a);
-  else if (nf4) lean_fwd_kernel<TV, TO, 4, 2><<<grid, LEAN_THREADS, 0, st>>>(a);
-  else if (ch1) lean_fwd_kernel<TV, TO, 8, 1><<<grid, LEAN_THREADS, 0, st>>>(a);
-  else lean_fwd_kernel<TV, TO, 8, 2><<<grid, LEAN_THREADS, 0, st>>>(a);
+  if (nf4 && ch1) RN_CUDA_OK(launch_pdl(lean_fwd_kernel<TV, TO, 4, 1>, grid, dim3(LEAN_THREADS), 0, st, a));
+  else if (nf4) RN_CUDA_OK(launch_pdl(lean_fwd_kernel<TV, TO, 4, 2>, grid, dim3(LEAN_THREADS), 0, st, a));
+  else if (ch1) RN_CUDA_OK(launch_pdl(lean_fwd_kernel<TV, TO, 8, 1>, grid, dim3(LEAN_THREADS), 0, st, a));
+  else RN_CUDA_OK(launch_pdl(lean_fwd_kernel<TV, TO, 8, 2>, grid, dim3(LEAN_THREADS), 0, st, a));
   RN_LAUNCH_OK();
   return 0;
 }
@@ -266,10 +270,10 @@ static int launch_lean_bwd(const BwdArgs& a, cudaStream_t st) {
   if (smem > 24 * 1024) return RECNET_ERR_BAD_SHAPE;
   const bool nf4 = a.Tn <= 4 * LEAN_NW, ch1 = a.A <= 128;
   ProfScope prof(KC_ATTN_BWD, a.B, a.Tn, a.D, st);
-  if (nf4 && ch1) lean_bwd_kernel<TV, TO, 4, 1><<<a.B, LEAN_THREADS, smem, st>>>(a);
-  else if (nf4) lean_bwd_kernel<TV, TO, 4, 2><<<a.B, LEAN_THREADS, smem, st>>>(a);
-  else if (ch1) lean_bwd_kernel<TV, TO, 8, 1><<<a.B, LEAN_THREADS, smem, st>>>(a);
-  else lean_bwd_kernel<TV, TO, 8, 2><<<a.B, LEAN_THREADS, smem, st>>>(a);
+  if (nf4 && ch1) RN_CUDA_OK(launch_pdl(lean_bwd_kernel<TV, TO, 4, 1>, dim3(a.B), dim3(LEAN_THREADS), smem, st, a));
+  else if (nf4) RN_CUDA_OK(launch_pdl(lean_bwd_kernel<TV, TO, 4, 2>, dim3(a.B), dim3(LEAN_THREADS), smem, st, a));
+  else if (ch1) RN_CUDA_OK(launch_pdl(lean_bwd_kernel<TV, TO, 8, 1>, dim3(a.B), dim3(LEAN_THREADS), smem, st, a));
+  else RN_CUDA_OK(launch_pdl(lean_bwd_kernel<TV, TO, 8, 2>, dim3(a.B), dim3(LEAN_THREADS), smem, st, a));
   RN_LAUNCH_OK();
   return 0;
 }

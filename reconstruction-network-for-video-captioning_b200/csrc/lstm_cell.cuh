@@ -74,8 +74,8 @@ __device__ __forceinline__ void lstm_cell_fwd_body(const FwdArgs& a, int bx, int
 
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(THREADS) lstm_cell_fwd_kernel(FwdArgs a) {
-  pdl_launch_next();
-  pdl_wait();
+  pdl_wait();            // prerequisites complete ...
+  pdl_launch_next();     // ... only then let the NEXT kernel be scheduled (depth-1 look-ahead, no cascade of resident waiters)
   lstm_cell_fwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
@@ -139,8 +139,8 @@ __device__ __forceinline__ void lstm_cell_bwd_body(const BwdArgs& a, int bx, int
 
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(THREADS) lstm_cell_bwd_kernel(BwdArgs a) {
-  pdl_launch_next();
-  pdl_wait();
+  pdl_wait();            // prerequisites complete ...
+  pdl_launch_next();     // ... only then let the NEXT kernel be scheduled (depth-1 look-ahead, no cascade of resident waiters)
   lstm_cell_bwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 

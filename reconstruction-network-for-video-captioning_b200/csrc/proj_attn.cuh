@@ -106,6 +106,8 @@ struct FwdArgs {
 template <typename TV, typename TO, int NCH, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) pf_fwd_kernel(FwdArgs a) {
   constexpr bool FAST = FastMath<TO>::value;
+  pdl_wait();
+  pdl_launch_next();
   __shared__ __align__(16) float e_s[2][MAX_T / 2];     // e_s[tau & 1][tau >> 1]; zero for tau >= Tn
   __shared__ float4 red[UPB];
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -337,6 +339,8 @@ template <typename TV, typename TO, int NF, int NCH>
 __global__ void __launch_bounds__(BTHREADS) pf_bwd_kernel(BwdArgs a) {
   constexpr bool FAST = FastMath<TO>::value;
   constexpr int QP = 32 / NF;                           // VW quads per lane, frame and pass (32 quads = 64 registers in flight)
+  pdl_wait();
+  pdl_launch_next();
   extern __shared__ float4 dg_s[];                      // [H]
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned b = blockIdx.x, Tn = a.Tn, H = a.H, A = a.A, row = 4u * H, nchunk = A >> 2;
@@ -531,9 +535,9 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
   static int minb = -1;
   if (minb < 0) { const char* e = getenv("RECNET_PF_MINB"); minb = e ? atoi(e) : 3; }
   const dim3 grid(rn_cdiv(a.H, UPB), a.B);
-  if (a.A <= 128 && minb == 3) pf_fwd_kernel<TV, TO, 1, 3><<<grid, THREADS, 0, st>>>(a);
-  else if (a.A <= 128) pf_fwd_kernel<TV, TO, 1, 2><<<grid, THREADS, 0, st>>>(a);
-  else pf_fwd_kernel<TV, TO, 2, 2><<<grid, THREADS, 0, st>>>(a);
+  if (a.A <= 128 && minb == 3) RN_CUDA_OK(launch_pdl(pf_fwd_kernel<TV, TO, 1, 3>, grid, dim3(THREADS), 0, st, a));
+  else if (a.A <= 128) RN_CUDA_OK(launch_pdl(pf_fwd_kernel<TV, TO, 1, 2>, grid, dim3(THREADS), 0, st, a));
+  else RN_CUDA_OK(launch_pdl(pf_fwd_kernel<TV, TO, 2, 2>, grid, dim3(THREADS), 0, st, a));
   RN_LAUNCH_OK();
   return 0;
 }
@@ -545,10 +549,10 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
   if (smem > 46 * 1024) return RECNET_ERR_BAD_SHAPE;
   const bool nf2 = a.Tn <= 2 * BNW, ch1 = a.A <= 128;
   ProfScope prof(KC_PF_BWD, a.B, a.Tn, a.H, st);
-  if (nf2 && ch1) pf_bwd_kernel<TV, TO, 2, 1><<<a.B, BTHREADS, smem, st>>>(a);
-  else if (nf2) pf_bwd_kernel<TV, TO, 2, 2><<<a.B, BTHREADS, smem, st>>>(a);
-  else if (ch1) pf_bwd_kernel<TV, TO, 4, 1><<<a.B, BTHREADS, smem, st>>>(a);
-  else pf_bwd_kernel<TV, TO, 4, 2><<<a.B, BTHREADS, smem, st>>>(a);
+  if (nf2 && ch1) RN_CUDA_OK(launch_pdl(pf_bwd_kernel<TV, TO, 2, 1>, dim3(a.B), dim3(BTHREADS), smem, st, a));
+  else if (nf2) RN_CUDA_OK(launch_pdl(pf_bwd_kernel<TV, TO, 2, 2>, dim3(a.B), dim3(BTHREADS), smem, st, a));
+  else if (ch1) RN_CUDA_OK(launch_pdl(pf_bwd_kernel<TV, TO, 4, 1>, dim3(a.B), dim3(BTHREADS), smem, st, a));
+  else RN_CUDA_OK(launch_pdl(pf_bwd_kernel<TV, TO, 4, 2>, dim3(a.B), dim3(BTHREADS), smem, st, a));
   RN_LAUNCH_OK();
   return 0;
 }

@@ -252,7 +252,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    dp_self = world == 1 and os.environ.get("RECNET_DP_SELF") == "1"   # developer probe: 1-rank NCCL group, collective captured in the graph
+    if dp_self:
+        for k, v in (("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29977"), ("RANK", "0"), ("WORLD_SIZE", "1")):
+            os.environ.setdefault(k, v)
+    if world > 1 or dp_self:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # whole-step CUDA-graph capture includes the NCCL all-reduces: the process group's watchdog must not poll
         # events while a capture is open (PyTorch's documented requirement for DDP + graph capture)
@@ -337,7 +341,7 @@ def main():
             dump = os.environ.get("RECNET_GRAPH_DUMP")           # developer probe: DOT file of the captured step graph
             if dump:
                 graph.enable_debug_mode()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if (world > 1 or dp_self) else "global"):
                 step()
             if dump and rank == 0:
                 graph.debug_dump(dump)

@@ -147,13 +147,18 @@ class GradAllReducer:
             self._raw_lib, self._raw_comm = lib, comm
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         NCCL_FLOAT32, NCCL_AVG = 7, 4                  # ncclDataType_t / ncclRedOp_t
+        self._raw_lib.ncclGroupStart()                 # one fused launch for all buffers
         for b in bufs:
             if b.dtype != torch.float32 or not b.is_contiguous():
                 raise RuntimeError("GradAllReducer: raw NCCL path expects contiguous float32 gradient buffers")
             self.bytes_last += b.numel() * 4
             rc = self._raw_lib.ncclAllReduce(b.data_ptr(), b.data_ptr(), b.numel(), NCCL_FLOAT32, NCCL_AVG, self._raw_comm, stream)
             if rc != 0:
+                self._raw_lib.ncclGroupEnd()
                 raise RuntimeError(f"ncclAllReduce failed with {rc}")
+        rc = self._raw_lib.ncclGroupEnd()
+        if rc != 0:
+            raise RuntimeError(f"ncclGroupEnd failed with {rc}")
 
     def _symm_allreduce(self, bufs):
         """Average `bufs` across ranks through ONE symmetric-memory buffer: pack -> all-reduce kernel over peer memory -> unpack * 1/N.

@@ -239,6 +239,21 @@ int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const 
                            const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, const float* sumsq,
                            const float* g, float lambda, int accumulate, void* stream);
 
+/* Fused gradient-norm clip + Adam step over a parameter list -- replaces torch.nn.utils.clip_grad_norm_ (reference
+ * train.py:269-270) followed by torch.optim.Adam.step (train.py:271-273; optimisers built at train.py:149-150,186-187:
+ * L2 weight decay, optional amsgrad).  Tables as for recnet_param_norms_*: device int64 address tables of the n
+ * parameters, their gradients and the optimiser state tensors (exp_avg, exp_avg_sq, max_exp_avg_sq or NULL = no
+ * amsgrad), sizes[n], and the block -> (tensor, 16384-element chunk) map.
+ * max_grad_norm > 0: total L2 norm over ALL n gradients, grads scaled by min(1, max_norm / (norm + 1e-6)) on the fly
+ * (written back to the gradient tensors only if write_clipped_grads); partial [n_blocks] fp32 scratch.
+ * state: device float[8], zero-initialised by the caller: [0] step count (advanced by one per call, on the device,
+ * so a captured CUDA graph keeps counting), [1] last total grad norm, [2] last clip coefficient, [3..7] internal. */
+int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs,
+                     const int64_t* exp_avg_sq_ptrs, const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n,
+                     const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, float max_grad_norm, float* partial, float* state,
+                     int write_clipped_grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,7 @@ SIGNATURES = {
     "recnet_debug_set_timeline": (_i, [_p]),
     "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
     "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _i, _p]),
+    "recnet_adam_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _f, _f, _p, _p, _i, _p]),
 }
 
 _lib = None

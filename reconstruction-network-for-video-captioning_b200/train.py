@@ -6,12 +6,21 @@ Python loop of ~400 ATen ops per step.
 """
 from __future__ import annotations
 
+import os
 import random
 
 import torch
 
 from .config import TrainConfig as C
 from .models import Decoder, GlobalReconstructor, LocalReconstructor
+from .optim import ClipAdam
+
+
+def _optimizer_impl() -> str:
+    impl = os.environ.get("RECNET_OPTIMIZER") or getattr(C, "optimizer_impl", "torch")
+    if impl not in ("torch", "recnet"):
+        raise ValueError(f"optimizer_impl must be 'torch' or 'recnet', got {impl!r}")
+    return impl
 
 
 def _num_steps(target_masks: torch.Tensor, caption_max_len: int) -> int:
@@ -69,8 +78,12 @@ def build_decoder(n_vocabs):
         embedding_size=C.embedding_size, embedding_scale=C.embedding_scale, hidden_size=C.decoder_hidden_size,
         attn_size=C.decoder_attn_size, output_size=n_vocabs, embedding_dropout=C.embedding_dropout,
         dropout=C.decoder_dropout, out_dropout=C.decoder_out_dropout, precision=C.precision).to(C.device)
-    optimizer = torch.optim.Adam(model.parameters(), lr=C.decoder_learning_rate, weight_decay=C.decoder_weight_decay,
-                                 amsgrad=C.decoder_use_amsgrad, fused=True, capturable=True)
+    if _optimizer_impl() == "recnet":      # clip (train.py:269-270) folded into the Adam pass
+        optimizer = ClipAdam(model.parameters(), lr=C.decoder_learning_rate, weight_decay=C.decoder_weight_decay,
+                             amsgrad=C.decoder_use_amsgrad, max_grad_norm=C.gradient_clip if C.use_gradient_clip else None)
+    else:
+        optimizer = torch.optim.Adam(model.parameters(), lr=C.decoder_learning_rate, weight_decay=C.decoder_weight_decay,
+                                     amsgrad=C.decoder_use_amsgrad, fused=True, capturable=True)
     lambda_reg = torch.tensor(0.001, device=C.device)
     return {'model': model, 'loss': torch.nn.CrossEntropyLoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg}
 
@@ -90,9 +103,13 @@ def build_reconstructor():
     else:
         raise NotImplementedError("Unknown reconstructor: {}".format(C.reconstructor_type))
     model = model.to(C.device)
-    optimizer = torch.optim.Adam(model.parameters(), lr=C.reconstructor_learning_rate,
-                                 weight_decay=C.reconstructor_weight_decay, amsgrad=C.reconstructor_use_amsgrad,
-                                 fused=True, capturable=True)
+    if _optimizer_impl() == "recnet":
+        optimizer = ClipAdam(model.parameters(), lr=C.reconstructor_learning_rate, weight_decay=C.reconstructor_weight_decay,
+                             amsgrad=C.reconstructor_use_amsgrad)
+    else:
+        optimizer = torch.optim.Adam(model.parameters(), lr=C.reconstructor_learning_rate,
+                                     weight_decay=C.reconstructor_weight_decay, amsgrad=C.reconstructor_use_amsgrad,
+                                     fused=True, capturable=True)
     lambda_reg = torch.tensor(0.01, device=C.device)
     return {'model': model, 'loss': torch.nn.MSELoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg}
 
@@ -129,7 +146,8 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
     if grad_hook is not None:
         grad_hook()
     if optimizer_step:
-        if C.use_gradient_clip:
+        own_clip = isinstance(decoder['optimizer'], ClipAdam) and decoder['optimizer'].param_groups[0].get('max_grad_norm')
+        if C.use_gradient_clip and not own_clip:
             torch.nn.utils.clip_grad_norm_(decoder['model'].parameters(), C.gradient_clip, foreach=True)    # train.py:269-270
         decoder['optimizer'].step()
         if reconstructor is not None:

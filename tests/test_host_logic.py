@@ -167,3 +167,30 @@ def test_beam_search_bookkeeping_matches_oracle_on_cpu():
             ref = O.beam_search(P, g["feats"], width, model_name=m["dec_model"], n_layers=1, caption_max_len=m["cap_len"])
             got = E.beam_search(Cfg, width, Vocab, decoder, tok, hid, g["feats"])
             assert got == ref, (name, width)
+
+
+def test_clip_adam_host_side_validation_and_optimizer_selection(monkeypatch):
+    """optim.ClipAdam (the fused clip + Adam of train.py:269-273): argument checks run on the host; there is no CPU compute path."""
+    import torch
+    from recnet_b200.optim import ClipAdam
+    from recnet_b200 import train as T
+    p = [torch.zeros(4, requires_grad=True)]
+    with pytest.raises(ValueError):
+        ClipAdam(p, lr=-1.0)
+    with pytest.raises(ValueError):
+        ClipAdam(p, lr=1e-3, betas=(1.0, 0.999))
+    with pytest.raises(NotImplementedError):
+        ClipAdam([{"params": p}, {"params": [torch.zeros(2, requires_grad=True)]}], lr=1e-3)
+    o = ClipAdam(p, lr=1e-3, weight_decay=1e-5, amsgrad=True, max_grad_norm=50.0)
+    g = o.param_groups[0]
+    assert (g["lr"], g["betas"], g["eps"], g["weight_decay"], g["amsgrad"], g["max_grad_norm"]) == (1e-3, (0.9, 0.999), 1e-8, 1e-5, True, 50.0)
+    p[0].grad = torch.zeros(4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        o.step()
+    monkeypatch.setenv("RECNET_OPTIMIZER", "recnet")
+    assert T._optimizer_impl() == "recnet"
+    monkeypatch.setenv("RECNET_OPTIMIZER", "sgd")
+    with pytest.raises(ValueError):
+        T._optimizer_impl()
+    monkeypatch.delenv("RECNET_OPTIMIZER")
+    assert T._optimizer_impl() == T.C.optimizer_impl

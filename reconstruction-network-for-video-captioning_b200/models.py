@@ -8,8 +8,14 @@ reference checkpoint loads with ``load_state_dict``.  The arithmetic runs in lib
 * ``forward_sequence`` (whole teacher-forced loop, what train.forward_* use) -> one C call (``functional.py``)
 
 One extra constructor kwarg, ``precision`` ("bf16" | "fp32"); everything else is positional-compatible.
-Built: Decoder and both reconstructors with LSTM or GRU cells (GRU is the reference's default decoder, config.py:31),
-n_layers == 1.  Anything else raises NotImplementedError (never a silent fallback).
+
+Every (cell, n_layers) combination the reference's constructors accept runs on our kernels:
+* fused sequence drivers (one C call per loop): LSTM decoder with 1-4 layers, GRU decoder with 1 layer, 1-layer LSTM
+  reconstructors over any such decoder, 1-layer GRU reconstructors over a 1-layer decoder -- the configurations the
+  reference's config.py / published runs use, and everything bench.py measures;
+* every other variant (stacked GRU decoder, GRU reconstructor over a stacked decoder, multi-layer reconstructors, > 4
+  decoder layers) runs ``forward_sequence`` as a Python loop over the per-step ``forward`` -- the same operator-level
+  CUDA kernels (ops.py), autograd glue in between.  Slower, never silent: ``uses_fused_sequence`` says which one runs.
 """
 from __future__ import annotations
 
@@ -47,11 +53,42 @@ class _RngMixin:
         self._rng[1] = 0
 
 
-def _require_supported(model_name: str, n_layers: int, what: str, gru_ok: bool = False, max_layers: int = 1):
-    if model_name != "LSTM" and not gru_ok:
-        raise NotImplementedError(f"{what}: model_name={model_name!r} (GRU) is not built yet in recnet_b200; use 'LSTM'")
-    if n_layers > max_layers or (n_layers > 1 and model_name != "LSTM"):
-        raise NotImplementedError(f"{what}: n_layers={n_layers} with {model_name} cells is not built yet in recnet_b200")
+def _is_lstm(model_name: str) -> bool:
+    return model_name == "LSTM"            # models/decoder.py:32-35: anything else is a GRU
+
+
+def _zero_state(model_name, n_layers, B, size, device):
+    """train.py:28-35 / 82-89 / 112-119: zero (h, c) for LSTM, zero h for GRU."""
+    z = lambda: torch.zeros(n_layers, B, size, device=device)
+    return (z(), z()) if _is_lstm(model_name) else z()
+
+
+def _rnn_stack_step(rnn: RNNParams, x, hidden, p, training):
+    """One time step through all layers of an nn.LSTM / nn.GRU-shaped stack (inter-layer dropout in train mode).
+    x (B,In); hidden ((NL,B,R),(NL,B,R)) [LSTM] or (NL,B,R) [GRU] -> (top-layer output (B,R), new hidden)."""
+    is_lstm = rnn.mode == "LSTM"
+    hs, cs = [], []
+    for l in range(rnn.num_layers):
+        w_ih, w_hh, b_ih, b_hh = rnn.layer(l)
+        h_prev = hidden[0][l] if is_lstm else hidden[l]
+        gi, gh = ops.linear(x, w_ih, b_ih, p), ops.linear(h_prev, w_hh, b_hh, p)
+        if is_lstm:
+            hl, cl = ops.lstm_cell(gi + gh, hidden[1][l], p)
+            cs.append(cl)
+        else:
+            hl = ops.gru_cell(gi, gh, h_prev, p)
+        hs.append(hl)
+        x = torch.nn.functional.dropout(hl, rnn.dropout, training) if l < rnn.num_layers - 1 else hl
+    return hs[-1], ((torch.stack(hs), torch.stack(cs)) if is_lstm else torch.stack(hs))
+
+
+def _hiddens4(decoder_hiddens: torch.Tensor) -> torch.Tensor:
+    """(L,B,H) -> (L,1,B,H); (L,NLdec,B,H) passes through (train.py:73: hiddens = stack of (NLdec,B,H))."""
+    if decoder_hiddens.dim() == 3:
+        return decoder_hiddens.unsqueeze(1)
+    if decoder_hiddens.dim() != 4:
+        raise ValueError(f"decoder_hiddens must be (L,B,H) or (L,n_layers,B,H), got {tuple(decoder_hiddens.shape)}")
+    return decoder_hiddens
 
 
 class Decoder(nn.Module, _RngMixin):
@@ -98,28 +135,62 @@ class Decoder(nn.Module, _RngMixin):
                     p_emb=self.embedding_dropout_p, p_out=self.out_dropout_p, p_layer=self.dropout_p,
                     cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)       # decoder.py:32-35
 
-    # ---- whole teacher-forced loop: one C call ----
+    @property
+    def uses_fused_sequence(self) -> bool:
+        """True when forward_sequence / greedy are ONE C call (csrc/seq_decoder*.cuh); False = per-step kernels in a Python loop."""
+        if _is_lstm(self.model_name):
+            return 1 <= self.n_layers <= L.MAX_LAYERS
+        return self.n_layers == 1
+
+    # ---- whole teacher-forced loop ----
     def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs):
         """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,NL,B,H), reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
+        if not self.uses_fused_sequence:
+            return self._forward_sequence_stepwise(tokens_in, targets, ce_weight, encoder_outputs)
         return Fn.DecoderSequenceFn.apply(self._meta(), encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(),
                                           *self._params())
 
+    def _forward_sequence_stepwise(self, tokens_in, targets, ce_weight, encoder_outputs):
+        """The loop body of train.forward_decoder (train.py:41-66) over the per-step ``forward`` (our operator kernels)."""
+        Lsteps, B = tokens_in.shape
+        hidden = _zero_state(self.model_name, self.n_layers, B, self.hidden_size, encoder_outputs.device)      # train.py:28-35
+        ce = 0.0
+        hiddens = []
+        for t in range(Lsteps):
+            logits, hidden = self.forward(tokens_in[t:t + 1], hidden, encoder_outputs)
+            if targets is not None and ce_weight is not None:
+                lg = logits if logits.dtype == torch.float64 else logits.float()
+                logp = torch.log_softmax(lg, dim=1).gather(1, targets[t].unsqueeze(1)).squeeze(1)
+                ce = ce - (ce_weight[t] * logp).sum()                                                           # train.py:54-60,68
+            hiddens.append(hidden[0] if _is_lstm(self.model_name) else hidden)                                  # train.py:61-64
+        reg = Fn.param_norm_sum([p for p in self.parameters()])                                                 # train.py:69
+        if not torch.is_tensor(ce):
+            ce = torch.zeros((), dtype=torch.float32, device=encoder_outputs.device)
+        return ce, torch.stack(hiddens), reg
+
     @torch.no_grad()
     def teacher_forced_logits(self, tokens_in, encoder_outputs):
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
+        if not self.uses_fused_sequence:
+            Lsteps, B = tokens_in.shape
+            hidden = _zero_state(self.model_name, self.n_layers, B, self.hidden_size, encoder_outputs.device)
+            logits, hiddens = [], []
+            for t in range(Lsteps):
+                lg, hidden = self.forward(tokens_in[t:t + 1], hidden, encoder_outputs)
+                logits.append(lg)
+                hiddens.append(hidden[0] if _is_lstm(self.model_name) else hidden)
+            return torch.stack(logits), torch.stack(hiddens)
         return Fn.decoder_teacher_forced_logits(self._meta(), encoder_outputs, tokens_in, self._rng, self._params())
 
     @torch.no_grad()
     def greedy(self, encoder_outputs, max_steps):
         """eval.greedy_search (eval.py:19-33) on device: returns (ids (n,B) int64 on device, n)."""
         import ctypes as C
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
-        if self.n_layers > 1:       # stacked decoder: step-by-step through Decoder.forward (our kernels), feedback on device
+        if self.n_layers > 1 or not self.uses_fused_sequence:
+            # stacked decoders: step by step through Decoder.forward (our kernels), arg-max feedback on device
             B = encoder_outputs.shape[0]
             dev = encoder_outputs.device
-            z = lambda: torch.zeros(self.n_layers, B, self.hidden_size, device=dev)
-            hid, tok = (z(), z()), torch.ones(1, B, dtype=torch.long, device=dev)
+            hid = _zero_state(self.model_name, self.n_layers, B, self.hidden_size, dev)
+            tok = torch.ones(1, B, dtype=torch.long, device=dev)
             was_training = self.training
             self.eval()
             ids = torch.zeros(max_steps, B, dtype=torch.long, device=dev)
@@ -152,11 +223,9 @@ class Decoder(nn.Module, _RngMixin):
 
     # ---- single timestep (reference API) ----
     def forward(self, input, hidden, encoder_outputs):
-        """input (1,B) int64; hidden ((NL,B,H),(NL,B,H)) [LSTM] or (1,B,H) [GRU]; encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""
-        _require_supported(self.model_name, self.n_layers, "Decoder", gru_ok=True, max_layers=L.MAX_LAYERS)
+        """input (1,B) int64; hidden ((NL,B,H),(NL,B,H)) [LSTM] or (NL,B,H) [GRU]; encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""
         p = _precision_id(self.precision)
-        is_lstm = self.model_name == "LSTM"
-        h, c = (hidden[0][-1], hidden[1][-1]) if is_lstm else (hidden[-1], None)
+        h = hidden[0][-1] if _is_lstm(self.model_name) else hidden[-1]                                     # decoder.py:50-53: top layer
         emb = torch.nn.functional.embedding(input[0], self.embedding.weight) * self.embedding_scale      # decoder.py:46-47
         emb = torch.nn.functional.dropout(emb, self.embedding_dropout_p, self.training)                   # decoder.py:48
         # U.v is time-invariant (the reference recomputes it every step, decoder.py:54).  Without autograd (greedy / beam
@@ -172,29 +241,27 @@ class Decoder(nn.Module, _RngMixin):
             Uv = self._uv_cache[1]
         Wh = ops.linear(h, self.attn_W.weight, None, p)                                                   # decoder.py:51
         ctx = ops.additive_attention(Wh, Uv, self.attn_b, self.attn_w.weight, encoder_outputs, p)          # decoder.py:55-61
-        w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        gi, gh = ops.linear(torch.cat((emb, ctx), dim=1), w_ih, b_ih, p), ops.linear(h, w_hh, b_hh, p)     # decoder.py:64-66
-        if self.n_layers > 1:          # stacked LSTM: layer 0 takes [emb ; ctx], layer l the (dropped-out) output of layer l-1
-            hs, cs, x = [], [], torch.cat((emb, ctx), dim=1)
-            for l in range(self.n_layers):
-                w_ih, w_hh, b_ih, b_hh = self.rnn.layer(l)
-                pre = ops.linear(x, w_ih, b_ih, p) + ops.linear(hidden[0][l], w_hh, b_hh, p)
-                hl, cl = ops.lstm_cell(pre, hidden[1][l], p)
-                hs.append(hl); cs.append(cl)
-                x = torch.nn.functional.dropout(hl, self.dropout_p, self.training) if l < self.n_layers - 1 else hl
-            logits = ops.linear(hs[-1], self.out.weight, self.out.bias, p)
-            logits = torch.nn.functional.dropout(logits, self.out_dropout_p, self.training)
-            return logits, (torch.stack(hs), torch.stack(cs))
-        if is_lstm:
-            h2, c2 = ops.lstm_cell(gi + gh, c, p)
-        else:
-            h2 = ops.gru_cell(gi, gh, h, p)
-        logits = ops.linear(h2, self.out.weight, self.out.bias, p)                                        # decoder.py:68
+        # layer 0 takes [emb ; ctx], layer l the (dropped-out) output of layer l-1 (nn.LSTM / nn.GRU, decoder.py:64-66)
+        h_top, hidden = _rnn_stack_step(self.rnn, torch.cat((emb, ctx), dim=1), hidden, p, self.training)
+        logits = ops.linear(h_top, self.out.weight, self.out.bias, p)                                     # decoder.py:68
         logits = torch.nn.functional.dropout(logits, self.out_dropout_p, self.training)                    # decoder.py:69
-        return logits, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
+        return logits, hidden
 
 
-class GlobalReconstructor(nn.Module, _RngMixin):
+class _ReconstructorBase(nn.Module, _RngMixin):
+    def _fused_ok(self, decoder_hiddens) -> bool:
+        """One C call (csrc/seq_recon*.cuh) for 1-layer reconstructors: LSTM cells over any decoder depth <= 4, GRU cells over a
+        1-layer decoder; everything else loops over the per-step ``forward``."""
+        nld = decoder_hiddens.size(1) if decoder_hiddens.dim() == 4 else 1
+        if self.n_layers != 1:
+            return False
+        return nld <= L.MAX_LAYERS if _is_lstm(self.model_name) else nld == 1
+
+    def _all_params(self):
+        return [p for p in self.parameters()]
+
+
+class GlobalReconstructor(_ReconstructorBase):
     """models/global_reconstructor.py:6-46."""
 
     def __init__(self, model_name, n_layers, decoder_hidden_size, hidden_size, dropout, decoder_dropout, caption_max_len,
@@ -217,34 +284,40 @@ class GlobalReconstructor(nn.Module, _RngMixin):
         return (w_ih, w_hh, b_ih, b_hh, self.out.weight, self.out.bias)
 
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
-        """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "GlobalReconstructor", gru_ok=True)
-        hid = _sequence_hiddens(decoder_hiddens, self.model_name)
+        """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||)."""
+        if not self._fused_ok(decoder_hiddens):
+            return self._forward_sequence_stepwise(decoder_hiddens, encoder_outputs)
+        hid = _sequence_hiddens(decoder_hiddens)
         meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p,
                     caption_max_len=self.caption_max_len, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.GlobalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
+    def _forward_sequence_stepwise(self, decoder_hiddens, encoder_outputs):
+        """train.forward_global_reconstructor (train.py:78-105) over the per-step ``forward``."""
+        hid = _hiddens4(decoder_hiddens)
+        Lsteps, B = hid.size(0), hid.size(2)
+        hidden = _zero_state(self.model_name, self.n_layers, B, self.hidden_size, hid.device)               # train.py:82-89
+        outs = []
+        for t in range(Lsteps):
+            out, hidden = self.forward(hid[t], hidden, hid)                                                 # train.py:93-95
+            outs.append(out)
+        loss = torch.nn.functional.mse_loss(torch.stack(outs).mean(0), encoder_outputs.mean(1)) / Lsteps   # train.py:96-100
+        return loss, Fn.param_norm_sum(self._all_params())                                                  # train.py:101
+
     def forward(self, input, hidden, decoder_hiddens):
-        """input (1,B,H) = decoder_hiddens[t]; hidden ((1,B,R),(1,B,R)) [LSTM] or (1,B,R) [GRU]; decoder_hiddens (L,1,B,H)."""
-        _require_supported(self.model_name, self.n_layers, "GlobalReconstructor", gru_ok=True)
+        """input (NLdec,B,H) = decoder_hiddens[t]; hidden ((NL,B,R),(NL,B,R)) [LSTM] or (NL,B,R) [GRU]; decoder_hiddens (L,NLdec,B,H)."""
         p = _precision_id(self.precision)
-        is_lstm = self.model_name == "LSTM"
-        h_prev = hidden[0][-1] if is_lstm else hidden[-1]
-        Lsteps = decoder_hiddens.size(0)
-        mp = decoder_hiddens.mean(0).mean(0) / Lsteps * self.caption_max_len            # global_reconstructor.py:33-37
+        hid = _hiddens4(decoder_hiddens)
+        Lsteps = hid.size(0)
+        mp = hid.mean(dim=(0, 1)) / Lsteps * self.caption_max_len                        # global_reconstructor.py:33-37
         mp = torch.nn.functional.dropout(mp, self.decoder_dropout_p, self.training)      # :38
-        x = torch.cat((input[0], mp), 1)                                                 # :40
-        w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        gi, gh = ops.linear(x, w_ih, b_ih, p), ops.linear(h_prev, w_hh, b_hh, p)         # :43
-        if is_lstm:
-            h2, c2 = ops.lstm_cell(gi + gh, hidden[1][-1], p)
-        else:
-            h2 = ops.gru_cell(gi, gh, h_prev, p)
-        out = ops.linear(h2, self.out.weight, self.out.bias, p)                          # :45
-        return out, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
+        x = torch.cat((input[0], mp), 1)                                                 # :40 (layer-0 state of step t)
+        h_top, hidden = _rnn_stack_step(self.rnn, x, hidden, p, self.training)           # :43
+        out = ops.linear(h_top, self.out.weight, self.out.bias, p)                       # :45
+        return out, hidden
 
 
-class LocalReconstructor(nn.Module, _RngMixin):
+class LocalReconstructor(_ReconstructorBase):
     """models/local_reconstructor.py:6-55."""
 
     def __init__(self, model_name, n_layers, decoder_hidden_size, hidden_size, dropout, decoder_dropout, attn_size,
@@ -272,47 +345,51 @@ class LocalReconstructor(nn.Module, _RngMixin):
                 self.out.weight, self.out.bias)
 
     def forward_sequence(self, decoder_hiddens, encoder_outputs):
-        """decoder_hiddens (L,1,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||)."""
-        _require_supported(self.model_name, self.n_layers, "LocalReconstructor", gru_ok=True)
-        hid = _sequence_hiddens(decoder_hiddens, self.model_name)
+        """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||)."""
+        if not self._fused_ok(decoder_hiddens):
+            return self._forward_sequence_stepwise(decoder_hiddens, encoder_outputs)
+        hid = _sequence_hiddens(decoder_hiddens)
         meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training,
                     p_drop=self.decoder_dropout_p, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.LocalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
+    def _forward_sequence_stepwise(self, decoder_hiddens, encoder_outputs):
+        """train.forward_local_reconstructor (train.py:108-131) over the per-step ``forward``."""
+        hid = _hiddens4(decoder_hiddens)
+        B, S = hid.size(2), encoder_outputs.size(1)
+        hidden = _zero_state(self.model_name, self.n_layers, B, self.hidden_size, hid.device)               # train.py:112-119
+        outs = []
+        for _ in range(S):                                                                                  # train.py:122-124
+            out, hidden = self.forward(hidden, hid)
+            outs.append(out)
+        loss = torch.nn.functional.mse_loss(torch.stack(outs).transpose(0, 1), encoder_outputs)             # train.py:125-128
+        return loss, Fn.param_norm_sum(self._all_params())                                                  # train.py:129
+
     def forward(self, hidden, decoder_hiddens):
-        """hidden ((1,B,R),(1,B,R)) [LSTM] or (1,B,R) [GRU]; decoder_hiddens (L,1,B,H) -> (out (B,R), hidden)."""
-        _require_supported(self.model_name, self.n_layers, "LocalReconstructor", gru_ok=True)
+        """hidden ((NL,B,R),(NL,B,R)) [LSTM] or (NL,B,R) [GRU]; decoder_hiddens (L,NLdec,B,H) -> (out (B,R), hidden)."""
         p = _precision_id(self.precision)
-        is_lstm = self.model_name == "LSTM"
-        h_prev = hidden[0][-1] if is_lstm else hidden[-1]
-        hid = _squeeze_layers(decoder_hiddens)                                           # (L,B,H)
-        Lsteps, B, H = hid.shape
-        Uv = ops.linear(hid.reshape(Lsteps * B, H), self.attn_U.weight, None, p).view(Lsteps, B, -1).transpose(0, 1)
-        Wh = ops.linear(h_prev, self.attn_W.weight, None, p)                             # local_reconstructor.py:39
-        x = ops.additive_attention(Wh, Uv.contiguous(), self.attn_b, self.attn_w.weight, hid.transpose(0, 1).contiguous(), p)
-        x = torch.nn.functional.dropout(x, self.decoder_dropout_p, self.training)        # :50
-        w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
-        gi, gh = ops.linear(x, w_ih, b_ih, p), ops.linear(h_prev, w_hh, b_hh, p)         # :52
-        if is_lstm:
-            h2, c2 = ops.lstm_cell(gi + gh, hidden[1][-1], p)
-        else:
-            h2 = ops.gru_cell(gi, gh, h_prev, p)
-        out = ops.linear(h2, self.out.weight, self.out.bias, p)                          # :54
-        return out, ((h2.unsqueeze(0), c2.unsqueeze(0)) if is_lstm else h2.unsqueeze(0))
+        h_prev = hidden[0][-1] if _is_lstm(self.model_name) else hidden[-1]
+        hid = _hiddens4(decoder_hiddens)                                                 # (L,NLdec,B,H)
+        Lsteps, NLd, B, H = hid.shape
+        Wh = ops.linear(h_prev, self.attn_W.weight, None, p)                             # local_reconstructor.py:39-42
+        xs = []
+        for j in range(NLd):             # the same query attends over the L states of every decoder layer (:43-49), mean over L
+            hj = hid[:, j]
+            Uv = ops.linear(hj.reshape(Lsteps * B, H), self.attn_U.weight, None, p).view(Lsteps, B, -1).transpose(0, 1)
+            xs.append(ops.additive_attention(Wh, Uv.contiguous(), self.attn_b, self.attn_w.weight, hj.transpose(0, 1).contiguous(), p))
+        x = torch.nn.functional.dropout(torch.stack(xs), self.decoder_dropout_p, self.training)      # (NLdec,B,H)  :50
+        # nn.LSTM / nn.GRU read dim 0 of its input as TIME: NLdec pseudo-steps (:52); the output of the FIRST one is projected (:54)
+        first = None
+        for j in range(NLd):
+            h_top, hidden = _rnn_stack_step(self.rnn, x[j], hidden, p, self.training)
+            if j == 0:
+                first = h_top
+        out = ops.linear(first, self.out.weight, self.out.bias, p)                       # :54
+        return out, hidden
 
 
-def _sequence_hiddens(decoder_hiddens: torch.Tensor, model_name: str) -> torch.Tensor:
-    """(L,1,B,H) -> (L,B,H); a stacked decoder's (L,NLdec,B,H) passes through (LSTM reconstructor cells only)."""
-    if decoder_hiddens.dim() == 4 and decoder_hiddens.size(1) != 1:
-        if model_name != "LSTM":
-            raise NotImplementedError("GRU reconstructors over a stacked decoder are not built in recnet_b200")
-        return decoder_hiddens
-    return _squeeze_layers(decoder_hiddens)
-
-
-def _squeeze_layers(decoder_hiddens: torch.Tensor) -> torch.Tensor:
-    if decoder_hiddens.dim() == 4:
-        if decoder_hiddens.size(1) != 1:
-            raise NotImplementedError("per-step reconstructor forward over a stacked decoder is not built in recnet_b200; use forward_sequence")
+def _sequence_hiddens(decoder_hiddens: torch.Tensor) -> torch.Tensor:
+    """(L,1,B,H) -> (L,B,H); a stacked decoder's (L,NLdec,B,H) passes through to the fused drivers."""
+    if decoder_hiddens.dim() == 4 and decoder_hiddens.size(1) == 1:
         return decoder_hiddens[:, 0]
     return decoder_hiddens

@@ -23,7 +23,9 @@ def gemm(precision: int, A: torch.Tensor, transA: bool, B: torch.Tensor, transB:
     """C[m,n] = sum_k A(m,k) B(n,k) (+bias).  A: [M,K] (or [K,M] if transA); B: [N,K] (or [K,N] if transB).
     Operands must already be in the precision's storage type and row-contiguous (stride(1) == 1)."""
     dt = _op_dtype(precision)
-    assert A.dtype == dt and B.dtype == dt and A.is_cuda and A.stride(1) == 1 and B.stride(1) == 1
+    if not (A.is_cuda and B.is_cuda):
+        raise RuntimeError(f"recnet_b200.ops.gemm: operands must be CUDA tensors, got {A.device} / {B.device} (recnet_b200 has no CPU path)")
+    assert A.dtype == dt and B.dtype == dt and A.stride(1) == 1 and B.stride(1) == 1
     M, K = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
     N = B.shape[1] if transB else B.shape[0]
     assert (B.shape[0] if transB else B.shape[1]) == K

@@ -60,6 +60,11 @@ CASES = {
     "tiny_lstm_ragged": dict(B=5, T=7, E=20, H=12, A=8, EMB=10, V=29, dec_layers=1, rec_layers=1, cap_len=9, dec_model="LSTM", rec_model="LSTM", seed=12, short=True),
     "tiny_lstm_2layer": dict(B=3, T=4, E=16, H=8, A=8, EMB=6, V=23, dec_layers=2, rec_layers=1, cap_len=5, dec_model="LSTM", rec_model="LSTM", seed=13),
     "tiny_gru":         dict(B=4, T=5, E=24, H=16, A=8, EMB=12, V=37, dec_layers=1, rec_layers=1, cap_len=6, dec_model="GRU", rec_model="GRU", seed=14),
+    # variants that run through the per-step operator path (no fused sequence driver): stacked GRU decoder, GRU reconstructors over
+    # a stacked decoder, multi-layer reconstructors
+    "tiny_gru_2layer":  dict(B=3, T=4, E=16, H=8, A=8, EMB=6, V=23, dec_layers=2, rec_layers=1, cap_len=5, dec_model="GRU", rec_model="GRU", seed=16),
+    "tiny_lstm_rec2":   dict(B=3, T=4, E=16, H=8, A=8, EMB=6, V=23, dec_layers=1, rec_layers=2, cap_len=5, dec_model="LSTM", rec_model="LSTM", seed=17),
+    "tiny_mixed_2x2":   dict(B=3, T=4, E=16, H=8, A=8, EMB=6, V=23, dec_layers=2, rec_layers=2, cap_len=5, dec_model="LSTM", rec_model="GRU", seed=18),
     "small_lstm":       dict(B=8, T=28, E=64, H=32, A=16, EMB=20, V=101, dec_layers=1, rec_layers=1, cap_len=30, dec_model="LSTM", rec_model="LSTM", seed=15),
 }
 
@@ -154,5 +159,7 @@ if __name__ == "__main__":
     rt, re_ = import_reference()
     # train.forward_* build their zero states with torch.zeros(...) (train.py:28-35): make that fp64 too
     torch.set_default_dtype(torch.float64)
+    only = sys.argv[1:]                      # optional: case names to (re)generate; default = all
     for n, c in CASES.items():
-        run_case(n, c, rt, re_)
+        if not only or n in only:
+            run_case(n, c, rt, re_)

@@ -1,0 +1,63 @@
+"""GPU parity of the variants that have no fused sequence driver and run `forward_sequence` as a loop over the per-step
+operator kernels (models.py): stacked GRU decoder, GRU reconstructors over a stacked decoder, multi-layer reconstructors.
+Checker: the reference-generated golden fixtures (tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+import recnet_b200
+from recnet_b200 import train as T
+from recnet_b200 import eval as E
+from tests.golden_util import load_golden
+from tests.test_gpu_parity import TOL, build, dev, rel
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = ["tiny_gru_2layer", "tiny_lstm_rec2", "tiny_mixed_2x2"]
+
+
+@pytest.mark.parametrize("kind", ["none", "global", "local"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", VARIANTS)
+def test_stepwise_variants_match_reference_golden(name, precision, kind):
+    g = load_golden(name)
+    m = g["meta"]
+    tol = TOL[precision]
+    dec, rec = build(m, precision, kind, g["dec"], g.get(kind, {}))
+    if m["dec_model"] == "GRU" and m["dec_layers"] > 1:
+        assert not dec["model"].uses_fused_sequence
+    feats, targets = g["feats"].float().to(dev()), g["targets"].to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, feats, targets, targets > 0, 1.0)
+    errs = {"dec_loss": rel(dloss, torch.tensor(g["dec_loss"])), "hiddens": rel(hiddens, g["hiddens"])}
+    assert hiddens.shape == g["hiddens"].shape                                       # (L, NLdec, B, H)
+    loss = dloss
+    if rec is not None:
+        rloss = T.forward_reconstructor_for(kind)(hiddens, feats, rec)
+        errs[kind + "_loss"] = rel(rloss, torch.tensor(g[kind + "_loss"]))
+        loss = dloss + 1.0 * rloss
+    loss.backward()
+    for k, ref in g["grads"][kind].items():
+        owner, key = k.split(".", 1)
+        p = dict((dec if owner == "dec" else rec)["model"].named_parameters())[key]
+        assert p.grad is not None, k
+        errs[k] = rel(p.grad, ref)
+    worst = max(errs, key=errs.get)
+    print(f"[variants] {name} {precision} {kind}: worst rel err {errs[worst]:.3e} ({worst})")
+    assert errs[worst] < tol, (worst, errs[worst])
+
+
+@pytest.mark.parametrize("name", ["tiny_gru_2layer", "tiny_mixed_2x2"])
+def test_stacked_decoder_greedy_and_step_logits_fp32(name):
+    g = load_golden(name)
+    m = g["meta"]
+    dec, _ = build(m, "fp32", "none", g["dec"], {})
+    feats = g["feats"].float().to(dev())
+    B = feats.shape[0]
+    T.C.batch_size = B
+    tok = torch.full((1, B), 1, dtype=torch.long, device=dev())
+    z = lambda: torch.zeros(m["dec_layers"], B, m["H"], device=dev())
+    hid = (z(), z()) if m["dec_model"] == "LSTM" else z()
+    with torch.no_grad():
+        logits, _ = dec["model"](tok, hid, feats)
+    assert rel(logits, g["step0_logits"]) < TOL["fp32"]
+    ids = E.greedy_search(T.C, dec["model"], tok, hid, feats)
+    assert torch.equal(torch.tensor(ids), g["greedy_ids"])

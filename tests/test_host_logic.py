@@ -63,15 +63,16 @@ def test_config_keeps_reference_attribute_names():
     assert C.init_word2idx == {'<PAD>': 0, '<SOS>': 1, '<EOS>': 2}
 
 
-def test_unsupported_variants_raise_not_silently_fall_back():
+def test_every_reference_variant_is_accepted_and_unknown_names_raise():
     gru = recnet_b200.Decoder("GRU", 1, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)
     assert tuple(gru.state_dict()["rnn.weight_ih_l0"].shape) == (24, 24)    # 3 gates: checkpoint-compatible holder
-    rec = recnet_b200.LocalReconstructor("LSTM", 2, 8, 16, 0.5, 0.5, 8)         # multi-layer reconstructors: not built yet -> must raise
-    with pytest.raises(NotImplementedError):
+    # variants without a fused sequence driver run as a loop over the per-step kernels -- visible, never silent
+    assert not recnet_b200.Decoder("GRU", 2, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5).uses_fused_sequence
+    rec = recnet_b200.LocalReconstructor("LSTM", 2, 8, 16, 0.5, 0.5, 8)
+    assert not rec._fused_ok(torch.zeros(3, 2, 8))
+    assert tuple(rec.state_dict()["rnn.weight_ih_l1"].shape) == (64, 16)
+    with pytest.raises(RuntimeError):           # ... and the per-step kernels have no CPU path either
         rec.forward_sequence(torch.zeros(3, 2, 8), torch.zeros(2, 4, 16))
-    two = recnet_b200.Decoder("GRU", 2, 16, 8, 1, 8, 8, 11, 0.5, 0.5, 0.5)      # stacked GRU: not built yet -> must raise
-    with pytest.raises(NotImplementedError):
-        two.forward_sequence(None, None, None, None)
     with pytest.raises(NotImplementedError):
         T.forward_reconstructor_for("bogus")
 

@@ -61,3 +61,35 @@ def test_stacked_decoder_greedy_and_step_logits_fp32(name):
     assert rel(logits, g["step0_logits"]) < TOL["fp32"]
     ids = E.greedy_search(T.C, dec["model"], tok, hid, feats)
     assert torch.equal(torch.tensor(ids), g["greedy_ids"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config5_msrvtt_two_layer_decoder_local_reconstructor_against_oracle(precision):
+    """BASELINE config 5 shape family: 40 frames x (1536 + 2048)-d features, 2-layer LSTM decoder, local reconstructor with
+    R = 3584 -- the fused stacked-decoder drivers (seq_decoder_ml / seq_recon_ml) at the stress widths; batch and caption
+    length reduced so the CPU oracle finishes in seconds."""
+    from oracle import recnet_oracle as O
+    m = dict(B=6, T=40, E=3584, H=512, A=128, EMB=468, V=600, cap_len=8, dec_layers=2, rec_layers=1, dec_model="LSTM", rec_model="LSTM")
+    feats, targets, masks = O.synthetic_batch(m["B"], m["T"], m["E"], m["V"], m["cap_len"], seed=9)
+    P = O.init_decoder_params(m["V"], m["EMB"], m["E"], m["H"], m["A"], n_layers=2, seed=4)
+    Q = O.init_reconstructor_params("local", m["H"], m["E"], m["A"], seed=5)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    Qr = {k: v.clone().requires_grad_(True) for k, v in Q.items()}
+    dl, hid, _, _ = O.forward_decoder(Pr, feats, targets, masks, n_layers=2, caption_max_len=m["cap_len"])
+    rl, _ = O.forward_local_reconstructor(Qr, hid, feats)
+    (dl + rl).backward()
+    dec, rec = build(m, precision, "local", P, Q)
+    assert dec["model"].uses_fused_sequence and rec["model"]._fused_ok(hid)
+    tol = TOL[precision]
+    f, t, k = feats.to(dev()), targets.to(dev()), masks.to(dev())
+    dloss, hiddens, _ = T.forward_decoder(dec, f, t, k, 1.0)
+    rloss = T.forward_local_reconstructor(hiddens, f, rec)
+    (dloss + rloss).backward()
+    errs = {"dec_loss": rel(dloss, dl.detach()), "rec_loss": rel(rloss, rl.detach()), "hiddens": rel(hiddens, hid.detach())}
+    for name, p in dec["model"].named_parameters():
+        errs["dec." + name] = rel(p.grad, Pr[name].grad)
+    for name, p in rec["model"].named_parameters():
+        errs["rec." + name] = rel(p.grad, Qr[name].grad)
+    worst = max(errs, key=errs.get)
+    print(f"[variants] config5 {precision}: worst rel err {errs[worst]:.3e} ({worst})")
+    assert errs[worst] < tol, (worst, errs[worst])

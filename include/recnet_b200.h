@@ -250,8 +250,8 @@ int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const 
  * so a captured CUDA graph keeps counting), [1] last total grad norm, [2] last clip coefficient, [3..7] internal. */
 int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs,
                      const int64_t* exp_avg_sq_ptrs, const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n,
-                     const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, float max_grad_norm, float* partial, float* state,
+                     const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2,
+                     double eps, double weight_decay, double max_grad_norm, float* partial, float* state,
                      int write_clipped_grads, void* stream);
 
 #ifdef __cplusplus

@@ -76,7 +76,7 @@ class global_tensors(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in FIELDS]
 
 
-_p, _i, _l, _f, _u = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
+_p, _i, _l, _f, _u, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_double
 
 # name -> (restype, argtypes); mirrors include/recnet_b200.h one to one
 SIGNATURES = {
@@ -117,7 +117,7 @@ SIGNATURES = {
     "recnet_debug_set_timeline": (_i, [_p]),
     "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
     "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _i, _p]),
-    "recnet_adam_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _f, _f, _p, _p, _i, _p]),
+    "recnet_adam_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _d, _d, _d, _d, _d, _d, _p, _p, _i, _p]),
 }
 
 _lib = None

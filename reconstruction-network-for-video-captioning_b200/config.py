@@ -19,8 +19,8 @@ class TrainConfig:
     # --- B200 additions ---
     precision = "bf16"               # "bf16": tcgen05 GEMMs, fp32 accumulate/state; "fp32": FFMA parity build
     attention_normalize = "none"     # "none" = what the reference computes (no softmax, mean over frames)
-    optimizer_impl = "torch"         # "torch": torch.optim.Adam(fused, capturable) + clip_grad_norm_; "recnet": optim.ClipAdam
-    #                                  (own fused clip + Adam kernels).  RECNET_OPTIMIZER=recnet|torch overrides.
+    optimizer_impl = "recnet"        # "recnet": optim.ClipAdam (own fused clip + Adam kernels, measured 21 us/step faster);
+    #                                  "torch": torch.optim.Adam(fused, capturable) + clip_grad_norm_.  RECNET_OPTIMIZER overrides.
 
     # --- batch / vocabulary (config.py:48-56) ---
     min_count = 5

@@ -15,8 +15,8 @@ namespace optim {
 //                          [3] lr / (1 - beta1^step), [4] 1 / sqrt(1 - beta2^step), [5..7] reserved
 enum { ST_STEP = 0, ST_GNORM = 1, ST_CLIP = 2, ST_STEPSIZE = 3, ST_RSQRT_BC2 = 4, ST_WORDS = 8 };
 
-__global__ void adam_prologue_kernel(const float* __restrict__ partial, int n_partial, float max_norm, float lr, float beta1,
-                                     float beta2, float* __restrict__ state) {
+__global__ void adam_prologue_kernel(const float* __restrict__ partial, int n_partial, float max_norm, double lr, double beta1,
+                                     double beta2, float* __restrict__ state) {
   __shared__ float red[32];
   float s = 0.f;
   if (partial)
@@ -29,23 +29,23 @@ __global__ void adam_prologue_kernel(const float* __restrict__ partial, int n_pa
       coef = fminf(1.f, max_norm / (gn + 1e-6f));                                      // clip_grad_norm_: max_norm / (norm + 1e-6), clamped to 1
     }
     const float step = state[ST_STEP] + 1.f;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     state[ST_STEP] = step;
     state[ST_GNORM] = gn;
     state[ST_CLIP] = coef;
-    state[ST_STEPSIZE] = (float)((double)lr / bc1);
+    state[ST_STEPSIZE] = (float)(lr / bc1);
     state[ST_RSQRT_BC2] = (float)(1.0 / sqrt(bc2));
   }
 }
 
-struct AdamHyper { float beta1, beta2, eps, weight_decay; };
+struct AdamHyper { float beta1, beta2, omb1, omb2, eps, weight_decay; };   // omb = 1 - beta, rounded once from double
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* vmax, const AdamHyper& h, float clip,
                                          float step_size, float rsqrt_bc2) {
   g *= clip;
   g = fmaf(h.weight_decay, p, g);                     // L2 (coupled) weight decay: grad += wd * p
-  m = fmaf(1.f - h.beta1, g - m, m);                  // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(h.beta2, v, (1.f - h.beta2) * g * g);
+  m = fmaf(h.omb1, g - m, m);                         // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(h.beta2, v, h.omb2 * g * g);
   float vv = v;
   if (vmax) { vv = fmaxf(*vmax, v); *vmax = vv; }
   const float denom = fmaf(sqrtf(vv), rsqrt_bc2, h.eps);
@@ -101,20 +101,20 @@ __global__ void adam_mt_kernel(const long long* __restrict__ pptrs, const long l
 
 static int adam_step(const long long* pptrs, const long long* gptrs, const long long* mptrs, const long long* vptrs,
                      const long long* xptrs, const long long* sizes, int n, const int* blk_tensor, const int* blk_chunk,
-                     int n_blocks, float lr, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                     int n_blocks, double lr, double beta1, double beta2, double eps, double weight_decay, double max_grad_norm,
                      float* partial, float* state, int write_clipped_grads, cudaStream_t st) {
   if (n <= 0 || n_blocks <= 0) return 0;
   if (!pptrs || !gptrs || !mptrs || !vptrs || !sizes || !blk_tensor || !blk_chunk || !state) return RECNET_ERR_BAD_SHAPE;
-  if (!(lr >= 0.f) || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f)) return RECNET_ERR_BAD_SHAPE;
-  const bool clip = max_grad_norm > 0.f;
+  if (!(lr >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0)) return RECNET_ERR_BAD_SHAPE;
+  const bool clip = max_grad_norm > 0.0;
   if (clip) {
     if (!partial) return RECNET_ERR_BAD_SHAPE;
     misc::mt_sumsq_kernel<<<n_blocks, 256, 0, st>>>(gptrs, sizes, blk_tensor, blk_chunk, partial);
     RN_LAUNCH_OK();
   }
-  adam_prologue_kernel<<<1, 512, 0, st>>>(clip ? partial : nullptr, n_blocks, max_grad_norm, lr, beta1, beta2, state);
+  adam_prologue_kernel<<<1, 512, 0, st>>>(clip ? partial : nullptr, n_blocks, (float)max_grad_norm, lr, beta1, beta2, state);
   RN_LAUNCH_OK();
-  AdamHyper h{beta1, beta2, eps, weight_decay};
+  AdamHyper h{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay};
   const int wg = (clip && write_clipped_grads) ? 1 : 0;
   if (xptrs) adam_mt_kernel<true><<<n_blocks, 256, 0, st>>>(pptrs, gptrs, mptrs, vptrs, xptrs, sizes, blk_tensor, blk_chunk, h, state, wg);
   else adam_mt_kernel<false><<<n_blocks, 256, 0, st>>>(pptrs, gptrs, mptrs, vptrs, nullptr, sizes, blk_tensor, blk_chunk, h, state, wg);

@@ -382,8 +382,8 @@ int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const 
 // ---- fused gradient clip + Adam (train.py:269-273) ---------------------------------------------------------------
 int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs, const int64_t* exp_avg_sq_ptrs,
                      const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
-                     const int32_t* blk_chunk, int n_blocks, float lr, float beta1, float beta2, float eps, float weight_decay,
-                     float max_grad_norm, float* partial, float* state, int write_clipped_grads, void* stream) {
+                     const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2, double eps, double weight_decay,
+                     double max_grad_norm, float* partial, float* state, int write_clipped_grads, void* stream) {
   typedef const long long* LP;
   return optim::adam_step(reinterpret_cast<LP>(param_ptrs), reinterpret_cast<LP>(grad_ptrs), reinterpret_cast<LP>(exp_avg_ptrs),
                           reinterpret_cast<LP>(exp_avg_sq_ptrs), reinterpret_cast<LP>(max_exp_avg_sq_ptrs), reinterpret_cast<LP>(sizes), n,

@@ -171,12 +171,60 @@ static inline int splitk_reduce(const float* P, int splits, long long split_stri
 
 constexpr size_t SPLITK_SCRATCH_FLOATS = (size_t)NUM_SMS * 2 * 128 * 128;   // enough for any plan with splits > 1
 
+// ---- tile / split-K plan of the BATCHED GEMMs (gemm_full: weight gradients, hoisted projections, vocabulary projection) ----------
+// Cost model fitted to a sweep of every batched GEMM of the MSVD train step over (N-tile width, split count) on the B200
+// (tools/gemm_sweep.py, profiles/r1_g_gemm_sweep.md).  What the sweep showed: the main loop is bound by L2 -> SM delivery, not by
+// the tensor pipe.  With all 148 SMs pulling, one k-block (64 deep) costs ~857 / 1030 / 1240 cycles for 64 / 128 / 256-wide tiles
+// (24 / 32 / 48 KB ingested per CTA: ~5.7 KB/clk chip-wide); a partially filled wave is bound per SM instead (~745 / 857 / 944
+// cycles); every wave pays prologue + epilogue (~2000 + 16 bn cycles); a split-K plan adds the reduce pass (~5 us + bytes at
+// 3.5 TB/s).  Wider tiles win whenever they do not cost an extra wave; split-K only pays for GEMMs with a handful of tiles.
+// Candidates are visited from the simplest plan up and must beat the incumbent by 5 % (the fit is good to about +-4 us).
+static inline GemmPlan plan_gemm_full_bf16(int M, int N, int K) {
+  static const float CF[3] = {857.f, 1030.f, 1240.f}, FL[3] = {745.f, 857.f, 944.f};
+  static const int SPL[6] = {1, 2, 3, 4, 6, 8};
+  const int mt = rn_cdiv(M, tc::BM), nkb = rn_cdiv(K, tc::BK);
+  const long long Np = round_up(N, 4);
+  GemmPlan best{64, 1};
+  float best_us = 1e30f;
+  for (int si = 0; si < 6; ++si) {
+    const int s = SPL[si];
+    if (s > nkb) break;
+    if (s > 1 && (size_t)s * M * Np > SPLITK_SCRATCH_FLOATS) break;
+    for (int bi = 0; bi < 3; ++bi) {
+      const int bn = 64 << bi;
+      if (s > 1 && bn == 256) continue;                  // split plans stay on the 64 / 128-wide kernels
+      if (bn > 64 && N <= bn / 2) continue;              // more than half of the tile would be padding
+      const long long ctas = (long long)mt * rn_cdiv(N, bn) * s;
+      const int kb = rn_cdiv(nkb, s);
+      const long long full = ctas / NUM_SMS;
+      const int rem = (int)(ctas % NUM_SMS);
+      const float wave = 2000.f + 16.f * bn;
+      float clk = (float)full * (kb * CF[bi] + wave);
+      if (rem) clk += kb * fmaxf(FL[bi], CF[bi] * rem / NUM_SMS) + wave;
+      float us = clk / 1965.f;
+      if (s > 1) us += 5.f + (float)(s + 1) * M * N * 4.f / 3.5e6f;
+      if (us < best_us * 0.95f) { best_us = us; best.bn = bn; best.splits = s; }
+    }
+  }
+  if (best.splits > 1) {                                   // every slice gets >= 1 k-block (same rounding as plan_gemm)
+    const int kb_per = rn_cdiv(nkb, best.splits);
+    best.splits = rn_cdiv(nkb, kb_per);
+  }
+  return best;
+}
+template <typename T> static inline GemmPlan plan_gemm_full(int M, int N, int K) { return plan_gemm<T>(M, N, K); }
+template <> inline GemmPlan plan_gemm_full<bf16>(int M, int N, int K) {
+  static int mode = -1;                                    // RECNET_GEMM_COSTMODEL: 2 (default) this model, 1 the r1_f model, 0 fixed tiles
+  if (mode < 0) { const char* e = getenv("RECNET_GEMM_COSTMODEL"); mode = e ? atoi(e) : 2; }
+  return mode >= 2 ? plan_gemm_full_bf16(M, N, K) : plan_gemm<bf16>(M, N, K);
+}
+
 // Full GEMM into a dense destination: splits the K loop when the tile grid alone cannot fill the GPU,
 // reducing the partials with one extra pass.  `scratch` holds SPLITK_SCRATCH_FLOATS floats.
 template <typename T>
 static int gemm_full(const T* A, long long lda, int tA, const T* B, long long ldb, int tB, float* C, long long ldc,
                      const float* bias, int M, int N, int K, int accumulate, float* scratch, cudaStream_t st) {
-  GemmPlan p = plan_gemm<T>(M, N, K);
+  GemmPlan p = plan_gemm_full<T>(M, N, K);
   const int Np = round_up(N, 4);
   if (p.splits > 1 && (size_t)p.splits * M * Np > SPLITK_SCRATCH_FLOATS) p.splits = 1;
   if (p.splits <= 1) {

@@ -110,7 +110,8 @@ static inline int gemm_to_operand(const float* A, long long lda, const float* B,
 }
 static inline int gemm_to_operand(const bf16* A, long long lda, const bf16* B, long long ldb, bf16* C, long long ldc, int M, int N,
                                   int K, float*, cudaStream_t st) {
-  const GemmPlan p = plan_gemm<bf16>(M, N, K);
+  GemmPlan p = plan_gemm_full<bf16>(M, N, K);
+  if (p.splits > 1) p = plan_gemm<bf16>(M, N, K);          // the operand-typed epilogue needs the whole K range in one CTA
   return tc::launch(A, lda, 0, B, ldb, 0, nullptr, 0, C, ldc, nullptr, M, N, K, 1, 0, 0, p.bn, st);
 }
 

@@ -71,30 +71,24 @@ class ClipAdam(torch.optim.Optimizer):
         for g in grads:
             if not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous():
                 raise RuntimeError("ClipAdam: gradients must be contiguous float32 CUDA tensors")
-        base = grads[0]._base
-        if base is not None and all(g._base is base for g in grads):
-            # views of ONE flat buffer (what the sequence Functions produce): table = per-view byte offsets (built once, on the
-            # host) + the buffer address (a device-side add, legal under CUDA-graph capture where the address is then fixed)
-            b0 = base.data_ptr()
-            rel = tuple(g.data_ptr() - b0 for g in grads)
-            key = ("flat", b0, rel)
-            t = self._gptr_cache.get(key)
-            if t is None:
-                rel_t = self._gptr_cache.get(("rel", rel))
-                if rel_t is None:
-                    self._no_capture("the gradient-offset table")
-                    rel_t = self._gptr_cache[("rel", rel)] = torch.tensor(rel, dtype=torch.int64, device=grads[0].device)
-                if len(self._gptr_cache) > 64:
-                    self._gptr_cache = {("rel", rel): rel_t}
-                t = self._gptr_cache[key] = rel_t + b0
-            return t
-        key = tuple(g.data_ptr() for g in grads)
-        t = self._gptr_cache.get(key)
+        # Address table = per-gradient byte offsets from the lowest address (built on the host once per layout) + that address
+        # (a device-side add, legal under CUDA-graph capture).  The sequence Functions hand autograd views of ONE flat buffer
+        # with a fixed layout, so after the first eager step every later step -- captured or not -- reuses the offset table.
+        # (autograd detaches what it stores in .grad, so ``_base`` is not available to recognise the flat buffer.)
+        ptrs = [g.data_ptr() for g in grads]
+        b0 = min(ptrs)
+        rel = tuple(q - b0 for q in ptrs)
+        t = self._gptr_cache.get((b0, rel))
         if t is None:
-            self._no_capture("the address table of gradients that are not views of one flat buffer")
+            rel_t = self._gptr_cache.get(("rel", rel))
+            if rel_t is None:
+                self._no_capture("the gradient address table (layout not seen in an eager step)")
+                if len(self._gptr_cache) > 64:
+                    self._gptr_cache.clear()
+                rel_t = self._gptr_cache[("rel", rel)] = torch.tensor(rel, dtype=torch.int64, device=grads[0].device)
             if len(self._gptr_cache) > 64:
-                self._gptr_cache.clear()
-            t = self._gptr_cache[key] = torch.tensor(key, dtype=torch.int64, device=grads[0].device)
+                self._gptr_cache = {("rel", rel): rel_t}
+            t = self._gptr_cache[(b0, rel)] = rel_t + b0
         return t
 
     @staticmethod

@@ -17,7 +17,7 @@ from .optim import ClipAdam
 
 
 def _optimizer_impl() -> str:
-    impl = os.environ.get("RECNET_OPTIMIZER") or getattr(C, "optimizer_impl", "torch")
+    impl = os.environ.get("RECNET_OPTIMIZER") or getattr(C, "optimizer_impl", "recnet")
     if impl not in ("torch", "recnet"):
         raise ValueError(f"optimizer_impl must be 'torch' or 'recnet', got {impl!r}")
     return impl

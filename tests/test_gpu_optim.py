@@ -13,6 +13,16 @@ from tests.test_gpu_parity import build, dev, rel
 
 pytestmark = pytest.mark.gpu
 
+
+def assert_same_update(p, q, p_before, ulps=4, what=""):
+    """p (ours) vs q (torch) after the same optimiser steps from p_before.  The weights are O(1) and the updates O(lr), so the
+    comparison is made where fp32 can resolve it: |p - q| within a few ulps of the weights, and the update itself to 1 %."""
+    p, q, z = p.detach().double(), q.detach().double(), p_before.detach().double()
+    ulp = 2.0 ** -23 * float(q.abs().max())
+    assert float((p - q).abs().max()) <= ulps * ulp, (what, float((p - q).abs().max()), ulp)
+    upd = float((q - z).abs().max())
+    assert upd > 0 and float(((p - z) - (q - z)).abs().max()) <= 1e-2 * upd + ulps * ulp, what
+
 SHAPES = [(4188, 468), (128, 512), (128,), (1, 128), (2048, 2004), (2048,), (7, 3), (1,), (16385,), (33, 5, 7)]
 
 
@@ -63,7 +73,7 @@ def test_clip_adam_matches_torch_clip_plus_adam(amsgrad, max_norm, gscale, flat)
             for p, q in zip(ours, ref):                       # clip_grad_norm_ scales .grad in place; so do we
                 assert rel(p.grad, q.grad) < 1e-5
     for p, q, z in zip(ours, ref, p0):
-        assert rel(p.detach() - z, q.detach() - z) < 2e-5      # the accumulated update, not the (much larger) weights
+        assert_same_update(p, q, z)
     sd, sd_ref = opt.state_dict(), opt_ref.state_dict()
     for i in sd_ref["state"]:
         assert float(sd["state"][i]["step"]) == float(sd_ref["state"][i]["step"]) == 6.0
@@ -91,7 +101,7 @@ def test_clip_adam_state_dict_round_trips_with_torch_adam():
     before = [q.detach().clone() for q in ref]
     opt.step(); opt_ref.step()
     for p, q, z in zip(ours, ref, before):
-        assert rel(p.detach() - z, q.detach() - z) < 2e-5
+        assert_same_update(p, q, z)
     fresh = _make(2)
     opt2 = torch.optim.Adam(fresh, **kw)
     opt2.load_state_dict(copy.deepcopy(opt.state_dict()))              # ours -> torch.optim.Adam
@@ -125,9 +135,9 @@ def test_train_step_with_own_optimizer_matches_torch_optimizer_and_graph_replay_
         for _ in range(3):
             T.train_step(dec, rec, feats, targets, n_steps=L_steps)
         torch.cuda.synchronize()
-        results[impl] = [p.detach() - z for p, z in zip(list(dec["model"].parameters()) + list(rec["model"].parameters()), w0)]
-    for a, b in zip(results["recnet"], results["torch"]):
-        assert rel(a, b) < 1e-3
+        results[impl] = [p.detach().clone() for p in list(dec["model"].parameters()) + list(rec["model"].parameters())]
+    for a, b, z in zip(results["recnet"], results["torch"], w0):
+        assert_same_update(a, b, z, ulps=8)
     # whole step incl. the own optimizer under CUDA-graph capture: the device-side step counter advances per replay
     monkeypatch.setenv("RECNET_OPTIMIZER", "recnet")
     dec, rec = build(g["meta"], "bf16", "local", g["dec"], g["local"])

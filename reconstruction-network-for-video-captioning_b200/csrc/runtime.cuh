@@ -70,6 +70,49 @@ struct Chains {
 };
 inline Chains& chains() { static Chains c; return c; }
 
+// ---- side stream for the batched work around the time loops (opt-in: RECNET_SIDE=1) ---------------------------------------
+// Before and after each time loop a driver issues a dozen mutually independent batched kernels (weight-gradient GEMMs, column
+// sums, operand staging); several of them are small grids (the 128-row attention weight gradients run on 32-64 CTAs) or end in
+// a partial wave.  fork() hands out a second stream ordered after everything issued so far on `main`; the driver splits the
+// independent work between the two and join()s before it returns, so nothing outlives the call and the pattern is a plain
+// fork/join inside a captured CUDA graph.  Concurrent split-K GEMMs / column sums use separate scratch (Ws::splitk2).
+// MEASURED on the B200 (profiles/r1_g_side_stream.md): parity-green, but the captured step gets SLOWER, 2.781 -> 2.839 ms
+// (4 fork/join regions per step): the batched kernels are L2-delivery bound, so running two of them side by side shares the same
+// bandwidth, and the extra graph edges cost more than the partial waves they fill.  Default off; everything runs on `main`.
+struct Side {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  int dev = -1;
+  static bool enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("RECNET_SIDE"); on = e ? atoi(e) : 0; }
+    return on != 0;
+  }
+  int fork(cudaStream_t main, cudaStream_t* out) {
+    *out = main;
+    if (!enabled()) return 0;
+    int cur = 0;
+    RN_CUDA_OK(cudaGetDevice(&cur));
+    if (cur != dev) {               // one process drives one GPU; re-create if a test switches devices
+      RN_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      RN_CUDA_OK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+      RN_CUDA_OK(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
+      dev = cur;
+    }
+    RN_CUDA_OK(cudaEventRecord(fork_ev, main));
+    RN_CUDA_OK(cudaStreamWaitEvent(s, fork_ev, 0));
+    *out = s;
+    return 0;
+  }
+  int join(cudaStream_t main, cudaStream_t side_stream) {
+    if (side_stream == main) return 0;
+    RN_CUDA_OK(cudaEventRecord(join_ev, side_stream));
+    RN_CUDA_OK(cudaStreamWaitEvent(main, join_ev, 0));
+    return 0;
+  }
+};
+inline Side& side() { static Side x; return x; }
+
 static inline int num_chains(int B) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("RECNET_CHAINS"); env = e ? atoi(e) : 0; }

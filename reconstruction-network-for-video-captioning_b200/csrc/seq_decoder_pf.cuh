@@ -18,7 +18,7 @@ struct PfWs {
   float* Uv; T* VW; T* Xe; float* Gx; T* Hop; float* P; float* Wh; float* e; T* gates; float* c;
   float *logits, *lse, *row_loss;
   T* dlogits; float* dHext; T* dGW; float* dhP; float* dWh; float* dUv; T* dUv_op; float* dw_acc; float* dc; float* dXe; T* dVW;
-  float* splitk; int* err;
+  float* splitk; float* splitk2; int* err;      // splitk2: scratch of the side stream (runtime.cuh:Side)
   size_t bytes;
 };
 
@@ -98,6 +98,7 @@ static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
   w.dXe = m.take<float>((size_t)L * B * w.EMBp);
   w.dVW = m.take<T>((size_t)B * Tn * 4 * H);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.splitk2 = m.take<float>(SPLITK_SCRATCH_FLOATS);
   w.err = m.take<int>(64);
   w.bytes = m.off + 256;
   return w;
@@ -126,24 +127,28 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
   const long long ldih = EMB + E;
   // operand copies of the weights / features (the optimiser changes the fp32 masters every step)
-  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, st));
-  pf::interleave_rows_kernel<T><<<4 * H, 128, 0, st>>>(p.w_ih + EMB, ldih, w.WctxI, H, E);
-  RN_LAUNCH_OK();
-  RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wcat, H, A, H, H, st));
-  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H, st));
-  RN_TRY(misc::cast_pad<T>(p.attn_U, E, w.U, E, A, E, E, st));
-  RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
+  // Two streams (runtime.cuh:Side).  `st`: features -> projected features VW (the big GEMM) and the per-step weight operands;
+  // side: key projection U v + b (a 44-CTA GEMM), embedding gather and the time-batched embedding half of the gate projection.
   RN_TRY(misc::cast_pad<T>(feats, E, w.feats, E, (long long)B * Tn, E, E, st));
-  // hoisted projections
-  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, p.attn_b, B * Tn, A, E, 0, w.splitk, st));      // U v + b (bias folded in)
-  RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
-  misc::embed_gather_kernel<T><<<L * B, 128, 0, st>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
+  cudaStream_t s2;
+  RN_TRY(side().fork(st, &s2));
+  RN_TRY(misc::cast_pad<T>(p.attn_U, E, w.U, E, A, E, E, s2));
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, p.attn_b, B * Tn, A, E, 0, w.splitk2, s2));      // U v + b (bias folded in)
+  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, s2));
+  misc::embed_gather_kernel<T><<<L * B, 128, 0, s2>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
                                                       p_emb, rng, SITE_EMB);
   RN_LAUNCH_OK();
-  RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk2, s2));
+  pf::interleave_rows_kernel<T><<<4 * H, 128, 0, st>>>(p.w_ih + EMB, ldih, w.WctxI, H, E);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
+  RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wcat, H, A, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H, st));
+  RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
   RN_CUDA_OK(cudaMemsetAsync(w.Hop, 0, (size_t)B * H * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
   RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
+  RN_TRY(side().join(st, s2));
   for (int t = 0; t < L; ++t) {
     const size_t r = (size_t)t * B;
     if (t > 0)      // h_{-1} = 0: no query, no recurrent term
@@ -189,8 +194,7 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   }
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
-  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk, st));
-  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk, st));
+  // (the vocabulary projection's own gradients do not feed the loop: they join the batched weight gradients below)
   // ---- BPTT
   for (int t = L - 1; t >= 0; --t) {
     const bool last = (t == L - 1);
@@ -208,29 +212,34 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
     // dh_{t-1} = [dWh_t | dG_t] [W_a ; W_hh]  (attention-query path and recurrent path in one K-concatenated GEMM)
     if (t > 0) RN_TRY(gemm_partials<T>(w.dGW + r * NP, NP, 0, w.Wcat, H, 1, w.dhP, B, H, NP, w.pl_dh, st));
   }
-  // ---- batched weight gradients over the stashed operands
+  // ---- batched weight gradients over the stashed operands, two streams (runtime.cuh:Side)
   const long long ldih = EMB + E;
   const T* dG = w.dGW + A;                       // [LB, 4H] gate gradients, ld = NP
+  cudaStream_t s2;
+  RN_TRY(side().fork(st, &s2));
+  // side: vocabulary projection, embedding path, attention query weights
+  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk2, s2));
+  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk2, s2));
+  RN_TRY(gemm_full<T>(dG, NP, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk2, s2));               // dW_emb
+  RN_TRY(gemm_full<T>(dG, NP, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk2, s2));            // dXe
+  RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), s2));
+  misc::embed_scatter_kernel<<<LB, 128, 0, s2>>>(g.embedding, tokens_in, w.dXe, w.EMBp, LB, EMB, V, d.embedding_scale, p_emb, rng,
+                                                 SITE_EMB);
+  RN_LAUNCH_OK();
+  RN_TRY(gemm_full<T>(w.dGW, NP, 1, w.Hop, H, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk2, s2));                       // dW_a = dWh^T h_{t-1}
+  // st: gate biases, context weights (dW_ctx = dVW^T feats,  dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b]), recurrent weights, keys
   RN_TRY(misc::colsum<T>(dG, NP, LB, 4 * H, g.b_ih, 0, w.splitk, st));
   RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // dW_ctx = dVW^T feats,  dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b]
   pf::pf_dvw_kernel<T><<<dim3(rn_cdiv(4 * H, 512), B), 256, (size_t)round_up(L, 32) * round_up(Tn, 4) * sizeof(float), st>>>(w.e, w.dGW, NP, A, w.dVW,
                                                                                                           L, B, Tn, 4 * H, 1.f / Tn);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dVW, 4 * H, 1, w.feats, E, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, B * Tn, 0, w.splitk, st));   // dW_ctx
   RN_TRY(gemm_full<T>(dG, NP, 1, w.Hop, H, 1, g.w_hh, H, nullptr, 4 * H, H, LB, 0, w.splitk, st));                        // dW_hh = dG^T h_{t-1}
-  RN_TRY(gemm_full<T>(dG, NP, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk, st));               // dW_emb
-  RN_TRY(gemm_full<T>(dG, NP, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk, st));            // dXe
-  RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), st));
-  misc::embed_scatter_kernel<<<LB, 128, 0, st>>>(g.embedding, tokens_in, w.dXe, w.EMBp, LB, EMB, V, d.embedding_scale, p_emb, rng,
-                                                 SITE_EMB);
-  RN_LAUNCH_OK();
-  // attention parameters
-  RN_TRY(gemm_full<T>(w.dGW, NP, 1, w.Hop, H, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk, st));                       // dW_a = dWh^T h_{t-1}
   RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)B * Tn, A, A, st));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.feats, E, 1, g.attn_U, E, nullptr, A, E, B * Tn, 0, w.splitk, st));               // dU = dUv^T v
   RN_TRY(misc::colsum<float>(w.dWh, A, LB, A, g.attn_b, 0, w.splitk, st));
   RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
+  RN_TRY(side().join(st, s2));
   return 0;
 }
 }  // namespace dec

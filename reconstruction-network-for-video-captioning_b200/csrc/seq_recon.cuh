@@ -24,7 +24,7 @@ struct LocalWs {
   T *Wrec, *U, *Wa, *Wout, *Hd;
   float* Uv; T* X; float* WhP; float* Wh; float* beta; float* P; float* P2; T* gates; float* c; float* out; float* partial;
   T* dOut; float* dHext; T* dG; T* dG2; float* dXp; float* dXp2; float* dQp; float* dWh; T* dWh_op; float* dUv; T* dUv_op; float* dw_acc; float* dc;
-  float* dx; float* splitk;
+  float* dx; float* splitk; float* splitk2;        // splitk2: scratch of the side stream (runtime.cuh:Side)
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
   T* Hout; T* Hq;                 // stacked decoder only: compact rows of h after pseudo-step (t,0) / at the start of outer step t
   size_t bytes;
@@ -87,6 +87,7 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.dc = m.take<float>((size_t)B * R);
   w.dx = m.take<float>((size_t)S * B * H);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.splitk2 = m.take<float>(SPLITK_SCRATCH_FLOATS);
   w.table_bytes = mega::table_bytes(S);
   w.table = m.take<uint8_t>(w.table_bytes);
   w.bar = m.take<unsigned>(64);
@@ -116,16 +117,20 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   const float p_drop = d.train ? d.p_drop : 0.f;
   const bool is_gru = d.cell == RECNET_CELL_GRU;
   const int GR = w.G * R;
+  // operand staging: the key projection U.hiddens (a 50-CTA GEMM) runs on the side stream next to the 25 MB weight casts
+  cudaStream_t s2;
+  RN_TRY(side().fork(st, &s2));
+  RN_TRY(misc::cast_pad<T>(p.attn_U, H, w.U, H, A, H, H, s2));
+  RN_TRY(misc::cast_pad<T>(hiddens, H, w.Hd, H, (long long)L * B, H, H, s2));
+  RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk2, s2));     // U.hiddens, once
   RN_TRY(misc::cast_pad<T>(p.w_ih, H, w.Wrec, w.KX, GR, H, H, st));
   RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Wrec + H, w.KX, GR, R, R, st));
-  RN_TRY(misc::cast_pad<T>(p.attn_U, H, w.U, H, A, H, H, st));
   RN_TRY(misc::cast_pad<T>(p.attn_W, R, w.Wa, R, A, R, R, st));
   RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
-  RN_TRY(misc::cast_pad<T>(hiddens, H, w.Hd, H, (long long)L * B, H, H, st));
-  RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
   RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
+  RN_TRY(side().join(st, s2));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
@@ -205,8 +210,6 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   loss::mse_local_bwd_kernel<T><<<MSE_BLOCKS, 256, 0, st>>>(w.out, feats, S, B, R, g_mse, 2.f / ((float)S * B * R), w.dOut);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dOut, R, 0, w.Wout, R, 1, w.dHext, R, nullptr, SB, R, R, 0, w.splitk, st));
-  RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk, st));
-  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk, st));
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   const bool is_gru = d.cell == RECNET_CELL_GRU;
@@ -273,20 +276,27 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   }
   RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 4));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
+  // ---- batched gradients over the stashed operands, two streams (runtime.cuh:Side): the big recurrent / input weight gradients
+  // on `st`; the output projection, the 128-row attention gradients and the gradient wrt the decoder states on the side stream
   const T* dGh = is_gru ? w.dG2 : w.dG;
+  cudaStream_t s2;
+  RN_TRY(side().fork(st, &s2));
+  RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk2, s2));
+  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk2, s2));
+  RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk2, s2));
+  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, s2));
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk2, s2));
+  RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, w.splitk2, s2));
+  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk2, s2));
+  // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk2, s2));
+  RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H, 1.f / L, 1, 1, 0, s2));
   RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st));
   if (is_gru) { RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st)); }
   else RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)GR * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RN_TRY(gemm_full<T>(w.dG, GR, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, GR, H, SB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(dGh, GR, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, GR, R, SB, 0, w.splitk, st));
-  RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk, st));
-  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, st));
-  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk, st));
-  RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, w.splitk, st));
-  RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk, st));
-  // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
-  RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk, st));
-  RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H, 1.f / L, 1, 1, 0, st));
+  RN_TRY(side().join(st, s2));
   return 0;
 }
 

@@ -22,6 +22,45 @@ SHAPES = {   # name: (M, N, K, transA, transB)
     "rec.g_hid": (LB, H, A, 0, 1),
 }
 SCRATCH = 148 * 2 * 128 * 128
+# per-step GEMMs of the two time loops (M = batch = 100): split-K partials are left for the consumer kernel (no reduce pass);
+# timed warm (operands L2-resident, as inside the loop), 20 back-to-back launches per event pair
+STEP_SHAPES = {
+    "rec.gate": (100, 4 * R, H + R, 0, 0), "rec.dX": (100, H + R, 4 * R, 0, 1), "rec.Wh": (100, A, R, 0, 0), "rec.dQ": (100, R, A, 0, 1),
+    "dec.gate": (100, A + 4 * H, H, 0, 0), "dec.dh": (100, H, A + 4 * H, 0, 1),
+}
+
+
+def sweep_steps(lib, dev, stream):
+    for name, (M, N, K, tA, tB) in STEP_SHAPES.items():
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        b = (torch.randn(K, N, device=dev) if tB else torch.randn(N, K, device=dev)).to(torch.bfloat16)
+        res = {}
+        for bn in (64, 128, 256):
+            if bn > 64 and N <= bn // 2:
+                continue
+            for splits in (1, 2, 3, 4, 6, 8, 9, 12, 16):
+                if (K + 63) // 64 < splits:
+                    continue
+                part = torch.empty(splits, M, N, dtype=torch.float32, device=dev)
+
+                def run():
+                    L.check(lib.recnet_gemm(L.PREC_BF16, a.data_ptr(), a.stride(0), tA, b.data_ptr(), b.stride(0), tB, part.data_ptr(), N,
+                                            None, 0, None, M, N, K, splits, M * N, 0, bn, stream), "gemm")
+                for _ in range(3):
+                    run()
+                ts = []
+                for _ in range(5):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(20):
+                        run()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3 / 20)
+                ts.sort()
+                res[f"{bn}x{splits}"] = round(ts[2], 2)
+        best = min((v, k) for k, v in res.items())
+        print(json.dumps({"shape": name, "MNK": [M, N, K], "tA": tA, "tB": tB, "best": best[1], "best_us": best[0], "us": res}), flush=True)
 
 
 def main():
@@ -30,6 +69,8 @@ def main():
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     only = sys.argv[1:]
+    if only and only[0] == "--steps":
+        return sweep_steps(lib, dev, stream)
     for name, (M, N, K, tA, tB) in SHAPES.items():
         if only and name not in only:
             continue

@@ -58,6 +58,105 @@ static int cast_pad(const float* src, long long ld_src, TO* dst, long long ld_ds
   return 0;
 }
 
+// ---- multi-tensor operand staging ------------------------------------------------------------------------------------
+// Every sequence forward re-stages the operand copies of its weights / inputs (the optimiser moves the fp32 masters) and clears
+// a few state buffers: 7 casts + 3 memsets in the decoder, 6 + 3 in the local reconstructor -- each a node of a captured graph
+// whose cost is its launch latency, not its bytes.  A Stager collects them and issues ONE kernel (table passed by value):
+//   dst[r', 0:cols] = (TO) src[r, 0:cols], dst[r', cols:cols_pad] = 0;   r' = r, or for interleave_H > 0 the unit-interleaved
+//   order  dst row 4j+g <- src row g*H+j  (W_ctx, makes the VW GEMM emit [.., H, 4]);   src == nullptr -> zero fill.
+// Items that cannot take 16-byte vectors fall back to a scalar launch of their own; RECNET_STAGE_MULTI=0 launches item by item.
+struct StageItem { const float* src; void* dst; unsigned ld_src, ld_dst, rows, cols4, cp4, interleave_H; };
+constexpr int STAGE_MAX = 12;
+struct StageTable { StageItem it[STAGE_MAX]; unsigned blk0[STAGE_MAX + 1]; int n; };
+
+template <typename TO>
+__global__ void stage_multi_kernel(const StageTable t) {
+  int e = 0;
+  while (e + 1 < t.n && blockIdx.x >= t.blk0[e + 1]) ++e;
+  const StageItem it = t.it[e];
+  const unsigned nb = t.blk0[e + 1] - t.blk0[e], lb = blockIdx.x - t.blk0[e];
+  const unsigned total4 = it.rows * it.cp4;
+  TO* dst = reinterpret_cast<TO*>(it.dst);
+  for (unsigned i = lb * blockDim.x + threadIdx.x; i < total4; i += nb * blockDim.x) {
+    const unsigned r = i / it.cp4, c4 = i - r * it.cp4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (it.src && c4 < it.cols4) {
+      const unsigned sr = it.interleave_H ? (r & 3u) * it.interleave_H + (r >> 2) : r;
+      v = *reinterpret_cast<const float4*>(it.src + (size_t)sr * it.ld_src + 4 * c4);
+    }
+    Store4<TO>::st(dst + (size_t)r * it.ld_dst + 4 * c4, v);
+  }
+}
+// scalar fallback for one item (any alignment, any column count)
+template <typename TO>
+__global__ void stage_scalar_kernel(const float* __restrict__ src, long long ld_src, TO* __restrict__ dst, long long ld_dst, long long rows,
+                                    int cols, int cols_pad, int interleave_H) {
+  const long long total = rows * cols_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_pad; const int c = (int)(i % cols_pad);
+    const long long sr = interleave_H ? (r & 3) * interleave_H + (r >> 2) : r;
+    dst[r * ld_dst + c] = from_f32<TO>((src && c < cols) ? src[sr * ld_src + c] : 0.f);
+  }
+}
+
+template <typename TO>
+struct Stager {
+  StageTable t;
+  struct Scalar { const float* src; long long ld_src; TO* dst; long long ld_dst, rows; int cols, cols_pad, interleave_H; };
+  Scalar sc[STAGE_MAX];
+  int n_sc = 0;
+  bool overflow = false;
+  Stager() { t.n = 0; t.blk0[0] = 0; }
+  // dst[rows, cols_pad] <- src[rows, cols]  (see above); src == nullptr: zero fill
+  void add(const float* src, long long ld_src, TO* dst, long long ld_dst, long long rows, int cols, int cols_pad, int interleave_H = 0) {
+    if (rows <= 0 || cols_pad <= 0) return;
+    const long long total = rows * cols_pad;
+    const bool vec = !(cols & 3) && !(cols_pad & 3) && !(ld_dst & 3) && !(reinterpret_cast<uintptr_t>(dst) & 15) &&
+                     (!src || (!(ld_src & 3) && !(reinterpret_cast<uintptr_t>(src) & 15))) && total / 4 < (1ll << 31) &&
+                     ld_src < (1ll << 31) && ld_dst < (1ll << 31) && rows < (1ll << 31);
+    if (vec && t.n < STAGE_MAX) {
+      StageItem& it = t.it[t.n];
+      it.src = src; it.dst = dst; it.ld_src = (unsigned)ld_src; it.ld_dst = (unsigned)ld_dst; it.rows = (unsigned)rows;
+      it.cols4 = (unsigned)cols / 4; it.cp4 = (unsigned)cols_pad / 4; it.interleave_H = (unsigned)interleave_H;
+      const long long total4 = total / 4;
+      long long nb = (total4 + 256 * 8 - 1) / (256 * 8);
+      if (nb > 148 * 8) nb = 148 * 8;
+      t.blk0[t.n + 1] = t.blk0[t.n] + (unsigned)nb;
+      ++t.n;
+    } else if (n_sc < STAGE_MAX) {
+      sc[n_sc++] = Scalar{src, ld_src, dst, ld_dst, rows, cols, cols_pad, interleave_H};
+    } else {
+      overflow = true;
+    }
+  }
+  // zero `bytes` bytes at p (a multiple of 4 elements of TO, 16-byte aligned -- every workspace slice is)
+  void zero(void* p, size_t bytes) { add(nullptr, 0, reinterpret_cast<TO*>(p), (long long)(bytes / sizeof(TO)), 1, 0, (int)(bytes / sizeof(TO))); }
+  int launch(cudaStream_t st) {
+    if (overflow) return RECNET_ERR_BAD_SHAPE;
+    static int multi = -1;
+    if (multi < 0) { const char* e = getenv("RECNET_STAGE_MULTI"); multi = e ? atoi(e) : 1; }
+    if (t.n > 0 && multi) {
+      stage_multi_kernel<TO><<<t.blk0[t.n], 256, 0, st>>>(t);
+      RN_LAUNCH_OK();
+    } else {
+      for (int i = 0; i < t.n; ++i) {           // one launch per item (A/B switch)
+        StageTable one;
+        one.n = 1; one.it[0] = t.it[i]; one.blk0[0] = 0; one.blk0[1] = t.blk0[i + 1] - t.blk0[i];
+        stage_multi_kernel<TO><<<one.blk0[1], 256, 0, st>>>(one);
+        RN_LAUNCH_OK();
+      }
+    }
+    for (int i = 0; i < n_sc; ++i) {
+      const Scalar& x = sc[i];
+      const long long total = x.rows * x.cols_pad;
+      const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+      stage_scalar_kernel<TO><<<blocks, 256, 0, st>>>(x.src, x.ld_src, x.dst, x.ld_dst, x.rows, x.cols, x.cols_pad, x.interleave_H);
+      RN_LAUNCH_OK();
+    }
+    return 0;
+  }
+};
+
 // Xe[r, c] = emb[tok[r], c] * scale * dropmask   (c < EMB), 0 for the K padding
 template <typename TO>
 __global__ void embed_gather_kernel(const float* __restrict__ emb, const long long* __restrict__ tok, TO* __restrict__ out,
@@ -92,7 +191,7 @@ __global__ void embed_scatter_kernel(float* __restrict__ demb, const long long* 
 // out[n] (+)= sum_m X[m*ld + n]      block = 32 columns x 8 row-lanes; blockIdx.y = row chunk (two-stage, fixed order)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, int rows_per_chunk, float* __restrict__ out,
-                              int accumulate) {
+                              int accumulate, float* __restrict__ out2 = nullptr) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -114,27 +213,34 @@ __global__ void colsum_kernel(const T* __restrict__ X, long long ld, int M, int 
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += red[k][tx];
     float* o = out + (long long)blockIdx.y * N + n;
-    *o = (accumulate && gridDim.y == 1) ? *o + t : t;
+    const float r = (accumulate && gridDim.y == 1) ? *o + t : t;
+    *o = r;
+    if (out2 && gridDim.y == 1) out2[n] = r;
   }
 }
-__global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out, int accumulate) {
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out, int accumulate,
+                                     float* __restrict__ out2 = nullptr) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
   for (int c = 0; c < chunks; ++c) s += part[(long long)c * N + n];
-  out[n] = accumulate ? out[n] + s : s;
+  const float r = accumulate ? out[n] + s : s;
+  out[n] = r;
+  if (out2) out2[n] = r;
 }
 // scratch: >= 64 * N floats (only used when M is large enough to be worth a second stage)
+// out2 (optional): a second copy of the result (b_hh gets the same gradient as b_ih in an LSTM: one node instead of a memcpy)
 template <typename T>
-static int colsum(const T* X, long long ld, int M, int N, float* out, int accumulate, float* scratch, cudaStream_t st) {
+static int colsum(const T* X, long long ld, int M, int N, float* out, int accumulate, float* scratch, cudaStream_t st,
+                  float* out2 = nullptr) {
   int chunks = (scratch && M >= 512) ? (M + 127) / 128 : 1;
   if (chunks > 64) chunks = 64;
   const int rpc = (M + chunks - 1) / chunks;
   dim3 grid(rn_cdiv(N, 32), chunks);
-  colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, M, N, rpc, chunks > 1 ? scratch : out, accumulate);
+  colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, M, N, rpc, chunks > 1 ? scratch : out, accumulate, chunks > 1 ? nullptr : out2);
   RN_LAUNCH_OK();
   if (chunks > 1) {
-    colsum_finish_kernel<<<rn_cdiv(N, 256), 256, 0, st>>>(scratch, chunks, N, out, accumulate);
+    colsum_finish_kernel<<<rn_cdiv(N, 256), 256, 0, st>>>(scratch, chunks, N, out, accumulate, out2);
     RN_LAUNCH_OK();
   }
   return 0;

@@ -127,27 +127,29 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
   const long long ldih = EMB + E;
   // operand copies of the weights / features (the optimiser changes the fp32 masters every step)
-  // Two streams (runtime.cuh:Side).  `st`: features -> projected features VW (the big GEMM) and the per-step weight operands;
-  // side: key projection U v + b (a 44-CTA GEMM), embedding gather and the time-batched embedding half of the gate projection.
-  RN_TRY(misc::cast_pad<T>(feats, E, w.feats, E, (long long)B * Tn, E, E, st));
+  // operand copies of the weights / features + cleared initial state: ONE multi-tensor staging kernel (misc.cuh:Stager)
+  misc::Stager<T> sg;
+  sg.add(feats, E, w.feats, E, (long long)B * Tn, E, E);
+  sg.add(p.attn_U, E, w.U, E, A, E, E);
+  sg.add(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp);
+  sg.add(p.w_ih + EMB, ldih, w.WctxI, E, 4 * H, E, E, H);                 // W_ctx rows in unit-interleaved order
+  sg.add(p.attn_W, H, w.Wcat, H, A, H, H);
+  sg.add(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H);
+  sg.add(p.out_w, H, w.Wout, H, V, H, H);
+  sg.zero(w.Hop, (size_t)B * H * sizeof(T));
+  sg.zero(w.c, (size_t)B * H * sizeof(float));
+  sg.zero(w.err, 64 * sizeof(int));
+  RN_TRY(sg.launch(st));
+  // hoisted projections.  With RECNET_SIDE=1 (runtime.cuh:Side) the key projection, the embedding gather and the time-batched
+  // embedding half of the gate projection run on a second stream next to the projected-feature GEMM.
   cudaStream_t s2;
   RN_TRY(side().fork(st, &s2));
-  RN_TRY(misc::cast_pad<T>(p.attn_U, E, w.U, E, A, E, E, s2));
   RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, p.attn_b, B * Tn, A, E, 0, w.splitk2, s2));      // U v + b (bias folded in)
-  RN_TRY(misc::cast_pad<T>(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp, s2));
   misc::embed_gather_kernel<T><<<L * B, 128, 0, s2>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
                                                       p_emb, rng, SITE_EMB);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk2, s2));
-  pf::interleave_rows_kernel<T><<<4 * H, 128, 0, st>>>(p.w_ih + EMB, ldih, w.WctxI, H, E);
-  RN_LAUNCH_OK();
   RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
-  RN_TRY(misc::cast_pad<T>(p.attn_W, H, w.Wcat, H, A, H, H, st));
-  RN_TRY(misc::cast_pad<T>(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H, st));
-  RN_TRY(misc::cast_pad<T>(p.out_w, H, w.Wout, H, V, H, H, st));
-  RN_CUDA_OK(cudaMemsetAsync(w.Hop, 0, (size_t)B * H * sizeof(T), st));
-  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * H * sizeof(float), st));
-  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
   RN_TRY(side().join(st, s2));
   for (int t = 0; t < L; ++t) {
     const size_t r = (size_t)t * B;
@@ -228,8 +230,7 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dGW, NP, 1, w.Hop, H, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk2, s2));                       // dW_a = dWh^T h_{t-1}
   // st: gate biases, context weights (dW_ctx = dVW^T feats,  dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b]), recurrent weights, keys
-  RN_TRY(misc::colsum<T>(dG, NP, LB, 4 * H, g.b_ih, 0, w.splitk, st));
-  RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(misc::colsum<T>(dG, NP, LB, 4 * H, g.b_ih, 0, w.splitk, st, g.b_hh));            // b_ih and b_hh get the same gradient
   pf::pf_dvw_kernel<T><<<dim3(rn_cdiv(4 * H, 512), B), 256, (size_t)round_up(L, 32) * round_up(Tn, 4) * sizeof(float), st>>>(w.e, w.dGW, NP, A, w.dVW,
                                                                                                           L, B, Tn, 4 * H, 1.f / Tn);
   RN_LAUNCH_OK();

@@ -117,20 +117,19 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   const float p_drop = d.train ? d.p_drop : 0.f;
   const bool is_gru = d.cell == RECNET_CELL_GRU;
   const int GR = w.G * R;
-  // operand staging: the key projection U.hiddens (a 50-CTA GEMM) runs on the side stream next to the 25 MB weight casts
-  cudaStream_t s2;
-  RN_TRY(side().fork(st, &s2));
-  RN_TRY(misc::cast_pad<T>(p.attn_U, H, w.U, H, A, H, H, s2));
-  RN_TRY(misc::cast_pad<T>(hiddens, H, w.Hd, H, (long long)L * B, H, H, s2));
-  RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk2, s2));     // U.hiddens, once
-  RN_TRY(misc::cast_pad<T>(p.w_ih, H, w.Wrec, w.KX, GR, H, H, st));
-  RN_TRY(misc::cast_pad<T>(p.w_hh, R, w.Wrec + H, w.KX, GR, R, R, st));
-  RN_TRY(misc::cast_pad<T>(p.attn_W, R, w.Wa, R, A, R, R, st));
-  RN_TRY(misc::cast_pad<T>(p.out_w, R, w.Wout, R, R, R, R, st));
-  RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * w.KX * sizeof(T), st));
-  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
-  RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
-  RN_TRY(side().join(st, s2));
+  // operand copies of the weights / decoder states + cleared initial state: ONE multi-tensor staging kernel (misc.cuh:Stager)
+  misc::Stager<T> sg;
+  sg.add(p.w_ih, H, w.Wrec, w.KX, GR, H, H);
+  sg.add(p.w_hh, R, w.Wrec + H, w.KX, GR, R, R);
+  sg.add(p.attn_U, H, w.U, H, A, H, H);
+  sg.add(p.attn_W, R, w.Wa, R, A, R, R);
+  sg.add(p.out_w, R, w.Wout, R, R, R, R);
+  sg.add(hiddens, H, w.Hd, H, (long long)L * B, H, H);
+  sg.zero(w.X, (size_t)B * w.KX * sizeof(T));
+  sg.zero(w.c, (size_t)B * R * sizeof(float));
+  sg.zero(w.err, 64 * sizeof(int));
+  RN_TRY(sg.launch(st));
+  RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
@@ -291,9 +290,8 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
   RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk2, s2));
   RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H, 1.f / L, 1, 1, 0, s2));
-  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st));
-  if (is_gru) { RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st)); }
-  else RN_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)GR * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st, is_gru ? nullptr : g.b_hh));     // LSTM: b_hh gets the same gradient
+  if (is_gru) RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dG, GR, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, GR, H, SB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(dGh, GR, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, GR, R, SB, 0, w.splitk, st));
   RN_TRY(side().join(st, s2));

@@ -231,13 +231,21 @@ int recnet_debug_set_timeline(void* buf);
 /* L2-norm regulariser over a parameter list (train.py:69,101,127): reg = sum_p ||p||_2.
  * ptrs/sizes: device int64 tables of n tensors; blk_tensor/blk_chunk: device int32 tables mapping block ->
  * (tensor, 16384-element chunk); partial [n_blocks] fp32 scratch (two-stage, fixed-order => bitwise reproducible);
- * sumsq [n] fp32 kept for the backward. */
+ * sumsq [n] fp32 kept for the backward.
+ * fused_out != NULL: also writes the assembled loss of train.py:70,102,128, fused_out[0] = base[0] + lambda_dev[0] * reg
+ * (base / lambda_dev: device scalars, NULL = 0 / 1) -- saves the elementwise mul + add nodes of every module. */
 int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
-                           const int32_t* blk_chunk, int n_blocks, float* partial, float* sumsq, float* reg_out, void* stream);
-/* grad_p (+)= lambda * g * p / ||p|| */
+                           const int32_t* blk_chunk, int n_blocks, float* partial, float* sumsq, float* reg_out,
+                           const float* base, const float* lambda_dev, float* fused_out, void* stream);
+/* grad_p (+)= lambda * lambda_dev[0] * g[0] * p / ||p||     (g, lambda_dev: device scalars, NULL = 1) */
 int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n,
                            const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, const float* sumsq,
-                           const float* g, float lambda, int accumulate, void* stream);
+                           const float* g, float lambda, const float* lambda_dev, int accumulate, void* stream);
+
+/* Teacher-forcing inputs of train.forward_decoder in one launch (train.py:25,44-45,54-60,68): targets (>= L rows of B int64,
+ * row-major) -> tokens_in [L,B] = (<SOS> row, targets[0..L-2]) and ce_weight [L,B] = [target > pad] / (max(n_t,1) * sum_t n_t). */
+int recnet_teacher_forcing_prep(const int64_t* targets, int L, int B, int64_t pad, int64_t sos, int64_t* tokens_in,
+                                float* ce_weight, void* stream);
 
 /* Fused gradient-norm clip + Adam step over a parameter list -- replaces torch.nn.utils.clip_grad_norm_ (reference
  * train.py:269-270) followed by torch.optim.Adam.step (train.py:271-273; optimisers built at train.py:149-150,186-187:

@@ -115,8 +115,9 @@ SIGNATURES = {
     "recnet_global_error_offset": (_l, [C.POINTER(global_desc)]),
     "recnet_debug_loop_overhead": (_i, [_i, _i, _p, _p]),
     "recnet_debug_set_timeline": (_i, [_p]),
-    "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
-    "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _i, _p]),
+    "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _p, _i, _p]),
+    "recnet_teacher_forcing_prep": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
     "recnet_adam_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _d, _d, _d, _d, _d, _d, _p, _p, _i, _p]),
 }
 

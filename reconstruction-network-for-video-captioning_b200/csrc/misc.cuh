@@ -307,6 +307,36 @@ __global__ void global_x_bwd_kernel(const float* __restrict__ dX, float* __restr
   dmp[i] = s;
 }
 
+// ---- teacher-forcing inputs of train.forward_decoder (train.py:25,44-45,54-60,68) in one launch -------------------------------
+//   tokens_in[0, :] = <SOS>; tokens_in[t, :] = targets[t-1, :]
+//   ce_weight[t, b] = [targets[t,b] > <PAD>] / (max(n_t, 1) * sum_t n_t),  n_t = #{b : targets[t,b] > <PAD>}
+// (mean over the n_t live samples of step t, then the division by sum_t n_t).  One block; L*B is a few thousand.
+__global__ void tf_prep_kernel(const long long* __restrict__ targets, int L, int B, long long pad, long long sos,
+                               long long* __restrict__ tokens_in, float* __restrict__ ce_weight) {
+  extern __shared__ float n_t[];          // [L] + 1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t < L; t += nw) {
+    float c = 0.f;
+    for (int b = lane; b < B; b += 32) c += targets[(long long)t * B + b] > pad ? 1.f : 0.f;
+    c = warp_sum(c);
+    if (lane == 0) n_t[t] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int t = 0; t < L; ++t) tot += n_t[t];
+    n_t[L] = tot;
+  }
+  __syncthreads();
+  const float tot = n_t[L];
+  for (int i = threadIdx.x; i < L * B; i += blockDim.x) {
+    const int t = i / B;
+    const float m = targets[i] > pad ? 1.f : 0.f;
+    ce_weight[i] = m / (fmaxf(n_t[t], 1.f) * tot);
+    tokens_in[i] = t == 0 ? sos : targets[i - B];
+  }
+}
+
 // ---- multi-tensor L2 norm regulariser: reg = sum_p ||p||_2 ; grad_p (+)= g * p / ||p|| -------------------------
 constexpr int MT_CHUNK = 16384;
 // table: ptrs[n] (device addresses), sizes[n]; blk_tensor[nb], blk_chunk[nb] map a block to a chunk of one tensor
@@ -332,7 +362,8 @@ __global__ void mt_sumsq_kernel(const long long* __restrict__ ptrs, const long l
 }
 // warp t sums tensor t's block partials (lane-strided, fixed order => reproducible), then reg = sum_t sqrt(sumsq[t])
 __global__ void mt_norm_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ blk_tensor, int n_blocks,
-                                        float* __restrict__ sumsq, int n, float* __restrict__ out) {
+                                        float* __restrict__ sumsq, int n, float* __restrict__ out, const float* __restrict__ base = nullptr,
+                                        const float* __restrict__ lambda_dev = nullptr, float* __restrict__ fused_out = nullptr) {
   __shared__ float nrm[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int t = warp; t < n; t += nw) {
@@ -346,18 +377,21 @@ __global__ void mt_norm_finalize_kernel(const float* __restrict__ partial, const
     float r = 0.f;
     for (int t = 0; t < n; ++t) r += nrm[t & 63];
     out[0] = r;
+    // loss assembly of train.py:70,102,128 folded in: fused = base + lambda * reg (saves two elementwise graph nodes per module)
+    if (fused_out) fused_out[0] = (base ? base[0] : 0.f) + (lambda_dev ? lambda_dev[0] : 1.f) * r;
   }
 }
 __global__ void mt_reg_grad_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ gptrs,
                                    const long long* __restrict__ sizes, const int* __restrict__ blk_tensor,
                                    const int* __restrict__ blk_chunk, const float* __restrict__ sumsq,
-                                   const float* __restrict__ gscale, float lambda, int accumulate) {
+                                   const float* __restrict__ gscale, float lambda, int accumulate,
+                                   const float* __restrict__ lambda_dev = nullptr) {
   const int t = blk_tensor[blockIdx.x];
   const float* p = reinterpret_cast<const float*>(ptrs[t]);
   float* g = reinterpret_cast<float*>(gptrs[t]);
   const long long n = sizes[t], lo = (long long)blk_chunk[blockIdx.x] * MT_CHUNK, hi = min(n, lo + MT_CHUNK);
   const float nrm = sqrtf(sumsq[t]);
-  const float k = (nrm > 0.f) ? lambda * (gscale ? *gscale : 1.f) / nrm : 0.f;
+  const float k = (nrm > 0.f) ? lambda * (gscale ? *gscale : 1.f) * (lambda_dev ? *lambda_dev : 1.f) / nrm : 0.f;
   if (!((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15)) {
     const long long hi4 = lo + ((hi - lo) & ~3ll);
     for (long long i = lo + 4 * threadIdx.x; i < hi4; i += 4 * blockDim.x) {

@@ -357,24 +357,36 @@ float* recnet_global_outputs(const recnet_global_desc* d, void* workspace) {
 
 // ---- regulariser -----------------------------------------------------------------------------------------------
 int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor, const int32_t* blk_chunk,
-                           int n_blocks, float* partial, float* sumsq, float* reg_out, void* stream) {
+                           int n_blocks, float* partial, float* sumsq, float* reg_out, const float* base, const float* lambda_dev,
+                           float* fused_out, void* stream) {
   cudaStream_t st = ST(stream);
   misc::mt_sumsq_kernel<<<n_blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(ptrs), reinterpret_cast<const long long*>(sizes),
                                                   blk_tensor, blk_chunk, partial);
   RN_LAUNCH_OK();
   if (n > 64) return RECNET_ERR_BAD_SHAPE;
-  misc::mt_norm_finalize_kernel<<<1, 512, 0, st>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out);
+  misc::mt_norm_finalize_kernel<<<1, 512, 0, st>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out, base, lambda_dev, fused_out);
   RN_LAUNCH_OK();
   return 0;
 }
 int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
-                           const int32_t* blk_chunk, int n_blocks, const float* sumsq, const float* g, float lambda, int accumulate,
-                           void* stream) {
+                           const int32_t* blk_chunk, int n_blocks, const float* sumsq, const float* g, float lambda,
+                           const float* lambda_dev, int accumulate, void* stream) {
   (void)n;
   misc::mt_reg_grad_kernel<<<n_blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(ptrs),
                                                              reinterpret_cast<const long long*>(grad_ptrs),
                                                              reinterpret_cast<const long long*>(sizes), blk_tensor, blk_chunk, sumsq, g,
-                                                             lambda, accumulate);
+                                                             lambda, accumulate, lambda_dev);
+  RN_LAUNCH_OK();
+  return 0;
+}
+
+// ---- teacher-forcing inputs (train.py:25,44-45,54-60,68) ----------------------------------------------------------
+int recnet_teacher_forcing_prep(const int64_t* targets, int L, int B, int64_t pad, int64_t sos, int64_t* tokens_in, float* ce_weight,
+                                void* stream) {
+  if (L < 1 || B < 1 || !targets || !tokens_in || !ce_weight) return RECNET_ERR_BAD_SHAPE;
+  misc::tf_prep_kernel<<<1, 1024, (size_t)(L + 1) * sizeof(float), ST(stream)>>>(reinterpret_cast<const long long*>(targets), L, B,
+                                                                                  (long long)pad, (long long)sos,
+                                                                                  reinterpret_cast<long long*>(tokens_in), ce_weight);
   RN_LAUNCH_OK();
   return 0;
 }

@@ -84,16 +84,33 @@ def _table_for(params) -> _NormTable:
     return t
 
 
-def _norms_fwd(params):
+def _norms_fwd(params, base=None, lambda_dev=None):
+    """reg = sum_p ||p||  (+ fused = base + lambda_dev * reg when ``lambda_dev`` is given: the loss assembly of train.py:70,102,128
+    inside the finalize kernel).  Returns (reg, sumsq, fused or None)."""
     tab = _table_for(params)
-    sumsq = torch.empty(tab.n, dtype=torch.float32, device=params[0].device)
-    partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=params[0].device)
-    reg = torch.empty((), dtype=torch.float32, device=params[0].device)
+    dev = params[0].device
+    sumsq = torch.empty(tab.n, dtype=torch.float32, device=dev)
+    partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=dev)
+    reg = torch.empty((), dtype=torch.float32, device=dev)
+    fused = torch.empty((), dtype=torch.float32, device=dev) if lambda_dev is not None else None
     L.check(L.lib().recnet_param_norms_fwd(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(),
                                            tab.blk_chunk.data_ptr(), tab.n_blocks, partial.data_ptr(), sumsq.data_ptr(),
-                                           reg.data_ptr(), _stream()),
+                                           reg.data_ptr(), _ptr(base), _ptr(lambda_dev), _ptr(fused), _stream()),
             "recnet_param_norms_fwd")
-    return reg, sumsq
+    return reg, sumsq, fused
+
+
+def _lambda_scalar(meta, dev):
+    """meta['lambda_reg'] (the module dict's device scalar, train.py:151,188) as a float32 CUDA 0-dim tensor, or None."""
+    lam = meta.get("lambda_reg")
+    if lam is None:
+        return None
+    if not torch.is_tensor(lam):
+        lam = torch.tensor(float(lam), dtype=torch.float32, device=dev)
+    lam = lam.detach()
+    if lam.dtype != torch.float32 or lam.device != dev:
+        lam = lam.to(device=dev, dtype=torch.float32)
+    return lam.reshape(())
 
 
 def _flat_grads(params) -> (torch.Tensor, List[torch.Tensor], torch.Tensor):
@@ -105,11 +122,12 @@ def _flat_grads(params) -> (torch.Tensor, List[torch.Tensor], torch.Tensor):
     return flat, views, tab.offset_bytes + flat.data_ptr()
 
 
-def _norms_bwd_into(params, sumsq, g_reg, gptrs, accumulate: bool):
+def _norms_bwd_into(params, sumsq, g_reg, gptrs, accumulate: bool, lambda_dev=None):
     tab = _table_for(params)
     L.check(L.lib().recnet_param_norms_bwd(tab.ptrs.data_ptr(), gptrs.data_ptr(), tab.sizes.data_ptr(), tab.n,
                                            tab.blk_tensor.data_ptr(), tab.blk_chunk.data_ptr(), tab.n_blocks, sumsq.data_ptr(),
-                                           g_reg.data_ptr(), 1.0, int(accumulate), _stream()), "recnet_param_norms_bwd")
+                                           g_reg.data_ptr(), 1.0, _ptr(lambda_dev), int(accumulate), _stream()),
+            "recnet_param_norms_bwd")
 
 
 # (workspace, byte offset of the loop kernel's error flag) of the most recent sequence calls, for check_loop_status()
@@ -155,7 +173,8 @@ def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
         L.check(int(nbytes), "recnet_decoder_workspace_bytes")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
     hiddens = torch.empty(Lsteps, NL, B, meta["H"], dtype=torch.float32, device=feats.device)     # train.py:61-64,73
-    ce = torch.zeros((), dtype=torch.float32, device=feats.device)
+    # the CE kernels overwrite `ce`; only the loss-free inference call (no targets) needs it pre-cleared
+    ce = (torch.empty if (targets is not None and ce_weight is not None) else torch.zeros)((), dtype=torch.float32, device=feats.device)
     tokens_in = tokens_in.contiguous()
     targets = targets.contiguous() if targets is not None else None
     ce_weight = ce_weight.contiguous() if ce_weight is not None else None
@@ -178,10 +197,15 @@ class DecoderSequenceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta: Dict, feats, tokens_in, targets, ce_weight, rng, *params):
         ce, hiddens, ws, d, nbytes, saved = _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params)
-        reg, sumsq = _norms_fwd(saved[5:])
+        lam = _lambda_scalar(meta, ce.device)
+        reg, sumsq, fused = _norms_fwd(saved[5:], ce, lam)
         ctx.desc, ctx.nbytes = d, nbytes
+        ctx.lam = lam                       # not an autograd input: a plain attribute keeps it alive for backward
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(*saved, ws, sumsq, hiddens)
+        if fused is not None:               # output 0 is the assembled loss ce + lambda * reg (train.py:70); reg is informational
+            ctx.mark_non_differentiable(reg)
+            return fused, hiddens, reg
         return ce, hiddens, reg
 
     @staticmethod
@@ -195,7 +219,9 @@ class DecoderSequenceFn(torch.autograd.Function):
         L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
                                        ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
                                        _ptr(g_hid), hiddens.data_ptr(), C.byref(g), _stream()), "recnet_decoder_bwd")
-        if g_reg is not None:
+        if ctx.lam is not None:
+            _norms_bwd_into(params, sumsq, g_ce, gptrs, accumulate=True, lambda_dev=ctx.lam)
+        elif g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
         return (None, None, None, None, None, None, *grads)
 
@@ -245,10 +271,15 @@ class LocalReconstructorFn(torch.autograd.Function):
         L.check(lib.recnet_local_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
                                      nbytes, mse.data_ptr(), _stream()), "recnet_local_fwd")
         _remember_status("local", ws, lib.recnet_local_error_offset(C.byref(d)))
-        reg, sumsq = _norms_fwd(params)
+        lam = _lambda_scalar(meta, mse.device)
+        reg, sumsq, fused = _norms_fwd(params, mse, lam)
         ctx.desc, ctx.nbytes = d, nbytes
+        ctx.lam = lam
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(hiddens, feats, rng, ws, sumsq, *params)
+        if fused is not None:               # output 0 is the assembled loss mse + lambda * reg (train.py:128-130)
+            ctx.mark_non_differentiable(reg)
+            return fused, reg
         return mse, reg
 
     @staticmethod
@@ -262,7 +293,9 @@ class LocalReconstructorFn(torch.autograd.Function):
         L.check(lib.recnet_local_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
                                      ws.data_ptr(), ctx.nbytes, g_mse.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
                 "recnet_local_bwd")
-        if g_reg is not None:
+        if ctx.lam is not None:
+            _norms_bwd_into(params, sumsq, g_mse, gptrs, accumulate=True, lambda_dev=ctx.lam)
+        elif g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
         return (None, g_hid, None, None, *grads)
 
@@ -291,10 +324,15 @@ class GlobalReconstructorFn(torch.autograd.Function):
         L.check(lib.recnet_global_fwd(C.byref(d), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(), ws.data_ptr(),
                                       nbytes, loss.data_ptr(), _stream()), "recnet_global_fwd")
         _remember_status("global", ws, lib.recnet_global_error_offset(C.byref(d)))
-        reg, sumsq = _norms_fwd(params)
+        lam = _lambda_scalar(meta, loss.device)
+        reg, sumsq, fused = _norms_fwd(params, loss, lam)
         ctx.desc, ctx.nbytes = d, nbytes
+        ctx.lam = lam
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(hiddens, feats, rng, ws, sumsq, *params)
+        if fused is not None:               # output 0 is the assembled loss (train.py:100-102)
+            ctx.mark_non_differentiable(reg)
+            return fused, reg
         return loss, reg
 
     @staticmethod
@@ -308,7 +346,9 @@ class GlobalReconstructorFn(torch.autograd.Function):
         L.check(lib.recnet_global_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
                                       ws.data_ptr(), ctx.nbytes, g_loss.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
                 "recnet_global_bwd")
-        if g_reg is not None:
+        if ctx.lam is not None:
+            _norms_bwd_into(params, sumsq, g_loss, gptrs, accumulate=True, lambda_dev=ctx.lam)
+        elif g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
         return (None, g_hid, None, None, *grads)
 
@@ -320,7 +360,7 @@ class ParamNormSumFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, *params):
         params = tuple(_f32c(p, "parameter") for p in params)
-        reg, sumsq = _norms_fwd(params)
+        reg, sumsq, _ = _norms_fwd(params)
         ctx.save_for_backward(sumsq, *params)
         return reg
 
@@ -334,3 +374,19 @@ class ParamNormSumFn(torch.autograd.Function):
 
 def param_norm_sum(params: Sequence[torch.Tensor]) -> torch.Tensor:
     return ParamNormSumFn.apply(*params)
+
+
+def teacher_forcing_inputs(targets: torch.Tensor, n_steps: int, pad: int, sos: int):
+    """tokens_in (L,B) int64 = (<SOS> row, targets[:L-1]) and ce_weight (L,B) f32 = mask / (max(n_t,1) * sum_t n_t) in one launch
+    (train.py:25,44-45,54-60,68)."""
+    if not targets.is_cuda or targets.dtype != torch.int64:
+        raise RuntimeError(f"targets: expected an int64 CUDA tensor, got {targets.dtype} on {targets.device} (recnet_b200 has no CPU path)")
+    targets = targets.contiguous()
+    Lmax, B = targets.shape
+    if not 1 <= n_steps <= Lmax:
+        raise ValueError(f"n_steps={n_steps} outside 1..{Lmax}")
+    tokens_in = torch.empty(n_steps, B, dtype=torch.int64, device=targets.device)
+    ce_weight = torch.empty(n_steps, B, dtype=torch.float32, device=targets.device)
+    L.check(L.lib().recnet_teacher_forcing_prep(targets.data_ptr(), n_steps, B, int(pad), int(sos), tokens_in.data_ptr(),
+                                                ce_weight.data_ptr(), _stream()), "recnet_teacher_forcing_prep")
+    return tokens_in, ce_weight

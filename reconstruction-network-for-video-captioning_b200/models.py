@@ -143,12 +143,16 @@ class Decoder(nn.Module, _RngMixin):
         return self.n_layers == 1
 
     # ---- whole teacher-forced loop ----
-    def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs):
-        """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,NL,B,H), reg = sum_p ||p||)."""
+    def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs, lambda_reg=None):
+        """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,NL,B,H), reg = sum_p ||p||).
+        With ``lambda_reg`` (the module dict's device scalar) output 0 is the assembled loss ce + lambda_reg * reg (train.py:70),
+        computed inside the regulariser kernel; reg is then returned for inspection only."""
         if not self.uses_fused_sequence:
-            return self._forward_sequence_stepwise(tokens_in, targets, ce_weight, encoder_outputs)
-        return Fn.DecoderSequenceFn.apply(self._meta(), encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(),
-                                          *self._params())
+            ce, hiddens, reg = self._forward_sequence_stepwise(tokens_in, targets, ce_weight, encoder_outputs)
+            return (ce if lambda_reg is None else ce + lambda_reg * reg), hiddens, reg
+        meta = self._meta()
+        meta["lambda_reg"] = lambda_reg
+        return Fn.DecoderSequenceFn.apply(meta, encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(), *self._params())
 
     def _forward_sequence_stepwise(self, tokens_in, targets, ce_weight, encoder_outputs):
         """The loop body of train.forward_decoder (train.py:41-66) over the per-step ``forward`` (our operator kernels)."""
@@ -283,12 +287,14 @@ class GlobalReconstructor(_ReconstructorBase):
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
         return (w_ih, w_hh, b_ih, b_hh, self.out.weight, self.out.bias)
 
-    def forward_sequence(self, decoder_hiddens, encoder_outputs):
-        """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||)."""
+    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None):
+        """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||).
+        With ``lambda_reg`` output 0 is the assembled loss (train.py:100-102)."""
         if not self._fused_ok(decoder_hiddens):
-            return self._forward_sequence_stepwise(decoder_hiddens, encoder_outputs)
+            loss, reg = self._forward_sequence_stepwise(decoder_hiddens, encoder_outputs)
+            return (loss if lambda_reg is None else loss + lambda_reg * reg), reg
         hid = _sequence_hiddens(decoder_hiddens)
-        meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p,
+        meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p, lambda_reg=lambda_reg,
                     caption_max_len=self.caption_max_len, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.GlobalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
@@ -344,12 +350,14 @@ class LocalReconstructor(_ReconstructorBase):
         return (self.attn_W.weight, self.attn_U.weight, self.attn_b, self.attn_w.weight, w_ih, w_hh, b_ih, b_hh,
                 self.out.weight, self.out.bias)
 
-    def forward_sequence(self, decoder_hiddens, encoder_outputs):
-        """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||)."""
+    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None):
+        """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||).
+        With ``lambda_reg`` output 0 is the assembled loss (train.py:128-130)."""
         if not self._fused_ok(decoder_hiddens):
-            return self._forward_sequence_stepwise(decoder_hiddens, encoder_outputs)
+            loss, reg = self._forward_sequence_stepwise(decoder_hiddens, encoder_outputs)
+            return (loss if lambda_reg is None else loss + lambda_reg * reg), reg
         hid = _sequence_hiddens(decoder_hiddens)
-        meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training,
+        meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training, lambda_reg=lambda_reg,
                     p_drop=self.decoder_dropout_p, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.LocalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 

@@ -12,6 +12,7 @@ import random
 import torch
 
 from .config import TrainConfig as C
+from . import functional as Fn
 from .models import Decoder, GlobalReconstructor, LocalReconstructor
 from .optim import ClipAdam
 
@@ -34,41 +35,53 @@ def _num_steps(target_masks: torch.Tensor, caption_max_len: int) -> int:
 
 def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_forcing_ratio=0., n_steps=None):
     """train.py:17-75.  Returns (loss, hiddens (L,NL,B,H), output_indices).
+    ``target_masks`` is ``targets > <PAD>`` as the reference builds it (train.py:246); it may be None when ``n_steps`` is given.
     ``n_steps``: optional static loop length (skips the host read; needed under CUDA-graph capture)."""
+    if target_masks is None:
+        if n_steps is None or not targets.is_cuda:
+            target_masks = targets > C.init_word2idx['<PAD>']
     model = decoder['model']
     L = n_steps if n_steps is not None else _num_steps(target_masks, C.caption_max_len)
     B = encoder_outputs.shape[0]
-    sos = torch.full((1, B), C.init_word2idx['<SOS>'], dtype=torch.long, device=encoder_outputs.device)   # train.py:25
+    dev = encoder_outputs.device
+    pad, sos_id = C.init_word2idx['<PAD>'], C.init_word2idx['<SOS>']
     use_teacher_forcing = random.random() <= teacher_forcing_ratio                                          # train.py:38
     output_indices = torch.empty(0, dtype=torch.long)
-    if use_teacher_forcing:
-        tokens_in = torch.cat((sos, targets[: L - 1]), dim=0)                                               # train.py:44-45
+    if use_teacher_forcing and targets.is_cuda:
+        # <SOS> row + shifted targets (train.py:25,44-45) and the CE weights mask / (n_t * sum_t n_t) (train.py:54-60,68): one launch
+        tokens_in, ce_weight = Fn.teacher_forcing_inputs(targets, L, pad, sos_id)
     else:
-        # argmax feedback (train.py:47-51): decode greedily on device, then replay those tokens through the
-        # differentiable sequence kernel (identical arithmetic in eval mode, where validation uses it, train.py:329)
-        ids, _ = model.greedy(encoder_outputs, L)
-        tokens_in = torch.cat((sos, ids[: L - 1]), dim=0)
-        output_indices = ids[:L].cpu()
-    m = target_masks[:L].to(torch.float32)
-    n_t = m.sum(dim=1, keepdim=True)                                                                        # train.py:57
-    ce_weight = m / (n_t.clamp_min(1.0) * n_t.sum())                                                                       # mean over n_t, then / sum n_t (train.py:54-60,68)
-    ce, hiddens, reg_loss = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs)     # reg: train.py:69
-    loss = ce + decoder['lambda_reg'] * reg_loss                                                            # train.py:70
+        sos = torch.full((1, B), sos_id, dtype=torch.long, device=dev)                                      # train.py:25
+        if use_teacher_forcing:
+            tokens_in = torch.cat((sos, targets[: L - 1]), dim=0)                                           # train.py:44-45
+        else:
+            # argmax feedback (train.py:47-51): decode greedily on device, then replay those tokens through the
+            # differentiable sequence kernel (identical arithmetic in eval mode, where validation uses it, train.py:329)
+            ids, _ = model.greedy(encoder_outputs, L)
+            tokens_in = torch.cat((sos, ids[: L - 1]), dim=0)
+            output_indices = ids[:L].cpu()
+        if target_masks is None:
+            target_masks = targets > pad
+        m = target_masks[:L].to(torch.float32)
+        n_t = m.sum(dim=1, keepdim=True)                                                                    # train.py:57
+        ce_weight = m / (n_t.clamp_min(1.0) * n_t.sum())                                                    # mean over n_t, then / sum n_t (train.py:54-60,68)
+    # loss = CE + lambda_reg * sum_p ||p|| (train.py:69-70), assembled inside the sequence call
+    loss, hiddens, _ = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs, lambda_reg=decoder['lambda_reg'])
     return loss, hiddens, output_indices                                                                    # (L,NL,B,H), train.py:73-75
 
 
 def forward_global_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
     """train.py:78-105."""
     model = reconstructor['model']
-    loss, reg_loss = model.forward_sequence(decoder_hiddens, encoder_outputs)                               # includes the /L of train.py:100
-    return loss + reconstructor['lambda_reg'] * reg_loss
+    loss, _ = model.forward_sequence(decoder_hiddens, encoder_outputs, lambda_reg=reconstructor['lambda_reg'])    # incl. /L (train.py:100) and + lambda * reg (:101-102)
+    return loss
 
 
 def forward_local_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
     """train.py:108-131."""
     model = reconstructor['model']
-    loss, reg_loss = model.forward_sequence(decoder_hiddens, encoder_outputs)
-    return loss + reconstructor['lambda_reg'] * reg_loss
+    loss, _ = model.forward_sequence(decoder_hiddens, encoder_outputs, lambda_reg=reconstructor['lambda_reg'])    # incl. + lambda * reg (train.py:129-130)
+    return loss
 
 
 def build_decoder(n_vocabs):
@@ -127,7 +140,8 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
     """One iteration of the reference's loop body (train.py:243-273): decoder + reconstructor forward, combined
     loss, backward, clip, two Adam steps.  ``grad_hook`` (if given) runs between backward and clip -- the
     data-parallel gradient all-reduce plugs in there.  Returns (loss, decoder_loss, recon_loss) device scalars."""
-    target_masks = targets > C.init_word2idx['<PAD>']                                                       # train.py:246
+    # train.py:246 (the fused path derives the mask from the targets itself; the host-side loop length needs it when n_steps is None)
+    target_masks = None if (n_steps is not None and targets.is_cuda) else targets > C.init_word2idx['<PAD>']
     decoder['model'].train()
     dec_loss, hiddens, _ = forward_decoder(decoder, encoder_outputs, targets, target_masks,
                                            C.decoder_teacher_forcing_ratio, n_steps=n_steps)
@@ -135,7 +149,7 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
     if reconstructor is not None:
         reconstructor['model'].train()
         rec_loss = forward_reconstructor_for(C.reconstructor_type)(hiddens, encoder_outputs, reconstructor)
-        loss = dec_loss + lambda_recon * rec_loss                                                           # train.py:260
+        loss = dec_loss + rec_loss if lambda_recon == 1.0 else dec_loss + lambda_recon * rec_loss           # train.py:260
     else:
         loss = dec_loss
     if zero_grad:

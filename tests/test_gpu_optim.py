@@ -159,3 +159,21 @@ def test_train_step_with_own_optimizer_matches_torch_optimizer_and_graph_replay_
     assert float(rec["optimizer"].state_dict()["state"][0]["step"]) == 3 + 4
     assert not torch.equal(w0, dec["model"].out.weight)
     assert all(bool(torch.isfinite(p).all()) for p in dec["model"].parameters())
+
+
+@pytest.mark.parametrize("name", ["tiny_lstm_ragged", "small_lstm"])
+def test_teacher_forcing_prep_matches_the_reference_formulas(name):
+    """recnet_teacher_forcing_prep: <SOS> row + shifted targets (train.py:25,44-45) and CE weights mask / (n_t * sum n_t) (train.py:54-60,68)."""
+    from recnet_b200 import functional as Fn
+    g = load_golden(name)
+    targets = g["targets"].to(dev())
+    L_steps, B = g["hiddens"].shape[0], targets.shape[1]
+    tok, w = Fn.teacher_forcing_inputs(targets, L_steps, 0, 1)
+    m = (targets > 0)[:L_steps].float()
+    n_t = m.sum(dim=1, keepdim=True)
+    ref_w = m / (n_t.clamp_min(1.0) * n_t.sum())
+    ref_tok = torch.cat((torch.ones(1, B, dtype=torch.long, device=dev()), targets[: L_steps - 1]), dim=0)
+    assert torch.equal(tok, ref_tok)
+    assert rel(w, ref_w) < 1e-6 and abs(float(w.sum()) - float(ref_w.sum())) < 1e-5
+    with pytest.raises(RuntimeError):
+        Fn.teacher_forcing_inputs(g["targets"], L_steps, 0, 1)          # CPU tensor: no CPU path

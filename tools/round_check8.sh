@@ -1,8 +1,7 @@
 #!/bin/bash
 set -u
-O=gpurun_out/check8; mkdir -p $O
-timeout 100 python bench.py --steps 50 --warmup 5 --cpu-iters 0 > $O/bench_multi1.json 2> $O/e1
-RECNET_STAGE_MULTI=0 timeout 100 python bench.py --steps 50 --warmup 5 --cpu-iters 0 > $O/bench_multi0.json 2> $O/e2
+O=gpurun_out/check9; mkdir -p $O
+timeout 100 python bench.py --steps 50 --warmup 5 --cpu-iters 0 > $O/bench_fusedloss.json 2> $O/e1
 timeout 300 python -m pytest tests -m gpu -q -p no:cacheprovider -x > $O/tests_all.log 2>&1
 echo "all tests exit $?" >> $O/status.txt
 cat $O/status.txt; tail -3 $O/tests_all.log; tail -2 $O/e1

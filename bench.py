@@ -169,7 +169,9 @@ def algorithmic_work(cls, M, N, K, elt):
     """(bound, flops-or-bytes per launch) -- DESIGN.md section 'Kernels and rooflines' states the same formulas."""
     s = SHAPE
     if cls in (1, 2):
-        return "tensor", 2.0 * M * N * K                                     # useful rows only (M = 100 of the 128-row UMMA tile)
+        # useful rows only (M = 100 of the 128-row UMMA tile).  Which roofline binds is decided by the caller from the arithmetic
+        # intensity (gemm_bytes): the M = 100 per-step GEMMs move ~90 flop per byte, far below the machine balance (~215).
+        return "tensor", 2.0 * M * N * K
     if cls == 3:     # (B, Tn, D): read V + Uv + Wh partials, write ctx
         return "hbm", M * N * K * elt + M * N * s["A"] * 4 + M * s["A"] * 4 + M * K * elt
     if cls == 4:     # read V, dctx partials (~1), Uv ; RMW dUv ; write dWh
@@ -193,6 +195,11 @@ def algorithmic_work(cls, M, N, K, elt):
         return "hbm", (M * N * 4 * K * elt + 3 * M * N * A * 4 + 12 * M * K * 4 + M * 4 * K * elt + 5 * M * K * 4
                        + M * (A + 4 * K) * elt + M * K * 4 + 3 * M * A * 4)
     return "hbm", 0.0
+
+
+def gemm_bytes(M, N, K, elt):
+    """Algorithmic bytes of one GEMM launch: both operands once + the fp32 result once."""
+    return (M * K + N * K) * elt + M * N * 4.0
 
 
 # ncu --set full captures committed under profiles/ (tools/collect_profiles.sh + tools/summarise_profiles.py): DRAM traffic per
@@ -486,13 +493,22 @@ def main():
         for (cls, M, N, K), (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             bound, work = algorithmic_work(cls, M, N, K, elt)
             avg_s = ms / cnt * 1e-3
+            extra = {}
+            if cls in (1, 2):
+                # a GEMM is bound by whichever roofline gives the LONGER lower bound on its time; the other one is kept alongside
+                nbytes = gemm_bytes(M, N, K, elt)
+                t_tensor, t_hbm = work / (pk["tf_sust"] * 1e12), nbytes / (pk["hbm"] * 1e9)
+                tensor_frac, hbm_frac = t_tensor / avg_s, t_hbm / avg_s
+                extra = {"flop_per_byte": round(work / nbytes, 1), "tensor_frac": round(tensor_frac, 4), "hbm_frac": round(hbm_frac, 4)}
+                if t_hbm > t_tensor:
+                    bound, work = "hbm", nbytes
             if bound == "tensor":
                 ach, peak, unit = work / avg_s / 1e12, pk["tf_sust"], "TFLOP/s"
             else:
                 ach, peak, unit = work / avg_s / 1e9, pk["hbm"], "GB/s"
             kernels.append({"kernel": KCLASS.get(cls, "other"), "shape": [M, N, K], "launches": cnt, "avg_us": round(ms / cnt * 1e3, 2),
                             "share": round(ms / prof_total_ms, 4) if prof_total_ms else None, "bound": bound,
-                            "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4)})
+                            "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4), **extra})
         top = kernels[0] if kernels else None
         roofline = None
         if top:
@@ -500,9 +516,14 @@ def main():
             roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
                         "traffic": tr_warm, "traffic_cold_cache": tr_cold, "traffic_source": tr_src,
                         "kernel": top["kernel"], "shape_MNK": top["shape"], "avg_us": top["avg_us"],
-                        "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy)"),
+                        "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy bandwidth)"),
                         "note": "avg_us is a per-launch CUDA-event pair in an eager step (adds ~4 us to every launch); traffic = dram bytes of one "
-                                "ncu --set full launch in steady state (operands L2-resident), traffic_cold_cache = same kernel after an L2 flush"}
+                                "ncu --set full launch in steady state (operands L2-resident), traffic_cold_cache = same kernel after an L2 flush; "
+                                "GEMMs: bound = the roofline with the longer time bound at this shape (flop_per_byte vs machine balance), "
+                                "tensor_frac / hbm_frac give both"}
+            for k in ("flop_per_byte", "tensor_frac", "hbm_frac"):
+                if k in top:
+                    roofline[k] = top[k]
         cpu = None
         if world == 1 and args.cpu_iters > 0:
             sps, sec = cpu_oracle_samples_per_s(args.recon, args.cpu_iters)

@@ -96,3 +96,38 @@ def test_config5_msrvtt_two_layer_decoder_local_reconstructor_against_oracle(pre
     worst = max(errs, key=errs.get)
     print(f"[variants] config5 {precision}: worst rel err {errs[worst]:.3e} ({worst})")
     assert errs[worst] < tol, (worst, errs[worst])
+
+
+def test_real_data_adapter_feeds_the_sequence_drivers(tmp_path):
+    """data.CaptionFeatureDataset -> collate -> PinnedBatchFeeder (pinned host -> device, double buffered) -> forward_decoder /
+    forward_local_reconstructor: the shapes and value conventions the adapter produces are the ones the hot path takes."""
+    import json
+    import os
+    import numpy as np
+    from recnet_b200 import data as D
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_pipeline.json")))
+    csv = tmp_path / "captions.csv"
+    csv.write_text(gold["csv"], encoding="utf-8")
+    vocab = D.Vocabulary.from_csv(str(csv), min_count=1, caption_max_len=gold["caption_max_len"])
+    rs = np.random.RandomState(0)
+    feats = {"vidA_0_10": rs.rand(40, 64).astype(np.float32), "vidB_5_9": rs.rand(12, 64).astype(np.float32),
+             "vidC_1_2": rs.rand(28, 64).astype(np.float32), "vidD_3_8": rs.rand(100, 64).astype(np.float32)}
+    ds = D.CaptionFeatureDataset(feats, str(csv), vocab, n_frames=28)
+    B = 4
+    batches = [D.collate([ds[i] for i in range(k, min(k + B, len(ds)))], batch_size=B) for k in range(0, len(ds), B)]
+    assert len(batches) == 2 and batches[1][0][-1] == "PAD"
+    m = dict(B=B, T=28, E=64, H=32, A=16, EMB=20, V=vocab.n_vocabs, cap_len=gold["caption_max_len"], dec_layers=1, rec_layers=1,
+             dec_model="LSTM", rec_model="LSTM")
+    from tests.test_gpu_parity import configure
+    configure(m, "fp32", "local")
+    dec, rec = T.build_decoder(vocab.n_vocabs), T.build_reconstructor()
+    dec["model"].eval(); rec["model"].eval()
+    seen = 0
+    for (f_dev, t_dev), (_, f_host, t_host) in zip(D.PinnedBatchFeeder(batches, dev()), batches):
+        assert f_dev.is_cuda and torch.equal(f_dev.cpu(), f_host) and torch.equal(t_dev.cpu(), t_host)
+        loss, hiddens, _ = T.forward_decoder(dec, f_dev, t_dev, t_dev > 0, 1.0)
+        rloss = T.forward_local_reconstructor(hiddens, f_dev, rec)
+        (loss + rloss).backward()
+        assert bool(torch.isfinite(loss)) and bool(torch.isfinite(rloss)) and hiddens.shape[2:] == (B, 32)
+        seen += 1
+    assert seen == 2

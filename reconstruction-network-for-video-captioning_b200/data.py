@@ -217,8 +217,11 @@ class PinnedBatchFeeder:
         k = self.k
         if self.slots[k] is None:
             raise StopIteration
-        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[k])
         feats, targets = self.slots[k][0], self.slots[k][1]
+        feats.record_stream(cur)                       # allocated on the copy stream, consumed on the compute stream
+        targets.record_stream(cur)
         self.k = k ^ 1
         self._issue(self.k)
         return feats, targets

@@ -113,9 +113,9 @@ def test_real_data_adapter_feeds_the_sequence_drivers(tmp_path):
     feats = {"vidA_0_10": rs.rand(40, 64).astype(np.float32), "vidB_5_9": rs.rand(12, 64).astype(np.float32),
              "vidC_1_2": rs.rand(28, 64).astype(np.float32), "vidD_3_8": rs.rand(100, 64).astype(np.float32)}
     ds = D.CaptionFeatureDataset(feats, str(csv), vocab, n_frames=28)
-    B = 4
+    B = 3                                             # 8 (clip, caption) pairs -> batches of 3, 3 and 2 (+ 1 padded copy)
     batches = [D.collate([ds[i] for i in range(k, min(k + B, len(ds)))], batch_size=B) for k in range(0, len(ds), B)]
-    assert len(batches) == 2 and batches[1][0][-1] == "PAD"
+    assert len(ds) == 8 and len(batches) == 3 and batches[2][0][-1] == "PAD"
     m = dict(B=B, T=28, E=64, H=32, A=16, EMB=20, V=vocab.n_vocabs, cap_len=gold["caption_max_len"], dec_layers=1, rec_layers=1,
              dec_model="LSTM", rec_model="LSTM")
     from tests.test_gpu_parity import configure
@@ -130,4 +130,4 @@ def test_real_data_adapter_feeds_the_sequence_drivers(tmp_path):
         (loss + rloss).backward()
         assert bool(torch.isfinite(loss)) and bool(torch.isfinite(rloss)) and hiddens.shape[2:] == (B, 32)
         seen += 1
-    assert seen == 2
+    assert seen == 3

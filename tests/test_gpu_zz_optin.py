@@ -1,0 +1,25 @@
+"""The measured-slower experiments stay in the tree as opt-in switches (profiles/r1_g_nodes.md, r1_g_side_stream.md); this keeps them
+parity-green: the golden-fixture and shape-variant parity tests are re-run in a child process with the switches on (they are read
+once per process, hence the subprocess).  Runs last (file name) so that a regression here cannot hide the default path's results."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SELECT = "test_losses_hiddens_grads_match_reference_golden or test_shape_variants_against_oracle or cuda_graph"
+
+
+@pytest.mark.parametrize("switches", [
+    {"RECNET_SIDE": "1", "RECNET_FUSED_QUERY": "1"},                        # second stream around the loops + query projection in the cell kernel
+    {"RECNET_STAGE_MULTI": "0", "RECNET_GEMM_COSTMODEL": "1", "RECNET_OPTIMIZER": "torch"},   # r1_f staging / planner / optimiser
+], ids=["side+fused_query", "r1_f_paths"])
+def test_opt_in_paths_stay_parity_green(switches):
+    env = dict(os.environ, **switches)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", SELECT], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and " failed" not in r.stdout, tail

@@ -119,7 +119,32 @@ def _flat_grads(params) -> (torch.Tensor, List[torch.Tensor], torch.Tensor):
     tab = _table_for(params)
     flat = torch.empty(tab.total, dtype=torch.float32, device=params[0].device)
     views = [flat[o: o + p.numel()].view_as(p) for o, p in zip(tab.offsets, params)]
+    key = tuple(p.data_ptr() for p in params)
+    _last_flat.pop(key, None)
+    _last_flat[key] = flat                                          # see flat_buffer_of(); newest last
+    while len(_last_flat) > 8:                                      # a process trains a handful of modules; do not pin old buffers
+        _last_flat.pop(next(iter(_last_flat)))
     return flat, views, tab.offset_bytes + flat.data_ptr()
+
+
+# The newest flat gradient buffer per parameter list.  autograd stores the views it is handed DETACHED (``p.grad._base`` is
+# None although the memory is still the flat buffer's), so whoever wants the contiguous buffer back -- the data-parallel reducer,
+# to send one all-reduce per module instead of one per tensor -- asks here.  Holding the reference also keeps the buffer from
+# being recycled while the optimiser still reads its views.
+_last_flat: Dict[tuple, torch.Tensor] = {}
+
+
+def flat_buffer_of(grads: Sequence[torch.Tensor]):
+    """The flat buffer of the most recent backward that contains every tensor of ``grads`` (all of them, each entirely), or None."""
+    if not grads:
+        return None
+    for flat in _last_flat.values():
+        if flat.device != grads[0].device or flat.dtype != grads[0].dtype:
+            continue
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+        if all(g.is_contiguous() and lo <= g.data_ptr() and g.data_ptr() + g.numel() * g.element_size() <= hi for g in grads):
+            return flat
+    return None
 
 
 def _norms_bwd_into(params, sumsq, g_reg, gptrs, accumulate: bool, lambda_dev=None):

@@ -74,7 +74,7 @@ class ClipAdam(torch.optim.Optimizer):
         # Address table = per-gradient byte offsets from the lowest address (built on the host once per layout) + that address
         # (a device-side add, legal under CUDA-graph capture).  The sequence Functions hand autograd views of ONE flat buffer
         # with a fixed layout, so after the first eager step every later step -- captured or not -- reuses the offset table.
-        # (autograd detaches what it stores in .grad, so ``_base`` is not available to recognise the flat buffer.)
+        # (Addresses rather than ``g._base`` identity: the flat buffer's Python object is gone once backward has returned.)
         ptrs = [g.data_ptr() for g in grads]
         b0 = min(ptrs)
         rel = tuple(q - b0 for q in ptrs)

@@ -34,6 +34,11 @@ class GradAllReducer:
         self.modules = list(modules)
         self.bytes_last = 0
         self.overlap = os.environ.get("RECNET_DP_OVERLAP", "0") == "1"
+        # autograd stores gradient views detached (``p.grad._base`` is None), so by default each module's gradients go out as one
+        # all-reduce per parameter tensor inside ONE NCCL group (21 tensors for decoder + local reconstructor).  RECNET_DP_FLAT=1
+        # looks the contiguous buffer up in functional.flat_buffer_of() and sends one all-reduce per module (2 in the group);
+        # CPU-tested over gloo, not yet measured on NVLink -> opt-in.
+        self.flat_lookup = os.environ.get("RECNET_DP_FLAT", "0") == "1"
         self.force = os.environ.get("RECNET_DP_SELF") == "1" and dist.is_initialized()    # probe: run the collective even with one rank
         # opt-in: raw NCCL communicator driven on the CURRENT stream through libnccl's C API (no ProcessGroup work objects, no side
         # stream, no fork/join in a captured graph).  Probe (1 x B200, 1-rank group, collective captured in the step graph,
@@ -86,9 +91,12 @@ class GradAllReducer:
         for mi, m in enumerate(self.modules):
             if self._fired.get(mi) is None:
                 grads = [p.grad for p in m.parameters() if p.grad is not None]
-                bases = {id(g._base): g._base for g in grads if g._base is not None}
-                if len(bases) == 1 and all(g._base is not None for g in grads):
-                    late.append(next(iter(bases.values())))          # still ONE flat buffer per module
+                flat = _common_base(grads)
+                if flat is None and self.flat_lookup:
+                    from .functional import flat_buffer_of
+                    flat = flat_buffer_of(grads)
+                if flat is not None:
+                    late.append(flat)                                # ONE flat buffer per module
                 else:
                     late.extend(grads)
         if late and self.symm and self.backend == "nccl" and all(b.dtype == torch.float32 for b in late):
@@ -200,6 +208,21 @@ class GradAllReducer:
         for h in self._handles:
             h.remove()
         self._handles = []
+
+
+def _common_base(grads):
+    """The tensor all ``grads`` are views of, or None (compared by storage address and size).  Gradients that went through
+    autograd's AccumulateGrad are stored detached, so this only recognises views that were assigned to ``.grad`` by hand."""
+    if not grads:
+        return None
+    bases = [g._base for g in grads]
+    if any(b is None for b in bases):
+        return None
+    b0 = bases[0]
+    key = (b0.data_ptr(), b0.numel(), b0.dtype)
+    if any((b.data_ptr(), b.numel(), b.dtype) != key for b in bases[1:]):
+        return None
+    return b0 if b0.is_contiguous() else None
 
 
 def broadcast_parameters(modules: Sequence[torch.nn.Module], src: int = 0, group=None):

@@ -105,8 +105,8 @@ def _gloo_worker(rank, world, port, out):
     m = torch.nn.Linear(4, 3)
     red = GradAllReducer([m])
     red.start_iteration()
-    # emulate what the sequence Functions do: all gradients of the module are views of ONE flat buffer
-    flat = torch.arange(15, dtype=torch.float32) * (rank + 1)
+    # emulate what the sequence Functions do: all gradients of the module are views of ONE flat buffer that is created INSIDE
+    # backward and referenced by nothing but its views afterwards (every later `.grad._base` is then a fresh Python wrapper)
 
     class Fn(torch.autograd.Function):
         @staticmethod
@@ -115,13 +115,42 @@ def _gloo_worker(rank, world, port, out):
 
         @staticmethod
         def backward(ctx, g):
+            flat = torch.arange(15, dtype=torch.float32) * (rank + 1)
             return flat[:12].view(3, 4), flat[12:15]
 
     Fn.apply(m.weight, m.bias).backward()
     red.wait()
     expect = torch.arange(15, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     ok = torch.allclose(m.weight.grad.flatten(), expect[:12]) and torch.allclose(m.bias.grad, expect[12:])
-    ok = ok and red.bytes_last == 15 * 4                                     # ONE all-reduce of the flat buffer
+    ok = ok and red.bytes_last == 15 * 4
+    # gradients written into ONE flat buffer by a sequence Function (functional._flat_grads): autograd stores the views detached,
+    # RECNET_DP_FLAT=1 finds the buffer again and sends ONE all-reduce for the module (padding included), default = one per tensor
+    from recnet_b200 import functional as RF
+    for flat_on in (True, False):
+        m3 = torch.nn.Linear(4, 3)
+        red3 = GradAllReducer([m3]); red3.flat_lookup = flat_on; red3.start_iteration()
+
+        class SeqFn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, w, b):
+                ctx.save_for_backward(w, b)
+                return (w.sum() + b.sum()) * 0
+
+            @staticmethod
+            def backward(ctx, g):
+                flat, views, _ = RF._flat_grads(ctx.saved_tensors)
+                flat.fill_(float("nan"))                                     # padding between the views: must not matter
+                views[0].copy_(torch.arange(12, dtype=torch.float32).view(3, 4) * (rank + 1))
+                views[1].copy_(torch.arange(3, dtype=torch.float32) * (rank + 1))
+                return tuple(views)
+
+        SeqFn.apply(m3.weight, m3.bias).backward()
+        assert m3.weight.grad._base is None                                  # what autograd does to the views it is handed
+        red3.wait()
+        scale = sum(range(1, world + 1)) / world
+        ok = ok and torch.allclose(m3.weight.grad, torch.arange(12, dtype=torch.float32).view(3, 4) * scale)
+        ok = ok and torch.allclose(m3.bias.grad, torch.arange(3, dtype=torch.float32) * scale)
+        ok = ok and red3.bytes_last == ((64 + 64) * 4 if flat_on else 15 * 4)
     # per-tensor fallback when grads are not flat views
     m2 = torch.nn.Linear(2, 2)
     red2 = GradAllReducer([m2]); red2.start_iteration()

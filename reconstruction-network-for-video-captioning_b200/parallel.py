@@ -4,9 +4,10 @@ all-reduce (average) per iteration over NCCL / NVLink.
 The reference has no distributed code at all.  The path shards cleanly: samples are independent through both
 loops, only parameter gradients couple the replicas, so the only collective is the gradient all-reduce.
 
-Every sequence Function writes its module's gradients into one flat buffer (functional.py); after backward the two
-buffers (61 MB local reconstructor + 38 MB decoder, fp32) go out as ONE fused NCCL group (ncclGroupStart/End), i.e.
-one rank synchronisation per step, then clip + Adam.  Measured on 2 x B200 (profiles/r1_d_dp.md): fused, after
+Every sequence Function writes its module's gradients into one flat buffer (functional.py); after backward the gradients
+(61 MB local reconstructor + 38 MB decoder, fp32) go out as ONE fused NCCL group (ncclGroupStart/End), i.e. one rank
+synchronisation per step, then clip + Adam.  autograd stores the views detached, so the group carries one all-reduce per
+parameter tensor unless RECNET_DP_FLAT=1 recovers the two flat buffers (functional.flat_buffer_of).  Measured on 2 x B200 (profiles/r1_d_dp.md): fused, after
 backward 4.67 ms/step; per-module all-reduces launched from grad hooks to overlap the decoder BPTT 5.00 ms/step --
 the NCCL CTAs slow the latency-bound BPTT chain as much as they hide, and a second collective is a second rank
 sync -- so overlap is opt-in (RECNET_DP_OVERLAP=1).

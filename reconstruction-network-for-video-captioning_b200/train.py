@@ -37,14 +37,13 @@ def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_for
     """train.py:17-75.  Returns (loss, hiddens (L,NL,B,H), output_indices).
     ``target_masks`` is ``targets > <PAD>`` as the reference builds it (train.py:246); it may be None when ``n_steps`` is given.
     ``n_steps``: optional static loop length (skips the host read; needed under CUDA-graph capture)."""
-    if target_masks is None:
-        if n_steps is None or not targets.is_cuda:
-            target_masks = targets > C.init_word2idx['<PAD>']
+    pad, sos_id = C.init_word2idx['<PAD>'], C.init_word2idx['<SOS>']
+    if target_masks is None and n_steps is None:
+        target_masks = targets > pad                               # the host-side loop length needs it
     model = decoder['model']
     L = n_steps if n_steps is not None else _num_steps(target_masks, C.caption_max_len)
     B = encoder_outputs.shape[0]
     dev = encoder_outputs.device
-    pad, sos_id = C.init_word2idx['<PAD>'], C.init_word2idx['<SOS>']
     use_teacher_forcing = random.random() <= teacher_forcing_ratio                                          # train.py:38
     output_indices = torch.empty(0, dtype=torch.long)
     if use_teacher_forcing and targets.is_cuda:

@@ -242,3 +242,26 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "decoder + local reconstructor" in d["config"]["workload"]
+
+
+def test_bench_roofline_work_formulas():
+    """bench.py's algorithmic-work helpers: GEMM flops count useful rows only, GEMM bytes are operands once +
+    result once, and a skinny per-step GEMM sits below the machine balance (so its binding roofline is bytes, not the tensor pipe)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    bound, flops = bench.algorithmic_work(1, 100, 6144, 2048, 2)
+    assert bound == "tensor" and flops == 2.0 * 100 * 6144 * 2048
+    nbytes = bench.gemm_bytes(100, 6144, 2048, 2)
+    assert nbytes == (100 * 2048 + 6144 * 2048) * 2 + 100 * 6144 * 4
+    pk = bench.peaks()
+    balance = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
+    assert flops / nbytes < balance                                   # per-step gate GEMM: memory-bound
+    big = bench.algorithmic_work(1, 6144, 1536, 2800, 2)[1] / bench.gemm_bytes(6144, 1536, 2800, 2)
+    assert big > balance                                              # batched weight-gradient GEMM: tensor-bound
+    for cls in (3, 4, 5, 6, 7, 8, 10, 11):
+        b, work = bench.algorithmic_work(cls, 100, 28, 512, 2)
+        assert b == "hbm" and work > 0
+    assert set(bench.KCLASS) >= {1, 3, 4, 5, 6, 10, 11}

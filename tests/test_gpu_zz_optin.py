@@ -23,3 +23,15 @@ def test_opt_in_paths_stay_parity_green(switches):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and " failed" not in r.stdout, tail
+
+
+@pytest.mark.skipif(os.environ.get("RECNET_TEST_EXPERIMENTAL") != "1",
+                    reason="cluster-resident decoder loop (csrc/seq_decoder_cluster.cuh) was written after the round's GPU budget was "
+                           "spent: compiles, never run; set RECNET_TEST_EXPERIMENTAL=1 to try it")
+def test_experimental_cluster_resident_decoder_loop_full_size_parity():
+    """RECNET_DEC_CLUSTER=1 at the MSVD shape (H = 512, A = 128, B = 100: the shape the kernel is written for), bf16, against the oracle."""
+    env = dict(os.environ, RECNET_DEC_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", "test_full_size_parity_against_oracle and bf16"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]

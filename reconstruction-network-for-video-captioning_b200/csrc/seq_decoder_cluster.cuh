@@ -134,55 +134,68 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_fwd_cluster_kernel(Args a)
     __syncthreads();
     cluster.sync();                                          // #2: scores of every sample are in their owner CTA's es
 
-    // ---- P3: context + cell for (samples warp, warp + 8) x (unit j)
+    // ---- P3: context + cell for (samples warp, warp + 8) x (unit j).  Latency-bound like pf_fwd_kernel, so the loads of BOTH samples
+    // are issued unconditionally on clamped indices, 16 frames per sample in flight (32 x 8-byte loads per lane), before any use.
+    {
+      const int s0 = warp, s1 = warp + 8;
+      const bool ok0 = s0 < nb, ok1 = s1 < nb;                 // warp-uniform
+      const int c0 = min(s0, nb - 1), c1 = min(s1, nb - 1);
+      const float* res0 = cluster.map_shared_rank(es, c0);     // scores of sample s live in CTA s
+      const float* res1 = cluster.map_shared_rank(es, c1);
+      const bf16* vw0 = a.VW + ((size_t)(b0 + c0) * Tn * H + j) * 4;
+      const bf16* vw1 = a.VW + ((size_t)(b0 + c1) * Tn * H + j) * 4;
+      float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int tau0 = 0; tau0 < Tn; tau0 += 16) {
+        pf::Quad<bf16> v0[16], v1[16];
+        float e0[16], e1[16];
 #pragma unroll
-    for (int sidx = 0; sidx < 2; ++sidx) {
-      const int s = warp + 8 * sidx;
-      if (s < nb) {                                          // warp-uniform
-        const int b = b0 + s;
-        const float* res = cluster.map_shared_rank(es, s);   // scores of sample s live in CTA s
-        const bf16* vw = a.VW + ((size_t)b * Tn * H + j) * 4;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int tau0 = 0; tau0 < Tn; tau0 += 8) {
-          pf::Quad<bf16> v[8];
-          float ev[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int tau = min(tau0 + k, Tn - 1);
-            v[k].load(vw + (size_t)tau * 4 * H);
-            ev[k] = tau0 + k < Tn ? res[tau] : 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float f[4];
-            v[k].get(f);
-#pragma unroll
-            for (int gg = 0; gg < 4; ++gg) acc[gg] = fmaf(ev[k], f[gg], acc[gg]);
-          }
+        for (int k = 0; k < 16; ++k) {
+          const int tau = min(tau0 + k, Tn - 1);
+          v0[k].load(vw0 + (size_t)tau * 4 * H);
+          v1[k].load(vw1 + (size_t)tau * 4 * H);
+          e0[k] = res0[tau];
+          e1[k] = res1[tau];
         }
-        const float* gx = a.Gx + ((size_t)t * B + b) * 4 * H + j;
-        float pre[4];
 #pragma unroll
-        for (int gg = 0; gg < 4; ++gg)
-          pre[gg] = gx[gg * H] + a.b_hh[gg * H + j] + og[s * NR + APC + gg * UPC + lane] + acc[gg] * a.inv_T;
-        const float gi = act_sigmoid<true>(pre[0]), gf = act_sigmoid<true>(pre[1]), gt = act_tanh<true>(pre[2]), go = act_sigmoid<true>(pre[3]);
-        const float cn = fmaf(gf, cstate[sidx], gi * gt);
-        const float hn = go * act_tanh<true>(cn);
-        cstate[sidx] = cn;
-        const size_t o1 = ((size_t)t * B + b) * H + j;
-        a.c[o1 + (size_t)B * H] = cn;                        // row block t + 1
-        a.hiddens[o1] = hn;
-        const bf16 hb = __float2bfloat16_rn(hn);
-        a.Hop[o1 + (size_t)B * H] = hb;
-        pf::Quad<bf16>::store(a.gates + o1 * 4, gi, gf, gt, go);
-        // h_t (operand type) into every CTA's operand rows: pairs of units packed by lane pairs, one 4-byte DSMEM store each
-        const uint32_t lo = (uint32_t)__bfloat16_as_ushort(hb);
-        const uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
-        if (!(lane & 1)) {
-          const uint32_t packed = lo | (hi << 16);
-          for (int dst = 0; dst < CS; ++dst) {
-            bf16* rhs = cluster.map_shared_rank(hs, dst);
-            *reinterpret_cast<uint32_t*>(rhs + (size_t)s * pitch + j) = packed;
+        for (int k = 0; k < 16; ++k) {
+          const float w0 = tau0 + k < Tn ? e0[k] : 0.f, w1 = tau0 + k < Tn ? e1[k] : 0.f;
+          float f0[4], f1[4];
+          v0[k].get(f0);
+          v1[k].get(f1);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) { acc0[gg] = fmaf(w0, f0[gg], acc0[gg]); acc1[gg] = fmaf(w1, f1[gg], acc1[gg]); }
+        }
+      }
+#pragma unroll
+      for (int sidx = 0; sidx < 2; ++sidx) {
+        const int s = sidx ? s1 : s0;
+        if (sidx ? ok1 : ok0) {                                // warp-uniform
+          const int b = b0 + s;
+          const float* acc = sidx ? acc1 : acc0;
+          const float* gx = a.Gx + ((size_t)t * B + b) * 4 * H + j;
+          float pre[4];
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg)
+            pre[gg] = gx[gg * H] + a.b_hh[gg * H + j] + og[s * NR + APC + gg * UPC + lane] + acc[gg] * a.inv_T;
+          const float gi = act_sigmoid<true>(pre[0]), gf = act_sigmoid<true>(pre[1]), gt = act_tanh<true>(pre[2]), go = act_sigmoid<true>(pre[3]);
+          const float cn = fmaf(gf, cstate[sidx], gi * gt);
+          const float hn = go * act_tanh<true>(cn);
+          cstate[sidx] = cn;
+          const size_t o1 = ((size_t)t * B + b) * H + j;
+          a.c[o1 + (size_t)B * H] = cn;                        // row block t + 1
+          a.hiddens[o1] = hn;
+          const bf16 hb = __float2bfloat16_rn(hn);
+          a.Hop[o1 + (size_t)B * H] = hb;
+          pf::Quad<bf16>::store(a.gates + o1 * 4, gi, gf, gt, go);
+          // h_t (operand type) into every CTA's operand rows: pairs of units packed by lane pairs, one 4-byte DSMEM store each
+          const uint32_t lo = (uint32_t)__bfloat16_as_ushort(hb);
+          const uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
+          if (!(lane & 1)) {
+            const uint32_t packed = lo | (hi << 16);
+            for (int dst = 0; dst < CS; ++dst) {
+              bf16* rhs = cluster.map_shared_rank(hs, dst);
+              *reinterpret_cast<uint32_t*>(rhs + (size_t)s * pitch + j) = packed;
+            }
           }
         }
       }

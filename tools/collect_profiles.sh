@@ -8,9 +8,9 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 SMI=$!
 timeout 400 python bench.py > $O/bench.json 2> $O/bench.err
 kill $SMI
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 420 --csv --log-file $O/launches_cold.csv $CMD > $O/l1.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 1700 -c 420 --csv --log-file $O/launches_warm.csv $CMD > $O/l2.log 2>&1
-for k in pf_fwd_kernel pf_bwd_kernel lean_fwd_kernel lean_bwd_kernel lstm_cell_fwd_kernel lstm_cell_bwd_kernel; do
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 1650 -c 440 --csv --log-file $O/launches_cold.csv $CMD > $O/l1.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 1650 -c 440 --csv --log-file $O/launches_warm.csv $CMD > $O/l2.log 2>&1
+for k in pf_fwd_kernel pf_bwd_kernel lean_fwd_kernel lean_bwd_kernel lstm_cell_fwd_kernel lstm_cell_bwd_kernel adam_mt_kernel stage_multi_kernel; do
   timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:$k -s 12 -c 1 -f -o $O/$k $CMD > $O/$k.log 2>&1
 done
 # the per-step gate GEMM of the local reconstructor ([100 x 2048] x [2048 x 6144]): warm and cold

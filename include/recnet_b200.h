@@ -262,6 +262,17 @@ int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const 
                      double eps, double weight_decay, double max_grad_norm, float* partial, float* state,
                      int write_clipped_grads, void* stream);
 
+/* EXPERIMENTAL (opt-in, not yet run on a GPU): recnet_adam_step that also forms the gradient of the L2-norm regulariser
+ * (train.py:69,101,127) inside the optimiser pass, g_total = g + reg_g[0] * reg_lambda[0] * p / sqrt(reg_sumsq[reg_index[t]]),
+ * clip norm taken over g_total -- replaces recnet_param_norms_bwd's read-modify-write of every gradient.  reg_sumsq: the squared
+ * norms recnet_param_norms_fwd left; reg_index [n] int32 maps optimiser tensor t to its slot there (NULL = identity). */
+int recnet_adam_step_reg(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs,
+                         const int64_t* exp_avg_sq_ptrs, const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n,
+                         const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2,
+                         double eps, double weight_decay, double max_grad_norm, float* partial, float* state,
+                         int write_clipped_grads, const float* reg_sumsq, const int32_t* reg_index, const float* reg_g,
+                         const float* reg_lambda, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

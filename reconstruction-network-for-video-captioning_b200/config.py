@@ -22,6 +22,8 @@ class TrainConfig:
     optimizer_impl = "recnet"        # "recnet": optim.ClipAdam (own fused clip + Adam kernels, measured 21 us/step faster);
     #                                  "torch": torch.optim.Adam(fused, capturable) + clip_grad_norm_.  RECNET_OPTIMIZER overrides.
 
+    defer_regulariser = False        # EXPERIMENTAL (never run on a GPU yet): regulariser gradient formed inside optim.ClipAdam's pass
+
     # --- batch / vocabulary (config.py:48-56) ---
     min_count = 5
     caption_max_len = 30

@@ -402,4 +402,17 @@ int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const 
                           blk_tensor, blk_chunk, n_blocks, lr, beta1, beta2, eps, weight_decay, max_grad_norm, partial, state,
                           write_clipped_grads, ST(stream));
 }
+// EXPERIMENTAL (opt-in, see optim.cuh): Adam step that also forms the norm regulariser's gradient k_t p from the forward's squared norms
+int recnet_adam_step_reg(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs, const int64_t* exp_avg_sq_ptrs,
+                         const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
+                         const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2, double eps, double weight_decay,
+                         double max_grad_norm, float* partial, float* state, int write_clipped_grads, const float* reg_sumsq,
+                         const int32_t* reg_index, const float* reg_g, const float* reg_lambda, void* stream) {
+  typedef const long long* LP;
+  optim::RegTerm r{reg_sumsq, reg_index, reg_g, reg_lambda};
+  return optim::adam_step_reg(reinterpret_cast<LP>(param_ptrs), reinterpret_cast<LP>(grad_ptrs), reinterpret_cast<LP>(exp_avg_ptrs),
+                              reinterpret_cast<LP>(exp_avg_sq_ptrs), reinterpret_cast<LP>(max_exp_avg_sq_ptrs), reinterpret_cast<LP>(sizes),
+                              n, blk_tensor, blk_chunk, n_blocks, lr, beta1, beta2, eps, weight_decay, max_grad_norm, partial, state,
+                              write_clipped_grads, r, ST(stream));
+}
 }  // extern "C"

@@ -143,7 +143,7 @@ class Decoder(nn.Module, _RngMixin):
         return self.n_layers == 1
 
     # ---- whole teacher-forced loop ----
-    def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs, lambda_reg=None):
+    def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs, lambda_reg=None, defer_reg=False):
         """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,NL,B,H), reg = sum_p ||p||).
         With ``lambda_reg`` (the module dict's device scalar) output 0 is the assembled loss ce + lambda_reg * reg (train.py:70),
         computed inside the regulariser kernel; reg is then returned for inspection only."""
@@ -152,6 +152,7 @@ class Decoder(nn.Module, _RngMixin):
             return (ce if lambda_reg is None else ce + lambda_reg * reg), hiddens, reg
         meta = self._meta()
         meta["lambda_reg"] = lambda_reg
+        meta["defer_reg"] = defer_reg             # experimental: regulariser gradient formed by optim.ClipAdam (functional._defer_reg)
         return Fn.DecoderSequenceFn.apply(meta, encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(), *self._params())
 
     def _forward_sequence_stepwise(self, tokens_in, targets, ce_weight, encoder_outputs):
@@ -287,7 +288,7 @@ class GlobalReconstructor(_ReconstructorBase):
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
         return (w_ih, w_hh, b_ih, b_hh, self.out.weight, self.out.bias)
 
-    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None):
+    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None, defer_reg=False):
         """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||).
         With ``lambda_reg`` output 0 is the assembled loss (train.py:100-102)."""
         if not self._fused_ok(decoder_hiddens):
@@ -295,6 +296,7 @@ class GlobalReconstructor(_ReconstructorBase):
             return (loss if lambda_reg is None else loss + lambda_reg * reg), reg
         hid = _sequence_hiddens(decoder_hiddens)
         meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p, lambda_reg=lambda_reg,
+                    defer_reg=defer_reg,
                     caption_max_len=self.caption_max_len, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.GlobalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
@@ -350,7 +352,7 @@ class LocalReconstructor(_ReconstructorBase):
         return (self.attn_W.weight, self.attn_U.weight, self.attn_b, self.attn_w.weight, w_ih, w_hh, b_ih, b_hh,
                 self.out.weight, self.out.bias)
 
-    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None):
+    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None, defer_reg=False):
         """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||).
         With ``lambda_reg`` output 0 is the assembled loss (train.py:128-130)."""
         if not self._fused_ok(decoder_hiddens):
@@ -358,6 +360,7 @@ class LocalReconstructor(_ReconstructorBase):
             return (loss if lambda_reg is None else loss + lambda_reg * reg), reg
         hid = _sequence_hiddens(decoder_hiddens)
         meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training, lambda_reg=lambda_reg,
+                    defer_reg=defer_reg,
                     p_drop=self.decoder_dropout_p, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.LocalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 

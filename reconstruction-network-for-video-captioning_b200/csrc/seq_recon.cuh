@@ -9,6 +9,7 @@
 #include "gru_cell.cuh"
 #include "mega.cuh"
 #include "runtime.cuh"
+#include "seq_recon_persist.cuh"
 
 namespace rec {
 using namespace rt;
@@ -27,9 +28,17 @@ struct LocalWs {
   float* dx; float* splitk; float* splitk2;        // splitk2: scratch of the side stream (runtime.cuh:Side)
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
   T* Hout; T* Hq;                 // stacked decoder only: compact rows of h after pseudo-step (t,0) / at the start of outer step t
+  float* pXP; float* pWhP; unsigned* psync;      // weight-resident persistent loop (seq_recon_persist.cuh): partial exchange + flags
   size_t bytes;
 };
 constexpr int MSE_BLOCKS = 592;
+
+// the weight-resident persistent forward loop covers: bf16, LSTM over a 1-layer decoder, shapes whose [W_ih | W_hh] fits the SMs' shared memory
+template <typename T>
+static inline bool persist_fwd_ok(const recnet_local_desc& d) {
+  if (!std::is_same<T, bf16>::value || d.cell != RECNET_CELL_LSTM || d.dec_layers > 1 || num_chains(d.B) != 1) return false;
+  return rp::local_fwd_ok(rp::Shape{d.B, d.S, d.R, d.H, d.A, d.L});
+}
 
 template <typename T>
 static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
@@ -94,6 +103,11 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.err = m.take<int>(64);
   w.Hout = m.take<T>(NLd > 1 ? (size_t)d.S * B * R : 1);
   w.Hq = m.take<T>(NLd > 1 ? (size_t)d.S * B * R : 1);
+  const bool pers = persist_fwd_ok<T>(d);
+  const rp::Shape shp{d.B, d.S, d.R, d.H, d.A, d.L};
+  w.pXP = m.take<float>(pers ? rp::xp_floats(shp) : 1);
+  w.pWhP = m.take<float>(pers ? rp::whp_floats(shp) : 1);
+  w.psync = m.take<unsigned>(rp::SYNC_WORDS);
   w.bytes = m.off + 256;
   return w;
 }
@@ -138,8 +152,29 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   sg.zero(w.X, (size_t)B * w.KX * sizeof(T));
   sg.zero(w.c, (size_t)B * R * sizeof(float));
   sg.zero(w.err, 64 * sizeof(int));
+  const bool persist = persist_fwd_ok<T>(d);
+  if (persist) sg.zero(w.psync, rp::SYNC_WORDS * sizeof(unsigned));
   RN_TRY(sg.launch(st));
   RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (persist) {
+      // ONE cooperative launch for all S steps, [W_ih | W_hh] resident in shared memory (seq_recon_persist.cuh); same stash layout
+      rp::FwdParams fp{};
+      fp.B = B; fp.S = S; fp.R = R; fp.H = H; fp.A = A; fp.L = L; fp.inv_L = 1.f / L; fp.p_drop = p_drop;
+      fp.X = w.X; fp.Hd = w.Hd; fp.Uv = w.Uv; fp.Wa = w.Wa; fp.attn_b = p.attn_b; fp.attn_w = p.attn_w; fp.b_ih = p.b_ih; fp.b_hh = p.b_hh;
+      fp.Wh = w.Wh; fp.beta = w.beta; fp.gates = w.gates; fp.c = w.c; fp.XP = w.pXP; fp.WhP = w.pWhP; fp.sync = w.psync; fp.err = w.err;
+      fp.rng = rng; fp.site = SITE_LOCAL_X;
+      RN_TRY(rp::launch_local_fwd(fp, w.Wrec, st));
+      RN_TRY(gemm_full<T>(w.X + (size_t)B * w.KX + H, w.KX, 0, w.Wout, R, 0, w.out, R, p.out_b, S * B, R, R, 0, w.splitk, st));
+      if (mse_out) {
+        loss::mse_local_fwd_kernel<<<MSE_BLOCKS, 256, 0, st>>>(w.out, feats, S, B, R, w.partial);
+        RN_LAUNCH_OK();
+        loss::sum_kernel<<<1, 1024, 0, st>>>(w.partial, MSE_BLOCKS, mse_out, 1.f / ((float)S * B * R));
+        RN_LAUNCH_OK();
+      }
+      return 0;
+    }
+  }
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);

@@ -39,6 +39,13 @@ static inline bool persist_fwd_ok(const recnet_local_desc& d) {
   if (!std::is_same<T, bf16>::value || d.cell != RECNET_CELL_LSTM || d.dec_layers > 1 || num_chains(d.B) != 1) return false;
   return rp::local_fwd_ok(rp::Shape{d.B, d.S, d.R, d.H, d.A, d.L});
 }
+template <typename T>
+static inline bool persist_bwd_ok(const recnet_local_desc& d) {
+  if (!std::is_same<T, bf16>::value || d.cell != RECNET_CELL_LSTM || d.dec_layers > 1 || num_chains(d.B) != 1) return false;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RECNET_PERSIST_BWD"); on = e ? atoi(e) : 1; }
+  return on && rp::local_bwd_ok(rp::Shape{d.B, d.S, d.R, d.H, d.A, d.L});
+}
 
 template <typename T>
 static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
@@ -105,9 +112,12 @@ static LocalWs<T> plan_local(const recnet_local_desc& d, void* base) {
   w.Hq = m.take<T>(NLd > 1 ? (size_t)d.S * B * R : 1);
   const bool pers = persist_fwd_ok<T>(d);
   const rp::Shape shp{d.B, d.S, d.R, d.H, d.A, d.L};
-  w.pXP = m.take<float>(pers ? rp::xp_floats(shp) : 1);
+  const bool persb = persist_bwd_ok<T>(d);
+  size_t xpn = pers ? rp::xp_floats(shp) : 1;                 // forward K-slice partials and backward gate-slice partials share the buffer
+  if (persb && rp::dp_floats(shp) > xpn) xpn = rp::dp_floats(shp);
+  w.pXP = m.take<float>(xpn);
   w.pWhP = m.take<float>(pers ? rp::whp_floats(shp) : 1);
-  w.psync = m.take<unsigned>(rp::SYNC_WORDS);
+  w.psync = m.take<unsigned>(2 * rp::SYNC_WORDS);              // forward flags | backward flags (both zeroed by the forward's staging kernel)
   w.bytes = m.off + 256;
   return w;
 }
@@ -153,7 +163,7 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
   sg.zero(w.c, (size_t)B * R * sizeof(float));
   sg.zero(w.err, 64 * sizeof(int));
   const bool persist = persist_fwd_ok<T>(d);
-  if (persist) sg.zero(w.psync, rp::SYNC_WORDS * sizeof(unsigned));
+  if (persist || persist_bwd_ok<T>(d)) sg.zero(w.psync, 2 * rp::SYNC_WORDS * sizeof(unsigned));
   RN_TRY(sg.launch(st));
   RN_TRY(gemm_full<T>(w.Hd, H, 0, w.U, H, 0, w.Uv, A, nullptr, L * B, A, H, 0, w.splitk, st));     // U.hiddens, once
   if constexpr (std::is_same<T, bf16>::value) {
@@ -262,8 +272,21 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   const bool is_gru = d.cell == RECNET_CELL_GRU;
   const int GR = w.G * R;
+  bool persist = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    persist = persist_bwd_ok<T>(d);
+    if (persist) {
+      // ONE cooperative launch for the whole BPTT loop, [W_ih | W_hh] resident in shared memory (seq_recon_persist.cuh)
+      rp::BwdParams bp{};
+      bp.B = B; bp.S = S; bp.R = R; bp.H = H; bp.A = A; bp.L = L; bp.inv_L = 1.f / L; bp.p_drop = p_drop;
+      bp.Hd = w.Hd; bp.Uv = w.Uv; bp.Wa = w.Wa; bp.attn_b = p.attn_b; bp.attn_w = p.attn_w; bp.Wh = w.Wh; bp.gates = w.gates; bp.c = w.c;
+      bp.dHext = w.dHext; bp.dG = w.dG; bp.dx = w.dx; bp.dWh = w.dWh; bp.dWh_op = w.dWh_op; bp.dUv = w.dUv; bp.dw_acc = w.dw_acc;
+      bp.DP = w.pXP; bp.sync = w.psync + rp::SYNC_WORDS; bp.err = w.err; bp.rng = rng; bp.site = SITE_LOCAL_X;
+      RN_TRY(rp::launch_local_bwd(bp, w.Wrec, st));
+    }
+  }
   mega::Emitter<T> em0(w.nch == 1 && !is_gru, st, (size_t)H + L + 8 * attn::BWD_THREADS + 2 * A);
-  for (int t = S - 1; t >= 0; --t) {
+  for (int t = S - 1; t >= 0 && !persist; --t) {
     const bool last = (t == S - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;

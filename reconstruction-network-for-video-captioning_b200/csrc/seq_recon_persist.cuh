@@ -573,7 +573,7 @@ static inline bool local_fwd_ok(const Shape& s) {
   const int ks = pick_ks(s.R, s.H);
   if (!ks) return false;
   const int UG = s.R / UNITS;
-  return s.A == 128 && s.B >= 1 && s.B <= 128 && s.B <= UG * ks && s.L >= 1 && s.L <= 32 && s.H <= 512 && UG <= MAX_UG && s.S >= 1 &&
+  return s.A == 128 && s.B >= ks && s.B <= 128 && s.B <= UG * ks && s.L >= 1 && s.L <= 32 && s.H <= 512 && UG <= MAX_UG && s.S >= 1 &&
          (s.B + ks - 1) / ks <= 4 * NWORK && smem_layout(s.B, ks).total <= 227 * 1024;
 }
 static inline size_t xp_floats(const Shape& s) { const int ks = pick_ks(s.R, s.H); return ks ? (size_t)(s.R / UNITS) * ks * s.B * NCOL : 4; }
@@ -610,5 +610,463 @@ static int launch_local_fwd(FwdParams p, const bf16* Wrec, cudaStream_t st) {
     case 4: return launch_ks<4>(mx, mw, p, st);
   }
   return RECNET_ERR_UNSUPPORTED;
+}
+// =====================================================================================================================
+// BPTT of the same loop, one cooperative launch for all S steps (mirrors local_fwd_kernel).
+//   per step t = S-1 .. 0 (reference: autograd of models/local_reconstructor.py:37-55):
+//     C  cell backward of (sample, unit) cells          -> dG_t (bf16 operand rows)                      [all CTAs, 12 warps]
+//        dh = dHext_t + dX_{t+1}[:, H + j] (sum of the NS K-slice partials) + dWh_{t+1} . W_a (mma.sync, W_a fragments in registers)
+//     G  dX_t = dG_t . [W_ih | W_hh]: CTA (cg, ns) keeps the 128 output columns cg x gate-row slice ns of the weight resident
+//        (MN-major A operand, <= 11 k-blocks = 176 KB) and leaves its fp32 partial in DP[cg][ns]             [TMA + tcgen05]
+//     A  attention backward of one sample: dctx = mask . sum_ns DP[x columns] -> d e -> dWh_t, dU.v, dw     [first B CTAs, 8 warps]
+//   three grid-wide flag waits per step (dG ready / partials ready / dWh ready); dU.v and dw accumulate in registers over
+//   all steps; V rows and U.v + b of the sample are parked in tensor memory.  Leaves dG, dx, dWh, dWh_op, dUv, dw_acc exactly
+//   as the kernel-per-phase path does, so the batched weight-gradient GEMMs after the loop run unchanged.
+struct BwdParams {
+  int B, S, R, H, A, L, KX, CG, NS, NB4, UG, KT;
+  float inv_L, p_drop;
+  const bf16* Hd; const float* Uv; const bf16* Wa;
+  const float *attn_b, *attn_w;
+  const float* Wh;                    // [S, B, A]
+  const bf16* gates;                  // [S*B, 4R]
+  const float* c;                     // [(S+1)*B, R]
+  const float* dHext;                 // [S*B, R]
+  bf16* dG;                           // [S*B, 4R]
+  float* dx;                          // [S, B, H]
+  float* dWh; bf16* dWh_op;           // [S, B, A]
+  float* dUv;                         // [L, B, A]
+  float* dw_acc;                      // [B, A]
+  float* DP;                          // [CG][NS][B][128]
+  unsigned* sync;                     // [0] dG ready, [32] partials ready, [64] dWh ready
+  int* err;
+  const unsigned long long* rng;
+  unsigned site;
+};
+constexpr int MAX_NS = 12;
+
+struct SmemB { int ring, wres, bars, dctx, red, total; };
+__host__ __device__ inline SmemB smem_layout_bwd(int B) {
+  SmemB s;
+  const int stage = ((B + 7) & ~7) * 128;
+  s.ring = 0;
+  s.wres = (STAGES * stage + 1023) & ~1023;
+  s.bars = s.wres + MAX_KB * WTILE;
+  s.dctx = s.bars + 128;                           // [512] floats
+  s.red = s.dctx + 512 * 4;                        // [8][128] floats
+  s.total = s.red + 8 * 128 * 4 + 1024;
+  return s;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmW, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const SmemB L_ = smem_layout_bwd(p.B);
+  const int stage_bytes = ((p.B + 7) & ~7) * 128;
+  const uint32_t ring = base + L_.ring, wres = base + L_.wres;
+  const uint32_t bar_full = base + L_.bars, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES, bar_w = bar_tmem + 8;
+  const uint32_t tmem_slot = bar_w + 8;
+  volatile int* abort_ = reinterpret_cast<volatile int*>(gen + L_.bars + 96);
+  float* dctx_s = reinterpret_cast<float*>(gen + L_.dctx);
+  float* red = reinterpret_cast<float*>(gen + L_.red);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int B = p.B, S = p.S, R = p.R, H = p.H, A = p.A, Ln = p.L, NS = p.NS;
+  const int cg = cta / NS, ns_i = cta % NS;
+  const int nb0 = (p.NB4 * ns_i) / NS, nb1 = (p.NB4 * (ns_i + 1)) / NS, nkb = nb1 - nb0;
+  const unsigned ncta = gridDim.x;
+  unsigned* bar1 = p.sync;            // dG_t of every cell is visible
+  unsigned* bar2 = p.sync + 32;       // partials of dX_t are visible
+  unsigned* bar3 = p.sync + 64;       // dWh_t of every sample is visible
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *abort_ = 0;
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+      // resident weight slice as an MN-major operand: k-block i = gate rows (nb0+i)*64 .., two boxes {64 columns, 64 rows}
+      mbar_expect_tx(bar_w, (uint32_t)nkb * WTILE);
+      for (int i = 0; i < nkb; ++i)
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) tma_load_2d(wres + i * WTILE + jb * (BK * 128), &tmW, bar_w, cg * 128 + jb * 64, (nb0 + i) * BK);
+      uint32_t it = 0;
+      const uint32_t tx = (uint32_t)B * 128u;
+      for (int t = S - 1; t >= 0; --t) {
+        wait_flag(bar1, ncta * (unsigned)(S - t), p.err, abort_);
+        proxy_fence();
+        if (cta == 0) stamp(1);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+          wait_mbar(bar_empty + 8 * s, ph ^ 1u, p.err, abort_);
+          if (*abort_) break;
+          mbar_expect_tx(bar_full + 8 * s, tx);
+          tma_load_2d(ring + s * stage_bytes, &tmG, bar_full + 8 * s, (nb0 + i) * BK, t * B);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ================================
+    // D[m = output column (128), b = sample] += W[n, cg*128 + m] . dG[b, n]   (A MN-major, B K-major)
+    const int NB = (B + 15) & ~15;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    wait_mbar(bar_w, 0, p.err, abort_);
+    uint32_t it = 0;
+    for (int t = S - 1; t >= 0; --t) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+        wait_mbar(bar_full + 8 * s, ph, p.err, abort_);
+        tc_fence_after();
+        if (lane == 0 && !*abort_) {
+          const uint32_t sact = ring + s * stage_bytes, sw = wres + i * WTILE;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk)
+            umma_bf16(tmem_base, umma_smem_desc(sw + kk * (UMMA_K * 128), BK * 128, 1024), umma_smem_desc(sact + kk * (UMMA_K * 2), 16, 1024), idesc,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+          if (i == nkb - 1) umma_commit(bar_tmem);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ worker warps ================================
+    const bool is_epi = warp < 4;
+    const bool do_attn = !is_epi && cta < B;
+    const int ww = is_epi ? warp : warp - 2;               // 0..11 in the cell phase
+    const int aw = warp - 6;                                // 0..7 in the attention phase
+    const int gid = lane >> 2, tig = lane & 3;
+    // ---- cell-phase role: unit group ug, sample class kt (samples b = kt + KT*i); warp (mt, nt) owns the mma tile of sample slots
+    //      16 mt .. +15 x units 8 nt .. +7; thread cells: slots i0 = 16 mt + gid, i1 = i0 + 8, units 8 nt + 2 tig (+1)
+    const int KT = p.KT, ug = cta / KT, kt = cta % KT;
+    const int nsl = (B - kt + KT - 1) / KT;                 // sample slots of this CTA (<= 48)
+    const int mt = ww >> 2, nt = ww & 3;
+    const int i0 = 16 * mt + gid, i1 = i0 + 8;
+    const bool ok0 = i0 < nsl, ok1 = i1 < nsl;
+    const int b0 = kt + KT * min(i0, nsl - 1), b1 = kt + KT * min(i1, nsl - 1);
+    const int j = ug * UNITS + 8 * nt + 2 * tig;            // first of this thread's two units
+    const int kcol = H + j, cgj = kcol >> 7, colj = kcol & 127;
+    // W_a fragments (B operand of mma.m16n8k16, k = a, n = unit): b0b1 = W_a[16 ks + 2 tig (+1)][unit 8 nt + gid], b2b3 = rows + 8
+    uint32_t wb[16];
+    {
+      const unsigned short* W = reinterpret_cast<const unsigned short*>(p.Wa) + ug * UNITS + 8 * nt + gid;
+#pragma unroll
+      for (int ks8 = 0; ks8 < 8; ++ks8) {
+        const int a0 = 16 * ks8 + 2 * tig;
+        wb[2 * ks8] = (uint32_t)W[(long long)min(a0, A - 1) * R] | ((uint32_t)W[(long long)min(a0 + 1, A - 1) * R] << 16);
+        wb[2 * ks8 + 1] = (uint32_t)W[(long long)min(a0 + 8, A - 1) * R] | ((uint32_t)W[(long long)min(a0 + 9, A - 1) * R] << 16);
+      }
+    }
+    float dcc[4] = {0.f, 0.f, 0.f, 0.f};                    // carry dc of this thread's 4 cells (rows 0/1 x units 0/1)
+    // ---- attention role (warps 6-13 of the first B CTAs): sample b_att = cta; warp aw owns frames aw + 8 f; lane owns 16-byte
+    //      chunks lane, lane + 32 of the value rows and a-chunk [4 lane, +4) of the score
+    const int b_att = cta;
+    float4 aw4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float duv[4][4], dww[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { duv[f][0] = duv[f][1] = duv[f][2] = duv[f][3] = 0.f; }
+    const uint32_t t_park = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 128u + 48u * (uint32_t)(max(aw, 0) >> 2);
+    const int acol = 2 * (aw * 32 + lane);                  // this thread's pair of dctx columns
+    float dr0 = 1.f, dr1 = 1.f;
+    auto draw_dropout = [&](int t) {
+      if (p.p_drop > 0.f && acol < H) {
+        const uint64_t idx = (uint64_t)((long long)t * B + b_att) * (uint64_t)H + (uint64_t)acol;
+        const float4 d4 = dropout_scale4(p.rng, p.site, idx & ~3ull, p.p_drop);
+        if ((idx & 3ull) == 0) { dr0 = d4.x; dr1 = d4.y; } else { dr0 = d4.z; dr1 = d4.w; }
+      }
+    };
+    if (do_attn) {
+      aw4 = reinterpret_cast<const float4*>(p.attn_w)[lane];
+      const float4 ab4 = reinterpret_cast<const float4*>(p.attn_b)[lane];
+      uint32_t v[32];
+      const int nch = H >> 3;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int ch = lane + 32 * u;
+          uint4 raw = *reinterpret_cast<const uint4*>(p.Hd + ((long long)min(aw + 8 * f, Ln - 1) * B + b_att) * H + (long long)min(ch, nch - 1) * 8);
+          if (ch >= nch || aw + 8 * f >= Ln) raw = make_uint4(0u, 0u, 0u, 0u);
+          v[8 * f + 4 * u] = raw.x; v[8 * f + 4 * u + 1] = raw.y; v[8 * f + 4 * u + 2] = raw.z; v[8 * f + 4 * u + 3] = raw.w;
+        }
+      tmem_st32(t_park, v);
+      uint32_t u16[16];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        float4 x = reinterpret_cast<const float4*>(p.Uv + ((long long)min(aw + 8 * f, Ln - 1) * B + b_att) * A)[lane];
+        x = attn::l4_add(x, ab4);
+        u16[4 * f] = __float_as_uint(x.x); u16[4 * f + 1] = __float_as_uint(x.y); u16[4 * f + 2] = __float_as_uint(x.z); u16[4 * f + 3] = __float_as_uint(x.w);
+      }
+      tmem_st16(t_park + 32u, u16);
+      tmem_st_wait();
+      draw_dropout(S - 1);
+    }
+
+    for (int t = S - 1; t >= 0; --t) {
+      const bool last = (t == S - 1);
+      // ======================= C: cell backward of step t =======================
+      {
+        const long long r0 = (long long)t * B + b0, r1 = (long long)t * B + b1;
+        float dh[2][2];
+        uint32_t gq[2][4];
+        float2 cp[2], cn[2];
+        if (!last) {
+          // partials of dX_{t+1} are visible once bar2 of step t+1 completed (attention warps of the first B CTAs saw that already)
+          if (is_epi) { if (tid == 0) wait_flag(bar2, ncta * (unsigned)(S - 1 - t), p.err, abort_); nbar(1, 128); }
+          else if (!do_attn) { if (aw == 0 && lane == 0) wait_flag(bar2, ncta * (unsigned)(S - 1 - t), p.err, abort_); nbar(5, 256); }
+        }
+        // everything that does not depend on dWh_{t+1}: issued before the wait for it
+        {
+          const float2 e0 = *reinterpret_cast<const float2*>(p.dHext + r0 * R + j), e1 = *reinterpret_cast<const float2*>(p.dHext + r1 * R + j);
+          dh[0][0] = e0.x; dh[0][1] = e0.y; dh[1][0] = e1.x; dh[1][1] = e1.y;
+          const bf16* g0 = p.gates + r0 * 4 * R + j; const bf16* g1 = p.gates + r1 * 4 * R + j;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { gq[0][g] = *reinterpret_cast<const uint32_t*>(g0 + (long long)g * R); gq[1][g] = *reinterpret_cast<const uint32_t*>(g1 + (long long)g * R); }
+          cp[0] = *reinterpret_cast<const float2*>(p.c + r0 * R + j); cp[1] = *reinterpret_cast<const float2*>(p.c + r1 * R + j);
+          cn[0] = *reinterpret_cast<const float2*>(p.c + (r0 + B) * R + j); cn[1] = *reinterpret_cast<const float2*>(p.c + (r1 + B) * R + j);
+          if (!last) {
+            const float* q0 = p.DP + ((long long)cgj * NS * B + b0) * 128 + colj;
+            const float* q1 = p.DP + ((long long)cgj * NS * B + b1) * 128 + colj;
+            float2 pa[MAX_NS], pb[MAX_NS];
+#pragma unroll
+            for (int s = 0; s < MAX_NS; ++s) {
+              pa[s] = *reinterpret_cast<const float2*>(q0 + (long long)min(s, NS - 1) * B * 128);
+              pb[s] = *reinterpret_cast<const float2*>(q1 + (long long)min(s, NS - 1) * B * 128);
+            }
+#pragma unroll
+            for (int s = 0; s < MAX_NS; ++s)
+              if (s < NS) { dh[0][0] += pa[s].x; dh[0][1] += pa[s].y; dh[1][0] += pb[s].x; dh[1][1] += pb[s].y; }
+          }
+        }
+        if (!last) {
+          // dWh_{t+1} . W_a over this CTA's 32 units: [slots x 128 a] . [128 a x 32 units], A fragments straight from dWh_op (L2)
+          if (is_epi) { if (tid == 0) wait_flag(bar3, (unsigned)B * (unsigned)(S - 1 - t), p.err, abort_); nbar(1, 128); }
+          else { if (aw == 0 && lane == 0) wait_flag(bar3, (unsigned)B * (unsigned)(S - 1 - t), p.err, abort_); nbar(5, 256); }
+          if (cta == 0 && tid == 0) stamp(7);
+          const bf16* a0p = p.dWh_op + ((long long)(t + 1) * B + b0) * A + 2 * tig;
+          const bf16* a1p = p.dWh_op + ((long long)(t + 1) * B + b1) * A + 2 * tig;
+          uint32_t af[8][4];
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            af[k8][0] = *reinterpret_cast<const uint32_t*>(a0p + 16 * k8);
+            af[k8][1] = *reinterpret_cast<const uint32_t*>(a1p + 16 * k8);
+            af[k8][2] = *reinterpret_cast<const uint32_t*>(a0p + 16 * k8 + 8);
+            af[k8][3] = *reinterpret_cast<const uint32_t*>(a1p + 16 * k8 + 8);
+          }
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                         : "r"(af[k8][0]), "r"(af[k8][1]), "r"(af[k8][2]), "r"(af[k8][3]), "r"(wb[2 * k8]), "r"(wb[2 * k8 + 1]));
+          dh[0][0] += d0; dh[0][1] += d1; dh[1][0] += d2; dh[1][1] += d3;
+        }
+        // cell backward (lstm_cell.cuh:lstm_cell_bwd_body), 2 sample rows x 2 units
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const bool ok = r == 0 ? ok0 : ok1;
+          const long long row = r == 0 ? r0 : r1;
+          uint32_t og[4];
+          const float cpx[2] = {cp[r].x, cp[r].y}, cnx[2] = {cn[r].x, cn[r].y};
+          float o4[4][2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float gi = __bfloat162float(__ushort_as_bfloat16((unsigned short)(u ? gq[r][0] >> 16 : gq[r][0] & 0xFFFFu)));
+            const float gf = __bfloat162float(__ushort_as_bfloat16((unsigned short)(u ? gq[r][1] >> 16 : gq[r][1] & 0xFFFFu)));
+            const float gg = __bfloat162float(__ushort_as_bfloat16((unsigned short)(u ? gq[r][2] >> 16 : gq[r][2] & 0xFFFFu)));
+            const float go = __bfloat162float(__ushort_as_bfloat16((unsigned short)(u ? gq[r][3] >> 16 : gq[r][3] & 0xFFFFu)));
+            const float dhv = dh[r][u];
+            const float tc = act_tanh<true>(cnx[u]);
+            const float dc = fmaf(dhv * go, 1.f - tc * tc, last ? 0.f : dcc[2 * r + u]);
+            dcc[2 * r + u] = dc * gf;
+            o4[0][u] = dc * gg * gi * (1.f - gi);
+            o4[1][u] = dc * cpx[u] * gf * (1.f - gf);
+            o4[2][u] = dc * gi * (1.f - gg * gg);
+            o4[3][u] = dhv * tc * go * (1.f - go);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { const __nv_bfloat162 x = __floats2bfloat162_rn(o4[g][0], o4[g][1]); og[g] = *reinterpret_cast<const uint32_t*>(&x); }
+          if (ok) {
+            bf16* dg = p.dG + row * 4 * R + j;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint32_t*>(dg + (long long)g * R) = og[g];
+          }
+        }
+        if (cta == 0 && tid == 0) stamp(8);
+        nbar(4, NWORK * 32);
+        if (tid == 0) { red_rel(bar1); if (cta == 0) stamp(9); }
+      }
+      // ======================= G epilogue: accumulator -> DP[cg][ns] (warp q: columns 32 q + lane, all samples) =======================
+      if (is_epi) {
+        wait_mbar(bar_tmem, (uint32_t)(S - 1 - t) & 1u, p.err, abort_);
+        tc_fence_after();
+        if (cta == 0 && tid == 0) stamp(4);
+        float* dst = p.DP + ((long long)cg * NS + ns_i) * B * 128 + warp * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < B; c0 += 64) {
+          uint32_t r[64];
+          tmem_ld32_nw(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+          tmem_ld32_nw(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 32), r + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 64; ++q)
+            if (c0 + q < B) dst[(long long)(c0 + q) * 128] = __uint_as_float(r[q]);
+        }
+        tc_fence_before();
+        nbar(1, 128);
+        if (tid == 0) { red_rel(bar2); if (cta == 0) stamp(5); }
+      }
+      // ======================= A: attention backward of sample b_att, step t =======================
+      if (do_attn) {
+        if (aw == 0 && lane == 0) { wait_flag(bar2, ncta * (unsigned)(S - t), p.err, abort_); if (cta == 0) stamp(12); }
+        nbar(5, 256);
+        const float4 wh = reinterpret_cast<const float4*>(p.Wh + ((long long)t * B + b_att) * A)[lane];
+        // dctx = dropout mask . sum of the NS partials of the x columns (2 columns per thread)
+        if (acol < H) {
+          const float* q = p.DP + ((long long)(acol >> 7) * NS * B + b_att) * 128 + (acol & 127);
+          float2 pa[MAX_NS];
+#pragma unroll
+          for (int s = 0; s < MAX_NS; ++s) pa[s] = *reinterpret_cast<const float2*>(q + (long long)min(s, NS - 1) * B * 128);
+          float sx = 0.f, sy = 0.f;
+#pragma unroll
+          for (int s = 0; s < MAX_NS; ++s) if (s < NS) { sx += pa[s].x; sy += pa[s].y; }
+          sx *= dr0; sy *= dr1;
+          *reinterpret_cast<float2*>(dctx_s + acol) = make_float2(sx, sy);
+          *reinterpret_cast<float2*>(p.dx + ((long long)t * B + b_att) * H + acol) = make_float2(sx, sy);
+        }
+        nbar(5, 256);
+        // d e[l] = (1/L) <dctx, v_l> for this warp's frames
+        float de[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t u16[16];
+        {
+          uint32_t v[32];
+          tmem_ld32_nw(t_park, v);
+          tmem_ld16_nw(t_park + 32u, u16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 x0 = *reinterpret_cast<const float4*>(dctx_s + (lane + 32 * u) * 8), x1 = *reinterpret_cast<const float4*>(dctx_s + (lane + 32 * u) * 8 + 4);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[8 * f + 4 * u]));
+              const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[8 * f + 4 * u + 1]));
+              const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[8 * f + 4 * u + 2]));
+              const float2 p3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[8 * f + 4 * u + 3]));
+              float a = de[f];
+              a = fmaf(x0.x, p0.x, a); a = fmaf(x0.y, p0.y, a); a = fmaf(x0.z, p1.x, a); a = fmaf(x0.w, p1.y, a);
+              a = fmaf(x1.x, p2.x, a); a = fmaf(x1.y, p2.y, a); a = fmaf(x1.z, p3.x, a); a = fmaf(x1.w, p3.y, a);
+              de[f] = a;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) de[f] += __shfl_xor_sync(0xffffffffu, de[f], o);
+        // score backward of the same frames (tanh recomputed)
+        float4 dwh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          if (aw + 8 * f < Ln) {
+            const float g = de[f] * p.inv_L;
+            const float tx = act_tanh<true>(wh.x + __uint_as_float(u16[4 * f])), ty = act_tanh<true>(wh.y + __uint_as_float(u16[4 * f + 1]));
+            const float tz = act_tanh<true>(wh.z + __uint_as_float(u16[4 * f + 2])), tw = act_tanh<true>(wh.w + __uint_as_float(u16[4 * f + 3]));
+            const float sx = g * aw4.x * (1.f - tx * tx), sy = g * aw4.y * (1.f - ty * ty), sz = g * aw4.z * (1.f - tz * tz), sw_ = g * aw4.w * (1.f - tw * tw);
+            dwh.x += sx; dwh.y += sy; dwh.z += sz; dwh.w += sw_;
+            dww[0] = fmaf(g, tx, dww[0]); dww[1] = fmaf(g, ty, dww[1]); dww[2] = fmaf(g, tz, dww[2]); dww[3] = fmaf(g, tw, dww[3]);
+            duv[f][0] += sx; duv[f][1] += sy; duv[f][2] += sz; duv[f][3] += sw_;
+          }
+        }
+        reinterpret_cast<float4*>(red + aw * 128)[lane] = dwh;
+        nbar(5, 256);
+        if (aw == 0) {
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum = attn::l4_add(sum, reinterpret_cast<const float4*>(red + i * 128)[lane]);
+          reinterpret_cast<float4*>(p.dWh + ((long long)t * B + b_att) * A)[lane] = sum;
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(sum.x, sum.y), hi = __floats2bfloat162_rn(sum.z, sum.w);
+          *reinterpret_cast<uint2*>(p.dWh_op + ((long long)t * B + b_att) * A + 4 * lane) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+        nbar(5, 256);
+        if (aw == 0 && lane == 0) { red_rel(bar3); if (cta == 0) stamp(3); }
+        if (t > 0) draw_dropout(t - 1);
+      }
+    }
+    // ---- accumulated over all steps: dU.v of this warp's frames, dw of the sample (summed over the 8 warps) ----
+    if (do_attn) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        if (aw + 8 * f < Ln)
+          reinterpret_cast<float4*>(p.dUv + ((long long)(aw + 8 * f) * B + b_att) * A)[lane] = make_float4(duv[f][0], duv[f][1], duv[f][2], duv[f][3]);
+      nbar(5, 256);
+      reinterpret_cast<float4*>(red + aw * 128)[lane] = make_float4(dww[0], dww[1], dww[2], dww[3]);
+      nbar(5, 256);
+      if (aw == 0) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum = attn::l4_add(sum, reinterpret_cast<const float4*>(red + i * 128)[lane]);
+        reinterpret_cast<float4*>(p.dw_acc + (long long)b_att * A)[lane] = sum;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// gate-row split that keeps every CTA's weight slice resident with CG*NS CTAs co-resident; 0 = shape not covered
+static inline int pick_ns(int R, int H) {
+  const int KX = R + H;
+  if (KX % 128 || R % 64) return 0;
+  const int CG = KX / 128, NB4 = 4 * R / BK;
+  for (int ns = 1; ns <= MAX_NS; ++ns)
+    if ((NB4 + ns - 1) / ns <= MAX_KB && CG * ns <= sm_count()) return ns;
+  return 0;
+}
+static inline bool local_bwd_ok(const Shape& s) {
+  if (!persist_enabled()) return false;
+  const int ns = pick_ns(s.R, s.H);
+  if (!ns || s.R % UNITS) return false;
+  const int G = (s.R + s.H) / 128 * ns, UG = s.R / UNITS;
+  if (G % UG) return false;
+  const int KT = G / UG;
+  return s.A == 128 && s.B >= KT && s.B <= 128 && s.B <= G && s.L >= 1 && s.L <= 32 && s.H <= 512 && s.H % 8 == 0 && s.S >= 1 &&
+         (s.B + KT - 1) / KT <= 48 && smem_layout_bwd(s.B).total <= 227 * 1024;
+}
+static inline size_t dp_floats(const Shape& s) { const int ns = pick_ns(s.R, s.H); return ns ? (size_t)((s.R + s.H) / 128) * ns * s.B * 128 : 4; }
+
+// dG / Wrec as the kernel-per-phase path lays them out; sync must be zeroed (SYNC_WORDS words) before the launch
+static int launch_local_bwd(BwdParams p, const bf16* Wrec, cudaStream_t st) {
+  p.KX = p.H + p.R; p.NS = pick_ns(p.R, p.H); p.CG = p.KX / 128; p.NB4 = 4 * p.R / BK; p.UG = p.R / UNITS; p.KT = p.CG * p.NS / p.UG;
+  CUtensorMap mg, mw;
+  RN_TRY(make_map(&mg, p.dG, (long long)p.S * p.B, 4LL * p.R, 4LL * p.R, BK, p.B));
+  RN_TRY(make_map(&mw, Wrec, 4LL * p.R, p.KX, p.KX, 64, BK));
+  const int smem = smem_layout_bwd(p.B).total;
+  static int attr_smem = 0;
+  if (attr_smem < smem) {
+    RN_CUDA_OK(cudaFuncSetAttribute(local_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  void* args[] = {(void*)&mg, (void*)&mw, (void*)&p};
+  ProfScope prof(KC_LOOP, p.S, p.CG * p.NS, 1, st);
+  RN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)local_bwd_kernel, dim3(p.CG * p.NS), dim3(THREADS), args, (size_t)smem, st));
+  RN_LAUNCH_OK();
+  return 0;
 }
 }  // namespace rp

@@ -215,18 +215,23 @@ int recnet_global_bwd(const recnet_global_desc* d, const recnet_global_tensors* 
                       const recnet_global_tensors* grads, float* g_hiddens, void* stream);
 float* recnet_global_outputs(const recnet_global_desc* d, void* workspace);  /* [L,B,R] fp32 */
 
-/* The time loops of the bf16 build run as ONE persistent cooperative "loop kernel" per loop (csrc/mega.cuh).  Its spins
- * have timeouts; on a protocol failure it raises an int32 flag inside the workspace instead of hanging the GPU.  These
- * return the flag's byte offset in the workspace (0 = ok, 2 = mbarrier timeout, 3 = grid-barrier timeout). */
+/* The weight-resident time loops of the bf16 build (local reconstructor, LSTM, MSVD-class shapes) run as ONE persistent
+ * cooperative kernel per loop (csrc/seq_recon_persist.cuh): [W_ih | W_hh] stays in the shared memory of 144 CTAs for all steps
+ * and the CTAs meet at three flag waits per step.  Every spin has a timeout; on a protocol failure the kernel raises an int32
+ * flag inside the workspace instead of hanging the GPU.  These return the flag's byte offset in the workspace
+ * (0 = ok, 2 = mbarrier timeout, 3 = flag-wait timeout). */
 int64_t recnet_decoder_error_offset(const recnet_decoder_desc* d);
 int64_t recnet_local_error_offset(const recnet_local_desc* d);
 int64_t recnet_global_error_offset(const recnet_global_desc* d);
 
-/* developer probe: loop kernel with n_phases empty phases (+ grid barrier each if sync_after); scratch >= n_phases*1024+1024 B */
-int recnet_debug_loop_overhead(int n_phases, int sync_after, void* scratch, void* stream);
-
-/* developer probe: %globaltimer stamp at the start of every loop-kernel phase -> buf (device u64[n_phases + 1]); NULL = off */
+/* developer probe: %globaltimer stamps of block 0 at the phase boundaries of the persistent loops -> buf (device u64[4096]); NULL = off */
 int recnet_debug_set_timeline(void* buf);
+
+/* test probe: out[i] = the inverted-dropout scale (0 or 1/(1-p)) the kernels apply to element i of dropout site `site`
+ * (1 embedding [L,B,EMB], 2 logits [L,B,V], 3 local-reconstructor input [S,B,H], 4 global-reconstructor mean-pool [L,B,H]; reference
+ * models/decoder.py:48,69, models/local_reconstructor.py:50, models/global_reconstructor.py:38) for rng = {seed, offset} on the device.
+ * Lets a checker feed the SAME masks to the oracle / the reference (tests/test_gpu_dropout_parity.py). */
+int recnet_debug_dropout_mask(const uint64_t* rng, uint32_t site, int64_t n, float p, float* out, void* stream);
 
 /* L2-norm regulariser over a parameter list (train.py:69,101,127): reg = sum_p ||p||_2.
  * ptrs/sizes: device int64 tables of n tensors; blk_tensor/blk_chunk: device int32 tables mapping block ->
@@ -261,17 +266,6 @@ int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const 
                      const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2,
                      double eps, double weight_decay, double max_grad_norm, float* partial, float* state,
                      int write_clipped_grads, void* stream);
-
-/* EXPERIMENTAL (opt-in, not yet run on a GPU): recnet_adam_step that also forms the gradient of the L2-norm regulariser
- * (train.py:69,101,127) inside the optimiser pass, g_total = g + reg_g[0] * reg_lambda[0] * p / sqrt(reg_sumsq[reg_index[t]]),
- * clip norm taken over g_total -- replaces recnet_param_norms_bwd's read-modify-write of every gradient.  reg_sumsq: the squared
- * norms recnet_param_norms_fwd left; reg_index [n] int32 maps optimiser tensor t to its slot there (NULL = identity). */
-int recnet_adam_step_reg(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs,
-                         const int64_t* exp_avg_sq_ptrs, const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n,
-                         const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2,
-                         double eps, double weight_decay, double max_grad_norm, float* partial, float* state,
-                         int write_clipped_grads, const float* reg_sumsq, const int32_t* reg_index, const float* reg_g,
-                         const float* reg_lambda, void* stream);
 
 #ifdef __cplusplus
 }

@@ -119,10 +119,14 @@ def additive_scores(query: Tensor, keys_proj: Tensor, W: Tensor, b: Tensor, w: T
 # Decoder  (models/decoder.py:45-70)
 # ----------------------------------------------------------------------------
 def decoder_step(P: Params, tok: Tensor, hidden, feats: Tensor, *, model_name: str = "LSTM",
-                 n_layers: int = 1, embedding_scale: float = 1.0):
+                 n_layers: int = 1, embedding_scale: float = 1.0, drop_emb: Optional[Tensor] = None,
+                 drop_logits: Optional[Tensor] = None):
     """tok (1,B) int64; hidden ((NL,B,H),(NL,B,H)) or (NL,B,H); feats (B,T,E).
-    Eval-mode (all dropouts identity).  Returns (logits (B,V), new hidden)."""
+    Eval mode by default (all dropouts identity); train mode = the caller supplies this step's inverted-dropout scale tensors
+    (0 or 1/(1-p)): drop_emb (B,EMB) for decoder.py:48, drop_logits (B,V) for decoder.py:69.  Returns (logits (B,V), new hidden)."""
     emb = P["embedding.weight"][tok[0]] * embedding_scale             # decoder.py:46-47
+    if drop_emb is not None:
+        emb = emb * drop_emb                                          # decoder.py:48
     top_h = hidden[0][-1] if model_name == "LSTM" else hidden[-1]    # decoder.py:50-53
     Uv = feats @ P["attn_U.weight"].t()                               # decoder.py:54 (B,T,A), recomputed per step
     Wh = (top_h @ P["attn_W.weight"].t()).unsqueeze(1)                # decoder.py:51,55
@@ -131,6 +135,8 @@ def decoder_step(P: Params, tok: Tensor, hidden, feats: Tensor, *, model_name: s
     x = torch.cat((emb, ctx), dim=1)                                  # decoder.py:64
     outs, hidden = _rnn_layers(P, "rnn", model_name, n_layers, [x], hidden)  # decoder.py:66
     logits = outs[0] @ P["out.weight"].t() + P["out.bias"]            # decoder.py:68
+    if drop_logits is not None:
+        logits = logits * drop_logits                                 # decoder.py:69: the LOGITS are dropped, before the loss
     return logits, hidden
 
 
@@ -147,8 +153,9 @@ def param_norm_sum(P: Params) -> Tensor:
 def forward_decoder(P: Params, feats: Tensor, targets: Tensor, masks: Tensor, *,
                     model_name: str = "LSTM", n_layers: int = 1, embedding_scale: float = 1.0,
                     caption_max_len: int = 30, lambda_reg: float = 1e-3,
-                    teacher_forcing: bool = True):
+                    teacher_forcing: bool = True, drop_emb: Optional[Tensor] = None, drop_logits: Optional[Tensor] = None):
     """train.py:17-75.  targets (caption_max_len+1, B) int64 ; masks = targets > 0.
+    Train mode: drop_emb (L,B,EMB) / drop_logits (L,B,V) hold the per-step inverted-dropout scales (None = eval mode).
     Returns (loss, hiddens (L,NL,B,H), output_indices list, aux dict)."""
     B = feats.shape[0]
     H = P["rnn.weight_hh_l0"].shape[1]
@@ -161,7 +168,9 @@ def forward_decoder(P: Params, feats: Tensor, targets: Tensor, masks: Tensor, *,
     logits_all: List[Tensor] = []
     for t in range(caption_max_len + 1):                               # train.py:41
         logits, hidden = decoder_step(P, tok, hidden, feats, model_name=model_name,
-                                      n_layers=n_layers, embedding_scale=embedding_scale)
+                                      n_layers=n_layers, embedding_scale=embedding_scale,
+                                      drop_emb=None if drop_emb is None else drop_emb[t],
+                                      drop_logits=None if drop_logits is None else drop_logits[t])
         logits_all.append(logits)
         if teacher_forcing:
             tok = targets[t].view(1, -1)                               # train.py:44-45
@@ -191,11 +200,14 @@ def forward_decoder(P: Params, feats: Tensor, targets: Tensor, masks: Tensor, *,
 # Global reconstructor (models/global_reconstructor.py:30-46, train.py:78-105)
 # ----------------------------------------------------------------------------
 def global_reconstructor_step(P: Params, inp: Tensor, hidden, decoder_hiddens: Tensor, *,
-                              model_name: str = "LSTM", n_layers: int = 1, caption_max_len: int = 30):
-    """inp = decoder_hiddens[t] (NLdec,B,H) ; decoder_hiddens (L,NLdec,B,H)."""
+                              model_name: str = "LSTM", n_layers: int = 1, caption_max_len: int = 30,
+                              drop_mp: Optional[Tensor] = None):
+    """inp = decoder_hiddens[t] (NLdec,B,H) ; decoder_hiddens (L,NLdec,B,H); drop_mp (B,H): this step's dropout scales (train mode)."""
     L = decoder_hiddens.shape[0]
     mp = decoder_hiddens.mean(dim=0).mean(dim=0)                        # global_reconstructor.py:33-36 (mean over L then layers)
     mp = mp / L * caption_max_len                                       # global_reconstructor.py:37
+    if drop_mp is not None:
+        mp = mp * drop_mp                                               # global_reconstructor.py:38
     x = torch.cat((inp[0], mp), dim=1)                                  # global_reconstructor.py:40 (layer-0 state only)
     outs, hidden = _rnn_layers(P, "rnn", model_name, n_layers, [x], hidden)   # :43
     out = outs[0] @ P["out.weight"].t() + P["out.bias"]                 # :45
@@ -204,7 +216,8 @@ def global_reconstructor_step(P: Params, inp: Tensor, hidden, decoder_hiddens: T
 
 def forward_global_reconstructor(P: Params, decoder_hiddens: Tensor, feats: Tensor, *,
                                  model_name: str = "LSTM", n_layers: int = 1, caption_max_len: int = 30,
-                                 lambda_reg: float = 1e-2):
+                                 lambda_reg: float = 1e-2, drop_mp: Optional[Tensor] = None):
+    """drop_mp (L,B,H): per-step dropout scales of the mean-pooled state (train mode), None = eval mode."""
     B = feats.shape[0]
     R = P["rnn.weight_hh_l0"].shape[1]
     hidden = zero_hidden(model_name, n_layers, B, R, feats)             # train.py:82-89
@@ -213,7 +226,8 @@ def forward_global_reconstructor(P: Params, decoder_hiddens: Tensor, feats: Tens
     for t in range(L):                                                  # train.py:93
         o, hidden = global_reconstructor_step(P, decoder_hiddens[t], hidden, decoder_hiddens,
                                               model_name=model_name, n_layers=n_layers,
-                                              caption_max_len=caption_max_len)
+                                              caption_max_len=caption_max_len,
+                                              drop_mp=None if drop_mp is None else drop_mp[t])
         outs.append(o)
     outs_t = torch.stack(outs)
     mse = ((outs_t.mean(0) - feats.mean(1)) ** 2).mean()                # train.py:96-99 MSELoss()
@@ -226,7 +240,7 @@ def forward_global_reconstructor(P: Params, decoder_hiddens: Tensor, feats: Tens
 # Local reconstructor (models/local_reconstructor.py:37-55, train.py:108-131)
 # ----------------------------------------------------------------------------
 def local_reconstructor_step(P: Params, hidden, decoder_hiddens: Tensor, *,
-                             model_name: str = "LSTM", n_layers: int = 1):
+                             model_name: str = "LSTM", n_layers: int = 1, drop_x: Optional[Tensor] = None):
     """decoder_hiddens (L,NLdec,B,H).  The attended input keeps the decoder-layer
     axis, and the RNN treats that axis as TIME (NLdec pseudo-steps) -- SURVEY 8a A7."""
     top_h = hidden[0][-1] if model_name == "LSTM" else hidden[-1]       # local_reconstructor.py:38-41
@@ -234,19 +248,24 @@ def local_reconstructor_step(P: Params, hidden, decoder_hiddens: Tensor, *,
     Wh = top_h @ P["attn_W.weight"].t()                                  # (B,A) broadcast over (L,NLdec)
     beta = torch.tanh(Wh + Uv + P["attn_b"]) @ P["attn_w.weight"].t()    # :44-46 (L,NLdec,B,1)
     x = (beta * decoder_hiddens).mean(dim=0)                             # :47-49 (NLdec,B,H) -- mean over L, no softmax
+    if drop_x is not None:
+        x = x * drop_x                                                   # :50 (train mode: this step's scales, (NLdec,B,H) or (B,H))
     outs, hidden = _rnn_layers(P, "rnn", model_name, n_layers, list(x.unbind(0)), hidden)  # :52
     out = outs[0] @ P["out.weight"].t() + P["out.bias"]                  # :54 first pseudo-step of the top layer
     return out, hidden
 
 
 def forward_local_reconstructor(P: Params, decoder_hiddens: Tensor, feats: Tensor, *,
-                                model_name: str = "LSTM", n_layers: int = 1, lambda_reg: float = 1e-2):
+                                model_name: str = "LSTM", n_layers: int = 1, lambda_reg: float = 1e-2,
+                                drop_x: Optional[Tensor] = None):
+    """drop_x (T,B,H): per-step dropout scales of the attended input (train mode), None = eval mode."""
     B, T, _ = feats.shape
     R = P["rnn.weight_hh_l0"].shape[1]
     hidden = zero_hidden(model_name, n_layers, B, R, feats)             # train.py:112-119
     outs = []
-    for _ in range(T):                                                  # train.py:122 (encoder_output_len steps)
-        o, hidden = local_reconstructor_step(P, hidden, decoder_hiddens, model_name=model_name, n_layers=n_layers)
+    for t in range(T):                                                  # train.py:122 (encoder_output_len steps)
+        o, hidden = local_reconstructor_step(P, hidden, decoder_hiddens, model_name=model_name, n_layers=n_layers,
+                                             drop_x=None if drop_x is None else drop_x[t])
         outs.append(o)
     outs_t = torch.stack(outs)                                          # (T,B,R)
     rec = ((outs_t.transpose(0, 1) - feats) ** 2).mean()                # train.py:126-128

@@ -113,13 +113,12 @@ SIGNATURES = {
     "recnet_decoder_error_offset": (_l, [C.POINTER(decoder_desc)]),
     "recnet_local_error_offset": (_l, [C.POINTER(local_desc)]),
     "recnet_global_error_offset": (_l, [C.POINTER(global_desc)]),
-    "recnet_debug_loop_overhead": (_i, [_i, _i, _p, _p]),
     "recnet_debug_set_timeline": (_i, [_p]),
+    "recnet_debug_dropout_mask": (_i, [_p, C.c_uint32, _l, C.c_float, _p, _p]),
     "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _p, _i, _p]),
     "recnet_teacher_forcing_prep": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
     "recnet_adam_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _d, _d, _d, _d, _d, _d, _p, _p, _i, _p]),
-    "recnet_adam_step_reg": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _d, _d, _d, _d, _d, _d, _p, _p, _i, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

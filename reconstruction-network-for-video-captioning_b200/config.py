@@ -3,7 +3,7 @@
 Attribute names and default values follow the reference's ``config.py`` (TrainConfig, config.py:27-93;
 EvalConfig, config.py:160-173) so that code written against ``from config import TrainConfig as C`` keeps
 working; everything that only served the reference's data loading, logging and checkpoint naming is left
-out (out of scope).  Two additions: ``precision`` and ``attention_normalize``.
+out (out of scope).  Two additions: ``precision`` and ``optimizer_impl``.
 """
 
 
@@ -18,11 +18,8 @@ class TrainConfig:
 
     # --- B200 additions ---
     precision = "bf16"               # "bf16": tcgen05 GEMMs, fp32 accumulate/state; "fp32": FFMA parity build
-    attention_normalize = "none"     # "none" = what the reference computes (no softmax, mean over frames)
     optimizer_impl = "recnet"        # "recnet": optim.ClipAdam (own fused clip + Adam kernels, measured 21 us/step faster);
     #                                  "torch": torch.optim.Adam(fused, capturable) + clip_grad_norm_.  RECNET_OPTIMIZER overrides.
-
-    defer_regulariser = False        # EXPERIMENTAL (never run on a GPU yet): regulariser gradient formed inside optim.ClipAdam's pass
 
     # --- batch / vocabulary (config.py:48-56) ---
     min_count = 5

@@ -45,18 +45,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// multicast variants (thread-block cluster): the box lands at the same CTA-relative offset in every CTA of `mask`, and the
-// complete_tx is signalled on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -65,20 +53,6 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
-}
-// bounded wait used by the cluster build: a protocol bug must not hang the GPU (returns false on timeout)
-__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (int it = 0; it < (1 << 18) && !ok; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-  return ok != 0;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -144,11 +118,7 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-// CL > 1: thread-block cluster of CL CTAs along the N-tile axis (same m0, same k-slice).  The 128-row A tile of every stage is
-// fetched ONCE per cluster -- CTA r loads rows [r, r+1) * 128/CL and TMA-multicasts them to all CL CTAs -- which removes
-// (CL-1)/CL of the A re-reads that make the M = 100 per-step GEMMs L2-ingest bound.  A ring slot may only be refilled when
-// all CL consumers have released it: the empty barriers count CL arrivals and every MMA warp commits to all of them.
-template <int BN, int STAGES, bool TA, bool TB, int CL = 1>
+template <int BN, int STAGES, bool TA, bool TB>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiArgs ep,
                int M, int N, int K, int kb_per_split) {
@@ -165,9 +135,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb0 = blockIdx.z * kb_per_split;
   const int nkb = max(0, min(nkb_total, kb0 + kb_per_split) - kb0);
 
-  static_assert(CL == 1 || !TA, "the multicast build covers K-major A only");
-  const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
-  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
   // one producer step: expect-tx + the TMA boxes of k-block i into ring slot i % STAGES
   auto produce = [&](int i) {
     const int s = i % STAGES;
@@ -175,8 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
     const int k = (kb0 + i) * BK;
     if (!TA) {
-      if (CL == 1) tma_load_2d(sa, &tmA, bar_full + 8 * s, k, m0);          // box {64 k, 128 m}
-      else tma_load_2d_mc(sa + crank * (BM / CL) * 128, &tmA, bar_full + 8 * s, k, m0 + (int)crank * (BM / CL), CMASK);   // box {64 k, 128/CL m} -> all CTAs
+      tma_load_2d(sa, &tmA, bar_full + 8 * s, k, m0);                       // box {64 k, 128 m}
     } else {
 #pragma unroll
       for (int j = 0; j < BM / 64; ++j)                                     // boxes {64 m, 64 k}
@@ -194,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // The per-step GEMMs have 1-11 k-blocks and are pure latency chains (launch -> TMA -> UMMA -> tcgen05.ld -> store): the
@@ -202,16 +168,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // initialised the barriers, while warp 1 is still allocating TMEM and the CTA has not yet met at the barrier below.
     pdl_wait();
     pdl_launch_next();
-    if (CL == 1) for (int i = 0; i < n_early; ++i) produce(i);
+    for (int i = 0; i < n_early; ++i) produce(i);
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);
   tc_fence_before();
-  if (CL == 1) {
-    __syncthreads();
-  } else {
-    cluster_sync_all();              // every CTA's barriers exist before any peer multicasts into them
-    if (threadIdx.x == 0) for (int i = 0; i < n_early; ++i) produce(i);
-  }
+  __syncthreads();
   tc_fence_after();
   pdl_wait();          // everything above overlapped the previous kernel's tail; operands / outputs are touched only below
   pdl_launch_next();   // after the wait: the next kernel may be scheduled now, but it cannot trigger ITS dependents before we finish
@@ -223,8 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = n_early; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        if (CL == 1) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        else if (!mbar_wait_bounded(bar_empty + 8 * s, ph ^ 1u)) break;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         produce(i);
       }
     }
@@ -235,8 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-      if (CL == 1) mbar_wait(bar_full + 8 * s, ph);
-      else if (!mbar_wait_bounded(bar_full + 8 * s, ph)) break;
+      mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
@@ -248,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                  : umma_smem_desc(sb + kk * (UMMA_K * 2), 16, 1024);
           umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
         }
-        if (CL == 1) umma_commit(bar_empty + 8 * s); else umma_commit_mc(bar_empty + 8 * s, CMASK);
+        umma_commit(bar_empty + 8 * s);
         if (i == nkb - 1) umma_commit(bar_tmem);
       }
       __syncwarp();
@@ -258,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
     if (nkb > 0) {
-      if (CL == 1) mbar_wait(bar_tmem, 0); else mbar_wait_bounded(bar_tmem, 0);
+      mbar_wait(bar_tmem, 0);
       tc_fence_after();
     }
     const bool z0 = (blockIdx.z == 0);
@@ -310,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   tc_fence_before();
-  if (CL == 1) __syncthreads(); else cluster_sync_all();     // no CTA leaves while a peer may still signal its barriers
+  __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
@@ -362,37 +321,6 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const EpiArg
   return 0;
 }
 
-// cluster launch of the multicast build (K-major A, shallow ring): grid.x must be a multiple of CL
-template <int BN, int STAGES, bool TB, int CL>
-static int launch_cluster(const CUtensorMap& ma, const CUtensorMap& mb, const EpiArgs& ep, int M, int N, int K, int splits, int kb_per,
-                          cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_tc_kernel<BN, STAGES, false, TB, CL>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(rn_cdiv(N, BN), rn_cdiv(M, BM), splits);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = L::TOTAL;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  ProfScope prof(KC_GEMM_TC, M, N, K, st);
-  RN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, ep, M, N, K, kb_per));
-  RN_LAUNCH_OK();
-  return 0;
-}
-static inline int cluster_size_env() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("RECNET_GEMM_CLUSTER"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 template <int BN, int STAGES>
 static int launch_bn(int transA, int transB, const CUtensorMap& ma, const CUtensorMap& mb, const EpiArgs& ep, int M,
                      int N, int K, int splits, int kb_per, cudaStream_t st) {
@@ -430,16 +358,6 @@ static inline int launch(const bf16* A, long long lda, int transA, const bf16* B
   static int shallow_kb = -1;
   if (shallow_kb < 0) { const char* e = getenv("RECNET_GEMM_SHALLOW_KB"); shallow_kb = e ? atoi(e) : 12; }
   const bool shallow = kb_per <= shallow_kb;
-  // per-step GEMMs (one M tile, K-major A, 128-wide N tiles): A tile multicast across a cluster of N-tile CTAs
-  const int cl = cluster_size_env();
-  if ((cl == 2 || cl == 4) && !transA && BN == 128 && shallow && M <= BM && (rn_cdiv(N, BN) % cl) == 0 && nkb / splits >= 2) {
-    CUtensorMap mac;
-    RN_TRY(make_map(&mac, A, M, K, lda, BK, BM / cl));
-    if (cl == 2) return transB ? launch_cluster<128, 3, true, 2>(mac, mb, ep, M, N, K, splits, kb_per, st)
-                               : launch_cluster<128, 3, false, 2>(mac, mb, ep, M, N, K, splits, kb_per, st);
-    return transB ? launch_cluster<128, 3, true, 4>(mac, mb, ep, M, N, K, splits, kb_per, st)
-                  : launch_cluster<128, 3, false, 4>(mac, mb, ep, M, N, K, splits, kb_per, st);
-  }
   if (BN == 64) return shallow ? launch_bn<64, 4>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st)
                                : launch_bn<64, 8>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
   if (BN == 128) return shallow ? launch_bn<128, 3>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st)

@@ -29,11 +29,6 @@ struct FwdArgs {
   void* h_op2; long long hop2_ld;                                 // second operand-typed copy (nullable)
   // inter-layer dropout (nn.LSTM(dropout=p), train mode): applied to the h_op2 copy only (the next layer's input)
   float op2_drop; const unsigned long long* rng; unsigned int site; long long drop_base;
-  // fused attention-query projection of the NEXT step (local reconstructor, models/local_reconstructor.py:39): every block
-  // leaves the partial  Wh[b, 0:Aq] = sum_{j in its 256 units} h'[b,j] * Wq[a,j]  in query_out[blockIdx.x][b, 0:Aq], summed
-  // by the attention kernel like split-K partials -- saves the 16-CTA query GEMM node between two dependent steps.
-  const void* Wq; long long wq_ld; int Aq;                        // operand-typed attention W [Aq, H] (nullable)
-  float* query_out; long long query_stride;                       // [gridDim.x][B, Aq]
 };
 
 // body: virtual block (bx = 256-wide slice of H, b = sample): no integer division, pointer-bump partial loop
@@ -79,50 +74,11 @@ __device__ __forceinline__ float lstm_cell_fwd_body(const FwdArgs& a, int bx, in
   return to_f32<TO>(from_f32<TO>(hn));
 }
 
-// Partial attention-query projection over this block's 256 units (see FwdArgs::Wq).  Warp w owns rows a = w, w+8, ...; a lane
-// covers one 16-byte vector of units per pass (8 bf16 / 4 fp32), four rows in flight; same rounded operands as the query GEMM.
-template <typename TO>
-__device__ __forceinline__ void query_partial(const FwdArgs& a, float hq, int bx, int b, int tid) {
-  __shared__ float hs[THREADS];
-  hs[tid] = hq;
-  __syncthreads();
-  constexpr int N = Vec16<TO>::N;
-  const int warp = tid >> 5, lane = tid & 31;
-  const TO* W = reinterpret_cast<const TO*>(a.Wq) + (long long)bx * THREADS;
-  float* out = a.query_out + (long long)bx * a.query_stride + (long long)b * a.Aq;
-  for (int r0 = warp; r0 < a.Aq; r0 += 32) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int u0 = lane * N; u0 < THREADS; u0 += 32 * N) {
-      if (bx * THREADS + u0 < a.H) {            // vectors are all-in or all-out: H % N == 0 (checked by the drivers)
-        Vec16<TO> v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q].load(W + (long long)min(r0 + 8 * q, a.Aq - 1) * a.wq_ld + u0);
-        float hv[N];
-#pragma unroll
-        for (int k = 0; k < N; ++k) hv[k] = hs[u0 + k];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[N];
-          v[q].get(f);
-#pragma unroll
-          for (int k = 0; k < N; ++k) acc[q] = fmaf(hv[k], f[k], acc[q]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float sum = warp_sum(acc[q]);
-      if (lane == 0 && r0 + 8 * q < a.Aq) out[r0 + 8 * q] = sum;
-    }
-  }
-}
-
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(THREADS) lstm_cell_fwd_kernel(FwdArgs a) {
   pdl_wait();            // prerequisites complete ...
   pdl_launch_next();     // ... only then let the NEXT kernel be scheduled (depth-1 look-ahead, no cascade of resident waiters)
-  const float hq = lstm_cell_fwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
-  if (a.Wq) query_partial<TO>(a, hq, blockIdx.x, blockIdx.y, threadIdx.x);
+  lstm_cell_fwd_body<TS, TO>(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 // Backward of one step.

@@ -364,18 +364,17 @@ __global__ void mt_sumsq_kernel(const long long* __restrict__ ptrs, const long l
 __global__ void mt_norm_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ blk_tensor, int n_blocks,
                                         float* __restrict__ sumsq, int n, float* __restrict__ out, const float* __restrict__ base = nullptr,
                                         const float* __restrict__ lambda_dev = nullptr, float* __restrict__ fused_out = nullptr) {
-  __shared__ float nrm[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int t = warp; t < n; t += nw) {
     float s = 0.f;
     for (int b = lane; b < n_blocks; b += 32) if (blk_tensor[b] == t) s += partial[b];
     s = warp_sum(s);
-    if (lane == 0) { sumsq[t] = s; nrm[t & 63] = sqrtf(s); }
+    if (lane == 0) sumsq[t] = s;
   }
-  __syncthreads();
+  __syncthreads();                      // sumsq[] written by this block is visible to thread 0 (any number of tensors)
   if (threadIdx.x == 0) {
     float r = 0.f;
-    for (int t = 0; t < n; ++t) r += nrm[t & 63];
+    for (int t = 0; t < n; ++t) r += sqrtf(sumsq[t]);
     out[0] = r;
     // loss assembly of train.py:70,102,128 folded in: fused = base + lambda * reg (saves two elementwise graph nodes per module)
     if (fused_out) fused_out[0] = (base ? base[0] : 0.f) + (lambda_dev ? lambda_dev[0] : 1.f) * r;

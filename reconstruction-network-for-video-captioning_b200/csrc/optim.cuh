@@ -99,78 +99,6 @@ __global__ void adam_mt_kernel(const long long* __restrict__ pptrs, const long l
   }
 }
 
-// ---- EXPERIMENTAL, OPT-IN (never run on a GPU yet): regulariser gradient formed inside the optimiser pass ---------------------
-// The L2-norm regulariser's gradient lambda * g_loss * p / ||p|| (train.py:69,101,127) is a read-modify-write of every gradient
-// (misc::mt_reg_grad_kernel, ~55 us per step).  Both operands are already read here, so with a RegTerm the update uses
-// g + k_t p (k_t per tensor, from the forward's squared norms) and the clip norm is taken over the same sum; `p.grad` then holds
-// the BPTT gradient only (plus, for a clipped module, the clipped total after the step when write_clipped_grads is set).
-struct RegTerm { const float* sumsq; const int* index; const float* g; const float* lambda_dev; };
-__device__ __forceinline__ float reg_coeff(const RegTerm& r, int t) {
-  if (!r.sumsq) return 0.f;
-  const float nrm = sqrtf(r.sumsq[r.index ? r.index[t] : t]);
-  return nrm > 0.f ? (r.g ? *r.g : 1.f) * (r.lambda_dev ? *r.lambda_dev : 1.f) / nrm : 0.f;
-}
-__global__ void mt_sumsq_reg_kernel(const long long* __restrict__ pptrs, const long long* __restrict__ gptrs,
-                                    const long long* __restrict__ sizes, const int* __restrict__ blk_tensor,
-                                    const int* __restrict__ blk_chunk, RegTerm r, float* __restrict__ partial) {
-  __shared__ float red[32];
-  const int t = blk_tensor[blockIdx.x];
-  const float* p = reinterpret_cast<const float*>(pptrs[t]);
-  const float* g = reinterpret_cast<const float*>(gptrs[t]);
-  const long long n = sizes[t], lo = (long long)blk_chunk[blockIdx.x] * misc::MT_CHUNK, hi = min(n, lo + misc::MT_CHUNK);
-  const float k = reg_coeff(r, t);
-  float s = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float v = fmaf(k, p[i], g[i]); s = fmaf(v, v, s); }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-template <bool AMSGRAD>
-__global__ void adam_mt_reg_kernel(const long long* __restrict__ pptrs, const long long* __restrict__ gptrs,
-                                   const long long* __restrict__ mptrs, const long long* __restrict__ vptrs,
-                                   const long long* __restrict__ xptrs, const long long* __restrict__ sizes,
-                                   const int* __restrict__ blk_tensor, const int* __restrict__ blk_chunk, AdamHyper h,
-                                   const float* __restrict__ state, int write_grads, RegTerm r) {
-  const int t = blk_tensor[blockIdx.x];
-  float* p = reinterpret_cast<float*>(pptrs[t]);
-  float* g = reinterpret_cast<float*>(gptrs[t]);
-  float* m = reinterpret_cast<float*>(mptrs[t]);
-  float* v = reinterpret_cast<float*>(vptrs[t]);
-  float* x = AMSGRAD ? reinterpret_cast<float*>(xptrs[t]) : nullptr;
-  const long long n = sizes[t], lo = (long long)blk_chunk[blockIdx.x] * misc::MT_CHUNK, hi = min(n, lo + misc::MT_CHUNK);
-  const float clip = state[ST_CLIP], step_size = state[ST_STEPSIZE], rs = state[ST_RSQRT_BC2];
-  const float k = reg_coeff(r, t);
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {       // scalar, coalesced: the experiment is about one pass less
-    float P = p[i], M = m[i], V = v[i], X = AMSGRAD ? x[i] : 0.f;
-    const float G = fmaf(k, P, g[i]);
-    adam_one(P, G, M, V, AMSGRAD ? &X : nullptr, h, clip, step_size, rs);
-    p[i] = P; m[i] = M; v[i] = V;
-    if (AMSGRAD) x[i] = X;
-    if (write_grads) g[i] = G * clip;
-  }
-}
-static int adam_step_reg(const long long* pptrs, const long long* gptrs, const long long* mptrs, const long long* vptrs,
-                         const long long* xptrs, const long long* sizes, int n, const int* blk_tensor, const int* blk_chunk,
-                         int n_blocks, double lr, double beta1, double beta2, double eps, double weight_decay, double max_grad_norm,
-                         float* partial, float* state, int write_clipped_grads, RegTerm r, cudaStream_t st) {
-  if (n <= 0 || n_blocks <= 0) return 0;
-  if (!pptrs || !gptrs || !mptrs || !vptrs || !sizes || !blk_tensor || !blk_chunk || !state || !r.sumsq) return RECNET_ERR_BAD_SHAPE;
-  if (!(lr >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0)) return RECNET_ERR_BAD_SHAPE;
-  const bool clip = max_grad_norm > 0.0;
-  if (clip) {
-    if (!partial) return RECNET_ERR_BAD_SHAPE;
-    mt_sumsq_reg_kernel<<<n_blocks, 256, 0, st>>>(pptrs, gptrs, sizes, blk_tensor, blk_chunk, r, partial);
-    RN_LAUNCH_OK();
-  }
-  adam_prologue_kernel<<<1, 512, 0, st>>>(clip ? partial : nullptr, n_blocks, (float)max_grad_norm, lr, beta1, beta2, state);
-  RN_LAUNCH_OK();
-  AdamHyper h{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay};
-  const int wg = (clip && write_clipped_grads) ? 1 : 0;
-  if (xptrs) adam_mt_reg_kernel<true><<<n_blocks, 256, 0, st>>>(pptrs, gptrs, mptrs, vptrs, xptrs, sizes, blk_tensor, blk_chunk, h, state, wg, r);
-  else adam_mt_reg_kernel<false><<<n_blocks, 256, 0, st>>>(pptrs, gptrs, mptrs, vptrs, nullptr, sizes, blk_tensor, blk_chunk, h, state, wg, r);
-  RN_LAUNCH_OK();
-  return 0;
-}
-
 static int adam_step(const long long* pptrs, const long long* gptrs, const long long* mptrs, const long long* vptrs,
                      const long long* xptrs, const long long* sizes, int n, const int* blk_tensor, const int* blk_chunk,
                      int n_blocks, double lr, double beta1, double beta2, double eps, double weight_decay, double max_grad_norm,

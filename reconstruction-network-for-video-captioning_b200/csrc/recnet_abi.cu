@@ -48,22 +48,20 @@ int recnet_profile_collect(float* out, int max_records) {
 
 // developer probe: a loop-kernel launch with n_phases empty phases (grid barrier after each if sync_after) -- measures
 // the per-phase overhead of the persistent loop kernel.  scratch: >= n_phases * 1024 + 1024 bytes of device memory.
-int recnet_debug_loop_overhead(int n_phases, int sync_after, void* scratch, void* stream) {
-  mega::Emitter<bf16> em(true, ST(stream));
-  if (!em.mega) return RECNET_ERR_UNSUPPORTED;
-  for (int i = 0; i < n_phases; ++i) {
-    mega::Phase ph; memset(&ph, 0, sizeof(ph));
-    ph.type = 0; ph.nvb = 0; ph.sync_after = sync_after;
-    em.phases.push_back(ph);
-  }
-  uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
-  unsigned* bar = reinterpret_cast<unsigned*>(base);
-  int* err = reinterpret_cast<int*>(base + 256);
-  RN_CUDA_OK(cudaMemsetAsync(base, 0, 512, ST(stream)));
-  return em.flush(base + 1024, (size_t)n_phases * sizeof(mega::Phase), bar, err, 100);
+// developer / test probe: the inverted-dropout scales (0 or 1/(1-p)) the kernels apply to elements 0..n-1 of dropout `site`
+// for the (seed, offset) pair in rng -- the same device function the forward and backward kernels call
+__global__ void debug_dropout_mask_kernel(const unsigned long long* rng, unsigned int site, long long n, float p, float* out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = dropout_scale(rng, site, (uint64_t)i, p);
 }
-
-// developer probe: per-phase %globaltimer stamps of the next loop-kernel launches are written to `buf` (device, u64[n+1]); null = off
+int recnet_debug_dropout_mask(const uint64_t* rng, uint32_t site, int64_t n, float p, float* out, void* stream) {
+  if (n <= 0) return 0;
+  if (!rng || !out) return RECNET_ERR_BAD_SHAPE;
+  const int blocks = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  debug_dropout_mask_kernel<<<blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const unsigned long long*>(rng), site, (long long)n, p, out);
+  RN_LAUNCH_OK();
+  return 0;
+}
 int recnet_debug_set_timeline(void* buf) {
   unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
   unsigned int zero = 0;
@@ -363,7 +361,6 @@ int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, con
   misc::mt_sumsq_kernel<<<n_blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(ptrs), reinterpret_cast<const long long*>(sizes),
                                                   blk_tensor, blk_chunk, partial);
   RN_LAUNCH_OK();
-  if (n > 64) return RECNET_ERR_BAD_SHAPE;
   misc::mt_norm_finalize_kernel<<<1, 512, 0, st>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out, base, lambda_dev, fused_out);
   RN_LAUNCH_OK();
   return 0;
@@ -401,18 +398,5 @@ int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const 
                           reinterpret_cast<LP>(exp_avg_sq_ptrs), reinterpret_cast<LP>(max_exp_avg_sq_ptrs), reinterpret_cast<LP>(sizes), n,
                           blk_tensor, blk_chunk, n_blocks, lr, beta1, beta2, eps, weight_decay, max_grad_norm, partial, state,
                           write_clipped_grads, ST(stream));
-}
-// EXPERIMENTAL (opt-in, see optim.cuh): Adam step that also forms the norm regulariser's gradient k_t p from the forward's squared norms
-int recnet_adam_step_reg(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs, const int64_t* exp_avg_sq_ptrs,
-                         const int64_t* max_exp_avg_sq_ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
-                         const int32_t* blk_chunk, int n_blocks, double lr, double beta1, double beta2, double eps, double weight_decay,
-                         double max_grad_norm, float* partial, float* state, int write_clipped_grads, const float* reg_sumsq,
-                         const int32_t* reg_index, const float* reg_g, const float* reg_lambda, void* stream) {
-  typedef const long long* LP;
-  optim::RegTerm r{reg_sumsq, reg_index, reg_g, reg_lambda};
-  return optim::adam_step_reg(reinterpret_cast<LP>(param_ptrs), reinterpret_cast<LP>(grad_ptrs), reinterpret_cast<LP>(exp_avg_ptrs),
-                              reinterpret_cast<LP>(exp_avg_sq_ptrs), reinterpret_cast<LP>(max_exp_avg_sq_ptrs), reinterpret_cast<LP>(sizes),
-                              n, blk_tensor, blk_chunk, n_blocks, lr, beta1, beta2, eps, weight_decay, max_grad_norm, partial, state,
-                              write_clipped_grads, r, ST(stream));
 }
 }  // extern "C"

@@ -7,7 +7,6 @@
 #pragma once
 #include "proj_attn.cuh"
 #include "seq_decoder.cuh"
-#include "seq_decoder_cluster.cuh"
 
 namespace dec {
 
@@ -31,7 +30,7 @@ static inline bool pf_enabled() {
 }
 static inline bool pf_ok(const recnet_decoder_desc& d) {
   if (!pf_enabled() || d.cell != RECNET_CELL_LSTM || d.n_layers > 1) return false;
-  if (num_chains(d.B) != 1 || mega::mega_enabled()) return false;
+  if (num_chains(d.B) != 1) return false;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if ((long long)d.B * d.T * 4 * d.H >= (1ll << 31) || (long long)d.L * d.B * (d.A + 4 * d.H) >= (1ll << 31)) return false;   // 32-bit index math
   return d.T >= 1 && d.T <= pf::MAX_T && d.A >= 4 && d.A <= pf::MAX_A && d.A % al == 0 && d.H % al == 0 &&
@@ -105,26 +104,6 @@ static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
   return w;
 }
 
-// Opt-in (RECNET_DEC_CLUSTER=1): the whole forward loop as one persistent kernel of 16-CTA clusters with [W_a ; W_hh] resident in
-// shared memory (seq_decoder_cluster.cuh).  Returns 1 if it ran the loop, 0 if the shape / precision / device is not eligible.
-template <typename T>
-static int try_cluster_loop(const recnet_decoder_desc&, const recnet_decoder_tensors&, const PfWs<T>&, float*, cudaStream_t) { return 0; }
-template <>
-int try_cluster_loop<bf16>(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const PfWs<bf16>& w, float* hiddens,
-                           cudaStream_t st) {
-  if (!dcl::cluster_enabled()) return 0;
-  int ncl = d.B < 8 ? d.B : 8;                                       // 8 GPCs: one 16-CTA cluster each
-  if ((d.B + ncl - 1) / ncl > dcl::MT) ncl = (d.B + dcl::MT - 1) / dcl::MT;
-  if (!dcl::cluster_ok(d.B, d.T, d.A, d.H, ncl)) return 0;
-  dcl::Args a{};
-  a.Wcat = w.Wcat; a.Uv = w.Uv; a.attn_w = p.attn_w; a.VW = w.VW; a.Gx = w.Gx; a.b_hh = p.b_hh;
-  a.c = w.c; a.hiddens = hiddens; a.Hop = w.Hop; a.Wh = w.Wh; a.e = w.e; a.gates = w.gates;
-  a.B = d.B; a.L = d.L; a.Tn = d.T; a.A = d.A; a.H = d.H; a.inv_T = 1.f / d.T;
-  const int rc = dcl::launch(a, ncl, st);
-  if (rc == RECNET_ERR_UNSUPPORTED) return 0;
-  return rc == 0 ? 1 : -rc - 1000;                                  // launch errors surface through the caller
-}
-
 // C (operand type) = A B^T, written straight in the operand precision
 static inline int gemm_to_operand(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M,
                                   int N, int K, float* scratch, cudaStream_t st) {
@@ -172,9 +151,7 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk2, s2));
   RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
   RN_TRY(side().join(st, s2));
-  const int clustered = try_cluster_loop<T>(d, p, w, hiddens, st);
-  if (clustered < 0) return RECNET_ERR_DRIVER;
-  for (int t = 0; t < L && !clustered; ++t) {
+  for (int t = 0; t < L; ++t) {
     const size_t r = (size_t)t * B;
     if (t > 0)      // h_{-1} = 0: no query, no recurrent term
       RN_TRY(gemm_partials<T>(w.Hop + r * H, H, 0, w.Wcat, H, 0, w.P, B, w.NP, H, w.pl_h, st));

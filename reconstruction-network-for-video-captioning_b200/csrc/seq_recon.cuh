@@ -131,16 +131,6 @@ static inline int check_local(const recnet_local_desc& d) {
   return 0;
 }
 
-// RECNET_FUSED_QUERY=1 (opt-in): the cell kernel of step t leaves the attention-query partials of step t+1 (lstm_cell.cuh:
-// query_partial) instead of a 16-CTA query GEMM per step.  Parity-green, 27 fewer graph nodes, but MEASURED SLOWER on the B200
-// (2.800 vs 2.747 ms/step, profiles/r1_g_nodes.md): every (unit-slice, sample) block re-reads its 64 KB slice of W, 39 MB of L2
-// traffic per step against 0.4 MB in the GEMM, which costs more than the node it removes.
-static inline bool fused_query_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("RECNET_FUSED_QUERY"); v = e ? atoi(e) : 0; }
-  return v != 0;
-}
-
 template <typename T>
 static int local_forward(const recnet_local_desc& d, const recnet_local_tensors& p, const float* hiddens, const float* feats,
                          const unsigned long long* rng, void* ws, long long ws_bytes, float* mse_out, cudaStream_t st) {
@@ -199,11 +189,9 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
       const size_t r = (size_t)t * B + b0;
       T* x_t = w.X + r * w.KX;
       T* x_n = x_t + (size_t)B * w.KX;
-      // attention query W.h_{t-1}: partials left by the previous step's cell kernel (fused_q), else its own small GEMM
-      const bool fused_q = fused_query_enabled() && !is_gru && w.nch == 1 && !em.mega;
+      // attention query W.h_{t-1}: its own small GEMM, partials summed by the attention kernel
       int n_whp = 0;
-      if (t > 0 && fused_q) n_whp = rn_cdiv(R, cell::THREADS);
-      else if (t > 0) {
+      if (t > 0) {
         RN_TRY(em.gemm_partials(x_t + H, w.KX, 0, w.Wa, R, 0, WhP, nb, A, R, w.pl_wh));
         n_whp = w.pl_wh.splits;
       }
@@ -238,7 +226,6 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
       ca.Gx = nullptr; ca.b1 = p.b_ih; ca.b2 = p.b_hh; ca.c_prev = w.c + r * R; ca.B = nb; ca.H = R;
       ca.gates_out = w.gates + r * 4 * R; ca.c_out = w.c + ((size_t)(t + 1) * B + b0) * R; ca.h_out = nullptr;
       ca.h_op = x_n + H; ca.hop_ld = w.KX; ca.h_op2 = nullptr;
-      if (fused_q && t + 1 < S) { ca.Wq = w.Wa; ca.wq_ld = R; ca.Aq = A; ca.query_out = WhP; ca.query_stride = (long long)nb * A; }
       RN_TRY(em.cell_fwd(ca));
     }
   }

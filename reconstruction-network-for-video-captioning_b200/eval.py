@@ -36,6 +36,16 @@ def beam_search(config, beam_width, vocab, decoder, input, hidden, encoder_outpu
     cum = [torch.zeros(B, dtype=torch.float32, device=dev)]      # log(1.)
     seqs = torch.zeros(B, 1, 0, dtype=torch.long, device=dev)    # (B, beams, t) ids so far
     last_eos = torch.full((B, 1), -1, dtype=torch.long, device=dev)   # position of the last <EOS> per (b, beam), -1 = none
+    import contextlib
+    scope = decoder.cached_uv(encoder_outputs) if hasattr(decoder, "cached_uv") else contextlib.nullcontext()
+    with scope:                       # U.v once for this batch (decoder.py:54 recomputes it every step); nothing survives the block
+        seqs = _beam_loop(config, beam_width, n_vocabs, eos, decoder, inputs, hiddens, cum, seqs, last_eos, encoder_outputs, is_lstm)
+    return seqs[:, 0].tolist()
+
+
+def _beam_loop(config, beam_width, n_vocabs, eos, decoder, inputs, hiddens, cum, seqs, last_eos, encoder_outputs, is_lstm):
+    B = encoder_outputs.shape[0]
+    dev = encoder_outputs.device
     for t in range(config.caption_max_len + 1):
         cand, next_hiddens = [], []
         for i, (tok, hid, cp) in enumerate(zip(inputs, hiddens, cum)):
@@ -63,7 +73,7 @@ def beam_search(config, beam_width, vocab, decoder, input, hidden, encoder_outpu
         hiddens, cum = new_hiddens, [top_p[:, k] for k in range(beam_width)]
         if t == config.caption_max_len or bool((tok_ids == 0).all()):
             break
-    return seqs[:, 0].tolist()
+    return seqs
 
 
 def save_checkpoint(path, iteration, decoder, reconstructor=None, loss=None, config=None):
@@ -77,10 +87,15 @@ def save_checkpoint(path, iteration, decoder, reconstructor=None, loss=None, con
     torch.save(blob, path)
 
 
-def load_checkpoint(path, decoder, reconstructor=None, map_location=None):
-    """Load a reference-format checkpoint (also ones written by the reference itself) into our modules."""
+def load_checkpoint(path, decoder, reconstructor=None, map_location=None, restore_optimizers=True):
+    """Load a reference-format checkpoint (also ones written by the reference itself) into our modules; the optimiser
+    states ('dec_opt' / 'rec_opt', torch.optim.Adam layout) are restored too unless ``restore_optimizers=False``."""
     blob = torch.load(path, map_location=map_location, weights_only=False)
     decoder['model'].load_state_dict(blob['dec'])
+    if restore_optimizers and blob.get('dec_opt') is not None and decoder.get('optimizer') is not None:
+        decoder['optimizer'].load_state_dict(blob['dec_opt'])            # Adam moments, amsgrad max, step count (train.py:409)
     if reconstructor is not None and 'rec' in blob:
         reconstructor['model'].load_state_dict(blob['rec'])
+        if restore_optimizers and blob.get('rec_opt') is not None and reconstructor.get('optimizer') is not None:
+            reconstructor['optimizer'].load_state_dict(blob['rec_opt'])
     return blob.get('iteration')

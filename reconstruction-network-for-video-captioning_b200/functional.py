@@ -147,18 +147,6 @@ def flat_buffer_of(grads: Sequence[torch.Tensor]):
     return None
 
 
-# EXPERIMENTAL, opt-in (module dict key 'defer_reg', config.defer_regulariser / RECNET_DEFER_REG=1; never run on a GPU yet):
-# instead of adding the regulariser's gradient to the flat buffer in backward (a read-modify-write of every gradient), leave a
-# note per parameter -- (squared norms of the forward, slot, upstream gradient of the loss, lambda) -- for optim.ClipAdam.step,
-# which forms g + lambda * g_loss * p / ||p|| while it reads p and g anyway (recnet_adam_step_reg).
-_pending_reg: Dict[int, tuple] = {}
-
-
-def _defer_reg(params, sumsq, g_loss, lam):
-    for i, p in enumerate(params):
-        _pending_reg[p.data_ptr()] = (sumsq, i, g_loss, lam)
-
-
 def _norms_bwd_into(params, sumsq, g_reg, gptrs, accumulate: bool, lambda_dev=None):
     tab = _table_for(params)
     L.check(L.lib().recnet_param_norms_bwd(tab.ptrs.data_ptr(), gptrs.data_ptr(), tab.sizes.data_ptr(), tab.n,
@@ -238,7 +226,6 @@ class DecoderSequenceFn(torch.autograd.Function):
         reg, sumsq, fused = _norms_fwd(saved[5:], ce, lam)
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.lam = lam                       # not an autograd input: a plain attribute keeps it alive for backward
-        ctx.defer_reg = bool(meta.get("defer_reg")) and lam is not None
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(*saved, ws, sumsq, hiddens)
         if fused is not None:               # output 0 is the assembled loss ce + lambda * reg (train.py:70); reg is informational
@@ -257,9 +244,7 @@ class DecoderSequenceFn(torch.autograd.Function):
         L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
                                        ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
                                        _ptr(g_hid), hiddens.data_ptr(), C.byref(g), _stream()), "recnet_decoder_bwd")
-        if ctx.lam is not None and ctx.defer_reg:
-            _defer_reg(params, sumsq, g_ce, ctx.lam)
-        elif ctx.lam is not None:
+        if ctx.lam is not None:
             _norms_bwd_into(params, sumsq, g_ce, gptrs, accumulate=True, lambda_dev=ctx.lam)
         elif g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
@@ -315,7 +300,6 @@ class LocalReconstructorFn(torch.autograd.Function):
         reg, sumsq, fused = _norms_fwd(params, mse, lam)
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.lam = lam
-        ctx.defer_reg = bool(meta.get("defer_reg")) and lam is not None
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(hiddens, feats, rng, ws, sumsq, *params)
         if fused is not None:               # output 0 is the assembled loss mse + lambda * reg (train.py:128-130)
@@ -334,9 +318,7 @@ class LocalReconstructorFn(torch.autograd.Function):
         L.check(lib.recnet_local_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
                                      ws.data_ptr(), ctx.nbytes, g_mse.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
                 "recnet_local_bwd")
-        if ctx.lam is not None and ctx.defer_reg:
-            _defer_reg(params, sumsq, g_mse, ctx.lam)
-        elif ctx.lam is not None:
+        if ctx.lam is not None:
             _norms_bwd_into(params, sumsq, g_mse, gptrs, accumulate=True, lambda_dev=ctx.lam)
         elif g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
@@ -371,7 +353,6 @@ class GlobalReconstructorFn(torch.autograd.Function):
         reg, sumsq, fused = _norms_fwd(params, loss, lam)
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.lam = lam
-        ctx.defer_reg = bool(meta.get("defer_reg")) and lam is not None
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(hiddens, feats, rng, ws, sumsq, *params)
         if fused is not None:               # output 0 is the assembled loss (train.py:100-102)
@@ -390,9 +371,7 @@ class GlobalReconstructorFn(torch.autograd.Function):
         L.check(lib.recnet_global_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
                                       ws.data_ptr(), ctx.nbytes, g_loss.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
                 "recnet_global_bwd")
-        if ctx.lam is not None and ctx.defer_reg:
-            _defer_reg(params, sumsq, g_loss, ctx.lam)
-        elif ctx.lam is not None:
+        if ctx.lam is not None:
             _norms_bwd_into(params, sumsq, g_loss, gptrs, accumulate=True, lambda_dev=ctx.lam)
         elif g_reg is not None:
             _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)

@@ -119,7 +119,7 @@ class Decoder(nn.Module, _RngMixin):
         self.rnn = RNNParams(model_name, embedding_size + encoder_size, hidden_size, n_layers, dropout)
         self.out = nn.Linear(hidden_size, output_size)
         self._init_rng(0xDEC0)
-        self._uv_cache = None
+        self._uv_scope = None          # [encoder_outputs, U.v or None] while a cached_uv() scope is open
 
     # ---- helpers ----
     def _params(self):
@@ -142,8 +142,25 @@ class Decoder(nn.Module, _RngMixin):
             return 1 <= self.n_layers <= L.MAX_LAYERS
         return self.n_layers == 1
 
+    def cached_uv(self, encoder_outputs):
+        """Context manager: inside it, per-step ``forward`` calls on exactly this ``encoder_outputs`` tensor compute
+        U.v (decoder.py:54) once instead of once per step.  Nothing is remembered after the block."""
+        dec = self
+
+        class _Scope:
+            def __enter__(self_):
+                self_.prev = dec._uv_scope
+                dec._uv_scope = [encoder_outputs, None]
+                return dec
+
+            def __exit__(self_, *exc):
+                dec._uv_scope = self_.prev
+                return False
+
+        return _Scope()
+
     # ---- whole teacher-forced loop ----
-    def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs, lambda_reg=None, defer_reg=False):
+    def forward_sequence(self, tokens_in, targets, ce_weight, encoder_outputs, lambda_reg=None):
         """tokens_in/targets (L,B) int64, ce_weight (L,B) f32 -> (ce scalar, hiddens (L,NL,B,H), reg = sum_p ||p||).
         With ``lambda_reg`` (the module dict's device scalar) output 0 is the assembled loss ce + lambda_reg * reg (train.py:70),
         computed inside the regulariser kernel; reg is then returned for inspection only."""
@@ -152,7 +169,6 @@ class Decoder(nn.Module, _RngMixin):
             return (ce if lambda_reg is None else ce + lambda_reg * reg), hiddens, reg
         meta = self._meta()
         meta["lambda_reg"] = lambda_reg
-        meta["defer_reg"] = defer_reg             # experimental: regulariser gradient formed by optim.ClipAdam (functional._defer_reg)
         return Fn.DecoderSequenceFn.apply(meta, encoder_outputs, tokens_in, targets, ce_weight, self._next_rng(), *self._params())
 
     def _forward_sequence_stepwise(self, tokens_in, targets, ce_weight, encoder_outputs):
@@ -179,10 +195,11 @@ class Decoder(nn.Module, _RngMixin):
             Lsteps, B = tokens_in.shape
             hidden = _zero_state(self.model_name, self.n_layers, B, self.hidden_size, encoder_outputs.device)
             logits, hiddens = [], []
-            for t in range(Lsteps):
-                lg, hidden = self.forward(tokens_in[t:t + 1], hidden, encoder_outputs)
-                logits.append(lg)
-                hiddens.append(hidden[0] if _is_lstm(self.model_name) else hidden)
+            with self.cached_uv(encoder_outputs):
+                for t in range(Lsteps):
+                    lg, hidden = self.forward(tokens_in[t:t + 1], hidden, encoder_outputs)
+                    logits.append(lg)
+                    hiddens.append(hidden[0] if _is_lstm(self.model_name) else hidden)
             return torch.stack(logits), torch.stack(hiddens)
         return Fn.decoder_teacher_forced_logits(self._meta(), encoder_outputs, tokens_in, self._rng, self._params())
 
@@ -200,13 +217,14 @@ class Decoder(nn.Module, _RngMixin):
             self.eval()
             ids = torch.zeros(max_steps, B, dtype=torch.long, device=dev)
             n = max_steps
-            for t in range(max_steps):
-                logits, hid = self.forward(tok, hid, encoder_outputs)
-                tok = logits.argmax(dim=1).view(1, -1)
-                ids[t] = tok[0]
-                if bool((tok == 0).all()):
-                    n = t + 1
-                    break
+            with self.cached_uv(encoder_outputs):
+                for t in range(max_steps):
+                    logits, hid = self.forward(tok, hid, encoder_outputs)
+                    tok = logits.argmax(dim=1).view(1, -1)
+                    ids[t] = tok[0]
+                    if bool((tok == 0).all()):
+                        n = t + 1
+                        break
             self.train(was_training)
             return ids, torch.tensor([n], dtype=torch.int32, device=dev)
         lib = L.lib()
@@ -233,17 +251,19 @@ class Decoder(nn.Module, _RngMixin):
         h = hidden[0][-1] if _is_lstm(self.model_name) else hidden[-1]                                     # decoder.py:50-53: top layer
         emb = torch.nn.functional.embedding(input[0], self.embedding.weight) * self.embedding_scale      # decoder.py:46-47
         emb = torch.nn.functional.dropout(emb, self.embedding_dropout_p, self.training)                   # decoder.py:48
-        # U.v is time-invariant (the reference recomputes it every step, decoder.py:54).  Without autograd (greedy / beam
-        # loops over this method) it is cached across the steps of one sequence; with autograd it is recomputed so that
-        # every step owns its graph.  The training hot path (forward_sequence) hoists it out of the loop altogether.
+        # U.v is time-invariant (the reference recomputes it every step, decoder.py:54).  It is recomputed here on every call
+        # unless the caller opened an explicit scope for ONE sequence (``with decoder.cached_uv(encoder_outputs):`` -- what
+        # the greedy / beam loops over this method do); the scope is tied to the identity of that tensor, holds a reference
+        # to it (so the allocator cannot hand its address to another batch), and ends with the ``with`` block.  The training
+        # hot path (forward_sequence) hoists the projection out of the loop altogether.
         B, T, E = encoder_outputs.shape
-        need_grad = torch.is_grad_enabled() and self.attn_U.weight.requires_grad
-        key = (encoder_outputs.data_ptr(), encoder_outputs._version, self.attn_U.weight._version, (B, T, E), p)
-        if need_grad or self._uv_cache is None or self._uv_cache[0] != key:
-            Uv = ops.linear(encoder_outputs.reshape(B * T, E), self.attn_U.weight, None, p).view(B, T, -1)
-            self._uv_cache = None if need_grad else (key, Uv)
+        scope = self._uv_scope
+        if scope is not None and scope[0] is encoder_outputs and not (torch.is_grad_enabled() and self.attn_U.weight.requires_grad):
+            if scope[1] is None:
+                scope[1] = ops.linear(encoder_outputs.reshape(B * T, E), self.attn_U.weight, None, p).view(B, T, -1)
+            Uv = scope[1]
         else:
-            Uv = self._uv_cache[1]
+            Uv = ops.linear(encoder_outputs.reshape(B * T, E), self.attn_U.weight, None, p).view(B, T, -1)
         Wh = ops.linear(h, self.attn_W.weight, None, p)                                                   # decoder.py:51
         ctx = ops.additive_attention(Wh, Uv, self.attn_b, self.attn_w.weight, encoder_outputs, p)          # decoder.py:55-61
         # layer 0 takes [emb ; ctx], layer l the (dropped-out) output of layer l-1 (nn.LSTM / nn.GRU, decoder.py:64-66)
@@ -288,7 +308,7 @@ class GlobalReconstructor(_ReconstructorBase):
         w_ih, w_hh, b_ih, b_hh = self.rnn.layer(0)
         return (w_ih, w_hh, b_ih, b_hh, self.out.weight, self.out.bias)
 
-    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None, defer_reg=False):
+    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None):
         """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,T,R) -> (MSE(mean_t out, mean_tau feats) / L, reg = sum_p ||p||).
         With ``lambda_reg`` output 0 is the assembled loss (train.py:100-102)."""
         if not self._fused_ok(decoder_hiddens):
@@ -296,7 +316,6 @@ class GlobalReconstructor(_ReconstructorBase):
             return (loss if lambda_reg is None else loss + lambda_reg * reg), reg
         hid = _sequence_hiddens(decoder_hiddens)
         meta = dict(precision=_precision_id(self.precision), train=self.training, p_drop=self.decoder_dropout_p, lambda_reg=lambda_reg,
-                    defer_reg=defer_reg,
                     caption_max_len=self.caption_max_len, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.GlobalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 
@@ -352,7 +371,7 @@ class LocalReconstructor(_ReconstructorBase):
         return (self.attn_W.weight, self.attn_U.weight, self.attn_b, self.attn_w.weight, w_ih, w_hh, b_ih, b_hh,
                 self.out.weight, self.out.bias)
 
-    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None, defer_reg=False):
+    def forward_sequence(self, decoder_hiddens, encoder_outputs, lambda_reg=None):
         """decoder_hiddens (L,NLdec,B,H) or (L,B,H); encoder_outputs (B,S,R) -> (MSELoss(outputs^T, encoder_outputs), reg = sum_p ||p||).
         With ``lambda_reg`` output 0 is the assembled loss (train.py:128-130)."""
         if not self._fused_ok(decoder_hiddens):
@@ -360,7 +379,6 @@ class LocalReconstructor(_ReconstructorBase):
             return (loss if lambda_reg is None else loss + lambda_reg * reg), reg
         hid = _sequence_hiddens(decoder_hiddens)
         meta = dict(A=self.attn_size, precision=_precision_id(self.precision), train=self.training, lambda_reg=lambda_reg,
-                    defer_reg=defer_reg,
                     p_drop=self.decoder_dropout_p, cell=L.CELL_LSTM if self.model_name == "LSTM" else L.CELL_GRU)
         return Fn.LocalReconstructorFn.apply(meta, hid, encoder_outputs, self._next_rng(), *self._params())
 

@@ -112,8 +112,6 @@ class ClipAdam(torch.optim.Optimizer):
         gptrs = self._grad_table(params)
         x = self._ptrs.get("max_exp_avg_sq")
         mgn = g.get("max_grad_norm")
-        if Fn._pending_reg and self._step_with_deferred_regulariser(params, tab, gptrs, x, g, mgn):
-            return loss
         L.check(L.lib().recnet_adam_step(
             tab.ptrs.data_ptr(), gptrs.data_ptr(), self._ptrs["exp_avg"].data_ptr(), self._ptrs["exp_avg_sq"].data_ptr(),
             None if x is None else x.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(), tab.blk_chunk.data_ptr(),
@@ -122,38 +120,27 @@ class ClipAdam(torch.optim.Optimizer):
             int(bool(g.get("write_clipped_grads", True))), Fn._stream()), "recnet_adam_step")
         return loss
 
-    def _step_with_deferred_regulariser(self, params, tab, gptrs, x, g, mgn) -> bool:
-        """EXPERIMENTAL (functional._defer_reg): if backward left regulariser notes for these parameters, run recnet_adam_step_reg,
-        which adds lambda * g_loss * p / ||p|| to the gradients while it reads them.  Returns False when there is nothing pending."""
-        notes = [Fn._pending_reg.get(p.data_ptr()) for p in params]
-        if all(n is None for n in notes):
-            return False
-        if any(n is None for n in notes) or any(n[0] is not notes[0][0] or n[2] is not notes[0][2] or n[3] is not notes[0][3] for n in notes):
-            raise RuntimeError("ClipAdam: deferred regulariser notes cover only part of this optimiser's parameters "
-                               "(one optimiser per module is assumed, train.py:149,186)")
-        sumsq, _, g_loss, lam = notes[0]
-        slots = tuple(n[1] for n in notes)
-        idx = self._gptr_cache.get(("reg_index", slots))
-        if idx is None:
-            self._no_capture("the regulariser slot table")
-            idx = self._gptr_cache[("reg_index", slots)] = torch.tensor(slots, dtype=torch.int32, device=params[0].device)
-        L.check(L.lib().recnet_adam_step_reg(
-            tab.ptrs.data_ptr(), gptrs.data_ptr(), self._ptrs["exp_avg"].data_ptr(), self._ptrs["exp_avg_sq"].data_ptr(),
-            None if x is None else x.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(), tab.blk_chunk.data_ptr(),
-            tab.n_blocks, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-            float(mgn) if mgn else 0.0, self._partial.data_ptr(), self._dev_state.data_ptr(),
-            int(bool(g.get("write_clipped_grads", True))), sumsq.data_ptr(), idx.data_ptr(), g_loss.data_ptr(), lam.data_ptr(),
-            Fn._stream()), "recnet_adam_step_reg")
-        for p in params:
-            Fn._pending_reg.pop(p.data_ptr(), None)
-        return True
-
     @property
     def last_grad_norm(self) -> torch.Tensor:
         """Total gradient norm seen by the last step (device scalar; 0 when max_grad_norm is unset)."""
         if not self._ready:
             self._build()
         return self._dev_state[1]
+
+    def state_dict(self):
+        """torch.optim.Adam's layout.  Every parameter gets its OWN ``step`` tensor (a copy of the shared device counter): the
+        live state aliases one scalar, and an aliased ``step`` loaded into torch.optim.Adam would be advanced once per
+        parameter per iteration."""
+        if not self._ready and any(p.requires_grad for p in self.param_groups[0]["params"]):
+            self._build()
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if "step" in st and torch.is_tensor(st["step"]):
+                st["step"] = st["step"].detach().clone()
+            for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                if k in st:
+                    st[k] = st[k].detach().clone()      # independent storage: not views of the flat buffers
+        return sd
 
     def load_state_dict(self, state_dict):
         """Accepts torch.optim.Adam's layout; values are copied INTO the flat buffers (the views stay bound)."""

@@ -41,17 +41,6 @@ class GradAllReducer:
         # CPU-tested over gloo, not yet measured on NVLink -> opt-in.
         self.flat_lookup = os.environ.get("RECNET_DP_FLAT", "0") == "1"
         self.force = os.environ.get("RECNET_DP_SELF") == "1" and dist.is_initialized()    # probe: run the collective even with one rank
-        # opt-in: raw NCCL communicator driven on the CURRENT stream through libnccl's C API (no ProcessGroup work objects, no side
-        # stream, no fork/join in a captured graph).  Probe (1 x B200, 1-rank group, collective captured in the step graph,
-        # RECNET_DP_SELF=1): a captured collective costs 0.1-0.3 ms of graph time even with one rank, and the raw path costs the
-        # same as ProcessGroupNCCL -- so the overhead is not torch's stream handling.
-        self.raw = os.environ.get("RECNET_DP_RAW", "0") == "1"
-        self._raw_comm = None
-        # symmetric-memory all-reduce over NVLink peer / NVSwitch multicast memory instead of an NCCL collective:
-        # "multimem" (in-switch reduction, multimem.ld_reduce / multimem.st), "two_shot" (P2P reduce-scatter + all-gather), "" = NCCL
-        self.symm = os.environ.get("RECNET_DP_SYMM", "")
-        self._symm_buf = None
-        self._symm_group_name = None
         if self.world > 1 and self.overlap:
             for mi, m in enumerate(self.modules):
                 params = [p for p in m.parameters() if p.requires_grad]
@@ -100,11 +89,7 @@ class GradAllReducer:
                     late.append(flat)                                # ONE flat buffer per module
                 else:
                     late.extend(grads)
-        if late and self.symm and self.backend == "nccl" and all(b.dtype == torch.float32 for b in late):
-            self._symm_allreduce(late)
-        elif late and self.raw and self.backend == "nccl" and os.environ.get("RECNET_DP_DRYRUN") is None:
-            self._raw_allreduce(late)
-        elif len(late) > 1 and self.backend == "nccl" and os.environ.get("RECNET_DP_DRYRUN") is None:
+        if len(late) > 1 and self.backend == "nccl" and os.environ.get("RECNET_DP_DRYRUN") is None:
             # one NCCL group (ncclGroupStart/End): all buffers in a single fused collective launch -> one rank sync per step
             with dist._coalescing_manager(group=self.group, device=late[0].device, async_ops=True) as cm:
                 for buf in late:
@@ -121,89 +106,6 @@ class GradAllReducer:
             else:
                 w.wait()
         self.pending = []
-
-    def _raw_allreduce(self, bufs):
-        """ncclAllReduce(float32, AVG) of every buffer on the CURRENT stream through a communicator of our own, driven straight through
-        libnccl's C API (ctypes).  The communicator is created on first use, outside graph capture: all ranks must get here together."""
-        import ctypes
-        if self._raw_comm is None:
-            if torch.cuda.is_current_stream_capturing():
-                raise RuntimeError("GradAllReducer: the NCCL communicator must be created before graph capture (run an eager step first)")
-
-            class NcclUniqueId(ctypes.Structure):
-                _fields_ = [("internal", ctypes.c_byte * 128)]
-
-            lib = ctypes.CDLL("libnccl.so.2")          # the copy PyTorch already loaded
-            lib.ncclGetUniqueId.restype = ctypes.c_int
-            lib.ncclCommInitRank.restype = ctypes.c_int
-            lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, NcclUniqueId, ctypes.c_int]
-            lib.ncclAllReduce.restype = ctypes.c_int
-            lib.ncclAllReduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                          ctypes.c_void_p]
-            world = max(self.world, 1)
-            rank = dist.get_rank(self.group)
-            uid = NcclUniqueId()
-            if rank == 0 and lib.ncclGetUniqueId(ctypes.byref(uid)) != 0:
-                raise RuntimeError("ncclGetUniqueId failed")
-            box = [bytes(uid.internal) if rank == 0 else None]
-            if world > 1:
-                dist.broadcast_object_list(box, src=0, group=self.group)
-            ctypes.memmove(ctypes.byref(uid), box[0], 128)
-            comm = ctypes.c_void_p()
-            rc = lib.ncclCommInitRank(ctypes.byref(comm), world, uid, rank)
-            if rc != 0:
-                raise RuntimeError(f"ncclCommInitRank failed with {rc}")
-            self._raw_lib, self._raw_comm = lib, comm
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        NCCL_FLOAT32, NCCL_AVG = 7, 4                  # ncclDataType_t / ncclRedOp_t
-        self._raw_lib.ncclGroupStart()                 # one fused launch for all buffers
-        for b in bufs:
-            if b.dtype != torch.float32 or not b.is_contiguous():
-                raise RuntimeError("GradAllReducer: raw NCCL path expects contiguous float32 gradient buffers")
-            self.bytes_last += b.numel() * 4
-            rc = self._raw_lib.ncclAllReduce(b.data_ptr(), b.data_ptr(), b.numel(), NCCL_FLOAT32, NCCL_AVG, self._raw_comm, stream)
-            if rc != 0:
-                self._raw_lib.ncclGroupEnd()
-                raise RuntimeError(f"ncclAllReduce failed with {rc}")
-        rc = self._raw_lib.ncclGroupEnd()
-        if rc != 0:
-            raise RuntimeError(f"ncclGroupEnd failed with {rc}")
-
-    def _symm_allreduce(self, bufs):
-        """Average `bufs` across ranks through ONE symmetric-memory buffer: pack -> all-reduce kernel over peer memory -> unpack * 1/N.
-        The buffer is allocated and rendezvous-ed on first use (must happen outside CUDA-graph capture: run one eager step first)."""
-        import torch.distributed._symmetric_memory as sm
-        if torch.cuda.is_current_stream_capturing():
-            # measured on 2 x B200: correct and 421 us per 99 MB eagerly (tools/dp_check.py), but the captured step graph never
-            # completed its first replay (signal-pad barrier vs graph replay); refuse rather than hang
-            raise RuntimeError("GradAllReducer: RECNET_DP_SYMM is an eager-mode experiment; it is not usable under CUDA-graph capture")
-        group = self.group if self.group is not None else dist.group.WORLD
-        total = sum(b.numel() for b in bufs)
-        padded = (total + 4095) // 4096 * 4096
-        if self._symm_buf is None or self._symm_buf.numel() < padded:
-            if torch.cuda.is_current_stream_capturing():
-                raise RuntimeError("GradAllReducer: the symmetric buffer must be created before graph capture (run an eager step first)")
-            self._symm_buf = sm.empty(padded, dtype=torch.float32, device=bufs[0].device)
-            self._symm_buf.zero_()
-            sm.rendezvous(self._symm_buf, group.group_name)
-            self._symm_group_name = group.group_name
-        off = 0
-        for b in bufs:
-            n = b.numel()
-            self._symm_buf[off:off + n].copy_(b.reshape(-1))
-            off += n
-            self.bytes_last += n * 4
-        if self.symm == "two_shot":
-            torch.ops.symm_mem.two_shot_all_reduce_(self._symm_buf, "sum", self._symm_group_name)
-        elif self.symm == "one_shot":
-            self._symm_buf.copy_(torch.ops.symm_mem.one_shot_all_reduce(self._symm_buf, "sum", self._symm_group_name))
-        else:
-            torch.ops.symm_mem.multimem_all_reduce_(self._symm_buf, "sum", self._symm_group_name)
-        off = 0
-        for b in bufs:
-            n = b.numel()
-            torch.mul(self._symm_buf[off:off + n], 1.0 / self.world, out=b.reshape(-1))
-            off += n
 
     def remove(self):
         for h in self._handles:

@@ -17,13 +17,6 @@ from .models import Decoder, GlobalReconstructor, LocalReconstructor
 from .optim import ClipAdam
 
 
-def _defer_regulariser() -> bool:
-    """EXPERIMENTAL (never run on a GPU yet): form the regulariser's gradient inside the own optimiser pass (functional._defer_reg)."""
-    v = os.environ.get("RECNET_DEFER_REG")
-    on = (v == "1") if v is not None else bool(getattr(C, "defer_regulariser", False))
-    return on and _optimizer_impl() == "recnet"
-
-
 def _optimizer_impl() -> str:
     impl = os.environ.get("RECNET_OPTIMIZER") or getattr(C, "optimizer_impl", "recnet")
     if impl not in ("torch", "recnet"):
@@ -72,24 +65,21 @@ def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_for
         n_t = m.sum(dim=1, keepdim=True)                                                                    # train.py:57
         ce_weight = m / (n_t.clamp_min(1.0) * n_t.sum())                                                    # mean over n_t, then / sum n_t (train.py:54-60,68)
     # loss = CE + lambda_reg * sum_p ||p|| (train.py:69-70), assembled inside the sequence call
-    loss, hiddens, _ = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs, lambda_reg=decoder['lambda_reg'],
-                                              defer_reg=bool(decoder.get('defer_reg')))
+    loss, hiddens, _ = model.forward_sequence(tokens_in, targets[:L], ce_weight, encoder_outputs, lambda_reg=decoder['lambda_reg'])
     return loss, hiddens, output_indices                                                                    # (L,NL,B,H), train.py:73-75
 
 
 def forward_global_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
     """train.py:78-105."""
     model = reconstructor['model']
-    loss, _ = model.forward_sequence(decoder_hiddens, encoder_outputs, lambda_reg=reconstructor['lambda_reg'],
-                                     defer_reg=bool(reconstructor.get('defer_reg')))    # incl. /L (train.py:100) and + lambda * reg (:101-102)
+    loss, _ = model.forward_sequence(decoder_hiddens, encoder_outputs, lambda_reg=reconstructor['lambda_reg'])    # incl. /L (train.py:100) and + lambda * reg (:101-102)
     return loss
 
 
 def forward_local_reconstructor(decoder_hiddens, encoder_outputs, reconstructor):
     """train.py:108-131."""
     model = reconstructor['model']
-    loss, _ = model.forward_sequence(decoder_hiddens, encoder_outputs, lambda_reg=reconstructor['lambda_reg'],
-                                     defer_reg=bool(reconstructor.get('defer_reg')))    # incl. + lambda * reg (train.py:129-130)
+    loss, _ = model.forward_sequence(decoder_hiddens, encoder_outputs, lambda_reg=reconstructor['lambda_reg'])    # incl. + lambda * reg (train.py:129-130)
     return loss
 
 
@@ -107,8 +97,7 @@ def build_decoder(n_vocabs):
         optimizer = torch.optim.Adam(model.parameters(), lr=C.decoder_learning_rate, weight_decay=C.decoder_weight_decay,
                                      amsgrad=C.decoder_use_amsgrad, fused=True, capturable=True)
     lambda_reg = torch.tensor(0.001, device=C.device)
-    return {'model': model, 'loss': torch.nn.CrossEntropyLoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg,
-            'defer_reg': _defer_regulariser()}
+    return {'model': model, 'loss': torch.nn.CrossEntropyLoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg}
 
 
 def build_reconstructor():
@@ -134,8 +123,7 @@ def build_reconstructor():
                                      weight_decay=C.reconstructor_weight_decay, amsgrad=C.reconstructor_use_amsgrad,
                                      fused=True, capturable=True)
     lambda_reg = torch.tensor(0.01, device=C.device)
-    return {'model': model, 'loss': torch.nn.MSELoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg,
-            'defer_reg': _defer_regulariser()}
+    return {'model': model, 'loss': torch.nn.MSELoss(), 'optimizer': optimizer, 'lambda_reg': lambda_reg}
 
 
 def forward_reconstructor_for(kind):

@@ -69,10 +69,10 @@ def test_stacked_decoder_greedy_and_step_logits_fp32(name):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_config5_msrvtt_two_layer_decoder_local_reconstructor_against_oracle(precision):
     """BASELINE config 5 shape family: 40 frames x (1536 + 2048)-d features, 2-layer LSTM decoder, local reconstructor with
-    R = 3584 -- the fused stacked-decoder drivers (seq_decoder_ml / seq_recon_ml) at the stress widths; batch and caption
-    length reduced so the CPU oracle finishes in seconds."""
+    R = 3584 -- the fused stacked-decoder drivers (seq_decoder_ml / seq_recon_ml) at the stress widths and the FULL caption length
+    (31 decoded steps, 40 reconstructor steps); only the batch is reduced so that the CPU oracle finishes in seconds."""
     from oracle import recnet_oracle as O
-    m = dict(B=6, T=40, E=3584, H=512, A=128, EMB=468, V=600, cap_len=8, dec_layers=2, rec_layers=1, dec_model="LSTM", rec_model="LSTM")
+    m = dict(B=8, T=40, E=3584, H=512, A=128, EMB=468, V=600, cap_len=30, dec_layers=2, rec_layers=1, dec_model="LSTM", rec_model="LSTM")
     feats, targets, masks = O.synthetic_batch(m["B"], m["T"], m["E"], m["V"], m["cap_len"], seed=9)
     P = O.init_decoder_params(m["V"], m["EMB"], m["E"], m["H"], m["A"], n_layers=2, seed=4)
     Q = O.init_reconstructor_params("local", m["H"], m["E"], m["A"], seed=5)

@@ -1,4 +1,4 @@
-"""The measured-slower experiments stay in the tree as opt-in switches (profiles/r1_g_nodes.md, r1_g_side_stream.md); this keeps them
+"""The measured-slower experiments stay in the tree as opt-in switches (profiles/r1_g_nodes.md, r1_g_side_stream.md, r1_b_chains.md, r1_c_loop_kernel.md); this keeps them
 parity-green: the golden-fixture and shape-variant parity tests are re-run in a child process with the switches on (they are read
 once per process, hence the subprocess).  Runs last (file name) so that a regression here cannot hide the default path's results."""
 import os
@@ -9,13 +9,14 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SELECT = "test_losses_hiddens_grads_match_reference_golden or test_shape_variants_against_oracle or cuda_graph"
+SELECT = "test_losses_hiddens_grads_match_reference_golden or test_shape_variants_against_oracle or cuda_graph or full_size"
 
 
 @pytest.mark.parametrize("switches", [
-    {"RECNET_SIDE": "1", "RECNET_FUSED_QUERY": "1"},                        # second stream around the loops + query projection in the cell kernel
+    {"RECNET_SIDE": "1", "RECNET_CHAINS": "2"},                             # second stream around the loops + two concurrent sample chains
+    {"RECNET_PERSIST": "0", "RECNET_PERSIST_BWD": "0", "RECNET_PDL": "1"},    # kernel-per-phase reconstructor loops (the pre-r2 default) + programmatic dependent launch
     {"RECNET_STAGE_MULTI": "0", "RECNET_GEMM_COSTMODEL": "1", "RECNET_OPTIMIZER": "torch"},   # r1_f staging / planner / optimiser
-], ids=["side+fused_query", "r1_f_paths"])
+], ids=["side+chains", "kernel_per_phase+pdl", "r1_f_paths"])
 def test_opt_in_paths_stay_parity_green(switches):
     env = dict(os.environ, **switches)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
@@ -23,46 +24,3 @@ def test_opt_in_paths_stay_parity_green(switches):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and " failed" not in r.stdout, tail
-
-
-@pytest.mark.skipif(os.environ.get("RECNET_TEST_EXPERIMENTAL") != "1",
-                    reason="cluster-resident decoder loop (csrc/seq_decoder_cluster.cuh) was written after the round's GPU budget was "
-                           "spent: compiles, never run; set RECNET_TEST_EXPERIMENTAL=1 to try it")
-def test_experimental_cluster_resident_decoder_loop_full_size_parity():
-    """RECNET_DEC_CLUSTER=1 at the MSVD shape (H = 512, A = 128, B = 100: the shape the kernel is written for), bf16, against the oracle."""
-    env = dict(os.environ, RECNET_DEC_CLUSTER="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
-                        "-p", "no:cacheprovider", "-k", "test_full_size_parity_against_oracle and bf16"],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
-    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
-
-
-@pytest.mark.skipif(os.environ.get("RECNET_TEST_EXPERIMENTAL") != "1",
-                    reason="deferred regulariser (recnet_adam_step_reg) was written after the round's GPU budget was spent: compiles, "
-                           "never run; set RECNET_TEST_EXPERIMENTAL=1 to try it")
-def test_experimental_deferred_regulariser_matches_default(monkeypatch):
-    """RECNET_DEFER_REG=1: the regulariser's gradient is formed inside ClipAdam's pass instead of in backward -- same weights after
-    three train steps (same dropout seeds) as the default path, and no notes left behind."""
-    import torch
-    from recnet_b200 import functional as Fn, train as T
-    from tests.golden_util import load_golden
-    from tests.test_gpu_optim import assert_same_update
-    from tests.test_gpu_parity import build, dev
-    g = load_golden("small_lstm")
-    feats, targets = g["feats"].float().to(dev()), g["targets"].to(dev())
-    L_steps = g["hiddens"].shape[0]
-    monkeypatch.setenv("RECNET_OPTIMIZER", "recnet")
-    out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("RECNET_DEFER_REG", flag)
-        dec, rec = build(g["meta"], "fp32", "local", g["dec"], g["local"])
-        assert dec["defer_reg"] == (flag == "1") and rec["defer_reg"] == (flag == "1")
-        dec["model"].seed_dropout(7); rec["model"].seed_dropout(8)
-        w0 = [p.detach().clone() for p in list(dec["model"].parameters()) + list(rec["model"].parameters())]
-        for _ in range(3):
-            T.train_step(dec, rec, feats, targets, n_steps=L_steps)
-        torch.cuda.synchronize()
-        assert not Fn._pending_reg
-        out[flag] = [p.detach().clone() for p in list(dec["model"].parameters()) + list(rec["model"].parameters())]
-    for a, b, z in zip(out["1"], out["0"], w0):
-        assert_same_update(a, b, z, ulps=8)

@@ -81,3 +81,55 @@ def test_synthetic_batch_shape_contract():
     assert int(masks[:, 0].sum()) == 31                     # sample 0 is full length -> L = 31
     assert bool(((targets == O.EOS).sum(0) == 1).all())     # exactly one <EOS> per caption
     assert not bool((targets == O.SOS).any())               # no <SOS> inside targets
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# train mode (dropout on) and beam search: fixtures of tests/golden/make_golden_train.py
+# ---------------------------------------------------------------------------------------------------------------
+from tests.golden_util import load_golden_beam, load_golden_train, philox_scales      # noqa: E402
+from tests.philox_ref import SITE_EMB, SITE_GLOBAL_MP, SITE_LOCAL_X, SITE_LOGITS      # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["small_lstm", "tiny_lstm_ragged"])
+@pytest.mark.parametrize("kind", ["none", "global", "local"])
+def test_oracle_train_mode_with_philox_masks_matches_reference(name, kind):
+    """Dropout on: the same Philox masks (tests/philox_ref.py) injected into the real reference's nn.Dropout modules and passed to the
+    oracle give the same losses and the same gradient for every parameter of dec_loss + 1.0 * rec_loss."""
+    g = load_golden_train(name)
+    m = g["meta"]
+    feats, targets = g["feats"], g["targets"]
+    Lmax, B = m["cap_len"] + 1, m["B"]
+    P = {k: v.clone().requires_grad_(True) for k, v in g["dec"].items()}
+    de = philox_scales(g["seed_dec"], 1, SITE_EMB, (Lmax, B, m["EMB"]), g["p_emb"])
+    dl_ = philox_scales(g["seed_dec"], 1, SITE_LOGITS, (Lmax, B, m["V"]), g["p_out"])
+    dloss, hid, _, _ = O.forward_decoder(P, feats, targets, targets > 0, caption_max_len=m["cap_len"], drop_emb=de, drop_logits=dl_)
+    assert abs(float(dloss) - g["dec_loss"]) < 1e-9 * max(1.0, abs(g["dec_loss"]))
+    assert torch.allclose(hid, g["hiddens"], rtol=1e-9, atol=1e-11)
+    loss = dloss
+    Q = None
+    if kind != "none":
+        Q = {k: v.clone().requires_grad_(True) for k, v in g[kind].items()}
+        L = hid.shape[0]
+        if kind == "local":
+            sc = philox_scales(g["seed_local"], 1, SITE_LOCAL_X, (m["T"], B, m["H"]), g["p_rec"])
+            rloss, _ = O.forward_local_reconstructor(Q, hid, feats, drop_x=sc)
+        else:
+            sc = philox_scales(g["seed_global"], 1, SITE_GLOBAL_MP, (L, B, m["H"]), g["p_rec"])
+            rloss, _ = O.forward_global_reconstructor(Q, hid, feats, caption_max_len=m["cap_len"], drop_mp=sc)
+        assert abs(float(rloss) - g[f"{kind}_loss"]) < 1e-9 * max(1.0, abs(g[f"{kind}_loss"]))
+        loss = loss + rloss
+    loss.backward()
+    for k, ref in g["grads"][kind].items():
+        mod, key = k.split(".", 1)
+        got = (P if mod == "dec" else Q)[key].grad
+        assert torch.allclose(got, ref, rtol=1e-8, atol=1e-11), k
+
+
+@pytest.mark.parametrize("name", ["tiny_lstm", "tiny_gru", "small_lstm"])
+def test_oracle_beam_search_matches_the_references_own_beam_search(name):
+    """eval.beam_search run by the reference itself (CPU alias for its torch.cuda.FloatTensor constructor) vs the oracle restatement."""
+    g = load_golden_beam(name)
+    m = g["meta"]
+    for width in (3, 5):
+        got = O.beam_search(g["dec"], g["feats"], width, model_name=m["dec_model"], n_layers=1, caption_max_len=m["cap_len"])
+        assert got == g["beams"][width], (width, got, g["beams"][width])

@@ -8,7 +8,11 @@ One process per GPU (torchrun for N > 1).  Prints ONE JSON line on rank 0 (contr
   value      device-timed throughput with inputs resident in HBM (CUDA-graph replay of the whole step)
   e2e        same step driven through the public API from PINNED HOST buffers: H2D of the batch + D2H of the loss
              inside the timed region
-  roofline   dominant kernel (by share of the step) timed live with CUDA events around each launch
+  roofline   dominant kernel (by share of the step) timed live with CUDA events around each launch; GEMM-class kernels (the
+             tcgen05 GEMMs and the weight-resident persistent loops) are scored against the tensor pipe (burst bf16 peak),
+             with the byte-side fraction alongside; `roofline.step` = SURVEY 8(d)'s 397 GFLOP / step time vs the sustained peak
+  fp32       the same step in the fp32 parity build (the reference's arithmetic type), value + e2e
+  workloads  the other BASELINE configs: global reconstructor, decoder only, greedy decoding at batch 1024, MSR-VTT-shaped stress
   cpu_baseline  the oracle (CPU port of the reference algorithm) timed on this box's host cores, N = 1 only
 `--impl reference` times only the CPU oracle (the reference is pure Python and cannot travel to the GPU box).
 """
@@ -39,6 +43,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=8)
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32 record and the other-config workloads (N = 1 only anyway)")
     return ap.parse_args()
 
 
@@ -162,12 +167,18 @@ class ClockSampler:
 
 
 KCLASS = {1: "gemm_tcgen05", 2: "sgemm_fp32", 3: "attn_fwd", 4: "attn_bwd", 5: "lstm_cell_fwd", 6: "lstm_cell_bwd", 7: "ce_loss",
-          8: "splitk_reduce", 10: "proj_attn_cell_fwd", 11: "proj_attn_cell_bwd"}
+          8: "splitk_reduce", 9: "persistent_loop", 10: "proj_attn_cell_fwd", 11: "proj_attn_cell_bwd"}
 
 
 def algorithmic_work(cls, M, N, K, elt):
     """(bound, flops-or-bytes per launch) -- DESIGN.md section 'Kernels and rooflines' states the same formulas."""
     s = SHAPE
+    if cls == 9:
+        # weight-resident persistent time loop of the local reconstructor (csrc/seq_recon_persist.cuh): (steps, CTAs, 0 fwd / 1 bwd).
+        # Per step: the gate GEMM [B x 4R x (H+R)] (fwd) or its transpose dX = dG.W (bwd) + the attention-query GEMM [B x A x R];
+        # useful rows only (B of the 112-column UMMA tile)
+        B, H, R, A = s["B"], s["H"], s["R"], s["A"]
+        return "tensor", M * (2.0 * B * 4 * R * (H + R) + 2.0 * B * A * R)
     if cls in (1, 2):
         # useful rows only (M = 100 of the 128-row UMMA tile).  Which roofline binds is decided by the caller from the arithmetic
         # intensity (gemm_bytes): the M = 100 per-step GEMMs move ~90 flop per byte, far below the machine balance (~215).
@@ -229,6 +240,171 @@ def ncu_traffic(kernel, shape):
 def workload_text(recon, batch):
     return (f"RecNet decoder + {recon} reconstructor train step (fwd+bwd+clip+Adam), MSVD shape: 28x1536 InceptionV4 feats, "
             f"caption len 30 (L=31 steps), emb 468, attn 128, hidden 512, rec hidden 1536, vocab 4188, batch {batch} per GPU, dropout on")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the other BASELINE configs and the fp32 build: compact sub-records (N = 1, inputs resident, CUDA-graph replay)
+# ------------------------------------------------------------------------------------------------------------
+def _configure(C, shp, recon, precision, dec_layers, device):
+    C.decoder_model = C.reconstructor_model = "LSTM"
+    C.batch_size, C.caption_max_len, C.encoder_output_len, C.encoder_output_size = shp["B"], shp["cap"], shp["T"], shp["E"]
+    C.decoder_n_layers, C.decoder_hidden_size, C.decoder_attn_size, C.embedding_size = dec_layers, shp["H"], shp["A"], shp["EMB"]
+    C.reconstructor_n_layers, C.reconstructor_hidden_size, C.reconstructor_attn_size = 1, shp["R"], shp["A"]
+    C.use_recon = recon != "none"
+    C.reconstructor_type = recon if C.use_recon else "local"
+    C.precision, C.device = precision, device
+
+
+def _graph_time(fn, steps, warmup, grad=True):
+    """ms per call of fn under CUDA-graph replay (eager if capture fails -- reported)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.set_grad_enabled(grad):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph, run = None, fn
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.set_grad_enabled(grad):
+            fn()
+        run = graph.replay
+    except Exception as ex:
+        print(f"[bench] sub-workload graph capture failed ({type(ex).__name__}: {ex}); timing eager launches", file=sys.stderr)
+        graph = None
+        torch.cuda.synchronize()
+    with torch.set_grad_enabled(grad):
+        for _ in range(max(3, warmup)):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, graph is not None
+
+
+def _top_kernel(lib, fn, shp, elt, pk, grad=True):
+    """Dominant kernel of one eager call of fn (same event-pair profile leg as the headline record)."""
+    import ctypes
+    with torch.set_grad_enabled(grad):
+        lib.recnet_profile_enable(1, 4096)
+        fn()
+        lib.recnet_profile_enable(0, 0)
+    buf = (ctypes.c_float * (4096 * 5))()
+    nrec = lib.recnet_profile_collect(ctypes.cast(buf, ctypes.c_void_p), 4096)
+    agg = {}
+    for i in range(max(nrec, 0)):
+        key = (int(buf[5 * i]), int(buf[5 * i + 1]), int(buf[5 * i + 2]), int(buf[5 * i + 3]))
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1; a[1] += buf[5 * i + 4]
+    if not agg:
+        return None
+    tot = sum(v[1] for v in agg.values())
+    (cls, M, N, K), (cnt, ms) = max(agg.items(), key=lambda kv: kv[1][1])
+    global SHAPE
+    saved, SHAPE = SHAPE, dict(SHAPE, **shp)
+    try:
+        bound, work = algorithmic_work(cls, M, N, K, elt)
+    finally:
+        SHAPE = saved
+    avg_s = ms / cnt * 1e-3
+    peak = pk["tf_burst"] * 1e12 if bound == "tensor" else pk["hbm"] * 1e9
+    return {"kernel": KCLASS.get(cls, "other"), "shape": [M, N, K], "launches": cnt, "avg_us": round(ms / cnt * 1e3, 2),
+            "share": round(ms / tot, 4), "bound": bound, "frac": round(work / avg_s / peak, 4) if work else None}
+
+
+def extra_records(args, dev, lib, T, synthetic_batch, pk):
+    """fp32 build of the headline step + BASELINE configs 1 (decoder only), 2 (global reconstructor), 4 (greedy, batch 1024) and
+    5 (MSR-VTT-shaped stress: 40 frames x 3584-d, 2-layer LSTM decoder, local reconstructor with R = 3584), batch 100 on this GPU."""
+    C = T.C
+    steps, warm = max(10, min(args.steps, 20)), 3
+    out = {}
+
+    def train_record(shp, recon, precision, dec_layers=1, with_e2e=False):
+        _configure(C, shp, recon, precision, dec_layers, str(dev))
+        torch.manual_seed(0)
+        dec = T.build_decoder(shp["V"])
+        rec = T.build_reconstructor() if recon != "none" else None
+        L = shp["cap"] + 1
+        fh, th, _ = synthetic_batch(shp["B"], shp["T"], shp["E"], shp["V"], shp["cap"], seed=1234)
+        fh, th = fh.pin_memory(), th.pin_memory()
+        f, t = fh.to(dev), th.to(dev)
+        loss_d = torch.zeros((), device=dev)
+
+        def step():
+            loss, _, _ = T.train_step(dec, rec, f, t, n_steps=L)
+            loss_d.copy_(loss.detach())
+        ms, graphed = _graph_time(step, steps, warm)
+        r = {"value": round(shp["B"] / (ms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms, 4), "dtype": precision,
+             "cuda_graph": graphed, "steps": steps}
+        n0 = lib.recnet_launch_count()
+        step()
+        r["launches_per_step"] = int(lib.recnet_launch_count() - n0)
+        r["top_kernel"] = _top_kernel(lib, step, shp, 2 if precision == "bf16" else 4, pk)
+        if with_e2e:      # host buffers -> H2D -> step -> D2H loss, every step inside the timed region (no overlap tricks)
+            lh = torch.zeros(1).pin_memory()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                f.copy_(fh, non_blocking=True); t.copy_(th, non_blocking=True)
+                step()
+                lh.copy_(loss_d.view(1), non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ems = e0.elapsed_time(e1) / steps
+            r["e2e"] = {"value": round(shp["B"] / (ems * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ems, 4),
+                        "h2d_bytes_per_step": fh.numel() * 4 + th.numel() * 8, "d2h_bytes_per_step": 4,
+                        "pipeline": "pinned host -> H2D -> eager launches of the step -> D2H loss (no overlap, no graph)"}
+        del dec, rec
+        torch.cuda.empty_cache()
+        return r
+
+    s = SHAPE
+    try:
+        out["fp32"] = dict(train_record(s, args.recon, "fp32", with_e2e=True),
+                           note="same step in the fp32 parity build: fp32 storage, FFMA GEMMs, libm activations (1e-3 vs the oracle)")
+    except Exception as ex:
+        out["fp32"] = {"error": f"{type(ex).__name__}: {ex}"}
+    wl = {}
+    for name, (shp, recon, layers, text) in {
+        "dec_only": (s, "none", 1, "config 1 shape on the GPU: decoder only (wo. reconstructor), batch 100"),
+        "global": (s, "global", 1, "config 2: RecNet + global reconstructor, bf16, batch 100"),
+        "msrvtt_stress": (dict(s, T=40, E=3584, R=3584), "local", 2,
+                          "config 5 per-GPU share: 40 frames x (1536 + 2048)-d features, 2-layer LSTM decoder, local reconstructor, batch 100"),
+    }.items():
+        try:
+            wl[name] = dict(train_record(shp, recon, "bf16", layers), workload=text)
+        except Exception as ex:
+            wl[name] = {"error": f"{type(ex).__name__}: {ex}", "workload": text}
+    # config 4: greedy decoding, decoder only, batch 1024, 28 frames, max len 30 (eval.greedy_search -> one C call, argmax feedback on device)
+    try:
+        _configure(C, dict(s, B=1024), "none", "bf16", 1, str(dev))
+        torch.manual_seed(0)
+        dec = T.build_decoder(s["V"])
+        dec["model"].eval()
+        f, _, _ = synthetic_batch(1024, s["T"], s["E"], s["V"], s["cap"], seed=77)
+        f = f.to(dev)
+        L = s["cap"] + 1
+        fn = lambda: dec["model"].greedy(f, L)
+        ms, graphed = _graph_time(fn, steps, warm, grad=False)
+        n0 = lib.recnet_launch_count()
+        fn()
+        wl["greedy_b1024"] = {"value": round(1024 / (ms * 1e-3), 2), "unit": "captions/s", "ms_per_batch": round(ms, 4), "dtype": "bf16",
+                              "cuda_graph": graphed, "steps": steps, "launches_per_batch": int(lib.recnet_launch_count() - n0),
+                              "gflop": 481.7, "tflops": round(481.7e9 / (ms * 1e-3) / 1e12, 2),
+                              "top_kernel": _top_kernel(lib, fn, dict(s, B=1024), 2, pk, grad=False),
+                              "workload": "config 4: greedy inference, decoder only, batch 1024, 28 frames, 31 steps (no early stop with random weights)"}
+        del dec
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        wl["greedy_b1024"] = {"error": f"{type(ex).__name__}: {ex}"}
+    out["workloads"] = wl
+    return out
 
 
 def dbg(rank, msg):
@@ -494,16 +670,15 @@ def main():
             bound, work = algorithmic_work(cls, M, N, K, elt)
             avg_s = ms / cnt * 1e-3
             extra = {}
-            if cls in (1, 2):
-                # a GEMM is bound by whichever roofline gives the LONGER lower bound on its time; the other one is kept alongside
-                nbytes = gemm_bytes(M, N, K, elt)
-                t_tensor, t_hbm = work / (pk["tf_sust"] * 1e12), nbytes / (pk["hbm"] * 1e9)
-                tensor_frac, hbm_frac = t_tensor / avg_s, t_hbm / avg_s
-                extra = {"flop_per_byte": round(work / nbytes, 1), "tensor_frac": round(tensor_frac, 4), "hbm_frac": round(hbm_frac, 4)}
-                if t_hbm > t_tensor:
-                    bound, work = "hbm", nbytes
+            if cls in (1, 2, 9):
+                # GEMM-class kernels are scored on the tensor pipe against the BURST bf16 peak (each is a 5-500 us
+                # kernel, not a seconds-long loop); the byte-side fraction (operands once + result once over the copy bandwidth)
+                # is kept alongside: the M = 100 per-step shapes move ~90 flop per byte, below the machine balance
+                nbytes = gemm_bytes(M, N, K, elt) if cls != 9 else M * gemm_bytes(s["B"], 4 * s["R"], s["H"] + s["R"], elt)
+                extra = {"flop_per_byte": round(work / nbytes, 1), "tensor_frac": round(work / avg_s / 1e12 / pk["tf_burst"], 4),
+                         "hbm_frac": round(nbytes / avg_s / 1e9 / pk["hbm"], 4)}
             if bound == "tensor":
-                ach, peak, unit = work / avg_s / 1e12, pk["tf_sust"], "TFLOP/s"
+                ach, peak, unit = work / avg_s / 1e12, pk["tf_burst"], "TFLOP/s"
             else:
                 ach, peak, unit = work / avg_s / 1e9, pk["hbm"], "GB/s"
             kernels.append({"kernel": KCLASS.get(cls, "other"), "shape": [M, N, K], "launches": cnt, "avg_us": round(ms / cnt * 1e3, 2),
@@ -516,11 +691,16 @@ def main():
             roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
                         "traffic": tr_warm, "traffic_cold_cache": tr_cold, "traffic_source": tr_src,
                         "kernel": top["kernel"], "shape_MNK": top["shape"], "avg_us": top["avg_us"],
-                        "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy bandwidth)"),
-                        "note": "avg_us is a per-launch CUDA-event pair in an eager step (adds ~4 us to every launch); traffic = dram bytes of one "
-                                "ncu --set full launch in steady state (operands L2-resident), traffic_cold_cache = same kernel after an L2 flush; "
-                                "GEMMs: bound = the roofline with the longer time bound at this shape (flop_per_byte vs machine balance), "
-                                "tensor_frac / hbm_frac give both"}
+                        "share_of_profiled_step": top["share"], "peak_source": pk["src"] + (" (burst bf16)" if top["bound"] == "tensor" else " (copy bandwidth)"),
+                        "note": "avg_us is a per-launch CUDA-event pair in an eager step (adds ~4 us to a launch: < 1 % of a persistent loop, "
+                                "up to 40 % of a 10 us per-step kernel -- compare with the committed ncu launch list under profiles/); traffic = dram "
+                                "bytes of one ncu --set full launch in steady state; GEMM-class kernels: bound = tensor pipe (SURVEY 8d), frac vs the "
+                                "burst bf16 peak, hbm_frac = operands-once + result-once bytes vs the copy bandwidth",
+                        "step": {"gflop": 397.0, "tflops": round(397.0e9 / (total_ms / args.steps * 1e-3) / 1e12, 2),
+                                 "frac": round(397.0e9 / (total_ms / args.steps * 1e-3) / 1e12 / pk["tf_sust"], 4),
+                                 "peak": pk["tf_sust"], "peak_source": pk["src"] + " (sustained bf16)",
+                                 "note": "SURVEY 8(d): 397.0 GFLOP per iteration of decoder + local reconstructor, fwd + bwd, batch 100 (config 3)"}
+                        if args.recon == "local" else None}
             for k in ("flop_per_byte", "tensor_frac", "hbm_frac"):
                 if k in top:
                     roofline[k] = top[k]
@@ -530,7 +710,10 @@ def main():
             cores = os.cpu_count() or 1
             cpu = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_iters} iterations of fwd+bwd+clip+Adam, batch {s['B']}, L=31, fp32 oracle, {cores} torch threads ({cpu_model_name()}), {sec * 1e3:.0f} ms/iter"}
-        ws_mb = 0
+        extras = {}
+        if world == 1 and not args.no_extras and not args.no_graph:
+            dbg(rank, "extra records (fp32 build, other configs)")
+            extras = extra_records(args, dev, lib, T, synthetic_batch, pk)
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -546,6 +729,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
             "allreduce_bytes_per_step": reducer.bytes_last,
+            **extras,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

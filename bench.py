@@ -431,7 +431,7 @@ def main():
     import recnet_b200
     from recnet_b200 import _lib as RL, train as T
     from recnet_b200.data import synthetic_batch
-    from recnet_b200.parallel import GradAllReducer, broadcast_parameters
+    from recnet_b200.parallel import broadcast_parameters, make_reducer
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -461,7 +461,7 @@ def main():
     modules = [dec["model"]] + ([rec["model"]] if rec else [])
     broadcast_parameters(modules)
     # reconstructor first: its gradients are final first (its backward runs before the decoder's BPTT)
-    reducer = GradAllReducer(([rec["model"]] if rec else []) + [dec["model"]])
+    reducer = make_reducer(([rec["model"]] if rec else []) + [dec["model"]])
     L = s["cap"] + 1
 
     # synthetic MSVD-shaped batch of this rank's shard, in pinned host memory (the e2e leg copies from here every step)
@@ -728,19 +728,25 @@ def main():
                                  if graph_b is not None else "pinned host -> H2D into a staging buffer (overlapped), device copy into the graph inputs")},
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
-            "allreduce_bytes_per_step": reducer.bytes_last,
+            "allreduce_bytes_per_step": reducer.bytes_last, "allreduce_impl": type(reducer).__name__,
             **extras,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
-        # tear down without ProcessGroupNCCL's destructor: with NCCL work captured inside a live CUDA graph
-        # destroy_process_group() blocks (observed on the 2-GPU box); everything is flushed, so exit directly
         sys.stdout.flush(); sys.stderr.flush()
         dist.barrier()
         torch.cuda.synchronize()
-        os._exit(0)
+        if type(reducer).__name__ == "NvlinkAllReducer":
+            # no NCCL work sits in the captured graphs (the gradient exchange is our own kernel): a regular teardown works
+            del graph, graph_b
+            reducer.remove()
+            dist.destroy_process_group()
+        else:
+            # RECNET_DP_IMPL=nccl: with NCCL work captured inside a live CUDA graph destroy_process_group() blocks (observed on the
+            # 2-GPU box); everything is flushed, so exit directly
+            os._exit(0)
 
 
 if __name__ == "__main__":

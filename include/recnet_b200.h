@@ -267,6 +267,17 @@ int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const 
                      double eps, double weight_decay, double max_grad_norm, float* partial, float* state,
                      int write_clipped_grads, void* stream);
 
+/* Data-parallel gradient all-reduce (average) over NVLink / NVSwitch as ONE kernel of this library (the reference has
+ * no distributed code; replaces an ncclAllReduce between backward, train.py:268, and clip + Adam, train.py:269-273).
+ * The gradients of all ranks live in SYMMETRIC memory: `local` = this rank's buffer, `multicast` = the NVSwitch multicast alias of all
+ * ranks' buffers (NULL -> two-shot over the peer pointers in the device table peer_ptrs[world]), flags / peer_flag_ptrs = a zeroed
+ * symmetric block of 2 * 64 * 16 uint32 per rank and the device table of every rank's block, epochs = 64 zeroed local uint32,
+ * err = local int32 (4 = a peer did not arrive within ~2 s).  Reduces floats [offset, offset + n) in place on every rank
+ * (two-shot: rank r sums slice r across ranks with multimem.ld_reduce and broadcasts it with multimem.st).  offset, n: multiples of 4.
+ * Every rank must launch it in the same order; `ctas` (<= 64) CTAs of 512 threads. */
+int recnet_allreduce_avg(float* local, float* multicast, const int64_t* peer_ptrs, uint32_t* flags, const int64_t* peer_flag_ptrs,
+                         uint32_t* epochs, int32_t* err, int64_t offset_floats, int64_t n_floats, int rank, int world, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include "seq_recon.cuh"
 #include "seq_recon_ml.cuh"
 #include "optim.cuh"
+#include "allreduce.cuh"
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -398,5 +399,14 @@ int recnet_adam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const 
                           reinterpret_cast<LP>(exp_avg_sq_ptrs), reinterpret_cast<LP>(max_exp_avg_sq_ptrs), reinterpret_cast<LP>(sizes), n,
                           blk_tensor, blk_chunk, n_blocks, lr, beta1, beta2, eps, weight_decay, max_grad_norm, partial, state,
                           write_clipped_grads, ST(stream));
+}
+int recnet_allreduce_avg(float* local, float* multicast, const int64_t* peer_ptrs, uint32_t* flags, const int64_t* peer_flag_ptrs,
+                         uint32_t* epochs, int32_t* err, int64_t offset_floats, int64_t n_floats, int rank, int world, int ctas, void* stream) {
+  if ((offset_floats & 3) || (n_floats & 3)) return RECNET_ERR_ALIGNMENT;
+  ar::Args a;
+  a.local = local; a.mc = multicast; a.peers = reinterpret_cast<const long long*>(peer_ptrs); a.flags = flags;
+  a.peer_flags = reinterpret_cast<const long long*>(peer_flag_ptrs); a.epochs = epochs; a.err = err;
+  a.off4 = offset_floats / 4; a.n4 = n_floats / 4; a.rank = rank; a.world = world; a.scale = 1.f / (float)world;
+  return ar::launch(a, ctas, ST(stream));
 }
 }  // extern "C"

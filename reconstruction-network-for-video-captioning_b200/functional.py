@@ -12,7 +12,7 @@ That single contiguous buffer per module is what the data-parallel all-reduce se
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
@@ -117,9 +117,11 @@ def _flat_grads(params) -> (torch.Tensor, List[torch.Tensor], torch.Tensor):
     """One flat fp32 buffer + per-parameter views + device table of the views' addresses (computed with a device-side
     add so that it is valid under CUDA-graph capture, where the buffer address is fixed)."""
     tab = _table_for(params)
-    flat = torch.empty(tab.total, dtype=torch.float32, device=params[0].device)
-    views = [flat[o: o + p.numel()].view_as(p) for o, p in zip(tab.offsets, params)]
     key = tuple(p.data_ptr() for p in params)
+    flat = _flat_placement.get(key)          # data-parallel runs: a fixed slice of symmetric memory (parallel.NvlinkAllReducer)
+    if flat is None or flat.numel() != tab.total:
+        flat = torch.empty(tab.total, dtype=torch.float32, device=params[0].device)
+    views = [flat[o: o + p.numel()].view_as(p) for o, p in zip(tab.offsets, params)]
     _last_flat.pop(key, None)
     _last_flat[key] = flat                                          # see flat_buffer_of(); newest last
     while len(_last_flat) > 8:                                      # a process trains a handful of modules; do not pin old buffers
@@ -132,6 +134,30 @@ def _flat_grads(params) -> (torch.Tensor, List[torch.Tensor], torch.Tensor):
 # to send one all-reduce per module instead of one per tensor -- asks here.  Holding the reference also keeps the buffer from
 # being recycled while the optimiser still reads its views.
 _last_flat: Dict[tuple, torch.Tensor] = {}
+
+# parameter list (tuple of data_ptrs) -> preallocated flat gradient buffer.  The NVLink all-reduce (csrc/allreduce.cuh) works in place
+# on symmetric memory, so the data-parallel reducer places every module's flat gradient buffer there once and backward writes into it.
+_flat_placement: Dict[tuple, torch.Tensor] = {}
+
+
+def place_flat_grads(params, buffer: Optional[torch.Tensor]) -> int:
+    """Make ``buffer`` (float32, >= flat_grad_numel(params) elements; None = back to fresh allocations) the flat gradient buffer of this
+    parameter list from now on.  Returns the number of elements used."""
+    params = [p for p in params]
+    tab = _table_for(params)
+    key = tuple(p.data_ptr() for p in params)
+    if buffer is None:
+        _flat_placement.pop(key, None)
+        return tab.total
+    if buffer.dtype != torch.float32 or not buffer.is_contiguous() or buffer.numel() < tab.total:
+        raise ValueError("place_flat_grads: need a contiguous float32 buffer of at least flat_grad_numel(params) elements")
+    _flat_placement[key] = buffer[: tab.total]
+    return tab.total
+
+
+def flat_grad_numel(params) -> int:
+    """Elements of the flat gradient buffer of a parameter list (every view 256-byte aligned)."""
+    return _table_for([p for p in params]).total
 
 
 def flat_buffer_of(grads: Sequence[torch.Tensor]):

@@ -113,6 +113,143 @@ class GradAllReducer:
         self._handles = []
 
 
+class NvlinkAllReducer:
+    """Data-parallel gradient exchange as ONE kernel of our own over NVLink / NVSwitch (csrc/allreduce.cuh) -- no NCCL collective in
+    the step.  The flat gradient buffers of all modules are placed in one symmetric-memory allocation (functional.place_flat_grads),
+    so backward writes the gradients where every peer (and the switch's multicast alias) can reach them; ``wait()`` launches
+    ``recnet_allreduce_avg`` in place on the current stream (a plain kernel node under CUDA-graph capture; its rank barriers count
+    epochs on the device, so replays need no reset).
+
+    ``modules`` in the order their gradients become final (reconstructor first).  With ``overlap=True`` the first module's slice is
+    reduced on a side stream as soon as its backward has finished (grad hook), hidden behind the decoder's BPTT; the rest goes
+    out in ``wait()``.  NCCL is only used at construction time (rendezvous of the symmetric allocations)."""
+
+    MAX_CTAS, MAX_WORLD = 64, 16
+
+    def __init__(self, modules: Sequence[torch.nn.Module], group=None, ctas: int = None, overlap: bool = None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        from . import functional as Fn
+        if not dist.is_initialized():
+            raise RuntimeError("NvlinkAllReducer needs an initialised process group (one process per GPU)")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > self.MAX_WORLD:
+            raise NotImplementedError(f"NvlinkAllReducer covers one NVSwitch domain (<= {self.MAX_WORLD} ranks)")
+        self.modules = list(modules)
+        self.ctas = int(ctas if ctas is not None else os.environ.get("RECNET_AR_CTAS", "32"))
+        self.overlap = (os.environ.get("RECNET_DP_OVERLAP", "1") == "1") if overlap is None else bool(overlap)
+        # parameter lists in the order the sequence Functions save them (models.*._params): functional._flat_grads keys the
+        # placement by exactly that tuple
+        plists = []
+        for m in self.modules:
+            pl = list(m._params()) if hasattr(m, "_params") else [p for p in m.parameters()]
+            if {id(p) for p in pl} != {id(p) for p in m.parameters()} or any(not p.requires_grad for p in pl):
+                raise NotImplementedError("NvlinkAllReducer: every parameter of a module must take part in its fused backward")
+            plists.append(pl)
+        self._plists = plists
+        dev = plists[0][0].device
+        sizes = [(Fn.flat_grad_numel(pl) + 63) // 64 * 64 for pl in plists]
+        total = sum(sizes)
+        self.buf = symm.empty(total, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.flags = symm.empty(2 * self.MAX_CTAS * self.MAX_WORLD, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        torch.cuda.synchronize()
+        name = self.group.group_name
+        hb, hf = symm.rendezvous(self.buf, name), symm.rendezvous(self.flags, name)
+        self.multicast = int(hb.multicast_ptr) if (hb.has_multicast_support and os.environ.get("RECNET_AR_MULTICAST", "1") == "1") else 0
+        self.peer_ptrs = torch.tensor([int(x) for x in hb.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.peer_flags = torch.tensor([int(x) for x in hf.buffer_ptrs], dtype=torch.int64, device=dev)
+        self._handles = (hb, hf)                      # keep the mappings alive
+        self.epochs = torch.zeros(self.MAX_CTAS, dtype=torch.int32, device=dev)     # per-CTA epoch counters, advanced by the kernel
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ranges, off = [], 0
+        for pl, n in zip(plists, sizes):
+            Fn.place_flat_grads(pl, self.buf[off: off + n])
+            self.ranges.append((off, n))
+            off += n
+        self.bytes_last = 0
+        self._lib, self._check, self._stream = L.lib(), L.check, Fn._stream
+        self._side = torch.cuda.Stream(device=dev) if self.overlap and len(self.modules) > 1 else None
+        self._early_done = False
+        self._hooks = []
+        if self._side is not None:
+            first = plists[0]
+            remaining = {"n": 0}
+
+            def hook(_p, first=first, remaining=remaining):
+                remaining["n"] += 1
+                if remaining["n"] == len(first):      # every gradient of the first module has been accumulated
+                    remaining["n"] = 0
+                    self._reduce_early()
+            for p in first:
+                self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+        dist.barrier(self.group)                      # every rank's flag block is zeroed and mapped before anyone signals into it
+        torch.cuda.synchronize()
+
+    def _launch(self, off: int, n: int):
+        self._check(self._lib.recnet_allreduce_avg(
+            self.buf.data_ptr(), self.multicast or None, self.peer_ptrs.data_ptr(), self.flags.data_ptr(), self.peer_flags.data_ptr(),
+            self.epochs.data_ptr(), self.err.data_ptr(), off, n, self.rank, self.world, self.ctas, self._stream()),
+            "recnet_allreduce_avg")
+        self.bytes_last += n * 4
+
+    def _reduce_early(self):
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            off, n = self.ranges[0]
+            self._launch(off, n)
+        self._early_done = True
+
+    def start_iteration(self):
+        self.bytes_last = 0
+        self._early_done = False
+
+    def _assert_placed(self):
+        lo = self.buf.data_ptr()
+        hi = lo + self.buf.numel() * 4
+        for pl in self._plists:
+            for p in pl:
+                if p.grad is None or not (lo <= p.grad.data_ptr() < hi):
+                    raise RuntimeError("NvlinkAllReducer: a gradient does not live in the symmetric buffer (backward did not go through "
+                                       "the fused sequence Functions, or the parameter list changed)")
+
+    def wait(self):
+        """Reduce whatever has not gone out yet and join: after this every rank holds the averaged gradients."""
+        self._assert_placed()
+        if self._early_done:
+            rest = self.ranges[1:]
+            off, n = rest[0][0], sum(r[1] for r in rest)
+            torch.cuda.current_stream().wait_stream(self._side)       # same flag set: the two kernels must not overlap each other
+            self._launch(off, n)
+        else:
+            self._launch(0, sum(r[1] for r in self.ranges))
+
+    def check(self):
+        torch.cuda.synchronize()
+        if int(self.err.item()) != 0:
+            raise RuntimeError("recnet_allreduce_avg: a peer did not reach the rank barrier in time (device status 4)")
+
+    def remove(self):
+        from . import functional as Fn
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for pl in self._plists:
+            Fn.place_flat_grads(pl, None)
+
+
+def make_reducer(modules: Sequence[torch.nn.Module], group=None):
+    """The gradient reducer of a data-parallel run: our NVLink kernel on CUDA + NCCL process groups (RECNET_DP_IMPL=nccl falls back to
+    the fused NCCL group), the NCCL / gloo path otherwise (CPU tests)."""
+    impl = os.environ.get("RECNET_DP_IMPL", "nvlink")
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl" and impl == "nvlink":
+        return NvlinkAllReducer(modules, group)
+    return GradAllReducer(modules, group)
+
+
 def _common_base(grads):
     """The tensor all ``grads`` are views of, or None (compared by storage address and size).  Gradients that went through
     autograd's AccumulateGrad are stored detached, so this only recognises views that were assigned to ``.grad`` by hand."""

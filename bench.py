@@ -475,7 +475,7 @@ def main():
     def make_step(fd, td):
         def _step():
             reducer.start_iteration()
-            loss, _, _ = T.train_step(dec, rec, fd, td, n_steps=L, grad_hook=reducer.wait)
+            loss, _, _ = T.train_step(dec, rec, fd, td, n_steps=L, reducer=reducer if world > 1 or dp_self else None)
             loss_d.copy_(loss.detach())
         return _step
 

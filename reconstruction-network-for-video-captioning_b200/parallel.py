@@ -72,11 +72,17 @@ class GradAllReducer:
 
     def start_iteration(self):
         self._fired, self.pending, self.bytes_last = {}, [], 0
+        self._done = False
+
+    def wait_first(self):
+        """Interface parity with NvlinkAllReducer: the NCCL group goes out in one piece."""
+        self.wait()
 
     def wait(self):
         """Join the outstanding all-reduces; modules whose grads were not flat views are reduced tensor by tensor."""
-        if self.world <= 1 and not self.force:
+        if (self.world <= 1 and not self.force) or getattr(self, "_done", False):
             return
+        self._done = True
         late = []
         for mi, m in enumerate(self.modules):
             if self._fired.get(mi) is None:
@@ -173,6 +179,9 @@ class NvlinkAllReducer:
         self._lib, self._check, self._stream = L.lib(), L.check, Fn._stream
         self._side = torch.cuda.Stream(device=dev) if self.overlap and len(self.modules) > 1 else None
         self._early_done = False
+        self._rest_launched = False
+        self._all_done = False
+        self._early_event = torch.cuda.Event()
         self._hooks = []
         if self._side is not None:
             first = plists[0]
@@ -201,6 +210,7 @@ class NvlinkAllReducer:
         with torch.cuda.stream(self._side):
             off, n = self.ranges[0]
             self._launch(off, n)
+            self._early_event.record(self._side)
         self._early_done = True
 
     def start_iteration(self):
@@ -216,16 +226,40 @@ class NvlinkAllReducer:
                     raise RuntimeError("NvlinkAllReducer: a gradient does not live in the symmetric buffer (backward did not go through "
                                        "the fused sequence Functions, or the parameter list changed)")
 
+    def wait_first(self):
+        """The FIRST module's averaged gradients are ready on the current stream when this returns; the remaining slices start on the
+        side stream right away, so the caller can run the first module's optimiser underneath them and ``wait()`` afterwards."""
+        self._assert_placed()
+        main = torch.cuda.current_stream()
+        if self._side is None or len(self.ranges) < 2:
+            return self.wait()
+        if not self._early_done:
+            self._reduce_early()
+        rest = self.ranges[1:]
+        self._side.wait_stream(main)                  # the other modules' backward has finished (queued after the early kernel on the side stream)
+        with torch.cuda.stream(self._side):
+            self._launch(rest[0][0], sum(r[1] for r in rest))
+        self._rest_launched = True
+        # the first slice is final once the early kernel has finished; it precedes the `rest` kernel on the side stream, so wait for an
+        # event recorded between them
+        main.wait_event(self._early_event)
+
     def wait(self):
         """Reduce whatever has not gone out yet and join: after this every rank holds the averaged gradients."""
+        if self._all_done:
+            return
         self._assert_placed()
-        if self._early_done:
+        self._all_done = True
+        main = torch.cuda.current_stream()
+        if self._rest_launched:
+            main.wait_stream(self._side)
+        elif self._early_done:
             rest = self.ranges[1:]
-            off, n = rest[0][0], sum(r[1] for r in rest)
-            torch.cuda.current_stream().wait_stream(self._side)       # same flag set: the two kernels must not overlap each other
-            self._launch(off, n)
+            main.wait_stream(self._side)              # same flag set: the two kernels must not overlap each other
+            self._launch(rest[0][0], sum(r[1] for r in rest))
         else:
             self._launch(0, sum(r[1] for r in self.ranges))
+        self._rest_launched = False
 
     def check(self):
         torch.cuda.synchronize()

@@ -135,10 +135,13 @@ def forward_reconstructor_for(kind):
 
 
 def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, lambda_recon=1.0, zero_grad=True,
-               optimizer_step=True, grad_hook=None):
+               optimizer_step=True, grad_hook=None, reducer=None):
     """One iteration of the reference's loop body (train.py:243-273): decoder + reconstructor forward, combined
     loss, backward, clip, two Adam steps.  ``grad_hook`` (if given) runs between backward and clip -- the
-    data-parallel gradient all-reduce plugs in there.  Returns (loss, decoder_loss, recon_loss) device scalars."""
+    data-parallel gradient all-reduce plugs in there.  ``reducer`` (parallel.make_reducer(...), modules in the order
+    [reconstructor, decoder]) does the same with overlap: the reconstructor's optimiser step runs while the decoder's gradients
+    are still being averaged (the two steps are independent; the clip, train.py:269-270, only concerns the decoder).
+    Returns (loss, decoder_loss, recon_loss) device scalars."""
     # train.py:246 (the fused path derives the mask from the targets itself; the host-side loop length needs it when n_steps is None)
     target_masks = None if (n_steps is not None and targets.is_cuda) else targets > C.init_word2idx['<PAD>']
     decoder['model'].train()
@@ -158,11 +161,18 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
     loss.backward()                                                                                         # train.py:268
     if grad_hook is not None:
         grad_hook()
+    rec_stepped = False
+    if reducer is not None:
+        if reconstructor is not None and optimizer_step:
+            reducer.wait_first()                       # reconstructor gradients averaged; the decoder's go out underneath ...
+            reconstructor['optimizer'].step()          # ... the reconstructor's Adam step (train.py:273; order of :271-273 is immaterial)
+            rec_stepped = True
+        reducer.wait()
     if optimizer_step:
         own_clip = isinstance(decoder['optimizer'], ClipAdam) and decoder['optimizer'].param_groups[0].get('max_grad_norm')
         if C.use_gradient_clip and not own_clip:
             torch.nn.utils.clip_grad_norm_(decoder['model'].parameters(), C.gradient_clip, foreach=True)    # train.py:269-270
         decoder['optimizer'].step()
-        if reconstructor is not None:
+        if reconstructor is not None and not rec_stepped:
             reconstructor['optimizer'].step()
     return loss, dec_loss, rec_loss

@@ -24,3 +24,20 @@ def test_opt_in_paths_stay_parity_green(switches):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and " failed" not in r.stdout, tail
+
+
+def test_nvlink_allreduce_kernel_matches_nccl_on_two_gpus():
+    """csrc/allreduce.cuh under torchrun on 2 GPUs of this box: gradients averaged in place in symmetric memory (NVSwitch multicast path
+    and peer-pointer path) equal NCCL's all_reduce(AVG) of a copy, and every rank ends with bitwise identical buffers.  Skipped on a
+    single-GPU box (the driver's scaling run exercises the kernel there; tools/dp_nvlink_check.py is the same check by hand)."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs on this box")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(ROOT, "tools", "dp_nvlink_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for mode in ("multicast", "peer"):
+        assert out[mode + "_worst_rel_err_vs_nccl"] < 1e-5 and out[mode + "_identical_on_all_ranks"], out

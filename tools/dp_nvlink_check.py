@@ -56,11 +56,11 @@ def main():
         # timing: the kernel alone, 20 launches back to back
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            red.wait()
+            red.start_iteration(); red.wait()
         dist.barrier(); torch.cuda.synchronize()
         e0.record()
         for _ in range(20):
-            red.wait()
+            red.start_iteration(); red.wait()
         e1.record()
         torch.cuda.synchronize()
         red.check()

@@ -7,6 +7,7 @@
 #pragma once
 #include "proj_attn.cuh"
 #include "seq_decoder.cuh"
+#include "seq_decoder_cluster.cuh"
 
 namespace dec {
 
@@ -151,7 +152,19 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk2, s2));
   RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
   RN_TRY(side().join(st, s2));
-  for (int t = 0; t < L; ++t) {
+  bool clustered = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (dcl::cluster_ok(B, Tn, A, H)) {
+      // the whole time loop as ONE kernel of independent 16-CTA clusters, [W_a ; W_hh] resident in distributed shared memory
+      dcl::FwdArgs ca{};
+      ca.Wcat = w.Wcat; ca.Uv = w.Uv; ca.attn_w = p.attn_w; ca.VW = w.VW; ca.Gx = w.Gx; ca.b_hh = p.b_hh; ca.c = w.c; ca.hiddens = hiddens;
+      ca.Hop = w.Hop; ca.Wh = w.Wh; ca.e = w.e; ca.gates = w.gates; ca.B = B; ca.L = L; ca.Tn = Tn; ca.inv_T = 1.f / Tn;
+      const int rc = dcl::launch_fwd(ca, st);
+      if (rc == 0) clustered = true;
+      else if (rc != RECNET_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  for (int t = 0; t < L && !clustered; ++t) {
     const size_t r = (size_t)t * B;
     if (t > 0)      // h_{-1} = 0: no query, no recurrent term
       RN_TRY(gemm_partials<T>(w.Hop + r * H, H, 0, w.Wcat, H, 0, w.P, B, w.NP, H, w.pl_h, st));

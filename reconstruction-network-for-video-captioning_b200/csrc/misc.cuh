@@ -404,4 +404,9 @@ __global__ void mt_reg_grad_kernel(const long long* __restrict__ ptrs, const lon
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) g[i] = fmaf(k, p[i], accumulate ? g[i] : 0.f);
   }
 }
+// x[r, c] = x[r, c] * scale + bias[c]   (hoisted embedding projection table of the greedy decoder)
+__global__ void scale_add_bias_kernel(float* __restrict__ x, long long total, int cols, float scale, const float* __restrict__ bias) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    x[i] = fmaf(x[i], scale, bias[(int)(i % cols)]);
+}
 }  // namespace misc

@@ -91,6 +91,7 @@ struct FwdArgs {
   const float* attn_w;                                    // [A]
   const void* VW;                                         // [B, Tn, H, 4] TV   hoisted v W_ctx^T, unit-interleaved
   const float* Gx;                                        // [B, 4H]  hoisted embedding projection + b_ih (gate-block order)
+  const long long* gx_rows;                               // nullable: row of Gx to use for sample b (greedy decoding: Gx = table over the vocabulary, rows = fed-back tokens)
   const float* b_hh;                                      // [4H]
   const float* c_prev;                                    // [B, H]
   int B, Tn, A, H; float inv_T;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, MINB) pf_fwd_kernel(FwdArgs a) {
   float pre[4] = {0.f, 0.f, 0.f, 0.f};
   float cp = 0.f;
   if (half == 0) {
-    const float* gx = a.Gx + (size_t)b * row + jc;
+    const float* gx = a.Gx + (size_t)(a.gx_rows ? (unsigned)a.gx_rows[b] : b) * row + jc;
     const float* bh = a.b_hh + jc;
 #pragma unroll
     for (unsigned g = 0; g < 4; ++g) pre[g] = gx[g * H] + bh[g * H];

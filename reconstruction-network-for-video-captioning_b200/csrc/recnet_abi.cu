@@ -258,7 +258,11 @@ float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int6
 }
 int64_t recnet_greedy_workspace_bytes(const recnet_decoder_desc* d) {
   if (d->precision == RECNET_PREC_FP32) return (int64_t)dec::plan_greedy<float>(*d, nullptr, 64).bytes;
-  if (d->precision == RECNET_PREC_BF16) return (int64_t)dec::plan_greedy<bf16>(*d, nullptr, 64).bytes;
+  if (d->precision == RECNET_PREC_BF16) {
+    const int64_t a = (int64_t)dec::plan_greedy<bf16>(*d, nullptr, 64).bytes;
+    const int64_t b = dec::greedy_pf_ok(*d) ? (int64_t)dec::plan_greedy_pf<bf16>(*d, nullptr, 64).bytes : 0;
+    return a > b ? a : b;
+  }
   return RECNET_ERR_UNSUPPORTED;
 }
 int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, int max_steps,
@@ -266,8 +270,12 @@ int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_ten
   if (max_steps < 1 || max_steps > 64) return RECNET_ERR_BAD_SHAPE;
   if (d->precision == RECNET_PREC_FP32)
     return dec::greedy<float>(*d, *w, feats, max_steps, workspace, workspace_bytes, reinterpret_cast<long long*>(ids_out), n_steps_out, ST(stream));
-  if (d->precision == RECNET_PREC_BF16)
+  if (d->precision == RECNET_PREC_BF16) {
+    recnet_decoder_desc d1 = *d; d1.L = 1; d1.train = 0;
+    if (dec::greedy_pf_ok(d1))      // projected-feature kernels, 4 launches per step
+      return dec::greedy_pf(*d, *w, feats, max_steps, workspace, workspace_bytes, reinterpret_cast<long long*>(ids_out), n_steps_out, ST(stream));
     return dec::greedy<bf16>(*d, *w, feats, max_steps, workspace, workspace_bytes, reinterpret_cast<long long*>(ids_out), n_steps_out, ST(stream));
+  }
   return RECNET_ERR_UNSUPPORTED;
 }
 

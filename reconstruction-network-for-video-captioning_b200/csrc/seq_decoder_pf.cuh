@@ -256,4 +256,105 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   RN_TRY(side().join(st, s2));
   return 0;
 }
+// ---- greedy decoding (eval.greedy_search, eval.py:19-33) on the projected-feature kernels: bf16 build -----------------------------
+// 4 launches per step instead of 8: the embedding half of the gate projection is a GATHER from EW = Embedding . W_emb^T + b_ih
+// (one [V x 4H x EMB] GEMM per call; eval mode has no dropout), the context half is the hoisted VW (as in training), so a step is
+//   h_{t-1} [W_a ; W_hh]^T  ->  pf_fwd_kernel (scores, context, cell; Gx row = fed-back token)  ->  vocabulary projection  ->  argmax feedback.
+// The fp32 build keeps the general path (seq_decoder.cuh:greedy): its summation order is the one the bit-exact id tests pin.
+template <typename T>
+struct GreedyPfWs {
+  int EMBp, Vld, NP;
+  GemmPlan pl_h;
+  T *Wemb, *WctxI, *Wcat, *U, *Wout, *feats, *Emb;
+  float* Uv; T* VW; float* EW; T* Hop; float* P; float* c; float* hid; float* logits; long long* tok; int* nonpad; float* splitk;
+  size_t bytes;
+};
+template <typename T>
+static GreedyPfWs<T> plan_greedy_pf(const recnet_decoder_desc& d, void* base, int max_steps) {
+  GreedyPfWs<T> w;
+  const int B = d.B, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T;
+  w.EMBp = round_up(d.EMB, Prec<T>::kpad);
+  w.Vld = round_up(V, 4);
+  w.NP = A + 4 * H;
+  w.pl_h = plan_gemm<T>(B, w.NP, H, NUM_SMS);
+  Bump m(base);
+  w.Wemb = m.take<T>((size_t)4 * H * w.EMBp);
+  w.WctxI = m.take<T>((size_t)4 * H * E);
+  w.Wcat = m.take<T>((size_t)w.NP * H);
+  w.U = m.take<T>((size_t)A * E);
+  w.Wout = m.take<T>((size_t)V * H);
+  w.feats = m.take<T>((size_t)B * Tn * E);
+  w.Emb = m.take<T>((size_t)V * w.EMBp);
+  w.Uv = m.take<float>((size_t)B * Tn * A);
+  w.VW = m.take<T>((size_t)B * Tn * 4 * H);
+  w.EW = m.take<float>((size_t)V * 4 * H);
+  w.Hop = m.take<T>((size_t)2 * B * H);
+  w.P = m.take<float>((size_t)w.pl_h.splits * B * w.NP);
+  w.c = m.take<float>((size_t)2 * B * H);
+  w.hid = m.take<float>((size_t)B * H);
+  w.logits = m.take<float>((size_t)B * w.Vld);
+  w.tok = m.take<long long>(B);
+  w.nonpad = m.take<int>(max_steps);
+  w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.bytes = m.off + 256;
+  return w;
+}
+static inline bool greedy_pf_ok(const recnet_decoder_desc& d) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RECNET_GREEDY_PF"); on = e ? atoi(e) : 1; }
+  return on && d.precision == RECNET_PREC_BF16 && pf_ok(d) && (long long)d.V * 4 * d.H < (1ll << 31);
+}
+
+static int greedy_pf(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p, const float* feats, int max_steps, void* ws,
+                     long long ws_bytes, long long* ids_out, int* n_steps_out, cudaStream_t st) {
+  typedef bf16 T;
+  recnet_decoder_desc d = d0; d.L = 1; d.train = 0;
+  RN_TRY(check(d));
+  GreedyPfWs<T> w = plan_greedy_pf<T>(d, ws, max_steps);
+  if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  const int B = d.B, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T, EMB = d.EMB;
+  const long long ldih = EMB + E;
+  misc::Stager<T> sg;
+  sg.add(feats, E, w.feats, E, (long long)B * Tn, E, E);
+  sg.add(p.attn_U, E, w.U, E, A, E, E);
+  sg.add(p.w_ih, ldih, w.Wemb, w.EMBp, 4 * H, EMB, w.EMBp);
+  sg.add(p.w_ih + EMB, ldih, w.WctxI, E, 4 * H, E, E, H);                 // W_ctx rows in unit-interleaved order
+  sg.add(p.attn_W, H, w.Wcat, H, A, H, H);
+  sg.add(p.w_hh, H, w.Wcat + (size_t)A * H, H, 4 * H, H, H);
+  sg.add(p.out_w, H, w.Wout, H, V, H, H);
+  sg.add(p.embedding, EMB, w.Emb, w.EMBp, V, EMB, w.EMBp);
+  sg.zero(w.Hop, (size_t)2 * B * H * sizeof(T));
+  sg.zero(w.c, (size_t)2 * B * H * sizeof(float));
+  sg.zero(w.nonpad, (size_t)max_steps * sizeof(int));
+  RN_TRY(sg.launch(st));
+  // hoisted once per call: U v + b, VW = feats W_ctx^T, EW = (embedding_scale * Embedding) W_emb^T + b_ih
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, p.attn_b, B * Tn, A, E, 0, w.splitk, st));
+  RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
+  RN_TRY(gemm_full<T>(w.Emb, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.EW, 4 * H, nullptr, V, 4 * H, w.EMBp, 0, w.splitk, st));
+  misc::scale_add_bias_kernel<<<NUM_SMS * 4, 256, 0, st>>>(w.EW, (long long)V * 4 * H, 4 * H, d.embedding_scale, p.b_ih);
+  RN_LAUNCH_OK();
+  fill_tokens_kernel<<<rn_cdiv(B, 128), 128, 0, st>>>(w.tok, B, 1 /* <SOS> */);
+  RN_LAUNCH_OK();
+  for (int t = 0; t < max_steps; ++t) {
+    T* h_p = w.Hop + (size_t)(t & 1) * B * H;
+    T* h_n = w.Hop + (size_t)((t + 1) & 1) * B * H;
+    float* c_p = w.c + (size_t)(t & 1) * B * H;
+    float* c_n = w.c + (size_t)((t + 1) & 1) * B * H;
+    if (t > 0) RN_TRY(gemm_partials<T>(h_p, H, 0, w.Wcat, H, 0, w.P, B, w.NP, H, w.pl_h, st));
+    pf::FwdArgs fa{};
+    fa.P = w.P; fa.n_p = t > 0 ? w.pl_h.splits : 0; fa.p_stride = (long long)B * w.NP; fa.NP = w.NP;
+    fa.Uv = w.Uv; fa.attn_w = p.attn_w; fa.VW = w.VW;
+    fa.Gx = w.EW; fa.gx_rows = w.tok; fa.b_hh = p.b_hh; fa.c_prev = c_p;
+    fa.B = B; fa.Tn = Tn; fa.A = A; fa.H = H; fa.inv_T = 1.f / Tn;
+    fa.Wh_out = nullptr; fa.e_out = nullptr; fa.gates_out = nullptr;
+    fa.c_out = c_n; fa.h_out = w.hid; fa.h_op = h_n;
+    RN_TRY((pf::launch_fwd<T, T>(fa, st)));
+    RN_TRY(gemm_full<T>(h_n, H, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, B, V, H, 0, w.splitk, st));
+    argmax_feedback_kernel<<<B, 256, 0, st>>>(w.logits, w.Vld, V, ids_out + (size_t)t * B, w.tok, w.nonpad + t);
+    RN_LAUNCH_OK();
+  }
+  greedy_finalize_kernel<<<1, 1, 0, st>>>(w.nonpad, max_steps, n_steps_out);
+  RN_LAUNCH_OK();
+  return 0;
+}
 }  // namespace dec

@@ -365,9 +365,19 @@ struct GlobalWs {
   T *Wih, *Whh, *Wout; float* mp; T* Xg; float* Gx; T* X; float* P; T* gates; float* c; float* out; float* diff; float* partial;
   T* dOut; float* dHext; T* dG; T* dG2; float* dXp; float* dc; float* dXg; float* dmp; float* splitk;
   uint8_t* table; size_t table_bytes; unsigned* bar; int* err;
+  float* pXP; unsigned* psync;                    // weight-resident persistent loops (seq_recon_persist.cuh)
   size_t bytes;
 };
 constexpr int GMSE_THREADS = 256;
+
+template <typename T>
+static inline bool persist_global_ok(const recnet_global_desc& d, bool bwd) {
+  if (!std::is_same<T, bf16>::value || d.cell != RECNET_CELL_LSTM || num_chains(d.B) != 1) return false;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RECNET_PERSIST_GLOBAL"); on = e ? atoi(e) : 1; }
+  if (!on) return false;
+  return bwd ? rp::global_bwd_ok(d.B, d.L, d.R) : rp::global_fwd_ok(d.B, d.L, d.R);
+}
 
 template <typename T>
 static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
@@ -407,6 +417,13 @@ static GlobalWs<T> plan_global(const recnet_global_desc& d, void* base) {
   w.table = m.take<uint8_t>(w.table_bytes);
   w.bar = m.take<unsigned>(64);
   w.err = m.take<int>(64);
+  {
+    size_t n = 4;
+    if (persist_global_ok<T>(d, false)) n = (size_t)(R / rp::UNITS) * rp::pick_ks(R, 0) * B * rp::NCOL;
+    if (persist_global_ok<T>(d, true)) { const size_t n2 = (size_t)(R / 128) * rp::pick_ns(R, 0) * B * 128; n = n2 > n ? n2 : n; }
+    w.pXP = m.take<float>(n);
+    w.psync = m.take<unsigned>(2 * rp::SYNC_WORDS);
+  }
   w.bytes = m.off + 256;
   return w;
 }
@@ -442,10 +459,23 @@ static int global_forward(const recnet_global_desc& d, const recnet_global_tenso
   RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)B * R * sizeof(T), st));
   RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)B * R * sizeof(float), st));
   RN_CUDA_OK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
+  bool persist = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    persist = persist_global_ok<T>(d, false);
+    if (persist || persist_global_ok<T>(d, true)) RN_CUDA_OK(cudaMemsetAsync(w.psync, 0, 2 * rp::SYNC_WORDS * sizeof(unsigned), st));
+    if (persist) {
+      // ONE cooperative launch for all L steps, W_hh resident in shared memory (seq_recon_persist.cuh, global mode)
+      rp::FwdParams fp{};
+      fp.B = B; fp.S = L; fp.R = R; fp.H = 0; fp.A = 0; fp.L = 1; fp.inv_L = 1.f; fp.p_drop = 0.f;
+      fp.X = w.X; fp.b_ih = p.b_ih; fp.b_hh = p.b_hh; fp.gates = w.gates; fp.c = w.c; fp.XP = w.pXP; fp.sync = w.psync; fp.err = w.err;
+      fp.global_mode = 1; fp.Gx = w.Gx;
+      RN_TRY(rp::launch_local_fwd(fp, w.Whh, st));
+    }
+  }
   Chains& cs = chains();
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   mega::Emitter<T> em0(w.nch == 1 && !is_gru, st);
-  for (int t = 0; t < L; ++t) {
+  for (int t = 0; t < L && !persist; ++t) {
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;
       chain_rows(B, w.nch, ch, &b0, &nb);
@@ -512,8 +542,19 @@ static int global_backward(const recnet_global_desc& d, const recnet_global_tens
   if (w.nch > 1) RN_TRY(cs.fork(st, w.nch));
   const bool is_gru = d.cell == RECNET_CELL_GRU;
   const int GR = w.G * R;
+  bool persist = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    persist = persist_global_ok<T>(d, true);
+    if (persist) {
+      rp::BwdParams bp{};
+      bp.B = B; bp.S = L; bp.R = R; bp.H = 0; bp.A = 0; bp.L = 1; bp.inv_L = 1.f; bp.p_drop = 0.f;
+      bp.gates = w.gates; bp.c = w.c; bp.dHext = w.dHext; bp.dG = w.dG; bp.DP = w.pXP; bp.sync = w.psync + rp::SYNC_WORDS; bp.err = w.err;
+      bp.global_mode = 1;
+      RN_TRY(rp::launch_local_bwd(bp, w.Whh, st));
+    }
+  }
   mega::Emitter<T> em0(w.nch == 1 && !is_gru, st);
-  for (int t = L - 1; t >= 0; --t) {
+  for (int t = L - 1; t >= 0 && !persist; --t) {
     const bool last = (t == L - 1);
     for (int ch = 0; ch < w.nch; ++ch) {
       int b0, nb;

@@ -24,7 +24,7 @@ namespace rp {
 using namespace tc;
 
 constexpr int THREADS = 448;          // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer, 6-13 attention
-constexpr int STAGES = 3;             // activation ring: B rows x 64 k per stage
+constexpr int MAX_STAGES = 8;         // activation ring (B rows x 64 k per stage): as deep as the shared memory left by the resident weights allows
 constexpr int UNITS = 32;             // hidden units per CTA
 constexpr int NCOL = 4 * UNITS;       // accumulator columns (gate g, unit u) -> column g*32 + u
 constexpr int MAX_KB = 11;            // resident k-blocks per CTA (16 KB each)
@@ -36,6 +36,7 @@ constexpr long long TIMEOUT = 600000000LL;      // ~0.3 s of SM clocks
 
 struct FwdParams {
   int B, S, R, H, A, L, KX, UG, KS, NHB, NXB;
+  int nst, res_kb;                    // ring stages / resident k-blocks per CTA (set by the launcher)
   float inv_L, p_drop;
   bf16* X;                            // [(S+1)*B, KX] operand rows [x_t | h_{t-1}]
   const bf16* Hd;                     // [L*B, H] decoder states (attention values)
@@ -52,6 +53,10 @@ struct FwdParams {
   int* err;
   const unsigned long long* rng;
   unsigned site;
+  // GLOBAL reconstructor mode (models/global_reconstructor.py:30-46): no attention, H = 0 (operand rows hold h only); the hoisted
+  // input projection Gx [S*B, 4R] (b_ih folded in) is added in the cell update instead
+  int global_mode;
+  const float* Gx;
 };
 
 __device__ __forceinline__ unsigned ld_acq(const unsigned* p) {
@@ -147,13 +152,13 @@ constexpr int TMEM_COLS = 256;        // [0,128) gate accumulator, [128, 224) at
 struct Smem {                // offsets from the 1024-aligned base
   int ring, wres, bars, e, whred, hs, total;
 };
-__host__ __device__ inline Smem smem_layout(int B, int KS) {
+__host__ __device__ inline Smem smem_layout(int B, int KS, int nst, int res_kb) {
   Smem s;
   const int stage = ((B + 7) & ~7) * 128;
   s.ring = 0;
-  s.wres = (STAGES * stage + 1023) & ~1023;
-  s.bars = s.wres + MAX_KB * WTILE;               // full[3] empty[3] tmem wload | tmem slot | abort
-  s.e = s.bars + 128;
+  s.wres = (nst * stage + 1023) & ~1023;
+  s.bars = s.wres + res_kb * WTILE;               // full[8] empty[8] tmem wload | tmem slot | abort
+  s.e = s.bars + 256;
   s.whred = s.e + 128;                            // [8][128] floats
   s.hs = s.whred + 8 * 128 * 4;                   // [48][HS_LD] bf16: h_t of this CTA's cells, A operand of the query mma
   s.total = s.hs + 4 * NWORK * HS_LD * 2 + 1024;  // + alignment slack
@@ -191,12 +196,17 @@ __device__ __forceinline__ void cell_query_phase(const FwdParams& p, const CellC
           for (int k2 = 0; k2 < KS; ++k2)
 #pragma unroll
             for (int g = 0; g < 4; ++g) part[k2][g] = q[(long long)k2 * B * NCOL + g * UNITS];
+          float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.global_mode) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gxv[g] = p.Gx[((long long)t * B + b) * 4 * R + (long long)g * R + j];
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float s = part[0][g];
 #pragma unroll
             for (int k2 = 1; k2 < KS; ++k2) s += part[k2][g];
-            pre[rr][g] = s;
+            pre[rr][g] = s + gxv[g];
           }
         }
 #pragma unroll
@@ -222,7 +232,7 @@ __device__ __forceinline__ void cell_query_phase(const FwdParams& p, const CellC
       // ---------------- partial attention query of the next step over this CTA's 32 units ----------------
       // WhP[ug][b, a] = sum_u h_t[b, u] W_a[a, u]: [ns x 32] . [32 x 128] on mma.sync m16n8k16 (bf16 in, fp32 out); warp ww < 8 owns
       // a-tiles 2ww, 2ww+1 (its W_a fragments live in registers), loops over the sample tiles; rows >= ns are never stored
-      if (t + 1 < S && ww < 8) {
+      if (t + 1 < S && ww < 8 && !p.global_mode) {
         const int gid = lane >> 2, tig = lane & 3;
         for (int mt = 0; mt * 16 < ns; ++mt) {
           uint32_t af[2][4];
@@ -272,12 +282,13 @@ local_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const Smem L_ = smem_layout(p.B, KS);
+  const Smem L_ = smem_layout(p.B, KS, p.nst, p.res_kb);
+  const uint32_t STAGES = (uint32_t)p.nst;
   const int stage_bytes = ((p.B + 7) & ~7) * 128;
   const uint32_t ring = base + L_.ring, wres = base + L_.wres;
-  const uint32_t bar_full = base + L_.bars, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES, bar_w = bar_tmem + 8;
+  const uint32_t bar_full = base + L_.bars, bar_empty = bar_full + 8 * MAX_STAGES, bar_tmem = bar_empty + 8 * MAX_STAGES, bar_w = bar_tmem + 8;
   const uint32_t tmem_slot = bar_w + 8;
-  volatile int* abort_ = reinterpret_cast<volatile int*>(gen + L_.bars + 96);
+  volatile int* abort_ = reinterpret_cast<volatile int*>(gen + L_.bars + 192);
   float* e_s = reinterpret_cast<float*>(gen + L_.e);
   float* whred = reinterpret_cast<float*>(gen + L_.whred);
   bf16* hs = reinterpret_cast<bf16*>(gen + L_.hs);
@@ -295,7 +306,7 @@ local_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   unsigned* flagX = p.sync + 64 + 32 * ug;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -333,6 +344,7 @@ local_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_expect_tx(bar_full + 8 * s, tx);
           tma_load_2d(ring + s * stage_bytes, &tmX, bar_full + 8 * s, (p.NXB + hb0 + i) * BK, t * B);
         }
+        if (nx == 0) continue;                                                   // global mode: the input projection is hoisted
         wait_flag(barB, (unsigned)B * (unsigned)(t + 1), p.err, abort_);       // x_t of every sample is visible
         proxy_fence();
         if (cta == 0) stamp(2);
@@ -383,10 +395,11 @@ local_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     cq.j = ug * UNITS + lane;                              // this lane's hidden unit
     {
       const int j = cq.j;
-      cq.bi = p.b_ih[j] + p.b_hh[j]; cq.bf_ = p.b_ih[R + j] + p.b_hh[R + j];
-      cq.bg = p.b_ih[2 * R + j] + p.b_hh[2 * R + j]; cq.bo = p.b_ih[3 * R + j] + p.b_hh[3 * R + j];
+      const float ih = p.global_mode ? 0.f : 1.f;            // global mode: b_ih is already inside Gx
+      cq.bi = ih * p.b_ih[j] + p.b_hh[j]; cq.bf_ = ih * p.b_ih[R + j] + p.b_hh[R + j];
+      cq.bg = ih * p.b_ih[2 * R + j] + p.b_hh[2 * R + j]; cq.bo = ih * p.b_ih[3 * R + j] + p.b_hh[3 * R + j];
       // W_a fragments of the query mma (B operand, col-major k x n): a = 16 ww + 8 nt + lane/4, units 16 k + 2 (lane%4) (+8)
-      if (cq.ww < 8) {
+      if (cq.ww < 8 && !p.global_mode) {
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -427,7 +440,7 @@ local_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         cell_query_phase<KS>(p, cq, t, creg, hs);
       }
-    } else if (cta >= B) {
+    } else if (cta >= B || p.global_mode) {
       for (int t = 0; t < S; ++t) cell_query_phase<KS>(p, cq, t, creg, hs);
     } else {
       // ---------------- attention of sample b_att = cta (warps 6-13 of the first B CTAs) ----------------
@@ -568,13 +581,32 @@ static inline int pick_ks(int R, int H) {
   return 0;
 }
 struct Shape { int B, S, R, H, A, L; };
+// deepest ring that fits next to res_kb resident k-blocks (at least 2, at most MAX_STAGES); 0 = does not fit
+static inline int pick_stages_fwd(int B, int ks, int res_kb) {
+  for (int n = MAX_STAGES; n >= 2; --n) if (smem_layout(B, ks, n, res_kb).total <= 227 * 1024) return n;
+  return 0;
+}
+static inline int max_res_kb_fwd(int R, int H, int ks) {
+  const int NHB = R / BK, NXB = H / BK;
+  int worst = 0;
+  for (int k = 0; k < ks; ++k) {
+    const int n = ((NHB * (k + 1)) / ks - (NHB * k) / ks) + ((NXB * (k + 1)) / ks - (NXB * k) / ks);
+    worst = n > worst ? n : worst;
+  }
+  return worst;
+}
+static inline bool global_fwd_ok(int B, int S, int R) {
+  if (!persist_enabled()) return false;
+  const int ks = pick_ks(R, 0);
+  return ks && B >= ks && B <= 128 && S >= 1 && R / UNITS <= MAX_UG && (B + ks - 1) / ks <= 4 * NWORK && pick_stages_fwd(B, ks, max_res_kb_fwd(R, 0, ks)) > 0;
+}
 static inline bool local_fwd_ok(const Shape& s) {
   if (!persist_enabled()) return false;
   const int ks = pick_ks(s.R, s.H);
   if (!ks) return false;
   const int UG = s.R / UNITS;
   return s.A == 128 && s.B >= ks && s.B <= 128 && s.B <= UG * ks && s.L >= 1 && s.L <= 32 && s.H <= 512 && UG <= MAX_UG && s.S >= 1 &&
-         (s.B + ks - 1) / ks <= 4 * NWORK && smem_layout(s.B, ks).total <= 227 * 1024;
+         (s.B + ks - 1) / ks <= 4 * NWORK && pick_stages_fwd(s.B, ks, max_res_kb_fwd(s.R, s.H, ks)) > 0;
 }
 static inline size_t xp_floats(const Shape& s) { const int ks = pick_ks(s.R, s.H); return ks ? (size_t)(s.R / UNITS) * ks * s.B * NCOL : 4; }
 static inline size_t whp_floats(const Shape& s) { return (size_t)(s.R / UNITS + 1) * s.B * s.A; }
@@ -583,7 +615,7 @@ constexpr int SYNC_WORDS = 64 + 32 * MAX_UG;
 template <int KS>
 static int launch_ks(const CUtensorMap& mx, const CUtensorMap& mw, const FwdParams& p, cudaStream_t st) {
   auto kern = local_fwd_kernel<KS>;
-  const int smem = smem_layout(p.B, KS).total;
+  const int smem = smem_layout(p.B, KS, p.nst, p.res_kb).total;
   static int attr_smem = 0;
   if (attr_smem < smem) {
     RN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -600,6 +632,8 @@ static int launch_ks(const CUtensorMap& mx, const CUtensorMap& mw, const FwdPara
 static int launch_local_fwd(FwdParams p, const bf16* Wrec, cudaStream_t st) {
   p.KS = pick_ks(p.R, p.H);
   p.UG = p.R / UNITS; p.NHB = p.R / BK; p.NXB = p.H / BK; p.KX = p.H + p.R;
+  p.res_kb = max_res_kb_fwd(p.R, p.H, p.KS); p.nst = pick_stages_fwd(p.B, p.KS, p.res_kb);
+  if (p.nst <= 0) return RECNET_ERR_UNSUPPORTED;
   CUtensorMap mx, mw;
   RN_TRY(make_map(&mx, p.X, (long long)(p.S + 1) * p.B, p.KX, p.KX, BK, p.B));
   RN_TRY(make_map(&mw, Wrec, 4LL * p.R, p.KX, p.KX, BK, UNITS));
@@ -624,6 +658,7 @@ static int launch_local_fwd(FwdParams p, const bf16* Wrec, cudaStream_t st) {
 //   as the kernel-per-phase path does, so the batched weight-gradient GEMMs after the loop run unchanged.
 struct BwdParams {
   int B, S, R, H, A, L, KX, CG, NS, NB4, UG, KT;
+  int nst, res_kb;                    // ring stages / resident k-blocks per CTA (set by the launcher)
   float inv_L, p_drop;
   const bf16* Hd; const float* Uv; const bf16* Wa;
   const float *attn_b, *attn_w;
@@ -641,17 +676,18 @@ struct BwdParams {
   int* err;
   const unsigned long long* rng;
   unsigned site;
+  int global_mode;                    // GLOBAL reconstructor: no attention / query path, H = 0 (dX = dG . W_hh only)
 };
 constexpr int MAX_NS = 12;
 
 struct SmemB { int ring, wres, bars, dctx, red, total; };
-__host__ __device__ inline SmemB smem_layout_bwd(int B) {
+__host__ __device__ inline SmemB smem_layout_bwd(int B, int nst, int res_kb) {
   SmemB s;
   const int stage = ((B + 7) & ~7) * 128;
   s.ring = 0;
-  s.wres = (STAGES * stage + 1023) & ~1023;
-  s.bars = s.wres + MAX_KB * WTILE;
-  s.dctx = s.bars + 128;                           // [512] floats
+  s.wres = (nst * stage + 1023) & ~1023;
+  s.bars = s.wres + res_kb * WTILE;
+  s.dctx = s.bars + 256;                           // [512] floats
   s.red = s.dctx + 512 * 4;                        // [8][128] floats
   s.total = s.red + 8 * 128 * 4 + 1024;
   return s;
@@ -662,12 +698,13 @@ local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const SmemB L_ = smem_layout_bwd(p.B);
+  const SmemB L_ = smem_layout_bwd(p.B, p.nst, p.res_kb);
+  const uint32_t STAGES = (uint32_t)p.nst;
   const int stage_bytes = ((p.B + 7) & ~7) * 128;
   const uint32_t ring = base + L_.ring, wres = base + L_.wres;
-  const uint32_t bar_full = base + L_.bars, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES, bar_w = bar_tmem + 8;
+  const uint32_t bar_full = base + L_.bars, bar_empty = bar_full + 8 * MAX_STAGES, bar_tmem = bar_empty + 8 * MAX_STAGES, bar_w = bar_tmem + 8;
   const uint32_t tmem_slot = bar_w + 8;
-  volatile int* abort_ = reinterpret_cast<volatile int*>(gen + L_.bars + 96);
+  volatile int* abort_ = reinterpret_cast<volatile int*>(gen + L_.bars + 192);
   float* dctx_s = reinterpret_cast<float*>(gen + L_.dctx);
   float* red = reinterpret_cast<float*>(gen + L_.red);
 
@@ -682,7 +719,7 @@ local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
   unsigned* bar3 = p.sync + 64;       // dWh_t of every sample is visible
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -747,7 +784,8 @@ local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
   } else {
     // ================================ worker warps ================================
     const bool is_epi = warp < 4;
-    const bool do_attn = !is_epi && cta < B;
+    const bool glob = p.global_mode != 0;
+    const bool do_attn = !is_epi && cta < B && !glob;
     const int ww = is_epi ? warp : warp - 2;               // 0..11 in the cell phase
     const int aw = warp - 6;                                // 0..7 in the attention phase
     const int gid = lane >> 2, tig = lane & 3;
@@ -763,7 +801,10 @@ local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     const int kcol = H + j, cgj = kcol >> 7, colj = kcol & 127;
     // W_a fragments (B operand of mma.m16n8k16, k = a, n = unit): b0b1 = W_a[16 ks + 2 tig (+1)][unit 8 nt + gid], b2b3 = rows + 8
     uint32_t wb[16];
-    {
+    if (glob) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wb[i] = 0u;
+    } else {
       const unsigned short* W = reinterpret_cast<const unsigned short*>(p.Wa) + ug * UNITS + 8 * nt + gid;
 #pragma unroll
       for (int ks8 = 0; ks8 < 8; ++ks8) {
@@ -853,7 +894,7 @@ local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
               if (s < NS) { dh[0][0] += pa[s].x; dh[0][1] += pa[s].y; dh[1][0] += pb[s].x; dh[1][1] += pb[s].y; }
           }
         }
-        if (!last) {
+        if (!last && !glob) {
           // dWh_{t+1} . W_a over this CTA's 32 units: [slots x 128 a] . [128 a x 32 units], A fragments straight from dWh_op (L2)
           if (is_epi) { if (tid == 0) wait_flag(bar3, (unsigned)B * (unsigned)(S - 1 - t), p.err, abort_); nbar(1, 128); }
           else { if (aw == 0 && lane == 0) wait_flag(bar3, (unsigned)B * (unsigned)(S - 1 - t), p.err, abort_); nbar(5, 256); }
@@ -1033,11 +1074,22 @@ local_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
 // gate-row split that keeps every CTA's weight slice resident with CG*NS CTAs co-resident; 0 = shape not covered
 static inline int pick_ns(int R, int H) {
   const int KX = R + H;
-  if (KX % 128 || R % 64) return 0;
-  const int CG = KX / 128, NB4 = 4 * R / BK;
-  for (int ns = 1; ns <= MAX_NS; ++ns)
-    if ((NB4 + ns - 1) / ns <= MAX_KB && CG * ns <= sm_count()) return ns;
+  if (KX % 128 || R % 64 || R % UNITS) return 0;
+  const int CG = KX / 128, NB4 = 4 * R / BK, UG = R / UNITS;
+  for (int ns = MAX_NS; ns >= 1; --ns)                      // as many CTAs as fit: shortest gate-row slice per CTA
+    if ((NB4 + ns - 1) / ns <= MAX_KB && CG * ns <= sm_count() && (CG * ns) % UG == 0) return ns;
   return 0;
+}
+static inline int pick_stages_bwd(int B, int res_kb) {
+  for (int n = MAX_STAGES; n >= 2; --n) if (smem_layout_bwd(B, n, res_kb).total <= 227 * 1024) return n;
+  return 0;
+}
+static inline bool global_bwd_ok(int B, int S, int R) {
+  if (!persist_enabled()) return false;
+  const int ns = pick_ns(R, 0);
+  if (!ns) return false;
+  const int KT = (R / 128) * ns / (R / UNITS);
+  return B >= KT && B <= 128 && S >= 1 && (B + KT - 1) / KT <= 48 && pick_stages_bwd(B, (4 * R / BK + ns - 1) / ns) > 0;
 }
 static inline bool local_bwd_ok(const Shape& s) {
   if (!persist_enabled()) return false;
@@ -1047,7 +1099,7 @@ static inline bool local_bwd_ok(const Shape& s) {
   if (G % UG) return false;
   const int KT = G / UG;
   return s.A == 128 && s.B >= KT && s.B <= 128 && s.B <= G && s.L >= 1 && s.L <= 32 && s.H <= 512 && s.H % 8 == 0 && s.S >= 1 &&
-         (s.B + KT - 1) / KT <= 48 && smem_layout_bwd(s.B).total <= 227 * 1024;
+         (s.B + KT - 1) / KT <= 48 && pick_stages_bwd(s.B, (4 * s.R / BK + ns - 1) / ns) > 0;
 }
 static inline size_t dp_floats(const Shape& s) { const int ns = pick_ns(s.R, s.H); return ns ? (size_t)((s.R + s.H) / 128) * ns * s.B * 128 : 4; }
 
@@ -1057,7 +1109,9 @@ static int launch_local_bwd(BwdParams p, const bf16* Wrec, cudaStream_t st) {
   CUtensorMap mg, mw;
   RN_TRY(make_map(&mg, p.dG, (long long)p.S * p.B, 4LL * p.R, 4LL * p.R, BK, p.B));
   RN_TRY(make_map(&mw, Wrec, 4LL * p.R, p.KX, p.KX, 64, BK));
-  const int smem = smem_layout_bwd(p.B).total;
+  p.res_kb = (p.NB4 + p.NS - 1) / p.NS; p.nst = pick_stages_bwd(p.B, p.res_kb);
+  if (p.nst <= 0) return RECNET_ERR_UNSUPPORTED;
+  const int smem = smem_layout_bwd(p.B, p.nst, p.res_kb).total;
   static int attr_smem = 0;
   if (attr_smem < smem) {
     RN_CUDA_OK(cudaFuncSetAttribute(local_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -175,6 +175,15 @@ int recnet_decoder_greedy(const recnet_decoder_desc* d, const recnet_decoder_ten
                           int max_steps, void* workspace, int64_t workspace_bytes, int64_t* ids_out,
                           int32_t* n_steps_out, void* stream);
 
+/* Beam search (eval.beam_search, eval.py:36-120) as a device loop with zero host syncs: d->B = beam_width * B0 rows, row k * B0 + b =
+ * beam k of sample b; feats_tiled [beam_width * B0, T, E] = the B0 samples repeated beam_width times.  Scores log(sigmoid(logit)),
+ * running score divided by len^0.7 at every step (len = position of the last <EOS> + 1, else t + 1), top-k over beams x vocabulary, stop
+ * when every fed-back token is <PAD> -- the reference's rules.  seq_out [B0, max_steps] int64 = the top-1 sequence of every sample
+ * (-1 beyond n_steps_out[0]); beam_width <= 8; single-layer decoders (LSTM or GRU). */
+int64_t recnet_beam_workspace_bytes(const recnet_decoder_desc* d, int beam_width, int max_steps);
+int recnet_decoder_beam(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats_tiled, int beam_width, int max_steps,
+                        int64_t eos_id, void* workspace, int64_t workspace_bytes, int64_t* seq_out, int32_t* n_steps_out, void* stream);
+
 /* Local reconstructor (models/local_reconstructor.py:37-55 + train.forward_local_reconstructor, train.py:108-131). */
 typedef struct {
   int32_t B, S, R, H, A, L;             /* S = encoder_output_len steps, R = hidden (= feature dim), H = decoder hidden */

@@ -100,6 +100,8 @@ SIGNATURES = {
     "recnet_decoder_logits": (_p, [C.POINTER(decoder_desc), _p, C.POINTER(_l)]),
     "recnet_greedy_workspace_bytes": (_l, [C.POINTER(decoder_desc)]),
     "recnet_decoder_greedy": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _i, _p, _l, _p, _p, _p]),
+    "recnet_beam_workspace_bytes": (_l, [C.POINTER(decoder_desc), _i, _i]),
+    "recnet_decoder_beam": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _i, _i, _l, _p, _l, _p, _p, _p]),
     "recnet_local_workspace_bytes": (_l, [C.POINTER(local_desc)]),
     "recnet_local_fwd": (_i, [C.POINTER(local_desc), C.POINTER(local_tensors), _p, _p, _p, _p, _l, _p, _p]),
     "recnet_local_bwd": (_i, [C.POINTER(local_desc), C.POINTER(local_tensors), _p, _p, _p, _p, _l, _p,

@@ -301,6 +301,24 @@ int64_t recnet_global_error_offset(const recnet_global_desc* d) {
 }
 
 // ---- local reconstructor ---------------------------------------------------------------------------------------
+int64_t recnet_beam_workspace_bytes(const recnet_decoder_desc* d, int beam_width, int max_steps) {
+  if (beam_width < 1 || beam_width > dec::BEAM_MAX_K || max_steps < 1 || max_steps > 64) return RECNET_ERR_BAD_SHAPE;
+  if (d->precision == RECNET_PREC_FP32) return (int64_t)dec::plan_beam<float>(*d, nullptr, beam_width, max_steps).bytes;
+  if (d->precision == RECNET_PREC_BF16) return (int64_t)dec::plan_beam<bf16>(*d, nullptr, beam_width, max_steps).bytes;
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_decoder_beam(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats_tiled, int beam_width, int max_steps,
+                        int64_t eos_id, void* workspace, int64_t workspace_bytes, int64_t* seq_out, int32_t* n_steps_out, void* stream) {
+  if (d->n_layers > 1) return RECNET_ERR_UNSUPPORTED;
+  if (d->precision == RECNET_PREC_FP32)
+    return dec::beam<float>(*d, *w, feats_tiled, beam_width, max_steps, (long long)eos_id, workspace, workspace_bytes,
+                            reinterpret_cast<long long*>(seq_out), n_steps_out, ST(stream));
+  if (d->precision == RECNET_PREC_BF16)
+    return dec::beam<bf16>(*d, *w, feats_tiled, beam_width, max_steps, (long long)eos_id, workspace, workspace_bytes,
+                           reinterpret_cast<long long*>(seq_out), n_steps_out, ST(stream));
+  return RECNET_ERR_UNSUPPORTED;
+}
+
 int64_t recnet_local_workspace_bytes(const recnet_local_desc* d) {
   if (d->precision == RECNET_PREC_FP32) return (int64_t)rec::plan_local<float>(*d, nullptr).bytes;
   if (d->precision == RECNET_PREC_BF16) return (int64_t)rec::plan_local<bf16>(*d, nullptr).bytes;

@@ -469,4 +469,169 @@ static int greedy(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p
   RN_LAUNCH_OK();
   return 0;
 }
+// ---- beam search (eval.beam_search, eval.py:36-120) as a device loop: zero host syncs ------------------------------------------
+// Rows of every per-step tensor are (beam k, sample b) -> k * B0 + b; the caller passes the features tiled K times.  Per step: the
+// decoder step on all K * B0 rows (same kernels as greedy), then ONE selection kernel per sample -- scores log(sigmoid(logit)) +
+// cum / len^0.7 (eval.py:53-61: the running score is divided by the length at EVERY step; len = position of the last <EOS> + 1 once
+// the beam has emitted one, else t + 1), top-K over the K_cur * V candidates, sequence / <EOS> / score bookkeeping -- and one gather
+// kernel that moves the recurrent state of the source beams into place.  The loop freezes on the device once every fed-back token of a
+// step is <PAD> (eval.py:116); the host never reads anything back until the end.
+constexpr int BEAM_MAX_K = 8;
+constexpr int BEAM_THREADS = 256;
+
+__global__ void beam_select_kernel(const float* __restrict__ logits, long long ld, int V, int B0, int K, int t, int max_steps, long long eos,
+                                   const float* __restrict__ cum_in, float* __restrict__ cum_out, const int* __restrict__ eos_in,
+                                   int* __restrict__ eos_out, const int* __restrict__ seq_in, int* __restrict__ seq_out,
+                                   long long* __restrict__ tok_out, int* __restrict__ src_out, int* __restrict__ nonpad) {
+  if (t > 0 && nonpad[t - 1] == 0) return;                  // frozen: every token fed back at the previous step was <PAD>
+  __shared__ float sv[BEAM_THREADS / 32];
+  __shared__ int si[BEAM_THREADS / 32];
+  __shared__ int chosen[BEAM_MAX_K];
+  __shared__ float base[BEAM_MAX_K];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Kc = t == 0 ? 1 : K;                            // one live beam before the first expansion
+  if (tid < Kc) {
+    const int le = eos_in[b * K + tid];
+    const float len = le >= 0 ? (float)(le + 1) : (float)(t + 1);
+    base[tid] = cum_in[tid * B0 + b] / powf(len, 0.7f);
+  }
+  __syncthreads();
+  const int total = Kc * V;
+  int n_nonpad = 0;
+  for (int k = 0; k < K; ++k) {
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int f = tid; f < total; f += BEAM_THREADS) {
+      bool taken = false;
+      for (int q = 0; q < k; ++q) taken |= (chosen[q] == f);
+      if (taken) continue;
+      const int i = f / V, v = f - i * V;
+      const float x = logits[(long long)(i * B0 + b) * ld + v];
+      const float sc = logf(1.f / (1.f + expf(-x))) + base[i];
+      if (sc > best || (sc == best && f < bi)) { best = sc; bi = f; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      best = lane < BEAM_THREADS / 32 ? sv[lane] : -INFINITY; bi = lane < BEAM_THREADS / 32 ? si[lane] : 0x7fffffff;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) {
+        chosen[k] = bi;
+        const int i = bi / V, v = bi - i * V;
+        tok_out[k * B0 + b] = v;
+        src_out[b * K + k] = i;
+        cum_out[k * B0 + b] = best;
+        eos_out[b * K + k] = (v == (int)eos) ? t : eos_in[b * K + i];
+        if (v != 0) ++n_nonpad;
+      }
+    }
+    __syncthreads();
+  }
+  // sequences: beam k continues beam src[k]
+  for (int x = tid; x < K * (t + 1); x += BEAM_THREADS) {
+    const int k = x / (t + 1), pos = x - k * (t + 1);
+    const int f = chosen[k], i = f / V, v = f - i * V;
+    seq_out[(b * K + k) * max_steps + pos] = pos < t ? seq_in[(b * K + i) * max_steps + pos] : v;
+  }
+  if (tid == 0 && n_nonpad) atomicAdd(nonpad + t, n_nonpad);
+}
+
+// recurrent state of row (k, b) <- state of row (src[b][k], b): h operand rows (ld elements apart) and the fp32 state rows
+template <typename T>
+__global__ void beam_gather_kernel(const T* __restrict__ h_src, T* __restrict__ h_dst, long long ld, const float* __restrict__ c_src,
+                                   float* __restrict__ c_dst, int H, int B0, int K, const int* __restrict__ src, const int* __restrict__ nonpad, int t) {
+  if (t > 0 && nonpad[t - 1] == 0) return;                  // frozen (see beam_select_kernel)
+  const int row = blockIdx.x, k = row / B0, b = row - k * B0;
+  const int srow = src[b * K + k] * B0 + b;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    h_dst[(long long)row * ld + j] = h_src[(long long)srow * ld + j];
+    c_dst[(long long)row * H + j] = c_src[(long long)srow * H + j];
+  }
+}
+__global__ void beam_finalize_kernel(const int* __restrict__ nonpad, int max_steps, int B0, int K, const int* __restrict__ seq0,
+                                     const int* __restrict__ seq1, long long* __restrict__ out, int* __restrict__ n_steps) {
+  int n = max_steps;
+  for (int t = 0; t < max_steps; ++t) if (nonpad[t] == 0) { n = t + 1; break; }
+  const int* seq = (n & 1) ? seq1 : seq0;                   // step t wrote buffer (t + 1) & 1; the last executed step is n - 1
+  for (int x = threadIdx.x; x < B0 * max_steps; x += blockDim.x) {
+    const int b = x / max_steps, pos = x - b * max_steps;
+    out[x] = pos < n ? seq[(b * K) * max_steps + pos] : -1;   // top-1 beam (eval.py:118-119)
+  }
+  if (threadIdx.x == 0) *n_steps = n;
+}
+__global__ void beam_init_kernel(float* cum, int* eos, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { cum[i] = 0.f; eos[i] = -1; }                  // log(1.) ; no <EOS> yet
+}
+
+template <typename T>
+struct BeamWs { GreedyWs<T> g; float* cum[2]; int* eos[2]; int* seq[2]; int* src; size_t bytes; };
+template <typename T>
+static BeamWs<T> plan_beam(const recnet_decoder_desc& d, void* base, int K, int max_steps) {
+  BeamWs<T> w;
+  w.g = plan_greedy<T>(d, base, max_steps);
+  Bump m(base); m.off = w.g.bytes;
+  const int B0 = d.B / (K > 0 ? K : 1);
+  for (int i = 0; i < 2; ++i) {
+    w.cum[i] = m.take<float>((size_t)d.B);
+    w.eos[i] = m.take<int>((size_t)d.B);
+    w.seq[i] = m.take<int>((size_t)d.B * max_steps);
+  }
+  w.src = m.take<int>((size_t)d.B);
+  (void)B0;
+  w.bytes = m.off + 256;
+  return w;
+}
+
+// d0.B = K * B0 rows; feats [K * B0, T, E] = the B0 samples tiled K times; seq_out [B0, max_steps] int64 (-1 beyond n_steps)
+template <typename T>
+static int beam(const recnet_decoder_desc& d0, const recnet_decoder_tensors& p, const float* feats, int K, int max_steps, long long eos,
+                void* ws, long long ws_bytes, long long* seq_out, int* n_steps_out, cudaStream_t st) {
+  recnet_decoder_desc d = d0; d.L = 1; d.train = 0;
+  RN_TRY(check(d));
+  if (K < 1 || K > BEAM_MAX_K || d.B % K || max_steps < 1 || max_steps > 64 || K > d.V) return RECNET_ERR_BAD_SHAPE;
+  BeamWs<T> bw = plan_beam<T>(d0, ws, K, max_steps);
+  if ((long long)bw.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  GreedyWs<T>& g = bw.g;
+  Ws<T>& w = g.w;
+  const int B = d.B, B0 = B / K, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T;
+  RN_TRY(prepare<T>(d, p, feats, w, st));
+  RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, nullptr, B * Tn, A, E, 0, w.splitk, st));
+  RN_CUDA_OK(cudaMemsetAsync(w.X, 0, (size_t)2 * B * w.KX * sizeof(T), st));
+  RN_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)2 * B * H * sizeof(float), st));
+  RN_CUDA_OK(cudaMemsetAsync(g.nonpad, 0, (size_t)max_steps * sizeof(int), st));
+  fill_tokens_kernel<<<rn_cdiv(B, 128), 128, 0, st>>>(g.tok, B, 1 /* <SOS> */);
+  RN_LAUNCH_OK();
+  beam_init_kernel<<<rn_cdiv(B, 128), 128, 0, st>>>(bw.cum[0], bw.eos[0], B);
+  RN_LAUNCH_OK();
+  // state buffers: step reads (x0, c0) and writes (x1, c1); the gather moves the selected beams' state back into (x0, c0)
+  T* x0 = w.X; T* x1 = w.X + (size_t)B * w.KX;
+  float* c0 = w.c; float* c1 = w.c + (size_t)B * H;
+  for (int t = 0; t < max_steps; ++t) {
+    misc::embed_gather_kernel<T><<<B, 128, 0, st>>>(p.embedding, g.tok, w.Xe, w.EMBp, B, d.EMB, w.EMBp, V, d.embedding_scale, 0.f,
+                                                    nullptr, SITE_EMB);
+    RN_LAUNCH_OK();
+    RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, w.G * H, p.b_ih, B, w.G * H, w.EMBp, 0, w.splitk, st));
+    mega::Emitter<T> em(false, st);
+    RN_TRY(step<T>(em, d, p, w, t, 0, 0, B, w.Gx, x0, x1, nullptr, nullptr, nullptr, c0, c1, d.cell == RECNET_CELL_GRU ? c1 : g.h_scratch));
+    RN_TRY(gemm_full<T>(x1 + E, w.KX, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, B, V, H, 0, w.splitk, st));
+    const int in = t & 1, out = (t + 1) & 1;
+    beam_select_kernel<<<B0, BEAM_THREADS, 0, st>>>(w.logits, w.Vld, V, B0, K, t, max_steps, eos, bw.cum[in], bw.cum[out], bw.eos[in], bw.eos[out],
+                                                    bw.seq[in], bw.seq[out], g.tok, bw.src, g.nonpad);
+    RN_LAUNCH_OK();
+    beam_gather_kernel<T><<<B, 128, 0, st>>>(x1 + E, x0 + E, w.KX, c1, c0, H, B0, K, bw.src, g.nonpad, t);
+    RN_LAUNCH_OK();
+  }
+  beam_finalize_kernel<<<1, 256, 0, st>>>(g.nonpad, max_steps, B0, K, bw.seq[0], bw.seq[1], seq_out, n_steps_out);
+  RN_LAUNCH_OK();
+  return 0;
+}
 }  // namespace dec

@@ -31,6 +31,10 @@ def beam_search(config, beam_width, vocab, decoder, input, hidden, encoder_outpu
     B = encoder_outputs.shape[0]
     dev = encoder_outputs.device
     is_lstm = config.decoder_model == "LSTM"
+    if _device_beam_applies(decoder, beam_width, input, hidden, vocab):
+        # the whole loop on the device (recnet_decoder_beam): one host read at the end instead of one per step
+        seqs, n = decoder.beam(encoder_outputs, beam_width, config.caption_max_len + 1, eos_id=eos)
+        return seqs[:, : int(n.item())].tolist()
     inputs = [input]                                             # list over beams of (1,B)
     hiddens = [hidden]
     cum = [torch.zeros(B, dtype=torch.float32, device=dev)]      # log(1.)
@@ -41,6 +45,19 @@ def beam_search(config, beam_width, vocab, decoder, input, hidden, encoder_outpu
     with scope:                       # U.v once for this batch (decoder.py:54 recomputes it every step); nothing survives the block
         seqs = _beam_loop(config, beam_width, n_vocabs, eos, decoder, inputs, hiddens, cum, seqs, last_eos, encoder_outputs, is_lstm)
     return seqs[:, 0].tolist()
+
+
+def _device_beam_applies(decoder, beam_width, input, hidden, vocab) -> bool:
+    """recnet_decoder_beam covers what eval.evaluate passes (eval.py:130-140): single-layer decoder, <SOS> start, zero state, <= 8 beams."""
+    import os
+    if os.environ.get("RECNET_BEAM_DEVICE", "1") != "1" or not hasattr(decoder, "beam"):
+        return False
+    if getattr(decoder, "n_layers", 1) != 1 or not getattr(decoder, "uses_fused_sequence", False) or not 1 <= beam_width <= 8:
+        return False
+    if not input.is_cuda or vocab.word2idx.get('<PAD>', 0) != 0:
+        return False
+    hs = hidden if isinstance(hidden, (tuple, list)) else (hidden,)
+    return bool((input == vocab.word2idx['<SOS>']).all()) and all(bool((h == 0).all()) for h in hs)
 
 
 def _beam_loop(config, beam_width, n_vocabs, eos, decoder, inputs, hiddens, cum, seqs, last_eos, encoder_outputs, is_lstm):

@@ -244,6 +244,32 @@ class Decoder(nn.Module, _RngMixin):
                                           ids.data_ptr(), n.data_ptr(), Fn._stream()), "recnet_decoder_greedy")
         return ids, n
 
+    @torch.no_grad()
+    def beam(self, encoder_outputs, beam_width, max_steps, eos_id=2):
+        """eval.beam_search (eval.py:36-120) as ONE C call: the whole loop, top-k and state gather included, runs on the device.
+        Returns (seqs (B, max_steps) int64 on device: top-1 beam per sample, -1 beyond n; n device int32)."""
+        import ctypes as C
+        lib = L.lib()
+        feats = Fn._f32c(encoder_outputs, "encoder_outputs")
+        B0, T, E = feats.shape
+        K = int(beam_width)
+        tiled = feats.repeat(K, 1, 1).contiguous()                 # row k * B0 + b = beam k of sample b
+        meta = self._meta()
+        d = L.decoder_desc(B=B0 * K, T=T, E=E, H=meta["H"], A=meta["A"], EMB=meta["EMB"], V=meta["V"], L=1,
+                           precision=meta["precision"], train=0, embedding_scale=float(meta["embedding_scale"]),
+                           p_emb_drop=0.0, p_out_drop=0.0, cell=meta["cell"])
+        nbytes = lib.recnet_beam_workspace_bytes(C.byref(d), K, max_steps)
+        if nbytes < 0:
+            L.check(int(nbytes), "recnet_beam_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=feats.device)
+        seqs = torch.empty(B0, max_steps, dtype=torch.int64, device=feats.device)
+        n = torch.zeros(1, dtype=torch.int32, device=feats.device)
+        params = tuple(Fn._f32c(p, "param") for p in self._params())
+        w = Fn._pack(L.decoder_tensors, params)
+        L.check(lib.recnet_decoder_beam(C.byref(d), C.byref(w), tiled.data_ptr(), K, max_steps, int(eos_id), ws.data_ptr(), nbytes,
+                                        seqs.data_ptr(), n.data_ptr(), Fn._stream()), "recnet_decoder_beam")
+        return seqs, n
+
     # ---- single timestep (reference API) ----
     def forward(self, input, hidden, encoder_outputs):
         """input (1,B) int64; hidden ((NL,B,H),(NL,B,H)) [LSTM] or (NL,B,H) [GRU]; encoder_outputs (B,T,E) -> (logits (B,V), hidden)."""

@@ -109,9 +109,12 @@ def test_full_size_train_mode_parity_against_oracle_with_the_same_masks(precisio
         assert rel(p.grad, Qr[k].grad) < tol, k
 
 
+@pytest.mark.parametrize("loop", ["device", "host"])
 @pytest.mark.parametrize("name", ["tiny_lstm", "tiny_gru", "small_lstm"])
-def test_beam_search_matches_the_references_own_beam_search(name):
-    """Fixtures hold what the reference's eval.beam_search itself returned (make_golden_train.py); fp32 build, widths 3 and 5."""
+def test_beam_search_matches_the_references_own_beam_search(name, loop, monkeypatch):
+    """Fixtures hold what the reference's eval.beam_search itself returned (make_golden_train.py); fp32 build, widths 3 and 5.
+    loop=device: recnet_decoder_beam (the whole loop in one C call); loop=host: the per-step path used for stacked decoders."""
+    monkeypatch.setenv("RECNET_BEAM_DEVICE", "1" if loop == "device" else "0")
     g = load_golden_beam(name)
     m = dict(g["meta"], rec_model="LSTM")
     P = {k: v.float() for k, v in g["dec"].items()}
@@ -125,6 +128,34 @@ def test_beam_search_matches_the_references_own_beam_search(name):
         hid = (z, z.clone()) if m["dec_model"] == "LSTM" else z
         got = E.beam_search(T.C, width, _Vocab(m["V"]), dec["model"], tok, hid, feats)
         assert got == g["beams"][width], (width, got, g["beams"][width])
+
+
+@pytest.mark.parametrize("width", [1, 4, 8])
+def test_device_beam_loop_agrees_with_the_per_step_loop_on_a_larger_batch(width, monkeypatch):
+    """The fixture's weights (well-separated scores) on 48 perturbed copies of its features: the one-call device loop and the per-step
+    loop must return the same sequences; width 1 must also equal greedy decoding up to the first <EOS>-free prefix."""
+    g = load_golden_beam("small_lstm")
+    m = dict(g["meta"], rec_model="LSTM")
+    P = {k: v.float() for k, v in g["dec"].items()}
+    dec, _ = build(m, "fp32", "none", P, {})
+    f0 = g["feats"].float()
+    gen = torch.Generator().manual_seed(11)
+    reps = (48 + f0.shape[0] - 1) // f0.shape[0]
+    feats = (f0.repeat(reps, 1, 1)[:48] * (1.0 + 0.2 * torch.randn(48, 1, 1, generator=gen))).to(dev())
+    B, H = 48, m["H"]
+    T.C.batch_size = B
+
+    def decode():
+        tok = torch.full((1, B), 1, dtype=torch.long, device=dev())
+        z = torch.zeros(1, B, H, device=dev())
+        return E.beam_search(T.C, width, _Vocab(m["V"]), dec["model"], tok, (z, z.clone()), feats)
+
+    monkeypatch.setenv("RECNET_BEAM_DEVICE", "1")
+    a = decode()
+    monkeypatch.setenv("RECNET_BEAM_DEVICE", "0")
+    b = decode()
+    assert a == b
+    assert len({tuple(x) for x in a}) > 1          # not degenerate
 
 
 def test_beam_search_recomputes_the_feature_projection_for_every_batch():

@@ -330,11 +330,24 @@ static int launch_bn(int transA, int transB, const CUtensorMap& ma, const CUtens
   return launch_cfg<BN, STAGES, true, true>(ma, mb, ep, M, N, K, splits, kb_per, st);
 }
 
-// bn_hint: 0 = auto, else 64/128/256.  splits >= 1; every slice gets >= 1 k-block.
+}  // namespace tc
+namespace tc2 {
+static inline int launch(const bf16* A, long long lda, int transA, const bf16* B, long long ldb, int transB, float* Cf, long long ldc,
+                         bf16* Cb, long long ldcb, const float* bias, int M, int N, int K, int accumulate, int BN, int ctas,
+                         cudaStream_t st);
+static inline bool supported(const float* Cf, long long ldc, const bf16* Cb, long long ldcb, int accumulate);
+}
+namespace tc {
+// bn_hint: 0 = auto, else 64/128/256 (this file's one-tile-per-CTA kernel), or 1000 + {128,256} / 2000 + {128,256}: the persistent
+// kernel of gemm_tc2.cuh with single CTAs / CTA pairs (splits must be 1).  splits >= 1; every slice gets >= 1 k-block.
 static inline int launch(const bf16* A, long long lda, int transA, const bf16* B, long long ldb, int transB, float* Cf,
                          long long ldc, bf16* Cb, long long ldcb, const float* bias, int M, int N, int K, int splits,
                          long long split_stride, int accumulate, int bn_hint, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return RECNET_ERR_BAD_SHAPE;
+  if (bn_hint >= 1000 && (splits > 1 || !tc2::supported(Cf, ldc, Cb, ldcb, accumulate))) bn_hint %= 1000;   // not covered: this file's kernel
+  if (bn_hint >= 1000) {
+    return tc2::launch(A, lda, transA, B, ldb, transB, Cf, ldc, Cb, ldcb, bias, M, N, K, accumulate, bn_hint % 1000, bn_hint / 1000, st);
+  }
   int BN = bn_hint;
   if (BN == 0) BN = (N >= 1024 && (long long)rn_cdiv(M, BM) * rn_cdiv(N, 128) >= 96) ? 128 : 64;
   if (BN != 64 && BN != 128 && BN != 256) return RECNET_ERR_BAD_SHAPE;
@@ -365,3 +378,4 @@ static inline int launch(const bf16* A, long long lda, int transA, const bf16* B
   return launch_bn<256, 4>(transA, transB, ma, mb, ep, M, N, K, splits, kb_per, st);
 }
 }  // namespace tc
+#include "gemm_tc2.cuh"

@@ -253,6 +253,19 @@ static inline GemmPlan plan_gemm_full_bf16(int M, int N, int K) {
     const int kb_per = rn_cdiv(nkb, best.splits);
     best.splits = rn_cdiv(nkb, kb_per);
   }
+  // r2: the persistent kernel of gemm_tc2.cuh (bn = 1000 + width: single CTAs, 2000 + width: CTA pairs) for everything that is not
+  // skinny -- sweep in profiles/r2_h_gemm_sweep.md: it wins or ties on every batched GEMM with M, N >= 256; the four 128-row
+  // attention weight gradients and the 128-column key projections stay on the split-K / 64-wide plans above.  256-wide tiles once
+  // they fill 2/3 of the SMs; CTA pairs (half the B traffic per SM) only for long K loops with at least 1.5 rounds of pair tiles.
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("RECNET_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }
+  if (persist && M >= 256 && N >= 256) {
+    const int t256 = mt * rn_cdiv(N, 256);
+    const int pairs = rn_cdiv(M, 256) * rn_cdiv(N, 256);
+    best.splits = 1;
+    if (t256 < 96) best.bn = 1128;
+    else best.bn = (nkb >= 16 && 2 * pairs >= 3 * (NUM_SMS / 2)) ? 2256 : 1256;
+  }
   return best;
 }
 template <typename T> static inline GemmPlan plan_gemm_full(int M, int N, int K) { return plan_gemm<T>(M, N, K); }

@@ -81,6 +81,17 @@ def test_gemm_all_operand_layouts(prec, tA, tB, shape):
     if prec == L.PREC_BF16:
         for bn in (64, 128):
             assert rel(ops.gemm(prec, A, tA, B, tB, bias=bias, bn_hint=bn), ref) < 1e-5
+        for bn in (1128, 1256, 2128, 2256):          # gemm_tc2.cuh: persistent kernel, single CTAs / CTA pairs (cta_group::2)
+            assert rel(ops.gemm(prec, A, tA, B, tB, bias=bias, bn_hint=bn), ref) < 1e-5, bn
+            acc = torch.ones(M, N, device=dev())
+            ops.gemm(prec, A, tA, B, tB, bias=bias, out=acc, accumulate=True, bn_hint=bn)
+            assert rel(acc, ref + 1.0) < 1e-5, bn
+            if N % 8 == 0:                           # operand-typed (bf16) output straight from the epilogue
+                cb = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=dev())
+                L.check(L.lib().recnet_gemm(prec, A.data_ptr(), A.stride(0), int(tA), B.data_ptr(), B.stride(0), int(tB), None, 0,
+                                            cb.data_ptr(), N, bias.data_ptr(), M, N, K, 1, 0, 0, bn,
+                                            torch.cuda.current_stream().cuda_stream), "recnet_gemm")
+                assert rel(cb.double(), ref) < 4e-3, bn
 
 
 def test_gemm_rejects_misaligned_bf16_pitch():

@@ -110,6 +110,24 @@ def main():
                     res[f"{bn}x{splits}"] = round(ts[len(ts) // 2], 1)
                 except RuntimeError as ex:
                     res[f"{bn}x{splits}"] = str(ex)[:40]
+        for code in (1128, 1256, 2128, 2256):              # gemm_tc2.cuh: persistent, 1 CTA / CTA pair per tile
+            def run2():
+                L.check(lib.recnet_gemm(L.PREC_BF16, a.data_ptr(), a.stride(0), tA, b.data_ptr(), b.stride(0), tB, out.data_ptr(), N,
+                                        None, 0, None, M, N, K, 1, 0, 0, code, stream), "gemm")
+            try:
+                for _ in range(2):
+                    run2()
+                ts = []
+                for _ in range(8):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); run2(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+                ts.sort()
+                res[f"p{code // 1000}x{code % 1000}"] = round(ts[len(ts) // 2], 1)
+            except RuntimeError as ex:
+                res[f"p{code // 1000}x{code % 1000}"] = str(ex)[:40]
         best = min((v, k) for k, v in res.items() if isinstance(v, float))
         print(json.dumps({"shape": name, "MNK": [M, N, K], "tA": tA, "tB": tB, "best": best[1], "best_us": best[0], "us": res}), flush=True)
 

@@ -524,7 +524,8 @@ def main():
             dump = os.environ.get("RECNET_GRAPH_DUMP")           # developer probe: DOT file of the captured step graph
             if dump:
                 graph.enable_debug_mode()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local" if (world > 1 or dp_self) else "global"):
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=int(os.environ.get("RECNET_CAPTURE_PRIO", "0"))),
+                                  capture_error_mode="thread_local" if (world > 1 or dp_self) else "global"):
                 step()
             if dump and rank == 0:
                 graph.debug_dump(dump)
@@ -544,7 +545,8 @@ def main():
             feats_b, targets_b = feats_d.clone(), targets_d.clone()
             step_b = make_step(feats_b, targets_b)
             graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph_b, pool=graph.pool(), capture_error_mode="thread_local" if (world > 1 or dp_self) else "global"):
+            with torch.cuda.graph(graph_b, pool=graph.pool(), stream=torch.cuda.Stream(priority=int(os.environ.get("RECNET_CAPTURE_PRIO", "0"))),
+                                  capture_error_mode="thread_local" if (world > 1 or dp_self) else "global"):
                 step_b()
         except Exception as ex:
             print(f"[bench] second capture for the e2e leg failed ({type(ex).__name__}: {ex}); using the staging-buffer pipeline", file=sys.stderr)

@@ -166,6 +166,16 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
                        const int64_t* tokens_in, const int64_t* targets, const float* ce_weight, const uint64_t* rng,
                        void* workspace, int64_t workspace_bytes, const float* g_ce, const float* g_hiddens,
                        const float* hiddens, const recnet_decoder_tensors* grads, void* stream);
+/* recnet_decoder_bwd in parts, same arguments (single-layer decoders on the projected-feature path; recnet_decoder_bwd_is_split says
+ * whether the split applies -- otherwise bit 0 runs everything and the other bits nothing):
+ *   1 = CE backward + gradient wrt the states through the vocabulary projection     2 = the BPTT loop (needs 1)
+ *   4 = the vocabulary projection's own gradients (need 1 only)                    8 = all other parameter gradients (need 2)
+ * phases = 4 alone may run on another stream while 2 runs (own scratch); 15 is recnet_decoder_bwd. */
+int recnet_decoder_bwd_phase(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
+                             const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
+                             int64_t workspace_bytes, const float* g_ce, const float* g_hiddens, const float* hiddens,
+                             const recnet_decoder_tensors* grads, int phases, void* stream);
+int recnet_decoder_bwd_is_split(const recnet_decoder_desc* d);
 float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld);
 
 /* Greedy decoding (eval.greedy_search, eval.py:19-33): argmax feedback on device, zero host syncs.
@@ -202,6 +212,15 @@ int recnet_local_fwd(const recnet_local_desc* d, const recnet_local_tensors* w, 
 int recnet_local_bwd(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
                      const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
                      const recnet_local_tensors* grads, float* g_hiddens, void* stream);
+/* recnet_local_bwd in two parts, same arguments: phases bit 0 = the BPTT loop and g_hiddens (what the decoder's backward waits for),
+ * bit 1 = the batched parameter gradients (read only the workspace; write only `grads`).  A trainer may issue bit 1 on a second
+ * stream underneath the decoder's backward loop; the workspace must stay alive until that stream is joined.  phases = 3 is
+ * recnet_local_bwd.  recnet_set_background_ctas(n): upper bound on the CTAs of the persistent batched GEMMs launched from now on
+ * by this process (0 = none) -- set it around such background work so that it never occupies the SMs the foreground loop needs. */
+int recnet_local_bwd_phase(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
+                           const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
+                           const recnet_local_tensors* grads, float* g_hiddens, int phases, void* stream);
+int recnet_set_background_ctas(int n);
 float* recnet_local_outputs(const recnet_local_desc* d, void* workspace);   /* [S,B,R] fp32 */
 
 /* Global reconstructor (models/global_reconstructor.py:30-46 + train.forward_global_reconstructor, train.py:78-105). */

@@ -97,6 +97,9 @@ SIGNATURES = {
     "recnet_decoder_fwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p, _p]),
     "recnet_decoder_bwd": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p, _p,
                                 C.POINTER(decoder_tensors), _p]),
+    "recnet_decoder_bwd_phase": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _p, _p, _p, _p, _p, _l, _p, _p, _p,
+                                      C.POINTER(decoder_tensors), _i, _p]),
+    "recnet_decoder_bwd_is_split": (_i, [C.POINTER(decoder_desc)]),
     "recnet_decoder_logits": (_p, [C.POINTER(decoder_desc), _p, C.POINTER(_l)]),
     "recnet_greedy_workspace_bytes": (_l, [C.POINTER(decoder_desc)]),
     "recnet_decoder_greedy": (_i, [C.POINTER(decoder_desc), C.POINTER(decoder_tensors), _p, _i, _p, _l, _p, _p, _p]),
@@ -106,6 +109,9 @@ SIGNATURES = {
     "recnet_local_fwd": (_i, [C.POINTER(local_desc), C.POINTER(local_tensors), _p, _p, _p, _p, _l, _p, _p]),
     "recnet_local_bwd": (_i, [C.POINTER(local_desc), C.POINTER(local_tensors), _p, _p, _p, _p, _l, _p,
                               C.POINTER(local_tensors), _p, _p]),
+    "recnet_local_bwd_phase": (_i, [C.POINTER(local_desc), C.POINTER(local_tensors), _p, _p, _p, _p, _l, _p,
+                                    C.POINTER(local_tensors), _p, _i, _p]),
+    "recnet_set_background_ctas": (_i, [_i]),
     "recnet_local_outputs": (_p, [C.POINTER(local_desc), _p]),
     "recnet_global_workspace_bytes": (_l, [C.POINTER(global_desc)]),
     "recnet_global_fwd": (_i, [C.POINTER(global_desc), C.POINTER(global_tensors), _p, _p, _p, _p, _l, _p, _p]),

@@ -123,8 +123,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   else
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -295,7 +295,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0 && m0 < M && n0 + c0 < N) tma_store_2d(&tmC, pb, n0 + c0, m0, add);
+        if (lane == 0) {
+          if (m0 < M && n0 + c0 < N) tma_store_2d(&tmC, pb, n0 + c0, m0, add);
+          bulk_commit();       // ALWAYS one group per block (empty when the block lies outside C): bulk_wait_read1 counts groups, and
+                               // "at most one pending" must mean "the store that read THIS pad two blocks ago is done"
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -310,6 +314,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+// Upper bound on the CTAs of one launch (0 = none).  A trainer that runs batched GEMMs on a second stream UNDERNEATH a latency-bound
+// kernel sequence (the decoder's backward loop: 100-CTA kernels) caps them so that the persistent CTAs never hold the SMs the
+// foreground kernels are waiting for (recnet_set_background_ctas).
+inline int& background_ctas() { static int v = 0; return v; }
+
 // output tensor [rows, cols] row-major (ld elements): fp32 boxes of 32 x 32, bf16 boxes of 32 rows x 64 columns -- 128-byte rows
 static inline int make_out_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, bool is_bf16) {
   tc::EncodeTiledFn enc = tc::get_encode_fn();
@@ -345,7 +354,8 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
     attr_set = true;
   }
   const int tiles_m = rn_cdiv(M, BM * CTAS), tiles_n = rn_cdiv(N, BN);
-  const int units = min(tiles_m * tiles_n, TC2_SMS / CTAS);
+  int units = min(tiles_m * tiles_n, TC2_SMS / CTAS);
+  if (background_ctas() > 0) units = min(units, max(1, background_ctas() / CTAS));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CTAS);
   cfg.blockDim = dim3(THREADS);

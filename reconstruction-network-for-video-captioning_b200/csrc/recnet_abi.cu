@@ -248,6 +248,26 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
     return dec::backward<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, hiddens, *grads, ST(stream));
   return RECNET_ERR_UNSUPPORTED;
 }
+int recnet_decoder_bwd_phase(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
+                             const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
+                             int64_t workspace_bytes, const float* g_ce, const float* g_hiddens, const float* hiddens,
+                             const recnet_decoder_tensors* grads, int phases, void* stream) {
+  if (phases < 1 || phases > 15) return RECNET_ERR_BAD_SHAPE;
+  if (d->n_layers > 1 || !dec::pf_ok(*d)) {          // not split on these paths: everything belongs to bit 0
+    if (!(phases & 1)) return 0;
+    return recnet_decoder_bwd(d, w, feats, tokens_in, targets, ce_weight, rng, workspace, workspace_bytes, g_ce, g_hiddens, hiddens,
+                              grads, stream);
+  }
+  const long long* ti = reinterpret_cast<const long long*>(tokens_in);
+  const long long* tg = reinterpret_cast<const long long*>(targets);
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32)
+    return dec::backward_pf<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream), phases);
+  if (d->precision == RECNET_PREC_BF16)
+    return dec::backward_pf<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, g_ce, g_hiddens, *grads, ST(stream), phases);
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_decoder_bwd_is_split(const recnet_decoder_desc* d) { return (d->n_layers > 1 || !dec::pf_ok(*d)) ? 0 : 1; }
 float* recnet_decoder_logits(const recnet_decoder_desc* d, void* workspace, int64_t* ld) {
   if (dec::pf_ok(*d)) {
     if (d->precision == RECNET_PREC_FP32) { auto w = dec::plan_pf<float>(*d, workspace); if (ld) *ld = w.Vld; return w.logits; }
@@ -348,6 +368,24 @@ int recnet_local_bwd(const recnet_local_desc* d, const recnet_local_tensors* w, 
   if (d->precision == RECNET_PREC_FP32) return rec::local_backward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
   if (d->precision == RECNET_PREC_BF16) return rec::local_backward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream));
   return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_local_bwd_phase(const recnet_local_desc* d, const recnet_local_tensors* w, const float* hiddens, const float* feats,
+                           const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
+                           const recnet_local_tensors* grads, float* g_hiddens, int phases, void* stream) {
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (phases < 1 || phases > 3) return RECNET_ERR_BAD_SHAPE;
+  if (d->dec_layers > 1) {                 // stacked decoders: not split -- everything belongs to phase bit 0
+    if (!(phases & 1)) return 0;
+    return recnet_local_bwd(d, w, hiddens, feats, rng, workspace, workspace_bytes, g_mse, grads, g_hiddens, stream);
+  }
+  if (d->precision == RECNET_PREC_FP32) return rec::local_backward<float>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream), phases);
+  if (d->precision == RECNET_PREC_BF16) return rec::local_backward<bf16>(*d, *w, hiddens, feats, r, workspace, workspace_bytes, g_mse, *grads, g_hiddens, ST(stream), phases);
+  return RECNET_ERR_UNSUPPORTED;
+}
+int recnet_set_background_ctas(int n) {
+  if (n < 0 || n > 4096) return RECNET_ERR_BAD_SHAPE;
+  tc2::background_ctas() = n;
+  return 0;
 }
 float* recnet_local_outputs(const recnet_local_desc* d, void* workspace) {
   if (d->precision == RECNET_PREC_FP32) return rec::plan_local<float>(*d, workspace).out;

@@ -70,22 +70,22 @@ struct Chains {
 };
 inline Chains& chains() { static Chains c; return c; }
 
-// ---- side stream for the batched work around the time loops (opt-in: RECNET_SIDE=1) ---------------------------------------
+// ---- side stream for the batched work around the time loops (default on; RECNET_SIDE=0 puts everything on `main`) -------------
 // Before and after each time loop a driver issues a dozen mutually independent batched kernels (weight-gradient GEMMs, column
 // sums, operand staging); several of them are small grids (the 128-row attention weight gradients run on 32-64 CTAs) or end in
 // a partial wave.  fork() hands out a second stream ordered after everything issued so far on `main`; the driver splits the
 // independent work between the two and join()s before it returns, so nothing outlives the call and the pattern is a plain
 // fork/join inside a captured CUDA graph.  Concurrent split-K GEMMs / column sums use separate scratch (Ws::splitk2).
-// MEASURED on the B200 (profiles/r1_g_side_stream.md): parity-green, but the captured step gets SLOWER, 2.781 -> 2.839 ms
-// (4 fork/join regions per step): the batched kernels are L2-delivery bound, so running two of them side by side shares the same
-// bandwidth, and the extra graph edges cost more than the partial waves they fill.  Default off; everything runs on `main`.
+// History: r1 measured this SLOWER (2.781 -> 2.839 ms, profiles/r1_g_side_stream.md) -- the one-tile-per-CTA GEMMs of that round each
+// filled the machine with 200-400 CTAs, so two of them side by side only shared the L2.  The persistent GEMMs of r2 (gemm_tc2.cuh) launch
+// min(tiles, 148) CTAs: a 72- or 96-tile GEMM leaves SMs free and its neighbour on the other stream takes them.  r2: 2.276 -> 2.232 ms.
 struct Side {
   cudaStream_t s = nullptr;
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   int dev = -1;
   static bool enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("RECNET_SIDE"); on = e ? atoi(e) : 0; }
+    if (on < 0) { const char* e = getenv("RECNET_SIDE"); on = e ? atoi(e) : 1; }
     return on != 0;
   }
   int fork(cudaStream_t main, cudaStream_t* out) {

@@ -19,7 +19,7 @@ struct PfWs {
   float* Uv; T* VW; T* Xe; float* Gx; T* Hop; float* P; float* Wh; float* e; T* gates; float* c;
   float *logits, *lse, *row_loss;
   T* dlogits; float* dHext; T* dGW; float* dhP; float* dWh; float* dUv; T* dUv_op; float* dw_acc; float* dc; float* dXe; T* dVW;
-  float* splitk; float* splitk2; int* err;      // splitk2: scratch of the side stream (runtime.cuh:Side)
+  float* splitk; float* splitk2; float* splitk3; int* err;      // splitk2: scratch of the side stream (runtime.cuh:Side), splitk3: of phase 4 alone
   size_t bytes;
 };
 
@@ -100,6 +100,7 @@ static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
   w.dVW = m.take<T>((size_t)B * Tn * 4 * H);
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
   w.splitk2 = m.take<float>(SPLITK_SCRATCH_FLOATS);
+  w.splitk3 = m.take<float>(SPLITK_SCRATCH_FLOATS);
   w.err = m.take<int>(64);
   w.bytes = m.off + 256;
   return w;
@@ -193,7 +194,9 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
 template <typename T>
 static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
                        const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
-                       const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors& g, cudaStream_t st) {
+                       const float* g_ce, const float* g_hiddens, const recnet_decoder_tensors& g, cudaStream_t st, int phases = 15) {
+  // phases (recnet_decoder_bwd_phase): 1 = CE backward + gradient wrt the states through the vocabulary projection, 2 = the BPTT loop,
+  // 4 = the vocabulary projection's own gradients (need only phase 1), 8 = every other parameter gradient (needs the loop)
   RN_TRY(check(d));
   PfWs<T> w = plan_pf<T>(d, ws);
   if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
@@ -202,16 +205,18 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   const int LB = L * B, NP = w.NP;
   const T* Hall = w.Hop + (size_t)B * H;          // h_t rows
   // ---- CE backward and the vocabulary projection
-  {
-    ProfScope prof(KC_CE, LB, V, 1, st);
-    loss::ce_bwd_kernel<T><<<LB, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, w.lse, g_ce, V, w.Vp, p_out, rng,
-                                                            SITE_LOGITS, w.dlogits, w.Vp);
+  if (phases & 1) {
+    {
+      ProfScope prof(KC_CE, LB, V, 1, st);
+      loss::ce_bwd_kernel<T><<<LB, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, w.lse, g_ce, V, w.Vp, p_out, rng,
+                                                              SITE_LOGITS, w.dlogits, w.Vp);
+    }
+    RN_LAUNCH_OK();
+    RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
   }
-  RN_LAUNCH_OK();
-  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 0, w.Wout, H, 1, w.dHext, H, nullptr, LB, H, V, 0, w.splitk, st));
-  // (the vocabulary projection's own gradients do not feed the loop: they join the batched weight gradients below)
+  // (the vocabulary projection's own gradients do not feed the loop: phase 4)
   // ---- BPTT
-  for (int t = L - 1; t >= 0; --t) {
+  for (int t = L - 1; t >= 0 && (phases & 2); --t) {
     const bool last = (t == L - 1);
     const size_t r = (size_t)t * B;
     pf::BwdArgs ba{};
@@ -230,11 +235,19 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   // ---- batched weight gradients over the stashed operands, two streams (runtime.cuh:Side)
   const long long ldih = EMB + E;
   const T* dG = w.dGW + A;                       // [LB, 4H] gate gradients, ld = NP
+  if (phases == 4) {                               // on its own (a trainer's background lane): third scratch, nothing else touches it
+    RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk3, st));
+    RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk3, st));
+    return 0;
+  }
+  if (!(phases & 8)) return 0;
   cudaStream_t s2;
   RN_TRY(side().fork(st, &s2));
   // side: vocabulary projection, embedding path, attention query weights
-  RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk2, s2));
-  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk2, s2));
+  if (phases & 4) {
+    RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk2, s2));
+    RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk2, s2));
+  }
   RN_TRY(gemm_full<T>(dG, NP, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk2, s2));               // dW_emb
   RN_TRY(gemm_full<T>(dG, NP, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk2, s2));            // dXe
   RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), s2));

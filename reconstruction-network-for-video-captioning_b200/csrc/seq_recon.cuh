@@ -242,16 +242,22 @@ static int local_forward(const recnet_local_desc& d, const recnet_local_tensors&
 }
 
 template <typename T>
+static int local_backward_weights(const recnet_local_desc& d, const LocalWs<T>& w, const recnet_local_tensors& g, cudaStream_t st);
+
+// phases: bit 0 = BPTT loop + gradient wrt the decoder states (everything the decoder's backward waits for), bit 1 = the batched
+// parameter gradients over the stashed operands.  recnet_local_bwd runs both; a trainer may run bit 1 on a second stream underneath
+// the decoder's backward loop (recnet_local_bwd_phase, functional.deferred_weight_grads).
+template <typename T>
 static int local_backward(const recnet_local_desc& d, const recnet_local_tensors& p, const float* hiddens, const float* feats,
                           const unsigned long long* rng, void* ws, long long ws_bytes, const float* g_mse,
-                          const recnet_local_tensors& g, float* g_hiddens, cudaStream_t st) {
+                          const recnet_local_tensors& g, float* g_hiddens, cudaStream_t st, int phases = 3) {
   RN_TRY(check_local(d));
   LocalWs<T> w = plan_local<T>(d, ws);
   if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
+  if (!(phases & 1)) return (phases & 2) ? local_backward_weights<T>(d, w, g, st) : 0;
   const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
   const float p_drop = d.train ? d.p_drop : 0.f;
   const int SB = S * B;
-  const T* Hr = w.X + (size_t)B * w.KX + H;       // h_t rows, ld = KX
   loss::mse_local_bwd_kernel<T><<<MSE_BLOCKS, 256, 0, st>>>(w.out, feats, S, B, R, g_mse, 2.f / ((float)S * B * R), w.dOut);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dOut, R, 0, w.Wout, R, 1, w.dHext, R, nullptr, SB, R, R, 0, w.splitk, st));
@@ -334,25 +340,38 @@ static int local_backward(const recnet_local_desc& d, const recnet_local_tensors
   }
   RN_TRY(em0.flush(w.table, w.table_bytes, w.bar, w.err, 4));
   if (w.nch > 1) RN_TRY(cs.join(st, w.nch));
-  // ---- batched gradients over the stashed operands, two streams (runtime.cuh:Side): the big recurrent / input weight gradients
-  // on `st`; the output projection, the 128-row attention gradients and the gradient wrt the decoder states on the side stream
+  // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
+  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, st));
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk2, st));
+  RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H, 1.f / L, 1, 1, 0, st));
+  if (phases & 2) RN_TRY(local_backward_weights<T>(d, w, g, st));
+  return 0;
+}
+
+// ---- batched parameter gradients over the stashed operands, two streams (runtime.cuh:Side): the big recurrent / input weight
+// gradients on `st`; the output projection and the 128-row attention gradients on the side stream
+template <typename T>
+static int local_backward_weights(const recnet_local_desc& d, const LocalWs<T>& w, const recnet_local_tensors& g, cudaStream_t st) {
+  const int B = d.B, S = d.S, R = d.R, H = d.H, A = d.A, L = d.L;
+  const int SB = S * B;
+  const bool is_gru = d.cell == RECNET_CELL_GRU;
+  const int GR = w.G * R;
+  const T* Hr = w.X + (size_t)B * w.KX + H;       // h_t rows, ld = KX
   const T* dGh = is_gru ? w.dG2 : w.dG;
+  // GEMMs first, column sums last: on a trainer's background lane the (capped) GEMMs leave the foreground kernels their SMs, while a
+  // column sum floods every SM for ~20 us -- better in the middle of the decoder's loop than in front of its first kernel
   cudaStream_t s2;
   RN_TRY(side().fork(st, &s2));
   RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk2, s2));
-  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk2, s2));
   RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk2, s2));
-  RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)L * B, A, A, s2));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk2, s2));
+  RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk2, s2));
   RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, w.splitk2, s2));
   RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk2, s2));
-  // gradient wrt the decoder states: through U (keys) and through the weighted mean (values)
-  RN_TRY(gemm_full<T>(w.dUv_op, A, 0, w.U, H, 1, g_hiddens, H, nullptr, L * B, H, A, 0, w.splitk2, s2));
-  RN_TRY(attn::launch_dv(w.beta, w.dx, g_hiddens, H, (long long)B * H, S, B, L, H, 1.f / L, 1, 1, 0, s2));
-  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st, is_gru ? nullptr : g.b_hh));     // LSTM: b_hh gets the same gradient
-  if (is_gru) RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(w.dG, GR, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, GR, H, SB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(dGh, GR, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, GR, R, SB, 0, w.splitk, st));
+  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st, is_gru ? nullptr : g.b_hh));     // LSTM: b_hh gets the same gradient
+  if (is_gru) RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st));
   RN_TRY(side().join(st, s2));
   return 0;
 }

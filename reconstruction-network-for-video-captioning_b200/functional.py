@@ -267,9 +267,28 @@ class DecoderSequenceFn(torch.autograd.Function):
         g_ce = _scalar(g_ce, feats.device)
         g_hid = g_hiddens.contiguous() if g_hiddens is not None else None
         w, g = _pack(L.decoder_tensors, params), _pack(L.decoder_tensors, grads)
-        L.check(lib.recnet_decoder_bwd(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), targets.data_ptr(),
-                                       ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes, g_ce.data_ptr(),
-                                       _ptr(g_hid), hiddens.data_ptr(), C.byref(g), _stream()), "recnet_decoder_bwd")
+
+        def phase(bits):
+            L.check(lib.recnet_decoder_bwd_phase(C.byref(ctx.desc), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(),
+                                                 targets.data_ptr(), ce_weight.data_ptr(), rng.data_ptr(), ws.data_ptr(), ctx.nbytes,
+                                                 g_ce.data_ptr(), _ptr(g_hid), hiddens.data_ptr(), C.byref(g), bits, _stream()),
+                    "recnet_decoder_bwd_phase")
+
+        if _bg.active and lib.recnet_decoder_bwd_is_split(C.byref(ctx.desc)):
+            phase(1)                                   # CE backward, gradient wrt the states through the vocabulary projection
+            vocab_done = torch.cuda.Event()
+
+            def vocab():
+                phase(4)                               # the vocabulary projection's own gradients: underneath the loop, on the lane
+                vocab_done.record(torch.cuda.current_stream())
+            background_gemms(vocab, feats, tokens_in, targets, ce_weight, rng, ws, g_ce, g_hid, hiddens, flat, gptrs, *params)
+            _flush(_bg.mid)
+            phase(2)                                   # the BPTT loop
+            _flush(_bg.late)                           # lane: from here on, next to the weight-gradient GEMMs below
+            phase(8)
+            torch.cuda.current_stream().wait_event(vocab_done)
+        else:
+            phase(15)
         if ctx.lam is not None:
             _norms_bwd_into(params, sumsq, g_ce, gptrs, accumulate=True, lambda_dev=ctx.lam)
         elif g_reg is not None:
@@ -299,6 +318,120 @@ def _layered_shape(hiddens):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# ---- background lane -------------------------------------------------------------------------------------------------
+# Between the end of the reconstructor's BPTT loop and the decoder's optimiser step the critical path is the decoder's backward loop:
+# a chain of 62 latency-bound kernels on 100 CTAs.  Everything else in that window only has to be finished by the end of the step.
+# With ``deferred_weight_grads()`` active (train.train_step) that work goes to a second stream, the LANE, in this order:
+#   1. the local reconstructor's batched weight-gradient GEMMs       (LocalReconstructorFn.backward, right after its loop)
+#   2. the decoder's vocabulary-projection gradients                  (DecoderSequenceFn.backward, right after the CE backward)
+#   3. ``mid`` items: the reconstructor's gradient all-reduce         (data parallel; queued by the trainer)
+#   -- the lane then waits for the decoder's loop --
+#   4. ``late`` items: reconstructor regulariser gradient + optimiser step: machine-filling elementwise kernels that would stall the
+#      loop (they take the register file), so they run next to the decoder's weight-gradient GEMMs instead.
+# The persistent GEMMs of 1-2 are capped to ``ctas`` CTAs (recnet_set_background_ctas) so they never hold the SMs the loop's kernels
+# are waiting for.  ``join_background()`` makes the main stream wait for the lane; everything the lane reads is kept alive until then.
+# Plain cross-stream dependencies: works under CUDA-graph capture.  Measured timelines: profiles/r2_i_step_timeline.md.
+class _Background:
+    active = False
+    ctas = 48
+    stream: Optional[torch.cuda.Stream] = None
+    pending = False
+    keep: list = []
+    mid: list = []
+    late: list = []
+
+
+_bg = _Background()
+
+
+def background_stream(device=None) -> torch.cuda.Stream:
+    if _bg.stream is None or (device is not None and _bg.stream.device != torch.device(device)):
+        _bg.stream = torch.cuda.Stream(device=device)
+    return _bg.stream
+
+
+class deferred_weight_grads:
+    """Context manager (see above).  ``background_ctas`` = SMs the lane's GEMMs may hold at any time."""
+
+    def __init__(self, enabled: bool = True, background_ctas: Optional[int] = None):
+        import os
+        self.enabled = enabled
+        self.ctas = int(os.environ.get("RECNET_BG_CTAS", "48")) if background_ctas is None else int(background_ctas)
+
+    def __enter__(self):
+        self.prev = (_bg.active, _bg.ctas)
+        _bg.active, _bg.ctas = bool(self.enabled), self.ctas
+        return self
+
+    def __exit__(self, *exc):
+        _bg.active, _bg.ctas = self.prev
+        if exc[0] is not None:
+            _bg.mid.clear()
+            _bg.late.clear()
+            join_background()
+        return False
+
+
+def background_active() -> bool:
+    return _bg.active
+
+
+def run_in_background(fn, *keep):
+    """Run ``fn()`` with the lane as the current stream, ordered after everything already on the lane AND after what the main stream has
+    issued so far.  ``keep``: tensors that must outlive the lane's work."""
+    main = torch.cuda.current_stream()
+    bg = background_stream(main.device)
+    bg.wait_stream(main)
+    _bg.pending = True
+    _bg.keep.extend(keep)
+    with torch.cuda.stream(bg):
+        return fn()
+
+
+def background_gemms(fn, *keep):
+    """``run_in_background`` with the persistent GEMMs capped to the lane's CTA budget."""
+    def capped():
+        lib = L.lib()
+        L.check(lib.recnet_set_background_ctas(_bg.ctas), "recnet_set_background_ctas")
+        try:
+            return fn()
+        finally:
+            lib.recnet_set_background_ctas(0)
+    return run_in_background(capped, *keep)
+
+
+def background_mid(fn, *keep):
+    _bg.mid.append(fn)
+    _bg.keep.extend(keep)
+
+
+def background_late(fn, *keep):
+    _bg.late.append(fn)
+    _bg.keep.extend(keep)
+
+
+def _flush(items: list):
+    if items:
+        todo = list(items)
+        items.clear()
+        run_in_background(lambda: [f() for f in todo])
+
+
+def background_pending() -> bool:
+    return _bg.pending or bool(_bg.mid) or bool(_bg.late)
+
+
+def join_background():
+    """Queue whatever is still waiting for its slot, then make the main stream wait for the lane; its results (reconstructor
+    gradients, optimiser step, vocabulary-projection gradients) may be used afterwards."""
+    _flush(_bg.mid)
+    _flush(_bg.late)
+    if _bg.pending:
+        torch.cuda.current_stream().wait_stream(_bg.stream)
+        _bg.pending = False
+    _bg.keep.clear()
+
+
 class LocalReconstructorFn(torch.autograd.Function):
     """train.forward_local_reconstructor (train.py:108-131) over LocalReconstructor.forward.
     inputs: meta, hiddens (L,B,H) or (L,NLdec,B,H), feats (B,S,R), rng, then the 10 parameters in local_tensors.FIELDS order.
@@ -341,13 +474,27 @@ class LocalReconstructorFn(torch.autograd.Function):
         g_hid = torch.empty_like(hiddens)
         g_mse = _scalar(g_mse, feats.device)
         w, g = _pack(L.local_tensors, params), _pack(L.local_tensors, grads)
-        L.check(lib.recnet_local_bwd(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
-                                     ws.data_ptr(), ctx.nbytes, g_mse.data_ptr(), C.byref(g), g_hid.data_ptr(), _stream()),
-                "recnet_local_bwd")
-        if ctx.lam is not None:
-            _norms_bwd_into(params, sumsq, g_mse, gptrs, accumulate=True, lambda_dev=ctx.lam)
-        elif g_reg is not None:
-            _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
+
+        def phase(bits):
+            L.check(lib.recnet_local_bwd_phase(C.byref(ctx.desc), C.byref(w), hiddens.data_ptr(), feats.data_ptr(), rng.data_ptr(),
+                                               ws.data_ptr(), ctx.nbytes, g_mse.data_ptr(), C.byref(g), g_hid.data_ptr(), bits,
+                                               _stream()), "recnet_local_bwd_phase")
+
+        def regulariser():
+            if ctx.lam is not None:
+                _norms_bwd_into(params, sumsq, g_mse, gptrs, accumulate=True, lambda_dev=ctx.lam)
+            elif g_reg is not None:
+                _norms_bwd_into(params, sumsq, _scalar(g_reg, feats.device), gptrs, accumulate=True)
+
+        if _bg.active and ctx.desc.dec_layers == 1:
+            phase(1)                                   # BPTT loop + g_hiddens: what the decoder's backward waits for
+            # keep-alive list: NOT the gradient views themselves -- autograd only adopts a gradient tensor as ``p.grad`` when nobody
+            # else holds it (otherwise it clones, on the main stream, before the lane has written it); `flat` owns their storage
+            background_gemms(lambda: phase(2), hiddens, feats, rng, ws, sumsq, g_mse, flat, gptrs, g_reg, ctx.lam, *params)
+            background_late(regulariser)
+        else:
+            phase(3)
+            regulariser()
         return (None, g_hid, None, None, *grads)
 
 

@@ -70,6 +70,14 @@ class GradAllReducer:
             w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.pending.append((w, buf))
 
+    def reduce_first_here(self):
+        """Average the FIRST module's slice on the CURRENT stream -- the trainer's background lane, right behind that module's deferred
+        weight gradients (train.train_step); ``wait()`` orders the remaining slices after it."""
+        off, n = self.ranges[0]
+        self._launch(off, n)
+        self._early_event.record(torch.cuda.current_stream())
+        self._early_done = True
+
     def start_iteration(self):
         self._fired, self.pending, self.bytes_last = {}, [], 0
         self._done = False
@@ -181,6 +189,7 @@ class NvlinkAllReducer:
         self._early_done = False
         self._rest_launched = False
         self._all_done = False
+        self.defer_first = False
         self._early_event = torch.cuda.Event()
         self._hooks = []
         if self._side is not None:
@@ -188,12 +197,18 @@ class NvlinkAllReducer:
             remaining = {"n": 0}
 
             def hook(_p, first=first, remaining=remaining):
+                if self.defer_first:                  # the trainer reduces the first module on its background lane (reduce_first_here)
+                    return
                 remaining["n"] += 1
                 if remaining["n"] == len(first):      # every gradient of the first module has been accumulated
                     remaining["n"] = 0
                     self._reduce_early()
             for p in first:
                 self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+        def fresh(_p):                                # a new backward has produced gradients: the next wait() has work to do
+            self._all_done = False
+        for pl in plists:
+            self._hooks.append(pl[0].register_post_accumulate_grad_hook(fresh))
         dist.barrier(self.group)                      # every rank's flag block is zeroed and mapped before anyone signals into it
         torch.cuda.synchronize()
 
@@ -216,6 +231,8 @@ class NvlinkAllReducer:
     def start_iteration(self):
         self.bytes_last = 0
         self._early_done = False
+        self._rest_launched = False
+        self._all_done = False
 
     def _assert_placed(self):
         lo = self.buf.data_ptr()
@@ -255,11 +272,12 @@ class NvlinkAllReducer:
             main.wait_stream(self._side)
         elif self._early_done:
             rest = self.ranges[1:]
-            main.wait_stream(self._side)              # same flag set: the two kernels must not overlap each other
+            main.wait_event(self._early_event)        # same flag set: the two kernels must not overlap each other
             self._launch(rest[0][0], sum(r[1] for r in rest))
         else:
             self._launch(0, sum(r[1] for r in self.ranges))
         self._rest_launched = False
+        self._early_done = False                      # consumed: the next backward starts over
 
     def check(self):
         torch.cuda.synchronize()

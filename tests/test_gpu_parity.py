@@ -61,7 +61,7 @@ def build(m, precision, kind, dec_sd, rec_sd):
 @pytest.mark.parametrize("tA", [False, True])
 @pytest.mark.parametrize("tB", [False, True])
 @pytest.mark.parametrize("shape", [(100, 2048, 2048), (100, 6144, 2048), (100, 128, 1536), (3100, 4188, 512), (2048, 2048, 3100),
-                                   (8, 8, 8), (300, 72, 200), (128, 1536, 2800)])
+                                   (8, 8, 8), (300, 72, 200), (128, 1536, 2800), (1312, 264, 136)])
 def test_gemm_all_operand_layouts(prec, tA, tB, shape):
     M, N, K = shape
     if prec == L.PREC_BF16 and (((M if tA else K) % 8) or ((N if tB else K) % 8)):

@@ -9,14 +9,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SELECT = "test_losses_hiddens_grads_match_reference_golden or test_shape_variants_against_oracle or cuda_graph or full_size"
+SELECT = "test_losses_hiddens_grads_match_reference_golden or test_shape_variants_against_oracle or cuda_graph or full_size or greedy"
 
 
 @pytest.mark.parametrize("switches", [
-    {"RECNET_SIDE": "1", "RECNET_CHAINS": "2"},                             # second stream around the loops + two concurrent sample chains
+    {"RECNET_SIDE": "0", "RECNET_CHAINS": "2"},                             # everything on one stream (the pre-r2_h default) + two concurrent sample chains
     {"RECNET_PERSIST": "0", "RECNET_PERSIST_BWD": "0", "RECNET_PDL": "1"},    # kernel-per-phase reconstructor loops (the pre-r2 default) + programmatic dependent launch
-    {"RECNET_STAGE_MULTI": "0", "RECNET_GEMM_COSTMODEL": "1", "RECNET_OPTIMIZER": "torch"},   # r1_f staging / planner / optimiser
-], ids=["side+chains", "kernel_per_phase+pdl", "r1_f_paths"])
+    {"RECNET_STAGE_MULTI": "0", "RECNET_GEMM_COSTMODEL": "1", "RECNET_OPTIMIZER": "torch", "RECNET_GEMM_PERSIST": "0"},   # r1_f staging / planner / optimiser, one-tile-per-CTA GEMMs
+    {"RECNET_DEC_CLUSTER": "0", "RECNET_PERSIST_GLOBAL": "0", "RECNET_GREEDY_PF": "0"},   # decoder forward loop / global reconstructor / greedy on the kernel-per-phase paths
+], ids=["one_stream+chains", "kernel_per_phase+pdl", "r1_f_paths", "r1_loops"])
 def test_opt_in_paths_stay_parity_green(switches):
     env = dict(os.environ, **switches)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",

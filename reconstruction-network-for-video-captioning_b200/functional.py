@@ -282,7 +282,6 @@ class DecoderSequenceFn(torch.autograd.Function):
                 phase(4)                               # the vocabulary projection's own gradients: underneath the loop, on the lane
                 vocab_done.record(torch.cuda.current_stream())
             background_gemms(vocab, feats, tokens_in, targets, ce_weight, rng, ws, g_ce, g_hid, hiddens, flat, gptrs, *params)
-            _flush(_bg.mid)
             phase(2)                                   # the BPTT loop
             _flush(_bg.late)                           # lane: from here on, next to the weight-gradient GEMMs below
             phase(8)
@@ -324,9 +323,8 @@ def _layered_shape(hiddens):
 # With ``deferred_weight_grads()`` active (train.train_step) that work goes to a second stream, the LANE, in this order:
 #   1. the local reconstructor's batched weight-gradient GEMMs       (LocalReconstructorFn.backward, right after its loop)
 #   2. the decoder's vocabulary-projection gradients                  (DecoderSequenceFn.backward, right after the CE backward)
-#   3. ``mid`` items: the reconstructor's gradient all-reduce         (data parallel; queued by the trainer)
 #   -- the lane then waits for the decoder's loop --
-#   4. ``late`` items: reconstructor regulariser gradient + optimiser step: machine-filling elementwise kernels that would stall the
+#   3. ``late`` items: reconstructor regulariser gradient + optimiser step: machine-filling elementwise kernels that would stall the
 #      loop (they take the register file), so they run next to the decoder's weight-gradient GEMMs instead.
 # The persistent GEMMs of 1-2 are capped to ``ctas`` CTAs (recnet_set_background_ctas) so they never hold the SMs the loop's kernels
 # are waiting for.  ``join_background()`` makes the main stream wait for the lane; everything the lane reads is kept alive until then.
@@ -337,7 +335,6 @@ class _Background:
     stream: Optional[torch.cuda.Stream] = None
     pending = False
     keep: list = []
-    mid: list = []
     late: list = []
 
 
@@ -366,7 +363,6 @@ class deferred_weight_grads:
     def __exit__(self, *exc):
         _bg.active, _bg.ctas = self.prev
         if exc[0] is not None:
-            _bg.mid.clear()
             _bg.late.clear()
             join_background()
         return False
@@ -400,11 +396,6 @@ def background_gemms(fn, *keep):
     return run_in_background(capped, *keep)
 
 
-def background_mid(fn, *keep):
-    _bg.mid.append(fn)
-    _bg.keep.extend(keep)
-
-
 def background_late(fn, *keep):
     _bg.late.append(fn)
     _bg.keep.extend(keep)
@@ -418,13 +409,12 @@ def _flush(items: list):
 
 
 def background_pending() -> bool:
-    return _bg.pending or bool(_bg.mid) or bool(_bg.late)
+    return _bg.pending or bool(_bg.late)
 
 
 def join_background():
     """Queue whatever is still waiting for its slot, then make the main stream wait for the lane; its results (reconstructor
     gradients, optimiser step, vocabulary-projection gradients) may be used afterwards."""
-    _flush(_bg.mid)
     _flush(_bg.late)
     if _bg.pending:
         torch.cuda.current_stream().wait_stream(_bg.stream)

@@ -70,14 +70,6 @@ class GradAllReducer:
             w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.pending.append((w, buf))
 
-    def reduce_first_here(self):
-        """Average the FIRST module's slice on the CURRENT stream -- the trainer's background lane, right behind that module's deferred
-        weight gradients (train.train_step); ``wait()`` orders the remaining slices after it."""
-        off, n = self.ranges[0]
-        self._launch(off, n)
-        self._early_event.record(torch.cuda.current_stream())
-        self._early_done = True
-
     def start_iteration(self):
         self._fired, self.pending, self.bytes_last = {}, [], 0
         self._done = False
@@ -151,7 +143,7 @@ class NvlinkAllReducer:
         if self.world > self.MAX_WORLD:
             raise NotImplementedError(f"NvlinkAllReducer covers one NVSwitch domain (<= {self.MAX_WORLD} ranks)")
         self.modules = list(modules)
-        self.ctas = int(ctas if ctas is not None else os.environ.get("RECNET_AR_CTAS", "32"))
+        self.ctas = int(ctas if ctas is not None else os.environ.get("RECNET_AR_CTAS", "16"))
         self.overlap = (os.environ.get("RECNET_DP_OVERLAP", "1") == "1") if overlap is None else bool(overlap)
         # parameter lists in the order the sequence Functions save them (models.*._params): functional._flat_grads keys the
         # placement by exactly that tuple
@@ -189,7 +181,6 @@ class NvlinkAllReducer:
         self._early_done = False
         self._rest_launched = False
         self._all_done = False
-        self.defer_first = False
         self._early_event = torch.cuda.Event()
         self._hooks = []
         if self._side is not None:
@@ -197,8 +188,6 @@ class NvlinkAllReducer:
             remaining = {"n": 0}
 
             def hook(_p, first=first, remaining=remaining):
-                if self.defer_first:                  # the trainer reduces the first module on its background lane (reduce_first_here)
-                    return
                 remaining["n"] += 1
                 if remaining["n"] == len(first):      # every gradient of the first module has been accumulated
                     remaining["n"] = 0

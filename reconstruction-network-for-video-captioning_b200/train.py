@@ -158,25 +158,20 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
         decoder['optimizer'].zero_grad(set_to_none=True)
         if reconstructor is not None:
             reconstructor['optimizer'].zero_grad(set_to_none=True)
-    # Background lane (functional.deferred_weight_grads): the local reconstructor's weight-gradient GEMMs, its all-reduce and its
-    # optimiser step run on a second stream underneath the decoder's backward loop; joined at the end of this function.
+    # Background lane (functional.deferred_weight_grads), single-GPU runs: the local reconstructor's weight-gradient GEMMs, its
+    # regulariser gradient + optimiser step and the decoder's vocabulary-projection gradients run on a second stream underneath /
+    # next to the decoder's backward; joined at the end of this function.  Data-parallel runs keep the plain order: there the
+    # reducer overlaps the reconstructor's all-reduce with the decoder's backward and its optimiser step with the decoder's
+    # all-reduce, and a third tenant on the SMs (measured at N = 2, profiles/r2_i_step_timeline.md) costs more than it hides.
     use_bg = _background_ok(grad_hook, reducer)
     local_rec = reconstructor is not None and isinstance(reconstructor['model'], LocalReconstructor)
-    if reducer is not None and reconstructor is not None and not (optimizer_step and local_rec):
-        use_bg = False                                 # the reducer's own early hook only knows the main stream
-    tail = _background_tail(reconstructor, reducer) if (use_bg and optimizer_step and local_rec) else None
-    if reducer is not None and hasattr(reducer, "defer_first"):
-        reducer.defer_first = tail is not None
+    tail = _background_tail(reconstructor) if (use_bg and optimizer_step and local_rec) else None
     with Fn.deferred_weight_grads(enabled=use_bg):
         loss.backward()                                                                                     # train.py:268
     if grad_hook is not None:
         grad_hook()
     rec_stepped = tail.disarm() if tail is not None else False
-    if reducer is not None and tail is not None:
-        if not rec_stepped:                            # the hooks did not fire (no gradient reached the reconstructor): plain order
-            Fn.join_background()
-        reducer.wait()                                 # the decoder's slice; ordered after the lane's all-reduce by an event
-    elif reducer is not None:
+    if reducer is not None:
         if reconstructor is not None and optimizer_step:
             reducer.wait_first()                       # reconstructor gradients averaged; the decoder's go out underneath ...
             reconstructor['optimizer'].step()          # ... the reconstructor's Adam step (train.py:273; order of :271-273 is immaterial)
@@ -195,21 +190,16 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
 
 
 def _background_ok(grad_hook, reducer) -> bool:
-    if grad_hook is not None or os.environ.get("RECNET_BG_WGRAD", "1") != "1":
-        return False
-    if reducer is not None and not hasattr(reducer, "reduce_first_here"):
-        return False                                   # NCCL reducer: keeps the plain order
-    return True
+    return grad_hook is None and reducer is None and os.environ.get("RECNET_BG_WGRAD", "1") == "1"
 
 
 class _BackgroundTail:
-    """Fires once every reconstructor gradient of this backward has been accumulated: queues the reconstructor's gradient all-reduce
-    (data parallel) and its optimiser step (train.py:273) on the background lane (functional.py: ``mid`` / ``late`` slots)."""
+    """Fires once every reconstructor gradient of this backward has been accumulated: queues the reconstructor's optimiser step
+    (train.py:273) on the background lane (functional.py: ``late`` slot, behind the regulariser gradient)."""
 
     def __init__(self, reconstructor):
         self.params = [p for p in reconstructor['model'].parameters() if p.requires_grad]
         self.optimizer = reconstructor['optimizer']
-        self.reducer = None
         self.armed = False
         self.fired = False
         self.count = 0
@@ -224,13 +214,11 @@ class _BackgroundTail:
         self.count = 0
         if not Fn.background_pending():                # the backward did not defer anything (e.g. a stacked decoder)
             return
-        if self.reducer is not None:
-            Fn.background_mid(self.reducer.reduce_first_here)
         Fn.background_late(self.optimizer.step)
         self.fired = True
 
-    def arm(self, reducer):
-        self.reducer, self.armed, self.fired, self.count = reducer, True, False, 0
+    def arm(self):
+        self.armed, self.fired, self.count = True, False, 0
         return self
 
     def disarm(self) -> bool:
@@ -238,8 +226,8 @@ class _BackgroundTail:
         return self.fired
 
 
-def _background_tail(reconstructor, reducer):
+def _background_tail(reconstructor):
     t = reconstructor.get('_bg_tail')
     if t is None or t.optimizer is not reconstructor['optimizer']:
         t = reconstructor['_bg_tail'] = _BackgroundTail(reconstructor)
-    return t.arm(reducer)
+    return t.arm()

@@ -16,6 +16,10 @@ timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --
 echo "check exit $?" >> $O/status.txt
 RECNET_DP_IMPL=nccl RECNET_DP_FLAT=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NMAX --steps 50 --warmup 5 --cpu-iters 0 > $O/bench_n${NMAX}_nccl.json 2> $O/bench_n${NMAX}_nccl.err
 echo "nccl exit $?" >> $O/status.txt
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --master-addr 127.0.0.1 --master-port 29551 tools/step_trace.py --out $O/step_trace_n$NMAX.txt > $O/trace.log 2>&1
+echo "trace exit $?" >> $O/status.txt
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/dp_step_check.py > $O/step_check_n2.log 2>&1
+echo "step check exit $?" >> $O/status.txt; grep "^{" $O/step_check_n2.log | tail -1
 cat $O/status.txt; cat $O/check_n$NMAX.json
 for f in $O/bench_*.json; do echo $f; python -c "
 import json

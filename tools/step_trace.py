@@ -22,7 +22,13 @@ def main():
     from recnet_b200.data import synthetic_batch
     from torch.profiler import ProfilerActivity, profile
     s = bench.SHAPE
-    dev = torch.device("cuda", 0)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                                   # under torchrun: the data-parallel step, rank 0's timeline
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     C = T.C
     C.decoder_model = C.reconstructor_model = "LSTM"
     C.batch_size, C.caption_max_len, C.encoder_output_len, C.encoder_output_size = s["B"], s["cap"], s["T"], s["E"]
@@ -30,16 +36,23 @@ def main():
     C.reconstructor_n_layers, C.reconstructor_hidden_size, C.reconstructor_attn_size = 1, s["R"], s["A"]
     C.use_recon = args.recon != "none"
     C.reconstructor_type = args.recon if C.use_recon else "local"
-    C.precision, C.device = "bf16", "cuda:0"
+    C.precision, C.device = "bf16", f"cuda:{local}"
     torch.manual_seed(0)
     dec = T.build_decoder(s["V"])
     rec = T.build_reconstructor() if C.use_recon else None
     L = s["cap"] + 1
-    feats, targets, _ = synthetic_batch(s["B"], s["T"], s["E"], s["V"], s["cap"], seed=1234)
+    feats, targets, _ = synthetic_batch(s["B"], s["T"], s["E"], s["V"], s["cap"], seed=1234 + rank)
     feats, targets = feats.to(dev), targets.to(dev)
+    reducer = None
+    if world > 1:
+        from recnet_b200.parallel import broadcast_parameters, make_reducer
+        broadcast_parameters([dec["model"]] + ([rec["model"]] if rec else []))
+        reducer = make_reducer(([rec["model"]] if rec else []) + [dec["model"]])
 
     def step():
-        T.train_step(dec, rec, feats, targets, n_steps=L)
+        if reducer is not None:
+            reducer.start_iteration()
+        T.train_step(dec, rec, feats, targets, n_steps=L, reducer=reducer)
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -50,7 +63,7 @@ def main():
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     prio = int(os.environ.get("RECNET_CAPTURE_PRIO", "0"))
-    with torch.cuda.graph(g, stream=torch.cuda.Stream(priority=prio)):
+    with torch.cuda.graph(g, stream=torch.cuda.Stream(priority=prio), capture_error_mode="thread_local" if world > 1 else "global"):
         step()
     for _ in range(5):
         g.replay()
@@ -59,6 +72,11 @@ def main():
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()
+    if rank != 0 and os.environ.get("RECNET_TRACE_ALL_RANKS", "0") != "1":
+        torch.distributed.barrier()
+        os._exit(0)
+    if rank != 0:
+        args.out = args.out.replace(".txt", f"_rank{rank}.txt")
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     if not evs:
@@ -67,7 +85,7 @@ def main():
     # split into replays by the largest gaps
     n = len(evs) // 3
     last = evs[2 * n:]
-    t0 = last[0].time_range.start
+    t0 = last[0].time_range.start if os.environ.get("RECNET_TRACE_ABS", "0") != "1" else 0
     lines = []
     for e in last:
         stream = getattr(e, "stream", None)
@@ -76,6 +94,9 @@ def main():
     with open(args.out, "w") as f:
         f.write("\n".join(lines) + "\n")
     print(f"{len(last)} kernels, span {last[-1].time_range.end - t0:.1f} us -> {args.out}")
+    if world > 1:
+        torch.distributed.barrier()
+        os._exit(0)       # NCCL objects captured in a live graph: see bench.py
 
 
 if __name__ == "__main__":

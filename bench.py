@@ -218,7 +218,10 @@ def gemm_bytes(M, N, K, elt):
 NCU_KEYS = {("gemm_tcgen05", (100, 6144, 2048)): "gate_gemm_warm", ("proj_attn_cell_fwd", (100, 28, 512)): "pf_fwd_kernel",
             ("proj_attn_cell_bwd", (100, 28, 512)): "pf_bwd_kernel", ("attn_fwd", (100, 31, 512)): "lean_fwd_kernel",
             ("attn_bwd", (100, 31, 512)): "lean_bwd_kernel", ("lstm_cell_fwd", (100, 1536, 3)): "lstm_cell_fwd_kernel",
-            ("lstm_cell_bwd", (100, 1536, 11)): "lstm_cell_bwd_kernel"}
+            ("lstm_cell_bwd", (100, 1536, 11)): "lstm_cell_bwd_kernel",
+            # r2: the weight-resident persistent loops (shape = steps, CTAs, 0 fwd / 1 bwd / 2 decoder cluster loop)
+            ("persistent_loop", (28, 144, 0)): "local_fwd_kernel", ("persistent_loop", (28, 144, 1)): "local_bwd_kernel",
+            ("persistent_loop", (31, 112, 2)): "decoder_fwd_cluster_kernel"}
 
 
 def ncu_traffic(kernel, shape):

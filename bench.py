@@ -178,6 +178,8 @@ def algorithmic_work(cls, M, N, K, elt):
         # Per step: the gate GEMM [B x 4R x (H+R)] (fwd) or its transpose dX = dG.W (bwd) + the attention-query GEMM [B x A x R];
         # useful rows only (B of the 112-column UMMA tile)
         B, H, R, A = s["B"], s["H"], s["R"], s["A"]
+        if K == 2:       # the decoder's forward loop in 16-CTA clusters (csrc/seq_decoder_cluster.cuh): h_{t-1} . [W_a ; W_hh]^T per step
+            return "tensor", M * 2.0 * B * (A + 4 * H) * H
         return "tensor", M * (2.0 * B * 4 * R * (H + R) + 2.0 * B * A * R)
     if cls in (1, 2):
         # useful rows only (M = 100 of the 128-row UMMA tile).  Which roofline binds is decided by the caller from the arithmetic

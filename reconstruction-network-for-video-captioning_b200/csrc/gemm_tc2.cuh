@@ -314,10 +314,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-// Upper bound on the CTAs of one launch (0 = none).  A trainer that runs batched GEMMs on a second stream UNDERNEATH a latency-bound
-// kernel sequence (the decoder's backward loop: 100-CTA kernels) caps them so that the persistent CTAs never hold the SMs the
-// foreground kernels are waiting for (recnet_set_background_ctas).
-inline int& background_ctas() { static int v = 0; return v; }
+inline int& background_ctas() { return rn_background_ctas(); }       // common.cuh
 
 // output tensor [rows, cols] row-major (ld elements): fp32 boxes of 32 x 32, bf16 boxes of 32 rows x 64 columns -- 128-byte rows
 static inline int make_out_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, bool is_bf16) {

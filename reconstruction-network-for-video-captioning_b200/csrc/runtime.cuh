@@ -206,6 +206,7 @@ static inline int splitk_reduce(const float* P, int splits, long long split_stri
   const long long total = (long long)M * N;
   if (total <= 0) return 0;
   int blocks = (int)min((long long)NUM_SMS * 8, (total + 255) / 256);
+  if (rn_background_ctas() > 0) blocks = min(blocks, rn_background_ctas());       // grid-stride loop: fewer CTAs, same result
   ProfScope prof(KC_REDUCE, M, N, splits, st);
   splitk_reduce_kernel<<<blocks, 256, 0, st>>>(P, splits, split_stride, ldp, out, ldo, M, N, bias, accumulate);
   RN_LAUNCH_OK();
@@ -238,6 +239,7 @@ static inline GemmPlan plan_gemm_full_bf16(int M, int N, int K) {
       if (s > 1 && bn == 256) continue;                  // split plans stay on the 64 / 128-wide kernels
       if (bn > 64 && N <= bn / 2) continue;              // more than half of the tile would be padding
       const long long ctas = (long long)mt * rn_cdiv(N, bn) * s;
+      if (rn_background_ctas() > 0 && s > 1 && ctas > rn_background_ctas()) continue;      // background lane: stay within the CTA budget
       const int kb = rn_cdiv(nkb, s);
       const long long full = ctas / NUM_SMS;
       const int rem = (int)(ctas % NUM_SMS);

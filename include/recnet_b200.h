@@ -271,6 +271,11 @@ int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, con
                            const int32_t* blk_chunk, int n_blocks, float* partial, float* sumsq, float* reg_out,
                            const float* base, const float* lambda_dev, float* fused_out, void* stream);
 /* grad_p (+)= lambda * lambda_dev[0] * g[0] * p / ||p||     (g, lambda_dev: device scalars, NULL = 1) */
+/* recnet_param_norms_fwd in two halves: `partial` (n_blocks floats) depends on the parameters only. */
+int recnet_param_norms_partial(const int64_t* ptrs, const int64_t* sizes, const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks,
+                               float* partial, void* stream);
+int recnet_param_norms_finalize(const float* partial, const int32_t* blk_tensor, int n_blocks, int n, float* sumsq, float* reg_out,
+                                const float* base, const float* lambda_dev, float* fused_out, void* stream);
 int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n,
                            const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks, const float* sumsq,
                            const float* g, float lambda, const float* lambda_dev, int accumulate, void* stream);

@@ -124,6 +124,8 @@ SIGNATURES = {
     "recnet_debug_set_timeline": (_i, [_p]),
     "recnet_debug_dropout_mask": (_i, [_p, C.c_uint32, _l, C.c_float, _p, _p]),
     "recnet_param_norms_fwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "recnet_param_norms_partial": (_i, [_p, _p, _p, _p, _i, _p, _p]),
+    "recnet_param_norms_finalize": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "recnet_param_norms_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _p, _f, _p, _i, _p]),
     "recnet_teacher_forcing_prep": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
     "recnet_allreduce_avg": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _i, _i, _p]),

@@ -430,6 +430,21 @@ int recnet_param_norms_fwd(const int64_t* ptrs, const int64_t* sizes, int n, con
   RN_LAUNCH_OK();
   return 0;
 }
+// the two halves of recnet_param_norms_fwd: the squared-norm partials depend on the parameters only, so a trainer can compute them ahead of
+// the forward pass (on another stream) and finalise -- including the loss assembly -- once the loss is there
+int recnet_param_norms_partial(const int64_t* ptrs, const int64_t* sizes, const int32_t* blk_tensor, const int32_t* blk_chunk, int n_blocks,
+                               float* partial, void* stream) {
+  misc::mt_sumsq_kernel<<<n_blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(ptrs), reinterpret_cast<const long long*>(sizes),
+                                                          blk_tensor, blk_chunk, partial);
+  RN_LAUNCH_OK();
+  return 0;
+}
+int recnet_param_norms_finalize(const float* partial, const int32_t* blk_tensor, int n_blocks, int n, float* sumsq, float* reg_out,
+                                const float* base, const float* lambda_dev, float* fused_out, void* stream) {
+  misc::mt_norm_finalize_kernel<<<1, 512, 0, ST(stream)>>>(partial, blk_tensor, n_blocks, sumsq, n, reg_out, base, lambda_dev, fused_out);
+  RN_LAUNCH_OK();
+  return 0;
+}
 int recnet_param_norms_bwd(const int64_t* ptrs, const int64_t* grad_ptrs, const int64_t* sizes, int n, const int32_t* blk_tensor,
                            const int32_t* blk_chunk, int n_blocks, const float* sumsq, const float* g, float lambda,
                            const float* lambda_dev, int accumulate, void* stream) {

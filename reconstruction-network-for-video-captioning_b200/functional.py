@@ -90,9 +90,18 @@ def _norms_fwd(params, base=None, lambda_dev=None):
     tab = _table_for(params)
     dev = params[0].device
     sumsq = torch.empty(tab.n, dtype=torch.float32, device=dev)
-    partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=dev)
     reg = torch.empty((), dtype=torch.float32, device=dev)
     fused = torch.empty((), dtype=torch.float32, device=dev) if lambda_dev is not None else None
+    pre = _prefetched_norms.pop(tuple((p.data_ptr(), p.numel()) for p in params), None)
+    if pre is not None:                     # the squared-norm partials were computed ahead of the forward pass (prefetch_param_norms)
+        partial, ready = pre
+        torch.cuda.current_stream().wait_event(ready)
+        L.check(L.lib().recnet_param_norms_finalize(partial.data_ptr(), tab.blk_tensor.data_ptr(), tab.n_blocks, tab.n, sumsq.data_ptr(),
+                                                    reg.data_ptr(), _ptr(base), _ptr(lambda_dev), _ptr(fused), _stream()),
+                "recnet_param_norms_finalize")
+        _bg.keep.append(partial)
+        return reg, sumsq, fused
+    partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=dev)
     L.check(L.lib().recnet_param_norms_fwd(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(),
                                            tab.blk_chunk.data_ptr(), tab.n_blocks, partial.data_ptr(), sumsq.data_ptr(),
                                            reg.data_ptr(), _ptr(base), _ptr(lambda_dev), _ptr(fused), _stream()),
@@ -394,6 +403,32 @@ def background_gemms(fn, *keep):
         finally:
             lib.recnet_set_background_ctas(0)
     return run_in_background(capped, *keep)
+
+
+# parameter list -> (squared-norm partials, event): computed on the lane at the start of a step, consumed by _norms_fwd of the same step
+_prefetched_norms: Dict[tuple, tuple] = {}
+
+
+def prefetch_param_norms(*param_lists):
+    """Squared-norm partials of the regularisers (train.py:69,101,127) on the lane, underneath the decoder's forward loop: they depend on
+    the parameters only.  ``_norms_fwd`` of the same step picks them up (and waits for the lane's event); anything left over is dropped by
+    the next call."""
+    _prefetched_norms.clear()
+    todo = [[p for p in pl] for pl in param_lists if pl]
+    if not todo:
+        return
+
+    def work():
+        for params in todo:
+            tab = _table_for(params)
+            partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=params[0].device)
+            L.check(L.lib().recnet_param_norms_partial(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.blk_tensor.data_ptr(),
+                                                       tab.blk_chunk.data_ptr(), tab.n_blocks, partial.data_ptr(), _stream()),
+                    "recnet_param_norms_partial")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            _prefetched_norms[tuple((p.data_ptr(), p.numel()) for p in params)] = (partial, ev)
+    run_in_background(work)
 
 
 def background_late(fn, *keep):

@@ -169,7 +169,7 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
 /* recnet_decoder_bwd in parts, same arguments (single-layer decoders on the projected-feature path; recnet_decoder_bwd_is_split says
  * whether the split applies -- otherwise bit 0 runs everything and the other bits nothing):
  *   1 = CE backward + gradient wrt the states through the vocabulary projection     2 = the BPTT loop (needs 1)
- *   4 = the vocabulary projection's own gradients (need 1 only)                    8 = all other parameter gradients (need 2)
+ *   4 = the vocabulary projection's weight gradient (needs 1 only)                 8 = all other parameter gradients (need 2)
  * phases = 4 alone may run on another stream while 2 runs (own scratch); 15 is recnet_decoder_bwd. */
 int recnet_decoder_bwd_phase(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
                              const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,

@@ -63,7 +63,7 @@ static inline int rn_cdiv(long long a, long long b) { return (int)((a + b - 1) /
 // ---- type conversion -------------------------------------------------------------------------
 // Upper bound on the CTAs of ONE launch of the batched kernels (0 = none): set by a trainer around work it runs on a second stream UNDERNEATH a
 // latency-bound foreground kernel sequence (recnet_set_background_ctas; functional.py "background lane").  Persistent GEMMs, split-K plans and the
-// split-K reduce honour it; the column sums never use more than 48 CTAs anyway.
+// split-K reduce and the column sums honour it.
 inline int& rn_background_ctas() { static int v = 0; return v; }
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);

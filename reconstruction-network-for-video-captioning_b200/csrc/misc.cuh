@@ -280,10 +280,12 @@ static int colsum(const T* X, long long ld, int M, int N, float* out, int accumu
   const bool vec = ((N + VEC - 1) / VEC * VEC <= ld) && !(reinterpret_cast<uintptr_t>(X) & 15) && !((ld * (long long)sizeof(T)) & 15) && M >= 64;
   int chunks;
   if (vec) {
-    // 16-byte loads, and never more than ~48 CTAs: these sums run next to GEMMs (side stream) or underneath the decoder's backward loop
-    // (background lane), whose CTAs need whole SMs -- 48 SMs pull a 34 MB operand in ~7 us, the 4224-CTA scalar version took 22 us
+    // 16-byte loads.  On a trainer's background lane (rn_background_ctas() > 0) never more CTAs than that budget: the sums run underneath
+    // the decoder's backward loop, whose CTAs need whole SMs; elsewhere ~2 CTAs per SM (next to GEMMs on the side stream, a 48-CTA sum over
+    // 34 MB crawled: 87 us)
     const int cb = rn_cdiv(N, 32 * VEC);
-    chunks = scratch ? 48 / cb : 1;
+    const int budget = rn_background_ctas() > 0 ? rn_background_ctas() : 296;
+    chunks = scratch ? budget / cb : 1;
     if (chunks > M / 64) chunks = M / 64;
     if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;

@@ -11,7 +11,7 @@
 //   K3  pf_bwd_kernel                   cell backward -> dG_t, d e_t = <dG_t, VW>, score backward -> dWh_t, dUv, dw
 //   K4  [dWh_t | dG_t] [W_a ; W_hh]     one split-K GEMM, K = A + 4H -> dh_{t-1}
 // i.e. 2 + 2 dependent kernels per step instead of 4 + 4, and the per-step weight traffic drops from 8.4 MB to 2.2 MB.
-// dW_ctx = dVW^T feats with dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b] (pf_dvw_kernel, once after the loop).
+// dW_ctx = dG^T ctx with ctx_t[b] = (1/T) sum_tau e_t[b,tau] v[b,tau] (pf_escore_kernel<.., true>, in the forward pass next to the vocabulary GEMM).
 //
 // VW and the gate stash are stored "unit-interleaved": [.., H, 4] (the 4 gate columns i,f,g,o of one hidden unit
 // adjacent) so that one thread fetches its unit's 4 columns of a frame with ONE 8-byte (bf16) / 16-byte (fp32) load.
@@ -453,9 +453,8 @@ __global__ void __launch_bounds__(BTHREADS) pf_bwd_kernel(BwdArgs a) {
   }
 }
 
-// dVW[b, tau, n] = (1/T) sum_t e[t, b, tau] * dG[t, b, n]   (n in gate-block order = the row order of W_ctx)
-// grid (ceil(N / 512), B), 256 threads x 2 adjacent columns, dynamic smem L * round_up(Tn, 4) floats (float4 broadcast reads:
-// the first version read e one float at a time and was LDS-issue bound, 53 us)
+// 256 threads x 2 adjacent columns, float4 broadcast reads of the scores from shared memory (the first version read e one float at a time and was
+// LDS-issue bound, 53 us)
 template <typename T> struct Pair;
 template <> struct Pair<float> {
   static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -465,46 +464,63 @@ template <> struct Pair<bf16> {
   static __device__ __forceinline__ float2 load(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
   static __device__ __forceinline__ void store(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
 };
-template <typename TO>
-__global__ void __launch_bounds__(256) pf_dvw_kernel(const float* __restrict__ e, const TO* __restrict__ dGW, long long ld, int col0,
-                                                     TO* __restrict__ dVW, int L, int B, int Tn, int N, float inv_T) {
-  extern __shared__ float4 e_sm4[];                     // [round_up(L, 32)][Tnp / 4], zero beyond L / Tn
+// Small per-sample products with the attention scores e[t, b, tau] (L steps x Tn frames), 2 output columns per thread, grid (N / 512, B):
+//   CTX = false:  out[b, tau, n] = inv_T sum_t   e[t, b, tau] X[(t, b), n]       (dVW: gradient of the projected features; rows of X = steps)
+//   CTX = true :  out[t, b, n]   = inv_T sum_tau e[t, b, tau] X[(b, tau), n]     (the attention context of every step; rows of X = frames)
+// S = number of summed rows (L resp. Tn), K = number of output rows per sample (Tn resp. L).  e is staged in shared memory as [S][Kp].
+template <typename TO, bool CTX>
+__global__ void __launch_bounds__(256) pf_escore_kernel(const float* __restrict__ e, const TO* __restrict__ X, long long ld, int col0,
+                                                        TO* __restrict__ out, int L, int B, int Tn, int N, float inv_T) {
+  extern __shared__ float4 e_sm4[];                     // [round_up(S, 16)][Kp], zero beyond S / K
   float* e_sm = reinterpret_cast<float*>(e_sm4);
-  const int Tnp = (Tn + 3) & ~3, Lp = (L + 31) & ~31;
+  const int S = CTX ? Tn : L, K = CTX ? L : Tn;
+  const int Kp = (K + 3) & ~3, Sp = (S + 15) & ~15;
   const int b = blockIdx.y, n = (blockIdx.x * 256 + threadIdx.x) * 2;
-  for (int i = threadIdx.x; i < Lp * Tnp; i += 256) {
-    const int t = i / Tnp, k = i - t * Tnp;
-    e_sm[i] = (t < L && k < Tn) ? e[((long long)t * B + b) * Tn + k] : 0.f;
+  for (int i = threadIdx.x; i < Sp * Kp; i += 256) {
+    const int s_ = i / Kp, k = i - s_ * Kp;
+    const int t = CTX ? k : s_, tau = CTX ? s_ : k;
+    e_sm[i] = (s_ < S && k < K) ? e[((long long)t * B + b) * Tn + tau] : 0.f;
   }
   __syncthreads();
   if (n >= N) return;
-  for (int t0 = 0; t0 < Tn; t0 += 32) {
+  for (int k0 = 0; k0 < K; k0 += 32) {
     float acc[32][2];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k][0] = acc[k][1] = 0.f;
-    for (int s0 = 0; s0 < L; s0 += 16) {
-      float2 dg[16];                                    // 16 steps of this column pair in flight at once
+    for (int s0 = 0; s0 < S; s0 += 16) {
+      float2 x[16];                                     // 16 summed rows of this column pair in flight at once
 #pragma unroll
-      for (int k = 0; k < 16; ++k) dg[k] = Pair<TO>::load(dGW + ((long long)min(s0 + k, L - 1) * B + b) * ld + col0 + n);
+      for (int k = 0; k < 16; ++k) {
+        const int s_ = min(s0 + k, S - 1);
+        const long long row = CTX ? (long long)b * Tn + s_ : (long long)s_ * B + b;
+        x[k] = Pair<TO>::load(X + row * ld + col0 + n);
+      }
 #pragma unroll
-      for (int tt = 0; tt < 16; ++tt) {                 // steps >= L carry zero weights
-        const float4* er = e_sm4 + ((s0 + tt) * Tnp + t0) / 4;
+      for (int ss = 0; ss < 16; ++ss) {                 // rows >= S carry zero weights
+        const float4* er = e_sm4 + ((s0 + ss) * Kp + k0) / 4;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          if (t0 + 4 * k4 < Tn) {
+          if (k0 + 4 * k4 < K) {
             const float4 e4 = er[k4];
-            acc[4 * k4 + 0][0] = fmaf(e4.x, dg[tt].x, acc[4 * k4 + 0][0]); acc[4 * k4 + 0][1] = fmaf(e4.x, dg[tt].y, acc[4 * k4 + 0][1]);
-            acc[4 * k4 + 1][0] = fmaf(e4.y, dg[tt].x, acc[4 * k4 + 1][0]); acc[4 * k4 + 1][1] = fmaf(e4.y, dg[tt].y, acc[4 * k4 + 1][1]);
-            acc[4 * k4 + 2][0] = fmaf(e4.z, dg[tt].x, acc[4 * k4 + 2][0]); acc[4 * k4 + 2][1] = fmaf(e4.z, dg[tt].y, acc[4 * k4 + 2][1]);
-            acc[4 * k4 + 3][0] = fmaf(e4.w, dg[tt].x, acc[4 * k4 + 3][0]); acc[4 * k4 + 3][1] = fmaf(e4.w, dg[tt].y, acc[4 * k4 + 3][1]);
+            acc[4 * k4 + 0][0] = fmaf(e4.x, x[ss].x, acc[4 * k4 + 0][0]); acc[4 * k4 + 0][1] = fmaf(e4.x, x[ss].y, acc[4 * k4 + 0][1]);
+            acc[4 * k4 + 1][0] = fmaf(e4.y, x[ss].x, acc[4 * k4 + 1][0]); acc[4 * k4 + 1][1] = fmaf(e4.y, x[ss].y, acc[4 * k4 + 1][1]);
+            acc[4 * k4 + 2][0] = fmaf(e4.z, x[ss].x, acc[4 * k4 + 2][0]); acc[4 * k4 + 2][1] = fmaf(e4.z, x[ss].y, acc[4 * k4 + 2][1]);
+            acc[4 * k4 + 3][0] = fmaf(e4.w, x[ss].x, acc[4 * k4 + 3][0]); acc[4 * k4 + 3][1] = fmaf(e4.w, x[ss].y, acc[4 * k4 + 3][1]);
           }
         }
       }
     }
 #pragma unroll
     for (int k = 0; k < 32; ++k)
-      if (t0 + k < Tn) Pair<TO>::store(dVW + ((long long)b * Tn + t0 + k) * N + n, acc[k][0] * inv_T, acc[k][1] * inv_T);
+      if (k0 + k < K) {
+        const long long row = CTX ? (long long)(k0 + k) * B + b : (long long)b * Tn + k0 + k;
+        Pair<TO>::store(out + row * N + n, acc[k][0] * inv_T, acc[k][1] * inv_T);
+      }
   }
+}
+static inline size_t escore_smem(int L, int Tn, bool ctx) {
+  const int S = ctx ? Tn : L, K = ctx ? L : Tn;
+  return (size_t)((S + 15) & ~15) * ((K + 3) & ~3) * sizeof(float);
 }
 
 // dst[(4j + g), :] = (TO) src[(g H + j), :]   -- W_ctx rows in unit-interleaved order (makes the VW GEMM emit [.., H, 4])

@@ -3,7 +3,7 @@
 // the algebra.  Per step: ONE split-K GEMM on h_{t-1} (K = H) + ONE fused attention/cell kernel; BPTT: one fused
 // cell/attention backward kernel + ONE split-K GEMM (K = A + 4H).
 //   hoisted once per sequence: U v, VW = feats W_ctx^T (unit-interleaved, operand precision), embedding projection Gx
-//   after the loop: vocabulary projection + CE (forward); dVW, all weight gradients as batched GEMMs (backward)
+//   after the loop: vocabulary projection + CE + the per-step attention contexts (forward); all weight gradients as batched GEMMs (backward)
 #pragma once
 #include "proj_attn.cuh"
 #include "seq_decoder.cuh"
@@ -18,7 +18,7 @@ struct PfWs {
   T *Wemb, *WctxI, *Wcat, *U, *Wout, *feats;
   float* Uv; T* VW; T* Xe; float* Gx; T* Hop; float* P; float* Wh; float* e; T* gates; float* c;
   float *logits, *lse, *row_loss;
-  T* dlogits; float* dHext; T* dGW; float* dhP; float* dWh; float* dUv; T* dUv_op; float* dw_acc; float* dc; float* dXe; T* dVW;
+  T* dlogits; float* dHext; T* dGW; float* dhP; float* dWh; float* dUv; T* dUv_op; float* dw_acc; float* dc; float* dXe; T* ctx;
   float* splitk; float* splitk2; float* splitk3; int* err;      // splitk2: scratch of the side stream (runtime.cuh:Side), splitk3: of phase 4 alone
   size_t bytes;
 };
@@ -34,6 +34,7 @@ static inline bool pf_ok(const recnet_decoder_desc& d) {
   if (num_chains(d.B) != 1) return false;
   const int al = d.precision == RECNET_PREC_BF16 ? 8 : 4;
   if ((long long)d.B * d.T * 4 * d.H >= (1ll << 31) || (long long)d.L * d.B * (d.A + 4 * d.H) >= (1ll << 31)) return false;   // 32-bit index math
+  if ((d.E & 1) || pf::escore_smem(d.L, d.T, true) > 46 * 1024) return false;          // pf_escore_kernel: column pairs, e[L x T] in shared memory
   return d.T >= 1 && d.T <= pf::MAX_T && d.A >= 4 && d.A <= pf::MAX_A && d.A % al == 0 && d.H % al == 0 &&
          pf::bwd_smem_bytes(d.H, d.A) <= 46 * 1024;
 }
@@ -97,7 +98,7 @@ static PfWs<T> plan_pf(const recnet_decoder_desc& d, void* base) {
   w.dw_acc = m.take<float>((size_t)B * A);
   w.dc = m.take<float>((size_t)B * H);
   w.dXe = m.take<float>((size_t)L * B * w.EMBp);
-  w.dVW = m.take<T>((size_t)B * Tn * 4 * H);
+  w.ctx = m.take<T>((size_t)L * B * E);          // attention context of every step (forward, training calls): B-operand of dW_ctx
   w.splitk = m.take<float>(SPLITK_SCRATCH_FLOATS);
   w.splitk2 = m.take<float>(SPLITK_SCRATCH_FLOATS);
   w.splitk3 = m.take<float>(SPLITK_SCRATCH_FLOATS);
@@ -130,6 +131,12 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   const long long ldih = EMB + E;
   // operand copies of the weights / features (the optimiser changes the fp32 masters every step)
   // operand copies of the weights / features + cleared initial state: ONE multi-tensor staging kernel (misc.cuh:Stager)
+  // (the embedding gather needs neither: it starts on the second stream right away, next to the staging kernel)
+  cudaStream_t s2;
+  RN_TRY(side().fork(st, &s2));
+  misc::embed_gather_kernel<T><<<L * B, 128, 0, s2>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
+                                                      p_emb, rng, SITE_EMB);
+  RN_LAUNCH_OK();
   misc::Stager<T> sg;
   sg.add(feats, E, w.feats, E, (long long)B * Tn, E, E);
   sg.add(p.attn_U, E, w.U, E, A, E, E);
@@ -142,14 +149,10 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   sg.zero(w.c, (size_t)B * H * sizeof(float));
   sg.zero(w.err, 64 * sizeof(int));
   RN_TRY(sg.launch(st));
-  // hoisted projections.  With RECNET_SIDE=1 (runtime.cuh:Side) the key projection, the embedding gather and the time-batched
-  // embedding half of the gate projection run on a second stream next to the projected-feature GEMM.
-  cudaStream_t s2;
+  // hoisted projections (runtime.cuh:Side): the key projection and the time-batched embedding half of the gate projection run on the
+  // second stream next to the projected-feature GEMM; the second fork orders that stream after the staging kernel.
   RN_TRY(side().fork(st, &s2));
   RN_TRY(gemm_full<T>(w.feats, E, 0, w.U, E, 0, w.Uv, A, p.attn_b, B * Tn, A, E, 0, w.splitk2, s2));      // U v + b (bias folded in)
-  misc::embed_gather_kernel<T><<<L * B, 128, 0, s2>>>(p.embedding, tokens_in, w.Xe, w.EMBp, L * B, EMB, w.EMBp, V, d.embedding_scale,
-                                                      p_emb, rng, SITE_EMB);
-  RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.Xe, w.EMBp, 0, w.Wemb, w.EMBp, 0, w.Gx, 4 * H, p.b_ih, L * B, 4 * H, w.EMBp, 0, w.splitk2, s2));
   RN_TRY(gemm_to_operand(w.feats, E, w.WctxI, E, w.VW, 4 * H, B * Tn, 4 * H, E, w.splitk, st));
   RN_TRY(side().join(st, s2));
@@ -178,8 +181,21 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
     fa.c_out = w.c + (r + B) * H; fa.h_out = hiddens + r * H; fa.h_op = w.Hop + (r + B) * H;
     RN_TRY((pf::launch_fwd<T, T>(fa, st)));
   }
+  // Training calls: the attention context of every step, ctx_t[b] = (1/T) sum_tau e_t[b,tau] v[b,tau] (decoder.py:57-62).  The forward pass never
+  // needs it (the projected features carry it), but dW_ctx = sum_t dG_t^T ctx_t does, and HERE it costs nothing: its 256-thread CTAs share the
+  // SMs with the vocabulary GEMM's.  (Until r2_i backward formed dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b] after its loop instead: 29-52 us on
+  // the critical path.)
+  const bool training = targets && ce_weight && ce_out;
+  cudaStream_t s3 = st;
+  if (training) RN_TRY(side().fork(st, &s3));
   // vocabulary projection over all steps, then the masked CE (train.py:54-60,68)
   RN_TRY(gemm_full<T>(w.Hop + (size_t)B * H, H, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, L * B, V, H, 0, w.splitk, st));
+  if (training) {
+    // launched AFTER the GEMM: CTAs are dispatched in launch order, and the GEMM's 148 must not queue behind these 300
+    pf::pf_escore_kernel<T, true><<<dim3(rn_cdiv(E, 512), B), 256, pf::escore_smem(L, Tn, true), s3>>>(w.e, w.feats, E, 0, w.ctx, L, B, Tn, E,
+                                                                                                  1.f / Tn);
+    RN_LAUNCH_OK();
+  }
   if (targets && ce_weight && ce_out) {
     ProfScope prof(KC_CE, L * B, V, 0, st);
     loss::ce_fwd_kernel<<<L * B, loss::CE_THREADS, 0, st>>>(w.logits, w.Vld, targets, ce_weight, V, p_out, rng, SITE_LOGITS, w.lse,
@@ -188,6 +204,7 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
     loss::sum_kernel<<<1, 1024, 0, st>>>(w.row_loss, L * B, ce_out, 1.f);
     RN_LAUNCH_OK();
   }
+  if (training) RN_TRY(side().join(st, s3));
   return 0;
 }
 
@@ -235,19 +252,16 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
   // ---- batched weight gradients over the stashed operands, two streams (runtime.cuh:Side)
   const long long ldih = EMB + E;
   const T* dG = w.dGW + A;                       // [LB, 4H] gate gradients, ld = NP
-  if (phases == 4) {                               // on its own (a trainer's background lane): third scratch, nothing else touches it
-    RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk3, st));
-    RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk3, st));
-    return 0;
+  if (phases == 4) {                               // on its own (a trainer's background lane): the 13 GFLOP weight gradient only -- the bias
+    RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk3, st));      // gradient (a 26 MB column
+    return 0;                                      // sum: 93 us within the lane's CTA budget, 10 us without) belongs to phase 8
   }
   if (!(phases & 8)) return 0;
   cudaStream_t s2;
   RN_TRY(side().fork(st, &s2));
   // side: vocabulary projection, embedding path, attention query weights
-  if (phases & 4) {
-    RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk2, s2));
-    RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk2, s2));
-  }
+  if (phases & 4) RN_TRY(gemm_full<T>(w.dlogits, w.Vp, 1, Hall, H, 1, g.out_w, H, nullptr, V, H, LB, 0, w.splitk2, s2));
+  RN_TRY(misc::colsum<T>(w.dlogits, w.Vp, LB, V, g.out_b, 0, w.splitk2, s2));
   RN_TRY(gemm_full<T>(dG, NP, 1, w.Xe, w.EMBp, 1, g.w_ih, ldih, nullptr, 4 * H, EMB, LB, 0, w.splitk2, s2));               // dW_emb
   RN_TRY(gemm_full<T>(dG, NP, 0, w.Wemb, w.EMBp, 1, w.dXe, w.EMBp, nullptr, LB, EMB, 4 * H, 0, w.splitk2, s2));            // dXe
   RN_CUDA_OK(cudaMemsetAsync(g.embedding, 0, (size_t)V * EMB * sizeof(float), s2));
@@ -255,12 +269,9 @@ static int backward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensor
                                                  SITE_EMB);
   RN_LAUNCH_OK();
   RN_TRY(gemm_full<T>(w.dGW, NP, 1, w.Hop, H, 1, g.attn_W, H, nullptr, A, H, LB, 0, w.splitk2, s2));                       // dW_a = dWh^T h_{t-1}
-  // st: gate biases, context weights (dW_ctx = dVW^T feats,  dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b]), recurrent weights, keys
+  // st: gate biases, context weights (dW_ctx = dG^T ctx, the contexts stashed by the forward pass), recurrent weights, keys
   RN_TRY(misc::colsum<T>(dG, NP, LB, 4 * H, g.b_ih, 0, w.splitk, st, g.b_hh));            // b_ih and b_hh get the same gradient
-  pf::pf_dvw_kernel<T><<<dim3(rn_cdiv(4 * H, 512), B), 256, (size_t)round_up(L, 32) * round_up(Tn, 4) * sizeof(float), st>>>(w.e, w.dGW, NP, A, w.dVW,
-                                                                                                          L, B, Tn, 4 * H, 1.f / Tn);
-  RN_LAUNCH_OK();
-  RN_TRY(gemm_full<T>(w.dVW, 4 * H, 1, w.feats, E, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, B * Tn, 0, w.splitk, st));   // dW_ctx
+  RN_TRY(gemm_full<T>(dG, NP, 1, w.ctx, E, 1, g.w_ih + EMB, ldih, nullptr, 4 * H, E, LB, 0, w.splitk, st));            // dW_ctx = dG^T ctx
   RN_TRY(gemm_full<T>(dG, NP, 1, w.Hop, H, 1, g.w_hh, H, nullptr, 4 * H, H, LB, 0, w.splitk, st));                        // dW_hh = dG^T h_{t-1}
   RN_TRY(misc::cast_pad<T>(w.dUv, A, w.dUv_op, A, (long long)B * Tn, A, A, st));
   RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.feats, E, 1, g.attn_U, E, nullptr, A, E, B * Tn, 0, w.splitk, st));               // dU = dUv^T v

@@ -358,21 +358,21 @@ static int local_backward_weights(const recnet_local_desc& d, const LocalWs<T>& 
   const int GR = w.G * R;
   const T* Hr = w.X + (size_t)B * w.KX + H;       // h_t rows, ld = KX
   const T* dGh = is_gru ? w.dG2 : w.dG;
-  // GEMMs first, column sums last: on a trainer's background lane the (capped) GEMMs leave the foreground kernels their SMs, while a
-  // column sum floods every SM for ~20 us -- better in the middle of the decoder's loop than in front of its first kernel
+  // Column sums first: on a trainer's background lane they stay within the lane's CTA budget (misc.cuh) and the first ~60 us still run next
+  // to the decoder's CE backward rather than its loop.
   cudaStream_t s2 = st;
-  const bool lane = tc2::background_ctas() > 0;   // on a trainer's background lane: one capped GEMM at a time (the foreground loop's
-  if (!lane) RN_TRY(side().fork(st, &s2));        // 512-thread, 128-register CTAs need SMs that are completely empty)
-  RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk2, s2));
-  RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk2, s2));
-  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk2, s2));
+  const bool lane = tc2::background_ctas() > 0;   // on the lane: one capped GEMM at a time (the foreground loop's 512-thread, 128-register
+  if (!lane) RN_TRY(side().fork(st, &s2));        // CTAs need SMs that are completely empty)
+  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st, is_gru ? nullptr : g.b_hh));     // LSTM: b_hh gets the same gradient
+  if (is_gru) RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st));
   RN_TRY(misc::colsum<T>(w.dOut, R, SB, R, g.out_b, 0, w.splitk2, s2));
   RN_TRY(misc::colsum<float>(w.dWh, A, SB, A, g.attn_b, 0, w.splitk2, s2));
   RN_TRY(misc::colsum<float>(w.dw_acc, A, B, A, g.attn_w, 0, w.splitk2, s2));
+  RN_TRY(gemm_full<T>(w.dOut, R, 1, Hr, w.KX, 1, g.out_w, R, nullptr, R, R, SB, 0, w.splitk2, s2));
+  RN_TRY(gemm_full<T>(w.dWh_op, A, 1, w.X + H, w.KX, 1, g.attn_W, R, nullptr, A, R, SB, 0, w.splitk2, s2));
+  RN_TRY(gemm_full<T>(w.dUv_op, A, 1, w.Hd, H, 1, g.attn_U, H, nullptr, A, H, L * B, 0, w.splitk2, s2));
   RN_TRY(gemm_full<T>(w.dG, GR, 1, w.X, w.KX, 1, g.w_ih, H, nullptr, GR, H, SB, 0, w.splitk, st));
   RN_TRY(gemm_full<T>(dGh, GR, 1, w.X + H, w.KX, 1, g.w_hh, R, nullptr, GR, R, SB, 0, w.splitk, st));
-  RN_TRY(misc::colsum<T>(w.dG, GR, SB, GR, g.b_ih, 0, w.splitk, st, is_gru ? nullptr : g.b_hh));     // LSTM: b_hh gets the same gradient
-  if (is_gru) RN_TRY(misc::colsum<T>(dGh, GR, SB, GR, g.b_hh, 0, w.splitk, st));
   if (!lane) RN_TRY(side().join(st, s2));
   return 0;
 }

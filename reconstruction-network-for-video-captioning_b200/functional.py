@@ -337,7 +337,7 @@ def _layered_shape(hiddens):
 #      loop (they take the register file), so they run next to the decoder's weight-gradient GEMMs instead.
 # The persistent GEMMs of 1-2 are capped to ``ctas`` CTAs (recnet_set_background_ctas) so they never hold the SMs the loop's kernels
 # are waiting for.  ``join_background()`` makes the main stream wait for the lane; everything the lane reads is kept alive until then.
-# Plain cross-stream dependencies: works under CUDA-graph capture.  Measured timelines: profiles/r2_i_step_timeline.md.
+# Plain cross-stream dependencies: works under CUDA-graph capture.  Measured timelines: profiles/r2_j_step_timeline.md.
 class _Background:
     active = False
     ctas = 48

@@ -166,7 +166,7 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
     # regulariser gradient + optimiser step and the decoder's vocabulary-projection gradients run on a second stream underneath /
     # next to the decoder's backward; joined at the end of this function.  Data-parallel runs keep the plain order: there the
     # reducer overlaps the reconstructor's all-reduce with the decoder's backward and its optimiser step with the decoder's
-    # all-reduce, and a third tenant on the SMs (measured at N = 2, profiles/r2_i_step_timeline.md) costs more than it hides.
+    # all-reduce, and a third tenant on the SMs (measured at N = 2, profiles/r2_j_step_timeline.md) costs more than it hides.
     use_bg = _background_ok(grad_hook, reducer)
     local_rec = reconstructor is not None and isinstance(reconstructor['model'], LocalReconstructor)
     tail = _background_tail(reconstructor) if (use_bg and optimizer_step and local_rec) else None

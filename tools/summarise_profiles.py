@@ -50,7 +50,7 @@ def main(tag):
     md = [f"# {tag}: ncu launch lists of one training step (`bench.py --steps 1 --warmup 3 --no-graph --cpu-iters 0 --no-extras`, 1 x B200)\n",
           "`ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c 150` (tools/collect_profiles_r2.sh): a window of 150 launches = one full step",
           "(129 launches of this library + a few torch glue kernels) and the head of the next, serialised by the profiler -- the concurrency of the",
-          "captured graph (side stream, background lane: profiles/r2_i_step_timeline.md) is NOT visible here.",
+          "captured graph (side stream, background lane: profiles/r2_j_step_timeline.md) is NOT visible here.",
           "cold = ncu's default cache control (L2 flushed before every launch); warm = `--cache-control none`",
           "(L2 as the previous kernel left it -- the steady state of the captured graph).  Per-launch durations carry ~2.5 us of fixed",
           "profiler overhead (a 1-CTA elementwise kernel reads 2.5 us): compare SHARES.\n"]

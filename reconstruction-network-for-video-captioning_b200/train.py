@@ -144,7 +144,8 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
     Returns (loss, decoder_loss, recon_loss) device scalars."""
     # train.py:246 (the fused path derives the mask from the targets itself; the host-side loop length needs it when n_steps is None)
     target_masks = None if (n_steps is not None and targets.is_cuda) else targets > C.init_word2idx['<PAD>']
-    if _background_ok(grad_hook, reducer) and targets.is_cuda and os.environ.get("RECNET_BG_NORMS", "1") == "1":
+    if (grad_hook is None and targets.is_cuda and os.environ.get("RECNET_BG_WGRAD", "1") == "1"
+            and os.environ.get("RECNET_BG_NORMS", "1") == "1"):                    # (also in data-parallel steps: no reducer involved)
         # the regularisers' squared norms depend on the parameters only: on the lane, underneath the decoder's forward loop
         Fn.prefetch_param_norms(*[m._params() for m in (decoder['model'], reconstructor['model'] if reconstructor else None)
                                   if m is not None and hasattr(m, "_params") and getattr(m, "uses_fused_sequence", True)])

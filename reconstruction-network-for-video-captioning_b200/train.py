@@ -55,7 +55,12 @@ def forward_decoder(decoder, encoder_outputs, targets, target_masks, teacher_for
             tokens_in = torch.cat((sos, targets[: L - 1]), dim=0)                                           # train.py:44-45
         else:
             # argmax feedback (train.py:47-51): decode greedily on device, then replay those tokens through the
-            # differentiable sequence kernel (identical arithmetic in eval mode, where validation uses it, train.py:329)
+            # differentiable sequence kernel (identical arithmetic in eval mode, where validation uses it, train.py:329).
+            # KNOWN DIFFERENCE in train mode with teacher_forcing_ratio < 1 (the reference's default is 1.0, config.py:71): the
+            # reference feeds back the argmax of the SAME pass's dropout-perturbed logits; here the tokens come from a dropout-free
+            # greedy pass, so the fed-back tokens follow the eval-mode distribution.  Losses / gradients for a GIVEN token sequence
+            # are identical.  (The step-wise greedy of stacked decoders also stops once every token is <PAD> and leaves the
+            # remaining rows 0 = <PAD>, which is what the reference would decode from an all-<PAD> row only by accident.)
             ids, _ = model.greedy(encoder_outputs, L)
             tokens_in = torch.cat((sos, ids[: L - 1]), dim=0)
             output_indices = ids[:L].cpu()

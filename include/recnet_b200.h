@@ -166,6 +166,12 @@ int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
                        const int64_t* tokens_in, const int64_t* targets, const float* ce_weight, const uint64_t* rng,
                        void* workspace, int64_t workspace_bytes, const float* g_ce, const float* g_hiddens,
                        const float* hiddens, const recnet_decoder_tensors* grads, void* stream);
+/* recnet_decoder_fwd in parts, same arguments (split where recnet_decoder_bwd_is_split says so; otherwise bit 0 runs everything):
+ *   1 = staging, hoisted projections, the time loop (-> hiddens)      2 = vocabulary projection, attention contexts, CE (-> ce_out; needs 1)
+ * Nothing of part 2 feeds the reconstructor: a trainer may run it on another stream next to the reconstructor's staging. */
+int recnet_decoder_fwd_phase(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
+                             const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
+                             int64_t workspace_bytes, float* hiddens, float* ce_out, int phases, void* stream);
 /* recnet_decoder_bwd in parts, same arguments (single-layer decoders on the projected-feature path; recnet_decoder_bwd_is_split says
  * whether the split applies -- otherwise bit 0 runs everything and the other bits nothing):
  *   1 = CE backward + gradient wrt the states through the vocabulary projection     2 = the BPTT loop (needs 1)

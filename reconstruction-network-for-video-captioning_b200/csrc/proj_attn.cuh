@@ -470,19 +470,23 @@ template <> struct Pair<bf16> {
 // S = number of summed rows (L resp. Tn), K = number of output rows per sample (Tn resp. L).  e is staged in shared memory as [S][Kp].
 template <typename TO, bool CTX>
 __global__ void __launch_bounds__(256) pf_escore_kernel(const float* __restrict__ e, const TO* __restrict__ X, long long ld, int col0,
-                                                        TO* __restrict__ out, int L, int B, int Tn, int N, float inv_T) {
+                                                        TO* __restrict__ out, int L, int B, int Tn, int N, float inv_T, int spc) {
+  // spc = samples per CTA (blockIdx.y covers samples [y * spc, (y + 1) * spc)): the launcher keeps the grid within ONE wave, so that a
+  // persistent GEMM launched next to it never queues behind a second wave of these CTAs (CTAs are dispatched in launch order)
   extern __shared__ float4 e_sm4[];                     // [round_up(S, 16)][Kp], zero beyond S / K
   float* e_sm = reinterpret_cast<float*>(e_sm4);
   const int S = CTX ? Tn : L, K = CTX ? L : Tn;
   const int Kp = (K + 3) & ~3, Sp = (S + 15) & ~15;
-  const int b = blockIdx.y, n = (blockIdx.x * 256 + threadIdx.x) * 2;
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 2;
+  for (int b = blockIdx.y * spc; b < min(B, (int)(blockIdx.y + 1) * spc); ++b) {
+  __syncthreads();                                      // the previous sample's scores are no longer read
   for (int i = threadIdx.x; i < Sp * Kp; i += 256) {
     const int s_ = i / Kp, k = i - s_ * Kp;
     const int t = CTX ? k : s_, tau = CTX ? s_ : k;
     e_sm[i] = (s_ < S && k < K) ? e[((long long)t * B + b) * Tn + tau] : 0.f;
   }
   __syncthreads();
-  if (n >= N) return;
+  if (n >= N) continue;
   for (int k0 = 0; k0 < K; k0 += 32) {
     float acc[32][2];
 #pragma unroll
@@ -517,6 +521,13 @@ __global__ void __launch_bounds__(256) pf_escore_kernel(const float* __restrict_
         Pair<TO>::store(out + row * N + n, acc[k][0] * inv_T, acc[k][1] * inv_T);
       }
   }
+  }   // samples of this CTA
+}
+// samples per CTA so that the grid (ceil(N / 512) column blocks x ceil(B / spc)) fits one wave of `sms` CTAs
+static inline int escore_spc(int N, int B, int sms) {
+  const int cb = (N + 511) / 512;
+  int spc = (cb * B + sms - 1) / sms;
+  return spc < 1 ? 1 : spc;
 }
 static inline size_t escore_smem(int L, int Tn, bool ctx) {
   const int S = ctx ? Tn : L, K = ctx ? L : Tn;

@@ -221,6 +221,23 @@ int recnet_decoder_fwd(const recnet_decoder_desc* d, const recnet_decoder_tensor
     return dec::forward<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream));
   return RECNET_ERR_UNSUPPORTED;
 }
+int recnet_decoder_fwd_phase(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
+                             const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
+                             int64_t workspace_bytes, float* hiddens, float* ce_out, int phases, void* stream) {
+  if (phases < 1 || phases > 3) return RECNET_ERR_BAD_SHAPE;
+  if (d->n_layers > 1 || !dec::pf_ok(*d)) {          // not split on these paths: everything belongs to bit 0
+    if (!(phases & 1)) return 0;
+    return recnet_decoder_fwd(d, w, feats, tokens_in, targets, ce_weight, rng, workspace, workspace_bytes, hiddens, ce_out, stream);
+  }
+  const long long* ti = reinterpret_cast<const long long*>(tokens_in);
+  const long long* tg = reinterpret_cast<const long long*>(targets);
+  const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+  if (d->precision == RECNET_PREC_FP32)
+    return dec::forward_pf<float>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream), phases);
+  if (d->precision == RECNET_PREC_BF16)
+    return dec::forward_pf<bf16>(*d, *w, feats, ti, tg, ce_weight, r, workspace, workspace_bytes, hiddens, ce_out, ST(stream), phases);
+  return RECNET_ERR_UNSUPPORTED;
+}
 int recnet_decoder_bwd(const recnet_decoder_desc* d, const recnet_decoder_tensors* w, const float* feats, const int64_t* tokens_in,
                        const int64_t* targets, const float* ce_weight, const uint64_t* rng, void* workspace,
                        int64_t workspace_bytes, const float* g_ce, const float* g_hiddens, const float* hiddens,

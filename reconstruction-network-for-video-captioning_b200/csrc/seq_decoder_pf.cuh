@@ -122,13 +122,16 @@ static inline int gemm_to_operand(const bf16* A, long long lda, const bf16* B, l
 template <typename T>
 static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors& p, const float* feats, const long long* tokens_in,
                       const long long* targets, const float* ce_weight, const unsigned long long* rng, void* ws, long long ws_bytes,
-                      float* hiddens, float* ce_out, cudaStream_t st) {
+                      float* hiddens, float* ce_out, cudaStream_t st, int phases = 3) {
+  // phases (recnet_decoder_fwd_phase): 1 = staging, hoisted projections and the time loop (-> hiddens), 2 = vocabulary projection, per-step
+  // attention contexts, CE (-> ce_out; needs 1).  Nothing after the loop feeds the reconstructor, so a trainer may run 2 on another stream.
   RN_TRY(check(d));
   PfWs<T> w = plan_pf<T>(d, ws);
   if ((long long)w.bytes > ws_bytes) return RECNET_ERR_WORKSPACE;
   const int B = d.B, L = d.L, H = d.H, E = d.E, A = d.A, V = d.V, Tn = d.T, EMB = d.EMB;
   const float p_emb = d.train ? d.p_emb_drop : 0.f, p_out = d.train ? d.p_out_drop : 0.f;
   const long long ldih = EMB + E;
+  if (phases & 1) {
   // operand copies of the weights / features (the optimiser changes the fp32 masters every step)
   // operand copies of the weights / features + cleared initial state: ONE multi-tensor staging kernel (misc.cuh:Stager)
   // (the embedding gather needs neither: it starts on the second stream right away, next to the staging kernel)
@@ -181,6 +184,8 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
     fa.c_out = w.c + (r + B) * H; fa.h_out = hiddens + r * H; fa.h_op = w.Hop + (r + B) * H;
     RN_TRY((pf::launch_fwd<T, T>(fa, st)));
   }
+  }   // phases & 1
+  if (!(phases & 2)) return 0;
   // Training calls: the attention context of every step, ctx_t[b] = (1/T) sum_tau e_t[b,tau] v[b,tau] (decoder.py:57-62).  The forward pass never
   // needs it (the projected features carry it), but dW_ctx = sum_t dG_t^T ctx_t does, and HERE it costs nothing: its 256-thread CTAs share the
   // SMs with the vocabulary GEMM's.  (Until r2_i backward formed dVW[b,tau] = (1/T) sum_t e_t[b,tau] dG_t[b] after its loop instead: 29-52 us on
@@ -191,9 +196,13 @@ static int forward_pf(const recnet_decoder_desc& d, const recnet_decoder_tensors
   // vocabulary projection over all steps, then the masked CE (train.py:54-60,68)
   RN_TRY(gemm_full<T>(w.Hop + (size_t)B * H, H, 0, w.Wout, H, 0, w.logits, w.Vld, p.out_b, L * B, V, H, 0, w.splitk, st));
   if (training) {
-    // launched AFTER the GEMM: CTAs are dispatched in launch order, and the GEMM's 148 must not queue behind these 300
-    pf::pf_escore_kernel<T, true><<<dim3(rn_cdiv(E, 512), B), 256, pf::escore_smem(L, Tn, true), s3>>>(w.e, w.feats, E, 0, w.ctx, L, B, Tn, E,
-                                                                                                  1.f / Tn);
+    // launched after the GEMM: CTAs are dispatched in launch order (inside a captured graph sibling branches may still start in either order)
+    // (one sample per CTA = two waves of CTAs.  A one-wave grid -- pf::escore_spc, three samples per CTA -- lets the GEMM start at once
+    // when the graph happens to launch this branch first, but its long-lived CTAs then slow the GEMM they share the SMs with: 65 vs 34 us,
+    // measured; the two-wave grid costs the GEMM a 20 us late start at worst)
+    const int spc = 1;
+    pf::pf_escore_kernel<T, true><<<dim3(rn_cdiv(E, 512), rn_cdiv(B, spc)), 256, pf::escore_smem(L, Tn, true), s3>>>(w.e, w.feats, E, 0, w.ctx, L, B,
+                                                                                                               Tn, E, 1.f / Tn, spc);
     RN_LAUNCH_OK();
   }
   if (targets && ce_weight && ce_out) {

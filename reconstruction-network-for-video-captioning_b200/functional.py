@@ -84,14 +84,24 @@ def _table_for(params) -> _NormTable:
     return t
 
 
-def _norms_fwd(params, base=None, lambda_dev=None):
+def _norms_alloc(params, lambda_dev=None):
+    """Output buffers of _norms_fwd (sumsq, reg, fused or None, partial), allocated on the CURRENT stream -- a caller that runs _norms_fwd
+    on another stream allocates them first, where they are used and freed."""
+    tab = _table_for(params)
+    dev = params[0].device
+    return (torch.empty(tab.n, dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev),
+            torch.empty((), dtype=torch.float32, device=dev) if lambda_dev is not None else None,
+            torch.empty(tab.n_blocks, dtype=torch.float32, device=dev))
+
+
+def _norms_fwd(params, base=None, lambda_dev=None, bufs=None):
     """reg = sum_p ||p||  (+ fused = base + lambda_dev * reg when ``lambda_dev`` is given: the loss assembly of train.py:70,102,128
     inside the finalize kernel).  Returns (reg, sumsq, fused or None)."""
     tab = _table_for(params)
     dev = params[0].device
-    sumsq = torch.empty(tab.n, dtype=torch.float32, device=dev)
-    reg = torch.empty((), dtype=torch.float32, device=dev)
-    fused = torch.empty((), dtype=torch.float32, device=dev) if lambda_dev is not None else None
+    if bufs is None:
+        bufs = _norms_alloc(params, lambda_dev)
+    sumsq, reg, fused, spare = bufs
     pre = _prefetched_norms.pop(tuple((p.data_ptr(), p.numel()) for p in params), None)
     if pre is not None:                     # the squared-norm partials were computed ahead of the forward pass (prefetch_param_norms)
         partial, ready = pre
@@ -101,7 +111,7 @@ def _norms_fwd(params, base=None, lambda_dev=None):
                 "recnet_param_norms_finalize")
         _bg.keep.append(partial)
         return reg, sumsq, fused
-    partial = torch.empty(tab.n_blocks, dtype=torch.float32, device=dev)
+    partial = spare
     L.check(L.lib().recnet_param_norms_fwd(tab.ptrs.data_ptr(), tab.sizes.data_ptr(), tab.n, tab.blk_tensor.data_ptr(),
                                            tab.blk_chunk.data_ptr(), tab.n_blocks, partial.data_ptr(), sumsq.data_ptr(),
                                            reg.data_ptr(), _ptr(base), _ptr(lambda_dev), _ptr(fused), _stream()),
@@ -215,7 +225,7 @@ def _scalar(g, dev):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
+def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params, split=False):
     lib = L.lib()
     feats = _f32c(feats, "encoder_outputs")
     params = tuple(_f32c(p, f"decoder parameter {i}") for i, p in enumerate(params))
@@ -239,11 +249,19 @@ def _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params):
     targets = targets.contiguous() if targets is not None else None
     ce_weight = ce_weight.contiguous() if ce_weight is not None else None
     w = _pack(L.decoder_tensors, params)
-    L.check(lib.recnet_decoder_fwd(C.byref(d), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), _ptr(targets),
-                                   _ptr(ce_weight), rng.data_ptr(), ws.data_ptr(), nbytes, hiddens.data_ptr(),
-                                   ce.data_ptr(), _stream()), "recnet_decoder_fwd")
+
+    def phase(bits):
+        L.check(lib.recnet_decoder_fwd_phase(C.byref(d), C.byref(w), feats.data_ptr(), tokens_in.data_ptr(), _ptr(targets),
+                                             _ptr(ce_weight), rng.data_ptr(), ws.data_ptr(), nbytes, hiddens.data_ptr(),
+                                             ce.data_ptr(), bits, _stream()), "recnet_decoder_fwd_phase")
+
+    saved = (feats, tokens_in, targets, ce_weight, rng, *params)
     _remember_status("decoder", ws, lib.recnet_decoder_error_offset(C.byref(d)))
-    return ce, hiddens, ws, d, nbytes, (feats, tokens_in, targets, ce_weight, rng, *params)
+    if split and targets is not None and ce_weight is not None and lib.recnet_decoder_bwd_is_split(C.byref(d)):
+        phase(1)                              # ... the loop: `hiddens` is complete; the caller runs phase(2) where it likes
+        return ce, hiddens, ws, d, nbytes, saved, (lambda: phase(2))
+    phase(3)
+    return ce, hiddens, ws, d, nbytes, saved, None
 
 
 class DecoderSequenceFn(torch.autograd.Function):
@@ -256,9 +274,24 @@ class DecoderSequenceFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta: Dict, feats, tokens_in, targets, ce_weight, rng, *params):
-        ce, hiddens, ws, d, nbytes, saved = _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params)
+        ce, hiddens, ws, d, nbytes, saved, tail = _decoder_fwd_raw(meta, feats, tokens_in, targets, ce_weight, rng, params,
+                                                                   split=_bg.split_forward)
         lam = _lambda_scalar(meta, ce.device)
-        reg, sumsq, fused = _norms_fwd(saved[5:], ce, lam)
+        if tail is None:
+            reg, sumsq, fused = _norms_fwd(saved[5:], ce, lam)
+        else:
+            # vocabulary projection + CE + loss assembly on the lane, next to the reconstructor's staging: nothing of it feeds the
+            # reconstructor.  The trainer waits (wait_forward_tail) before it touches the loss.  Output buffers allocated HERE (main stream).
+            bufs = _norms_alloc(saved[5:], lam)
+            done = torch.cuda.Event()
+
+            def work():
+                tail()
+                out = _norms_fwd(saved[5:], ce, lam, bufs)
+                done.record(torch.cuda.current_stream())
+                return out
+            reg, sumsq, fused = run_in_background(work, ws, ce, hiddens, *bufs, *saved)
+            _bg.forward_tails.append(done)
         ctx.desc, ctx.nbytes = d, nbytes
         ctx.lam = lam                       # not an autograd input: a plain attribute keeps it alive for backward
         ctx.set_materialize_grads(False)
@@ -307,7 +340,7 @@ class DecoderSequenceFn(torch.autograd.Function):
 @torch.no_grad()
 def decoder_teacher_forced_logits(meta: Dict, feats, tokens_in, rng, params):
     """Inference helper: stacked logits (L,B,V) and hiddens (L,B,H) of the teacher-forced loop (no loss)."""
-    ce, hiddens, ws, d, nbytes, _ = _decoder_fwd_raw(meta, feats, tokens_in, None, None, rng, params)
+    ce, hiddens, ws, d, nbytes, _, _ = _decoder_fwd_raw(meta, feats, tokens_in, None, None, rng, params)
     ld = C.c_int64()
     ptr = L.lib().recnet_decoder_logits(C.byref(d), ws.data_ptr(), C.byref(ld))
     off = ptr - ws.data_ptr()
@@ -345,6 +378,8 @@ class _Background:
     pending = False
     keep: list = []
     late: list = []
+    split_forward = False
+    forward_tails: list = []
 
 
 _bg = _Background()
@@ -441,6 +476,31 @@ def _flush(items: list):
         todo = list(items)
         items.clear()
         run_in_background(lambda: [f() for f in todo])
+
+
+class split_decoder_forward:
+    """Context manager for a trainer: inside it DecoderSequenceFn.forward puts everything after its time loop (vocabulary projection, CE, loss
+    assembly) on the lane.  The trainer MUST call ``wait_forward_tail()`` before it uses the decoder's loss."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = bool(enabled)
+
+    def __enter__(self):
+        self.prev = _bg.split_forward
+        _bg.split_forward = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _bg.split_forward = self.prev
+        return False
+
+
+def wait_forward_tail():
+    """The main stream waits for the forward tails issued under ``split_decoder_forward``."""
+    main = torch.cuda.current_stream() if _bg.forward_tails else None
+    for ev in _bg.forward_tails:
+        main.wait_event(ev)
+    _bg.forward_tails.clear()
 
 
 def background_pending() -> bool:

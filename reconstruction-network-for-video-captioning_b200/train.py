@@ -155,12 +155,17 @@ def train_step(decoder, reconstructor, encoder_outputs, targets, n_steps=None, l
         Fn.prefetch_param_norms(*[m._params() for m in (decoder['model'], reconstructor['model'] if reconstructor else None)
                                   if m is not None and hasattr(m, "_params") and getattr(m, "uses_fused_sequence", True)])
     decoder['model'].train()
-    dec_loss, hiddens, _ = forward_decoder(decoder, encoder_outputs, targets, target_masks,
-                                           C.decoder_teacher_forcing_ratio, n_steps=n_steps)
+    split_fwd = (grad_hook is None and reconstructor is not None and targets.is_cuda and os.environ.get("RECNET_BG_WGRAD", "1") == "1"
+                 and os.environ.get("RECNET_BG_FWD", "1") == "1")
+    with Fn.split_decoder_forward(enabled=split_fwd):      # vocabulary projection + CE on the lane, next to the reconstructor's staging
+        dec_loss, hiddens, _ = forward_decoder(decoder, encoder_outputs, targets, target_masks,
+                                               C.decoder_teacher_forcing_ratio, n_steps=n_steps)
     rec_loss = None
     if reconstructor is not None:
         reconstructor['model'].train()
         rec_loss = forward_reconstructor_for(C.reconstructor_type)(hiddens, encoder_outputs, reconstructor)
+    Fn.wait_forward_tail()                                 # the decoder's loss is final on the main stream from here on
+    if reconstructor is not None:
         loss = dec_loss + rec_loss if lambda_recon == 1.0 else dec_loss + lambda_recon * rec_loss           # train.py:260
     else:
         loss = dec_loss

@@ -73,6 +73,10 @@ int recnet_gemm(int precision, const void* A, int64_t lda, int transA, const voi
                 int splits, int64_t split_stride, int accumulate, int bn_hint, void* stream);
 
 /* out[m*ldo + n] (+)= sum_s partial[s*split_stride + m*ldp + n] */
+/* Host-only: the tile / split-K plan the batched GEMMs of the sequence calls use for an [M x N x K] product (bf16: bn = 64 / 128 / 256 for the
+ * one-tile-per-CTA kernel, 1000 + width for the persistent kernel with single CTAs, 2000 + width with CTA pairs; splits = split-K slices).
+ * No device work: lets tests pin the planner's decisions (profiles/r2_h_gemm_sweep.md). */
+int recnet_plan_batched_gemm(int precision, int M, int N, int K, int32_t* bn_out, int32_t* splits_out);
 int recnet_splitk_reduce(const float* partial, int splits, int64_t split_stride, int64_t ldp, float* out, int64_t ldo,
                          int M, int N, int accumulate, void* stream);
 

@@ -96,6 +96,13 @@ int recnet_gemm(int precision, const void* A, int64_t lda, int transA, const voi
   return RECNET_ERR_UNSUPPORTED;
 }
 
+int recnet_plan_batched_gemm(int precision, int M, int N, int K, int32_t* bn_out, int32_t* splits_out) {
+  if (M <= 0 || N <= 0 || K <= 0 || !bn_out || !splits_out) return RECNET_ERR_BAD_SHAPE;
+  rt::GemmPlan p = precision == RECNET_PREC_BF16 ? rt::plan_gemm_full<bf16>(M, N, K) : rt::plan_gemm_full<float>(M, N, K);
+  *bn_out = p.bn;
+  *splits_out = p.splits;
+  return 0;
+}
 int recnet_splitk_reduce(const float* partial, int splits, int64_t split_stride, int64_t ldp, float* out, int64_t ldo, int M,
                          int N, int accumulate, void* stream) {
   return rt::splitk_reduce(partial, splits, split_stride, ldp, out, ldo, M, N, nullptr, accumulate, ST(stream));

@@ -231,6 +231,10 @@ int recnet_local_bwd_phase(const recnet_local_desc* d, const recnet_local_tensor
                            const uint64_t* rng, void* workspace, int64_t workspace_bytes, const float* g_mse,
                            const recnet_local_tensors* grads, float* g_hiddens, int phases, void* stream);
 int recnet_set_background_ctas(int n);
+/* Host-only: how the weight-resident persistent loops (csrc/seq_recon_persist.cuh) would lay a local-reconstructor call out, 12 ints:
+ * forward {covered, K-splits, unit groups, resident k-blocks per CTA, ring stages, CTAs}, backward {covered, gate-row splits, column groups,
+ * resident k-blocks per CTA, ring stages, CTAs}; covered = 0 means the call takes the kernel-per-phase path. */
+int recnet_plan_persistent_loops(const recnet_local_desc* d, int32_t* out);
 float* recnet_local_outputs(const recnet_local_desc* d, void* workspace);   /* [S,B,R] fp32 */
 
 /* Global reconstructor (models/global_reconstructor.py:30-46 + train.forward_global_reconstructor, train.py:78-105). */

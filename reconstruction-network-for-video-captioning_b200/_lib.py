@@ -86,6 +86,7 @@ SIGNATURES = {
     "recnet_profile_enable": (_i, [_i, _i]),
     "recnet_profile_collect": (_i, [_p, _i]),
     "recnet_gemm": (_i, [_i, _p, _l, _i, _p, _l, _i, _p, _l, _p, _l, _p, _i, _i, _i, _i, _l, _i, _i, _p]),
+    "recnet_plan_persistent_loops": (_i, [C.POINTER(local_desc), _p]),
     "recnet_plan_batched_gemm": (_i, [_i, _i, _i, _i, _p, _p]),
     "recnet_splitk_reduce": (_i, [_p, _i, _l, _l, _p, _l, _i, _i, _i, _p]),
     "recnet_attn_fwd": (_i, [_i, _p, _i, _l, _p, _l, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _p, _p, _l, _f, _p, _u, _l, _p]),

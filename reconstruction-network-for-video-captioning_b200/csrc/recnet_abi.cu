@@ -96,6 +96,23 @@ int recnet_gemm(int precision, const void* A, int64_t lda, int transA, const voi
   return RECNET_ERR_UNSUPPORTED;
 }
 
+int recnet_plan_persistent_loops(const recnet_local_desc* d, int32_t* out) {
+  // out[0..5]  forward : covered?, K-splits, unit groups, resident k-blocks per CTA, activation ring stages, CTAs
+  // out[6..11] backward: covered?, gate-row splits, column groups, resident k-blocks per CTA, ring stages, CTAs
+  if (!d || !out) return RECNET_ERR_BAD_SHAPE;
+  for (int i = 0; i < 12; ++i) out[i] = 0;
+  const rp::Shape s{d->B, d->S, d->R, d->H, d->A, d->L};
+  const bool lstm_bf16 = d->precision == RECNET_PREC_BF16 && d->cell == RECNET_CELL_LSTM && d->dec_layers <= 1;
+  if (lstm_bf16 && rp::local_fwd_ok(s)) {
+    const int ks = rp::pick_ks(s.R, s.H), res = rp::max_res_kb_fwd(s.R, s.H, ks);
+    out[0] = 1; out[1] = ks; out[2] = s.R / rp::UNITS; out[3] = res; out[4] = rp::pick_stages_fwd(s.B, ks, res); out[5] = out[2] * ks;
+  }
+  if (lstm_bf16 && rp::local_bwd_ok(s)) {
+    const int ns = rp::pick_ns(s.R, s.H), res = (4 * s.R / rp::BK + ns - 1) / ns;
+    out[6] = 1; out[7] = ns; out[8] = (s.R + s.H) / 128; out[9] = res; out[10] = rp::pick_stages_bwd(s.B, res); out[11] = out[8] * ns;
+  }
+  return 0;
+}
 int recnet_plan_batched_gemm(int precision, int M, int N, int K, int32_t* bn_out, int32_t* splits_out) {
   if (M <= 0 || N <= 0 || K <= 0 || !bn_out || !splits_out) return RECNET_ERR_BAD_SHAPE;
   rt::GemmPlan p = precision == RECNET_PREC_BF16 ? rt::plan_gemm_full<bf16>(M, N, K) : rt::plan_gemm_full<float>(M, N, K);

@@ -66,3 +66,34 @@ def test_background_budget_limits_split_k_plans():
 def test_rejects_empty_shapes():
     bn, splits = C.c_int32(), C.c_int32()
     assert L.lib().recnet_plan_batched_gemm(L.PREC_BF16, 0, 8, 8, C.byref(bn), C.byref(splits)) < 0
+
+
+def _loops(**kw):
+    base = dict(B=100, S=28, R=1536, H=512, A=128, L=31, precision=L.PREC_BF16, train=1, p_drop=0.5, cell=L.CELL_LSTM, dec_layers=1)
+    base.update(kw)
+    d = L.local_desc(**base)
+    out = (C.c_int32 * 12)()
+    L.check(L.lib().recnet_plan_persistent_loops(C.byref(d), out), "recnet_plan_persistent_loops")
+    return list(out)
+
+
+def test_persistent_loop_layout_of_the_msvd_shape():
+    """144 CTAs = 48 unit groups x 3 K-splits forward (11 resident k-blocks = 176 KB of weights per CTA), 16 column groups x 9
+    gate-row splits backward."""
+    o = _loops()
+    assert o[:4] == [1, 3, 48, 11] and o[4] >= 3 and o[5] == 144
+    assert o[6:10] == [1, 9, 16, 11] and o[10] >= 2 and o[11] == 144
+
+
+@pytest.mark.parametrize("kw", [dict(R=3584, H=512), dict(precision=L.PREC_FP32), dict(cell=L.CELL_GRU), dict(A=256), dict(L=40), dict(B=200),
+                                dict(dec_layers=2)])
+def test_shapes_outside_the_persistent_loops_take_the_kernel_per_phase_path(kw):
+    o = _loops(**kw)
+    assert o[0] == 0 and o[6] == 0, (kw, o)
+
+
+def test_smaller_batches_and_widths_stay_covered():
+    assert _loops(B=64)[0] == 1 and _loops(B=64)[6] == 1
+    o = _loops(R=1024, H=512, B=64)             # (B = 100 at R = 1024 is NOT covered: the forward needs B <= unit groups x K-splits = 96)
+    assert o[0] == 1 and o[5] <= 148 and o[6] == 1 and o[11] <= 148
+    assert _loops(R=1024, H=512)[0] == 0

@@ -76,3 +76,35 @@ def test_no_cpu_path():
     tok = torch.ones(3, 2, dtype=torch.long)
     with pytest.raises(RuntimeError, match="no CPU path"):
         dec.forward_sequence(tok, tok, torch.ones(3, 2), torch.randn(2, 4, 16))
+
+
+def test_round2_entry_points_reject_bad_arguments_before_touching_a_device():
+    """Argument checks of the phase-split / beam / background entry points are host code: they must answer on a box without a GPU."""
+    lib = L.lib()
+    d = L.decoder_desc(B=100, T=28, E=1536, H=512, A=128, EMB=468, V=4188, L=31, precision=L.PREC_BF16, train=1,
+                       embedding_scale=1.0, p_emb_drop=0.5, p_out_drop=0.5)
+    w = L.decoder_tensors()
+    for bad in (0, 4, -1):
+        assert lib.recnet_decoder_fwd_phase(ctypes.byref(d), ctypes.byref(w), None, None, None, None, None, None, 0, None, None, bad, None) < 0
+    for bad in (0, 16):
+        assert lib.recnet_decoder_bwd_phase(ctypes.byref(d), ctypes.byref(w), None, None, None, None, None, None, 0, None, None, None,
+                                            ctypes.byref(w), bad, None) < 0
+    ld = L.local_desc(B=100, S=28, R=1536, H=512, A=128, L=31, precision=L.PREC_BF16, train=1, p_drop=0.5, cell=L.CELL_LSTM, dec_layers=1)
+    lw = L.local_tensors()
+    for bad in (0, 4):
+        assert lib.recnet_local_bwd_phase(ctypes.byref(ld), ctypes.byref(lw), None, None, None, None, 0, None, ctypes.byref(lw), None, bad, None) < 0
+    assert lib.recnet_set_background_ctas(5000) < 0 and lib.recnet_set_background_ctas(0) == 0
+    # the split applies to single-layer LSTM decoders on the projected-feature path only
+    assert lib.recnet_decoder_bwd_is_split(ctypes.byref(d)) == 1
+    d2 = L.decoder_desc(B=100, T=28, E=1536, H=512, A=128, EMB=468, V=4188, L=31, precision=L.PREC_BF16, train=1,
+                        embedding_scale=1.0, p_emb_drop=0.5, p_out_drop=0.5, n_layers=2)
+    assert lib.recnet_decoder_bwd_is_split(ctypes.byref(d2)) == 0
+    dg = L.decoder_desc(B=100, T=28, E=1536, H=512, A=128, EMB=468, V=4188, L=31, precision=L.PREC_BF16, train=1,
+                        embedding_scale=1.0, p_emb_drop=0.5, p_out_drop=0.5, cell=L.CELL_GRU)
+    assert lib.recnet_decoder_bwd_is_split(ctypes.byref(dg)) == 0
+    # beam search: width 1..8, at most 64 steps; workspace grows with the width
+    db = L.decoder_desc(B=8 * 4, T=28, E=1536, H=512, A=128, EMB=468, V=4188, L=1, precision=L.PREC_BF16, train=0,
+                        embedding_scale=1.0, p_emb_drop=0.0, p_out_drop=0.0)
+    assert lib.recnet_beam_workspace_bytes(ctypes.byref(db), 9, 31) < 0 and lib.recnet_beam_workspace_bytes(ctypes.byref(db), 0, 31) < 0
+    assert lib.recnet_beam_workspace_bytes(ctypes.byref(db), 4, 65) < 0
+    assert lib.recnet_beam_workspace_bytes(ctypes.byref(db), 4, 31) > 0
